@@ -1,0 +1,112 @@
+"""Seeded synthetic frames for the grasp-selection path.
+
+One definition shared by the oracle, the CUDA path, the CPU baseline and the
+tests.  A frame is what the reference's two subscribers hand to
+``LeafGraspNode.select_optimal_leaf`` (reference scripts/leaf_grasp_node_v3.py:185-205):
+
+* ``labels``  int16 [H, W]  - 0 = background, leaf ids 1..N, one id per pixel
+  (wire format msg/masks.msg: uint16[] imageData), later ids occlude earlier;
+* ``depth``   float32 [H, W] - metres (msg/depth.msg: float32[] imageData);
+* ``P``       float64 [3, 4] - CameraInfo.P; the path reads P[0,0], P[0,2],
+  P[1,2] and P[0,3] (grasp_point_selector.py:145-150).
+
+This is input generation, not product compute: it runs on the host with NumPy
+and cv2.ellipse and is never timed.
+"""
+from __future__ import annotations
+
+import dataclasses
+
+import cv2
+import numpy as np
+
+# intrinsics of the reference's rig (scripts/leaf_grasp_node_2.py:24-27)
+REF_F, REF_CX, REF_CY = 1750.68, 707.87, 494.07
+REF_W, REF_H = 1440, 1080
+
+
+@dataclasses.dataclass(frozen=True)
+class FrameSpec:
+    """Shape of one synthetic workload (BASELINE.json configs)."""
+
+    height: int = REF_H
+    width: int = REF_W
+    n_leaves: int = 30
+    # semi-axes in pixels; None = the SURVEY 8d figures scaled by width/1440
+    a_range: tuple | None = None
+    b_range: tuple | None = None
+    margin: float | None = None
+
+    @property
+    def scale(self) -> float:
+        return self.width / float(REF_W)
+
+    def resolved(self):
+        s = self.scale
+        a = self.a_range or (90.0 * s, 180.0 * s)
+        b = self.b_range or (50.0 * s, 100.0 * s)
+        m = self.margin if self.margin is not None else 135.0 * s
+        return a, b, m
+
+
+CFG1 = FrameSpec(n_leaves=10)                                  # configs[0]
+CFG2 = FrameSpec(n_leaves=30)                                  # configs[1] (the metric's workload)
+CFG3 = FrameSpec(height=2160, width=3840, n_leaves=100)        # configs[2]
+# small shapes for parity tests: leaves keep >= 10 000 px (leaf_scorer.py:80)
+SMALL = FrameSpec(height=360, width=480, n_leaves=4, a_range=(80.0, 120.0),
+                  b_range=(50.0, 70.0), margin=100.0)
+
+
+def projection_matrix(spec: FrameSpec) -> np.ndarray:
+    s = spec.scale
+    f = REF_F * s
+    P = np.zeros((3, 4), dtype=np.float64)
+    P[0, 0] = f
+    P[1, 1] = f
+    P[0, 2] = REF_CX * s
+    P[1, 2] = REF_CY * s
+    P[2, 2] = 1.0
+    P[0, 3] = -f * 0.1
+    return P
+
+
+def frame_seed(config_seed: int, frame_index: int) -> int:
+    return int(config_seed) * 1_000_003 + int(frame_index)
+
+
+def make_frame(spec: FrameSpec, config_seed: int, frame_index: int):
+    """Return (labels int16 [H,W], depth float32 [H,W]) for one seeded frame."""
+    H, W, N = spec.height, spec.width, spec.n_leaves
+    (a_lo, a_hi), (b_lo, b_hi), margin = spec.resolved()
+    rng = np.random.default_rng(frame_seed(config_seed, frame_index))
+    labels = np.zeros((H, W), dtype=np.int16)
+    depth = np.full((H, W), 0.8, dtype=np.float64)
+    yy, xx = np.mgrid[0:H, 0:W]
+    slope = 2e-4 / spec.scale
+    for leaf in range(1, N + 1):
+        cx = rng.uniform(margin, W - margin)
+        cy = rng.uniform(margin, H - margin)
+        a = rng.uniform(a_lo, a_hi)
+        b = rng.uniform(b_lo, b_hi)
+        ang = rng.uniform(0.0, 180.0)
+        z0 = rng.uniform(0.3, 0.6)
+        sx = rng.uniform(-slope, slope)
+        sy = rng.uniform(-slope, slope)
+        stamp = np.zeros((H, W), dtype=np.uint8)
+        cv2.ellipse(stamp, (int(round(cx)), int(round(cy))), (int(round(a)), int(round(b))),
+                    float(ang), 0.0, 360.0, 1, -1)
+        sel = stamp.astype(bool)
+        labels[sel] = leaf
+        plane = z0 + sx * (xx - cx) + sy * (yy - cy)
+        depth[sel] = plane[sel]
+    depth += rng.normal(0.0, 1e-3, size=(H, W))
+    return labels, depth.astype(np.float32)
+
+
+def make_batch(spec: FrameSpec, config_seed: int, first_index: int, count: int):
+    """Stack ``count`` consecutive frames: labels [B,H,W] int16, depth [B,H,W] float32."""
+    lab = np.empty((count, spec.height, spec.width), dtype=np.int16)
+    dep = np.empty((count, spec.height, spec.width), dtype=np.float32)
+    for i in range(count):
+        lab[i], dep[i] = make_frame(spec, config_seed, first_index + i)
+    return lab, dep
