@@ -1,0 +1,192 @@
+/*
+ * leafgrasp.h - C-ABI of the B200-native grasp-selection hot path.
+ *
+ * The reference (Srecharan/Leaf-Grasping-Vision-ML) is pure Python and has no FFI of its own; the
+ * boundary it offers is three Python classes called from scripts/leaf_grasp_node_v3.py:114-119.
+ * Each entry point below names the reference routine it replaces (paths relative to the reference
+ * checkout).  INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; plain C types only;
+ *   - images are row-major [frames][H][W]; pixel (x, y) = (column, row); flat index y*W + x;
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream); no entry point synchronises
+ *     the host unless its comment says so;
+ *   - return value: 0 = ok, negative = LG_E_* below.  Data-dependent problems found on the device
+ *     (label out of range, region too large ...) are reported per frame in lg_frame_result.status.
+ *   - there is no CPU implementation behind any of these: without a CUDA device they fail.
+ */
+#ifndef LEAFGRASP_H_
+#define LEAFGRASP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LG_OK 0
+#define LG_E_ARG (-1)      /* bad argument (null pointer, size out of range) */
+#define LG_E_CUDA (-2)     /* a CUDA runtime call failed; see lg_last_error() */
+#define LG_E_CAPACITY (-3) /* batch / image larger than the context was created for */
+
+#define LG_TOP_K 20        /* grasp_point_selector.py:197 */
+#define LG_PATCH 32        /* grasp_point_selector.py:66  */
+#define LG_CHANNELS 9      /* grasp_point_selector.py:127 */
+
+/* per-frame status bits (lg_frame_result.status) */
+#define LG_ST_NO_LEAF 1u        /* select_optimal_leaf would return None (leaf_scorer.py:49-50,144-146) */
+#define LG_ST_LABEL_RANGE 2u    /* a label id outside [0, max_labels) was seen; frame result undefined */
+#define LG_ST_RUNS_OVERFLOW 4u  /* chosen leaf has more row runs than the orientation scratch holds */
+#define LG_ST_NO_CANDIDATE 8u   /* _get_candidate_points returned [] */
+
+typedef struct lg_context lg_context; /* opaque: device scratch sized for (max_frames, H, W) */
+
+/* Camera constants, as set by GraspPointSelector.set_camera_params / OptimalLeafSelector.set_camera_params
+ * (grasp_point_selector.py:145-150, leaf_scorer.py:19-23): f = P[0,0], cx = P[0,2], cy = P[1,2]. */
+typedef struct lg_camera {
+    double f, cx, cy;
+} lg_camera;
+
+/* One leaf's stage-1 record (leaf_scorer.py:74-138). */
+typedef struct lg_leaf_record {
+    int32_t leaf_id;
+    uint32_t area;         /* pixel count */
+    float median_depth;    /* np.median(depth[mask]) */
+    float mean_depth;      /* np.mean(depth[mask]) */
+    double centroid_x, centroid_y;
+    double clutter, distance, visibility; /* the three scores */
+    double mean_distance;  /* raw_scores['distance'] */
+    int32_t is_tall;       /* median < mean of medians */
+    int32_t is_candidate;  /* area >= 10000 */
+} lg_leaf_record;
+
+/* Everything select_optimal_leaf + select_grasp_point return for one frame
+ * (leaf_grasp_node_v3.py:114-119, grasp_point_selector.py:184-253). */
+typedef struct lg_frame_result {
+    uint32_t status;             /* LG_ST_* bits */
+    int32_t leaf_id;             /* -1 when no leaf */
+    int32_t n_candidates;        /* <= LG_TOP_K */
+    int32_t n_positive;          /* candidates whose key (traditional score x valid) is > 0 */
+    int32_t cand_x[LG_TOP_K], cand_y[LG_TOP_K];
+    double trad[LG_TOP_K];       /* traditional_score at each candidate */
+    float logit[LG_TOP_K];       /* CNN output; NaN where no ML score was produced */
+    double ml[LG_TOP_K];         /* tanh(3*sigmoid(logit))/2 + 1/2 */
+    int32_t ml_valid[LG_TOP_K];  /* 1 where the reference's get_ml_score returns a value */
+    int32_t best_index;          /* index into cand_* of the fused pick */
+    int32_t ml_used;             /* a fused score beat candidate 0's traditional score */
+    double best_score;
+    int32_t grasp_x, grasp_y;    /* grasp_point_2d */
+    double grasp_3d[3];          /* get_3d_grasp_point */
+    double pre_grasp[3];         /* calculate_pre_grasp_point */
+    double angle;                /* estimate_leaf_orientation angle (rad), NaN if no contour */
+    float sdf_max;               /* max |dist_inside - dist_outside| */
+    int32_t region[4];           /* x0, y0, x1, y1 (exclusive) of the chosen leaf's bounding box */
+} lg_frame_result;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+
+/* Allocate device scratch for batches of up to max_frames images of height x width whose label ids
+ * lie in [0, max_labels).  Uses the current CUDA device. */
+int lg_create(lg_context** out, int max_frames, int height, int width, int max_labels);
+void lg_destroy(lg_context* ctx);
+const char* lg_last_error(void);
+/* Bytes of device memory the context holds. */
+uint64_t lg_context_bytes(const lg_context* ctx);
+
+/* Folded GraspPointCNN weights (model.py:5-100 with eval-mode BatchNorm folded into the preceding
+ * conv / linear).  `blob_host` is a HOST float array laid out as described in cnn.py:pack_weights;
+ * it is copied to the device (synchronous).  Passing NULL clears the model (CV-only path,
+ * grasp_point_selector.py:52-57). */
+int lg_set_cnn_weights(lg_context* ctx, const float* blob_host, uint64_t n_floats);
+
+/* ---- whole path ----------------------------------------------------------------------------- */
+
+/* The per-frame path of leaf_grasp_node_v3.py:110-119 for `frames` independent frames:
+ * OptimalLeafSelector.select_optimal_leaf (leaf_scorer.py:25) then GraspPointSelector.select_grasp_point
+ * (grasp_point_selector.py:184) on the chosen leaf, including the batched GraspPointCNN forward and the
+ * CV/ML fusion.  labels int16 [frames][H][W], depth float32 [frames][H][W]; results (device)
+ * lg_frame_result[frames].  use_bf16_cnn != 0 runs the tensor-core CNN, 0 the fp32 one. */
+int lg_process_batch(lg_context* ctx, const int16_t* labels, const float* depth, int frames,
+                     const lg_camera* cam_host, lg_frame_result* results, int use_bf16_cnn, void* stream);
+
+/* Same, but labels/depth/results are HOST buffers (pinned for speed): copies in, runs, copies the
+ * results back and synchronises the stream.  This is the call the drop-in Python classes and the
+ * end-to-end benchmark make. */
+int lg_process_batch_host(lg_context* ctx, const int16_t* labels_host, const float* depth_host, int frames,
+                          const lg_camera* cam_host, lg_frame_result* results_host, int use_bf16_cnn,
+                          void* stream);
+
+/* ---- stage 1: OptimalLeafSelector.select_optimal_leaf (leaf_scorer.py:25-203) ---------------- */
+
+/* leaf_id int32 [frames] (-1 = None); records lg_leaf_record [frames][max_labels] (entry i describes
+ * label id i; area 0 = absent), either may be NULL.  Also fills the context's per-frame regions used
+ * by stage 2. */
+int lg_select_leaf(lg_context* ctx, const int16_t* labels, const float* depth, int frames,
+                   const lg_camera* cam_host, int32_t* leaf_id, lg_leaf_record* records, void* stream);
+
+/* ---- distance transforms -------------------------------------------------------------------- */
+
+/* cv2.distanceTransform(mask, DIST_L2, 5) with IPP off (grasp_point_selector.py:266,529-530), batched:
+ * mask uint8 [n][H][W] (non-zero = inside, zero pixels are the sources).  dist float32 [n][H][W] and/or
+ * q16 uint32 [n][H][W] (OpenCV's integer field before the float conversion); either may be NULL.
+ * max_q16 uint32 [n] may be NULL. */
+int lg_chamfer_transform(lg_context* ctx, const uint8_t* mask, int n, int invert, float* dist,
+                         uint32_t* q16, uint32_t* max_q16, void* stream);
+
+/* Exact squared Euclidean distance transform (two-pass, Meijster lower envelope): for every non-zero
+ * pixel of mask the squared distance to the nearest zero pixel; uint32 [n][H][W].  The leaf-selection
+ * stage uses the same kernels on (labels < 1) to find the background pixel farthest from any leaf
+ * (leaf_scorer.py:67-71, scikit-fmm substitute).  argmax int32 [n] (flat index of the first maximum)
+ * may be NULL; d2 may be NULL. */
+int lg_edt_squared(lg_context* ctx, const uint8_t* mask, int n, uint32_t* d2, int32_t* argmax, void* stream);
+
+/* ---- stage 2: GraspPointSelector._calculate_all_scores (grasp_point_selector.py:256-288) ----- */
+
+/* Full-frame score maps of ONE leaf mask per frame, as the reference returns them:
+ * mask uint8 [frames][H][W]; outputs (each may be NULL) sdf_score/approach/accessibility/isolation/
+ * traditional float64, flatness/distance/stem float32, valid uint8, all [frames][H][W].
+ * angle_out double [frames] (estimate_leaf_orientation, :718-752) may be NULL. */
+int lg_score_maps(lg_context* ctx, const uint8_t* mask, const float* depth, int frames,
+                  const lg_camera* cam_host, double* sdf_score, double* approach, float* flatness,
+                  double* isolation, float* distance, double* accessibility, float* stem, double* traditional,
+                  uint8_t* valid, double* angle_out, void* stream);
+
+/* GraspPointSelector._get_candidate_points (grasp_point_selector.py:447-482): score float64 and valid
+ * uint8 [frames][H][W] -> xy int32 [frames][LG_TOP_K][2], count int32 [frames]. */
+int lg_candidate_points(lg_context* ctx, const double* score, const uint8_t* valid, int frames,
+                        int32_t* xy, int32_t* count, void* stream);
+
+/* ---- stage 3: GraspPointCNN.forward (ml_grasp_optimizer/model.py:102-128) ------------------- */
+
+/* patches float32 [n][9][32][32] -> logits float32 [n].  Needs lg_set_cnn_weights first. */
+int lg_cnn_forward(lg_context* ctx, const float* patches, int n, float* logits, int use_bf16, void* stream);
+
+/* ---- stage 2 on a caller-supplied leaf mask --------------------------------------------------- */
+
+/* GraspPointSelector.select_grasp_point (grasp_point_selector.py:184-253) for one binary leaf mask per
+ * frame: mask uint8 [frames][H][W] (non-zero = leaf), depth float32; results (device) as lg_process_batch
+ * (leaf_id is 1 for a non-empty mask). */
+int lg_select_grasp_point(lg_context* ctx, const uint8_t* mask, const float* depth, int frames,
+                          const lg_camera* cam_host, lg_frame_result* results, int use_bf16_cnn, void* stream);
+
+/* GraspPointSelector.estimate_leaf_orientation (grasp_point_selector.py:718-752): out5 double [frames][5] =
+ * angle (rad; NaN when there is no contour), major axis, minor axis, centre x, centre y. */
+int lg_leaf_orientation(lg_context* ctx, const uint8_t* mask, int frames, double* out5, void* stream);
+
+/* The [frames][LG_TOP_K][9][32][32] float32 patch tensor the last lg_process_batch / lg_select_grasp_point
+ * call fed to the CNN (rows of candidates without an ML score are zero). */
+int lg_patches(lg_context* ctx, float* patches_out, int frames, void* stream);
+
+/* Per-patch min-max normalisation of get_ml_score (grasp_point_selector.py:83-123) on caller-built raw
+ * patches float32 [n][9][32][32] (channel 1, the mask, is passed through). */
+int lg_normalize_patches(lg_context* ctx, const float* raw, int n, float* out, void* stream);
+
+/* ---- ABI self-description (the Python binding checks its struct layouts against these) ---------- */
+uint64_t lg_sizeof_frame_result(void);
+uint64_t lg_sizeof_leaf_record(void);
+uint64_t lg_cnn_weight_floats(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LEAFGRASP_H_ */

@@ -1,0 +1,277 @@
+// C-ABI entry points (include/leafgrasp.h): context lifetime, the whole-path pipeline and the
+// per-stage calls the drop-in Python classes and the parity tests use.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <new>
+
+#include "lg_internal.cuh"
+
+int lg_run_export_maps(lg_context* c, int n, double* sdf, double* app, float* flat, float* dist, double* acc, float* stem,
+                       double* trad, uint8_t* valid, double* angle, cudaStream_t st);
+int lg_run_candidates_from_maps(lg_context* c, const double* score, const uint8_t* valid, int n, int32_t* xy, int32_t* count,
+                                cudaStream_t st);
+uint64_t lg_cnn_blob_floats();
+int lg_cnn_prepare_bf16(lg_context* c);
+int lg_run_export_orient(lg_context* c, int n, double* out5, cudaStream_t st);
+int lg_run_normalize_patches(const float* raw, int n, float* out, cudaStream_t st);
+
+static thread_local char g_err[512] = "";
+
+void lg_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* lg_last_error(void) { return g_err; }
+
+namespace {
+
+// 5x5 Gaussian, sigma = 5/6, normalised in float64 and stored as float32 exactly as
+// ImageProcessor._create_gaussian_kernel does (image_processor.py:25-32); bit patterns from NumPy.
+const uint32_t kGaussBits[25] = {
+    0x3a3de028u, 0x3bcdce01u, 0x3c5367f0u, 0x3bcdce01u, 0x3a3de028u, 0x3bcdce01u, 0x3d5f11f3u, 0x3de5242eu, 0x3d5f11f3u,
+    0x3bcdce01u, 0x3c5367f0u, 0x3de5242eu, 0x3e6b60b5u, 0x3de5242eu, 0x3c5367f0u, 0x3bcdce01u, 0x3d5f11f3u, 0x3de5242eu,
+    0x3d5f11f3u, 0x3bcdce01u, 0x3a3de028u, 0x3bcdce01u, 0x3c5367f0u, 0x3bcdce01u, 0x3a3de028u};
+
+// cv2.getStructuringElement(MORPH_ELLIPSE, (n, n)) restated: row i spans columns [a, b)
+void ellipse_rows(int n, int* a, int* b) {
+    const int r = n / 2, c = n / 2;
+    const double inv_r2 = r ? 1.0 / ((double)r * r) : 0.0;
+    for (int i = 0; i < n; ++i) {
+        const int dy = i - r;
+        int j1 = 0, j2 = 0;
+        if (abs(dy) <= r) {
+            const int dx = (int)lrint(c * sqrt((r * r - dy * dy) * inv_r2));
+            j1 = c - dx > 0 ? c - dx : 0;
+            j2 = c + dx + 1 < n ? c + dx + 1 : n;
+        }
+        a[i] = j1; b[i] = j2;
+    }
+}
+
+template <typename T>
+int dev_alloc(lg_context* c, T** p, size_t count) {
+    size_t bytes = count * sizeof(T);
+    if (bytes == 0) bytes = sizeof(T);
+    LG_CUDA(cudaMalloc((void**)p, bytes));
+    c->bytes += bytes;
+    return LG_OK;
+}
+
+}  // namespace
+
+#define TRY(x)                \
+    do {                      \
+        int rc__ = (x);       \
+        if (rc__) return rc__; \
+    } while (0)
+
+extern "C" int lg_create(lg_context** out, int max_frames, int height, int width, int max_labels) {
+    if (!out || max_frames < 1 || height < 8 || width < 8 || max_labels < 2 || max_labels > 1024 || width > 4096 ||
+        height > 16384) {
+        lg_set_error("lg_create: bad arguments (frames=%d H=%d W=%d labels=%d)", max_frames, height, width, max_labels);
+        return LG_E_ARG;
+    }
+    lg_context* c = new (std::nothrow) lg_context();
+    if (!c) return LG_E_ARG;
+    memset(c, 0, sizeof(*c));
+    c->B = max_frames; c->H = height; c->W = width; c->L = max_labels;
+    c->P = (size_t)height * width;
+    const size_t B = max_frames, L = max_labels, P = c->P;
+    int rc = LG_OK;
+    auto A = [&](auto pp, size_t count) { if (!rc) rc = dev_alloc(c, pp, count); };
+    A(&c->cnt, B * L); A(&c->sx, B * L); A(&c->sy, B * L); A(&c->sdep, B * L); A(&c->sdist, B * L);
+    A(&c->bx0, B * L); A(&c->bx1, B * L); A(&c->by0, B * L); A(&c->by1, B * L); A(&c->border, B * L);
+    A(&c->first_leaf, B); A(&c->seg_off, B * (L + 1)); A(&c->seg_cur, B * L); A(&c->seg, B * P); A(&c->median, B * L);
+    A(&c->edt_g, B * P); A(&c->edt_best, B); A(&c->leaf_id, B); A(&c->records, B * L); A(&c->status, B); A(&c->region, B);
+    A(&c->dt_fwd, 2 * B * P); A(&c->di, B * P); A(&c->dt_max, B * 2);
+    c->bits_stride = (size_t)((width + 2 + 31) / 32) * (height + 2);
+    A(&c->bits, B * c->bits_stride);
+    c->run_cap = 8 * (height + 2);
+    A(&c->run_x0, B * (size_t)c->run_cap); A(&c->run_x1, B * (size_t)c->run_cap); A(&c->run_y, B * (size_t)c->run_cap);
+    A(&c->run_parent, B * (size_t)c->run_cap * 6); A(&c->row_first, B * (size_t)(height + 3));
+    A(&c->hull, B * (size_t)(12 * (height + 2))); A(&c->orient, B);
+    A(&c->m_sdf, B * P); A(&c->m_app, B * P); A(&c->m_acc, B * P); A(&c->m_trad, B * P);
+    A(&c->m_flat, B * P); A(&c->m_stem, B * P); A(&c->m_valid, B * P);
+    A(&c->list_key, B * P); A(&c->list_idx, B * P); A(&c->list_n, B);
+    A(&c->patches, B * LG_TOP_K * (size_t)(LG_CHANNELS * LG_PATCH * LG_PATCH)); A(&c->logits, B * LG_TOP_K);
+    A(&c->results, B);
+    c->cnn_cap = (int)(B * LG_TOP_K < 2048 ? 2048 : B * LG_TOP_K);
+    c->cnn_act_bytes = (size_t)c->cnn_cap * 32 * 32 * 64 * sizeof(float);
+    if (!rc) { rc = dev_alloc(c, (unsigned char**)&c->cnn_act0, c->cnn_act_bytes); }
+    if (!rc) { rc = dev_alloc(c, (unsigned char**)&c->cnn_act1, c->cnn_act_bytes); }
+    A(&c->in_labels, B * P); A(&c->in_depth, B * P);
+    if (rc) { lg_destroy(c); return rc; }
+    memcpy(c->gauss, kGaussBits, sizeof(kGaussBits));
+    ellipse_rows(LG_SE_STEM, c->se30_a, c->se30_b);
+    ellipse_rows(LG_SE_PRE, c->se31_a, c->se31_b);
+    cudaError_t e = cudaMemset(c->results, 0, sizeof(lg_frame_result) * B);
+    if (e == cudaSuccess) e = cudaMemset(c->dt_max, 0, sizeof(uint32_t) * 2 * B);
+    if (e == cudaSuccess) e = cudaMemset(c->orient, 0, sizeof(LgOrient) * B);
+    if (e != cudaSuccess) { lg_set_error("lg_create: %s", cudaGetErrorString(e)); lg_destroy(c); return LG_E_CUDA; }
+    *out = c;
+    return LG_OK;
+}
+
+extern "C" void lg_destroy(lg_context* c) {
+    if (!c) return;
+    void* ptrs[] = {c->cnt, c->sx, c->sy, c->sdep, c->sdist, c->bx0, c->bx1, c->by0, c->by1, c->border, c->first_leaf,
+                    c->seg_off, c->seg_cur, c->seg, c->median, c->edt_g, c->edt_best, c->leaf_id, c->records, c->status,
+                    c->region, c->dt_fwd, c->di, c->dt_max, c->bits, c->run_x0, c->run_x1, c->run_y, c->run_parent,
+                    c->row_first, c->hull, c->orient, c->m_sdf, c->m_app, c->m_acc, c->m_trad, c->m_flat, c->m_stem,
+                    c->m_valid, c->list_key, c->list_idx, c->list_n, c->patches, c->logits, c->results, c->cnn_act0,
+                    c->cnn_act1, c->in_labels, c->in_depth, c->cnn.blob, c->cnn.bf16_blob};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    delete c;
+}
+
+extern "C" uint64_t lg_context_bytes(const lg_context* c) { return c ? c->bytes : 0; }
+
+extern "C" int lg_set_cnn_weights(lg_context* c, const float* blob_host, uint64_t n_floats) {
+    if (!c) return LG_E_ARG;
+    if (!blob_host) { c->cnn.loaded = 0; return LG_OK; }
+    if (n_floats != lg_cnn_blob_floats()) {
+        lg_set_error("lg_set_cnn_weights: blob has %llu floats, expected %llu", (unsigned long long)n_floats,
+                     (unsigned long long)lg_cnn_blob_floats());
+        return LG_E_ARG;
+    }
+    if (!c->cnn.blob) LG_CUDA(cudaMalloc((void**)&c->cnn.blob, n_floats * sizeof(float)));
+    LG_CUDA(cudaMemcpy(c->cnn.blob, blob_host, n_floats * sizeof(float), cudaMemcpyHostToDevice));
+    c->cnn.n_floats = n_floats;
+    c->cnn.loaded = 1;
+    return lg_cnn_prepare_bf16(c);
+}
+
+static int check_batch(lg_context* c, const void* a, const void* b, int frames) {
+    if (!c || !a || !b || frames < 1) { lg_set_error("null pointer or empty batch"); return LG_E_ARG; }
+    if (frames > c->B) { lg_set_error("batch of %d frames exceeds context capacity %d", frames, c->B); return LG_E_CAPACITY; }
+    return LG_OK;
+}
+
+extern "C" int lg_select_leaf(lg_context* c, const int16_t* labels, const float* depth, int frames, const lg_camera* cam,
+                              int32_t* leaf_id, lg_leaf_record* records, void* stream) {
+    TRY(check_batch(c, labels, depth, frames));
+    if (!cam) return LG_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    TRY(lg_run_stage1(c, labels, depth, frames, *cam, st));
+    TRY(lg_run_select(c, frames, *cam, leaf_id, records, st));
+    return LG_OK;
+}
+
+static int run_stage2(lg_context* c, LgMaskSrc src, const float* depth, int n, lg_camera cam, int full, double* iso_out,
+                      cudaStream_t st) {
+    // inside transform on the leaf rectangle (+ its distance map), outside transform on the whole frame (max only)
+    TRY(lg_run_chamfer(c, src, n, full ? 0 : 1, 0, 2, c->di, nullptr, c->dt_max, st));
+    TRY(lg_run_orientation(c, src, n, st));
+    TRY(lg_run_scores(c, src, depth, n, cam, full, iso_out, st));
+    return LG_OK;
+}
+
+extern "C" int lg_process_batch(lg_context* c, const int16_t* labels, const float* depth, int frames, const lg_camera* cam,
+                                lg_frame_result* results, int use_bf16_cnn, void* stream) {
+    TRY(check_batch(c, labels, depth, frames));
+    if (!cam) return LG_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    TRY(lg_run_stage1(c, labels, depth, frames, *cam, st));
+    TRY(lg_run_select(c, frames, *cam, nullptr, c->records, st));
+    LgMaskSrc src{labels, nullptr, c->leaf_id};
+    TRY(run_stage2(c, src, depth, frames, *cam, 0, nullptr, st));
+    TRY(lg_run_nms(c, frames, st));
+    const int have_ml = c->cnn.loaded;
+    if (have_ml) {
+        TRY(lg_run_gather(c, src, depth, frames, *cam, st));
+        TRY(lg_run_cnn(c, c->patches, frames * LG_TOP_K, c->logits, use_bf16_cnn, st));
+    }
+    TRY(lg_run_fuse(c, src, depth, frames, *cam, have_ml, results, st));
+    return LG_OK;
+}
+
+extern "C" int lg_process_batch_host(lg_context* c, const int16_t* labels_host, const float* depth_host, int frames,
+                                     const lg_camera* cam, lg_frame_result* results_host, int use_bf16_cnn, void* stream) {
+    TRY(check_batch(c, labels_host, depth_host, frames));
+    if (!results_host) return LG_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)frames * c->P;
+    LG_CUDA(cudaMemcpyAsync(c->in_labels, labels_host, n * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+    LG_CUDA(cudaMemcpyAsync(c->in_depth, depth_host, n * sizeof(float), cudaMemcpyHostToDevice, st));
+    TRY(lg_process_batch(c, c->in_labels, c->in_depth, frames, cam, c->results, use_bf16_cnn, stream));
+    LG_CUDA(cudaMemcpyAsync(results_host, c->results, sizeof(lg_frame_result) * frames, cudaMemcpyDeviceToHost, st));
+    LG_CUDA(cudaStreamSynchronize(st));
+    return LG_OK;
+}
+
+extern "C" int lg_score_maps(lg_context* c, const uint8_t* mask, const float* depth, int frames, const lg_camera* cam,
+                             double* sdf_score, double* approach, float* flatness, double* isolation, float* distance,
+                             double* accessibility, float* stem, double* traditional, uint8_t* valid, double* angle_out,
+                             void* stream) {
+    TRY(check_batch(c, mask, depth, frames));
+    if (!cam) return LG_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    TRY(lg_run_mask_regions(c, mask, frames, 1, st));
+    LgMaskSrc src{nullptr, mask, nullptr};
+    TRY(run_stage2(c, src, depth, frames, *cam, 1, isolation, st));
+    TRY(lg_run_export_maps(c, frames, sdf_score, approach, flatness, distance, accessibility, stem, traditional, valid,
+                           angle_out, st));
+    return LG_OK;
+}
+
+extern "C" int lg_candidate_points(lg_context* c, const double* score, const uint8_t* valid, int frames, int32_t* xy,
+                                   int32_t* count, void* stream) {
+    TRY(check_batch(c, score, valid, frames));
+    if (!xy || !count) return LG_E_ARG;
+    return lg_run_candidates_from_maps(c, score, valid, frames, xy, count, (cudaStream_t)stream);
+}
+
+extern "C" int lg_cnn_forward(lg_context* c, const float* patches, int n, float* logits, int use_bf16, void* stream) {
+    if (!c || !patches || !logits || n < 1) return LG_E_ARG;
+    return lg_run_cnn(c, patches, n, logits, use_bf16, (cudaStream_t)stream);
+}
+
+extern "C" int lg_select_grasp_point(lg_context* c, const uint8_t* mask, const float* depth, int frames,
+                                     const lg_camera* cam, lg_frame_result* results, int use_bf16_cnn, void* stream) {
+    TRY(check_batch(c, mask, depth, frames));
+    if (!cam) return LG_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    TRY(lg_run_mask_regions(c, mask, frames, 0, st));
+    LgMaskSrc src{nullptr, mask, nullptr};
+    TRY(run_stage2(c, src, depth, frames, *cam, 0, nullptr, st));
+    TRY(lg_run_nms(c, frames, st));
+    const int have_ml = c->cnn.loaded;
+    if (have_ml) {
+        TRY(lg_run_gather(c, src, depth, frames, *cam, st));
+        TRY(lg_run_cnn(c, c->patches, frames * LG_TOP_K, c->logits, use_bf16_cnn, st));
+    }
+    TRY(lg_run_fuse(c, src, depth, frames, *cam, have_ml, results, st));
+    return LG_OK;
+}
+
+extern "C" int lg_leaf_orientation(lg_context* c, const uint8_t* mask, int frames, double* out5, void* stream) {
+    if (!c || !mask || !out5 || frames < 1) return LG_E_ARG;
+    if (frames > c->B) return LG_E_CAPACITY;
+    cudaStream_t st = (cudaStream_t)stream;
+    TRY(lg_run_mask_regions(c, mask, frames, 0, st));
+    LgMaskSrc src{nullptr, mask, nullptr};
+    TRY(lg_run_orientation(c, src, frames, st));
+    return lg_run_export_orient(c, frames, out5, st);
+}
+
+extern "C" int lg_patches(lg_context* c, float* patches_out, int frames, void* stream) {
+    if (!c || !patches_out || frames < 1 || frames > c->B) return LG_E_ARG;
+    LG_CUDA(cudaMemcpyAsync(patches_out, c->patches, sizeof(float) * (size_t)frames * LG_TOP_K * LG_CHANNELS * LG_PATCH * LG_PATCH,
+                            cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return LG_OK;
+}
+
+extern "C" int lg_normalize_patches(lg_context* c, const float* raw, int n, float* out, void* stream) {
+    if (!c || !raw || !out || n < 1) return LG_E_ARG;
+    return lg_run_normalize_patches(raw, n, out, (cudaStream_t)stream);
+}
+
+extern "C" uint64_t lg_sizeof_frame_result(void) { return sizeof(lg_frame_result); }
+extern "C" uint64_t lg_sizeof_leaf_record(void) { return sizeof(lg_leaf_record); }
+extern "C" uint64_t lg_cnn_weight_floats(void) { return lg_cnn_blob_floats(); }

@@ -1,0 +1,196 @@
+// 5x5 chamfer distance transform, bit-exact with cv2.distanceTransform(mask, DIST_L2, 5) (IPP off)
+// as the reference calls it at scripts/utils/grasp_point_selector.py:266,529-530.
+//
+// OpenCV's algorithm is two raster sweeps over an integer (Q16) field.  Within one row the only
+// sequential tap is t[x] = min(t[x], t[x-1] + a), which is a running minimum of (t[x] - a*x); the
+// other seven taps read the two previous rows.  So a row is: 7-tap stencil (parallel) + one prefix-min
+// scan (parallel), and rows follow each other.  One CTA owns one transform and walks its rows with the
+// last three rows of the field in shared memory; many transforms (frames x {inside, outside}) run
+// side by side, which is where the HBM bandwidth comes from.
+//
+// Traffic per transform of h x w pixels: source read once (1 or 2 B/px), forward field written and
+// read back (4+4 B/px, L2-resident when the batch is small), result written once (4 B/px) when asked.
+#include "lg_internal.cuh"
+
+namespace {
+
+constexpr int CH_NT = 512;
+constexpr int CH_MAXI = 8;   // pixels per thread per row -> rows up to 4096 wide
+
+struct ChamferArgs {
+    LgMaskSrc src;
+    const LgRegion* region;   // used when rect_mode (variant 0 only)
+    int n, H, W;
+    int rect_mode;            // 1: variant 0 runs on region bbox grown by 1 px, 0: full frame
+    int invert_base;          // variant v transforms (mask != 0) ^ invert_base ^ v
+    int32_t* fwd;             // [nvar][n][P]
+    float* out_f32;           // variant 0 only, [n][P] (may be null)
+    uint32_t* out_q16;        // variant 0 only
+    uint32_t* out_max;        // [n][nvar] (may be null)
+    size_t P;
+};
+
+__global__ void __launch_bounds__(CH_NT) chamfer_kernel(ChamferArgs A) {
+    extern __shared__ int smem[];
+    __shared__ int wtot[2][CH_NT / 32];
+    __shared__ unsigned smax[CH_NT / 32];
+    const int b = blockIdx.x, var = blockIdx.y, nvar = gridDim.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int W = A.W, H = A.H;
+    int rx0 = 0, ry0 = 0, rx1 = W, ry1 = H;
+    int id = 1;
+    if (A.src.labels) {
+        id = A.src.leaf_id[b];
+        if (id < 0) {
+            if (A.out_max && tid == 0) A.out_max[b * nvar + var] = 0;
+            return;
+        }
+    }
+    if (A.rect_mode && var == 0) {
+        LgRegion r = A.region[b];
+        if (!r.ok) {
+            if (A.out_max && tid == 0) A.out_max[b * nvar + var] = 0;
+            return;
+        }
+        rx0 = max(0, r.x0 - 1); ry0 = max(0, r.y0 - 1); rx1 = min(W, r.x1 + 1); ry1 = min(H, r.y1 + 1);
+    }
+    const int w = rx1 - rx0, h = ry1 - ry0;
+    const int wpad = w + 4;
+    const int ipt = (w + CH_NT - 1) / CH_NT;
+    const bool invert = ((A.invert_base ^ var) & 1) != 0;
+    int* ring = smem;              // 3 rows of wpad ints
+    int* sbuf = smem + 3 * wpad;   // 2 rows of w ints: sources (pass 0) or forward values (pass 1)
+    const size_t fo = (size_t)b * A.P;
+    int32_t* fwd = A.fwd + ((size_t)var * A.n + b) * A.P;
+    float* of = (var == 0 && A.out_f32) ? A.out_f32 + fo : nullptr;
+    uint32_t* oq = (var == 0 && A.out_q16) ? A.out_q16 + fo : nullptr;
+    unsigned my_max = 0;
+
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool flip = pass == 1;
+        auto phys = [&](int lx, int ly) -> size_t {
+            int x = flip ? (rx1 - 1 - lx) : (rx0 + lx);
+            int y = flip ? (ry1 - 1 - ly) : (ry0 + ly);
+            return (size_t)y * W + x;
+        };
+        auto load_row = [&](int ly, int* dst) {
+            for (int lx = tid; lx < w; lx += CH_NT) {
+                size_t p = phys(lx, ly);
+                if (pass == 0) {
+                    bool inside = A.src.at(fo, p, id) != invert;
+                    dst[lx] = inside ? 1 : 0;      // 0 = source pixel
+                } else {
+                    dst[lx] = fwd[p];
+                }
+            }
+        };
+        auto store_row = [&](int ly, const int* row) {   // row has the +2 border offset
+            for (int lx = tid; lx < w; lx += CH_NT) {
+                int t = row[lx + 2];
+                size_t p = phys(lx, ly);
+                if (pass == 0) {
+                    fwd[p] = t;
+                } else {
+                    unsigned q = (t >= LG_CH_INF) ? LG_CH_DIST_MAX : (unsigned)t;
+                    my_max = max(my_max, q);
+                    if (oq) oq[p] = q;
+                    if (of) of[p] = __fmul_rn((float)q, 1.0f / 65536.0f);
+                }
+            }
+        };
+        for (int i = tid; i < 3 * wpad; i += CH_NT) ring[i] = LG_CH_INF;
+        load_row(0, sbuf);
+        __syncthreads();
+        for (int ly = 0; ly < h; ++ly) {
+            int* cur = ring + (ly % 3) * wpad;
+            const int* p1 = ring + ((ly + 2) % 3) * wpad;
+            const int* p2 = ring + ((ly + 1) % 3) * wpad;
+            const int* sb = sbuf + (ly & 1) * w;
+            if (ly + 1 < h) load_row(ly + 1, sbuf + ((ly + 1) & 1) * w);
+            if (ly > 0) store_row(ly - 1, p1);
+            const int xb = tid * ipt;
+            int pv[CH_MAXI];
+            int run = 0x7FFFFFFF;
+#pragma unroll
+            for (int i = 0; i < CH_MAXI; ++i) {
+                const int x = xb + i;
+                if (i < ipt && x < w) {
+                    const int s = sb[x];
+                    int m = min(p2[x + 1], p2[x + 3]) + LG_CH_C;
+                    m = min(m, min(p1[x], p1[x + 4]) + LG_CH_C);
+                    m = min(m, min(p1[x + 1], p1[x + 3]) + LG_CH_B);
+                    m = min(m, p1[x + 2] + LG_CH_A);
+                    int u;
+                    if (pass == 0) u = s ? min(m, LG_CH_INF) : 0;
+                    else u = min(s, m);
+                    run = min(run, u - LG_CH_A * x);
+                }
+                pv[i] = run;
+            }
+            int incl = run;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= d) incl = min(incl, t);
+            }
+            int excl = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+            if (lane == 0) excl = 0x7FFFFFFF;
+            if (lane == 31) wtot[ly & 1][warp] = incl;
+            __syncthreads();
+            for (int k = 0; k < warp; ++k) excl = min(excl, wtot[ly & 1][k]);
+#pragma unroll
+            for (int i = 0; i < CH_MAXI; ++i) {
+                const int x = xb + i;
+                if (i < ipt && x < w) {
+                    int t = min(pv[i], excl);
+                    // t can only stay at the sentinel when nothing finite precedes x
+                    t = (t > LG_CH_INF) ? LG_CH_INF : min(t + LG_CH_A * x, LG_CH_INF);
+                    cur[x + 2] = t;
+                }
+            }
+            __syncthreads();
+        }
+        store_row(h - 1, ring + ((h - 1) % 3) * wpad);
+        __syncthreads();
+    }
+    if (A.out_max) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) my_max = max(my_max, __shfl_xor_sync(0xFFFFFFFFu, my_max, d));
+        if (lane == 0) smax[warp] = my_max;
+        __syncthreads();
+        if (tid == 0) {
+            for (int k = 1; k < CH_NT / 32; ++k) my_max = max(my_max, smax[k]);
+            A.out_max[b * nvar + var] = my_max;
+        }
+    }
+}
+
+}  // namespace
+
+int lg_run_chamfer(lg_context* c, LgMaskSrc src, int n, int rect_mode, int invert_base, int nvar,
+                   float* out0, uint32_t* q0, uint32_t* out_max, cudaStream_t st) {
+    if (c->W > CH_NT * CH_MAXI) {
+        lg_set_error("chamfer transform supports widths up to %d", CH_NT * CH_MAXI);
+        return LG_E_ARG;
+    }
+    ChamferArgs A;
+    A.src = src; A.region = c->region; A.n = n; A.H = c->H; A.W = c->W; A.rect_mode = rect_mode;
+    A.invert_base = invert_base; A.fwd = c->dt_fwd; A.out_f32 = out0; A.out_q16 = q0; A.out_max = out_max; A.P = c->P;
+    size_t sm = (size_t)(3 * (c->W + 4) + 2 * c->W) * sizeof(int);
+    static size_t configured = 0;
+    if (sm > configured) {
+        LG_CUDA(cudaFuncSetAttribute(chamfer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        configured = sm;
+    }
+    chamfer_kernel<<<dim3(n, nvar), CH_NT, sm, st>>>(A);
+    LG_LAUNCH_CHECK();
+    return LG_OK;
+}
+
+extern "C" int lg_chamfer_transform(lg_context* c, const uint8_t* mask, int n, int invert, float* dist,
+                                    uint32_t* q16, uint32_t* max_q16, void* stream) {
+    if (!c || !mask || n < 1) return LG_E_ARG;
+    if (n > c->B) return LG_E_CAPACITY;
+    LgMaskSrc src{nullptr, mask, nullptr};
+    return lg_run_chamfer(c, src, n, 0, invert ? 1 : 0, 1, dist, q16, max_q16, (cudaStream_t)stream);
+}

@@ -1,0 +1,215 @@
+// GraspPointCNN forward, eval mode (reference scripts/utils/ml_grasp_optimizer/model.py:102-128):
+//   3 x [conv3x3-BN-ReLU, conv3x3-BN-ReLU, maxpool2]  ->  x * sigmoid(conv1x1)  ->  global average
+//   ->  Linear-BN-ReLU x3  ->  Linear(64, 1).      Dropout is the identity in eval mode; BatchNorm is
+//   folded into the preceding conv / linear on the host (cnn.py:fold_batchnorm).
+//
+// fp32 path (this file, part 1): direct convolution as a register-tiled implicit GEMM on CUDA cores,
+// NHWC activations, weights [ky][kx][Cin][Cout]; max-pool fused into the second conv of each block.
+// It is the parity anchor (1e-5 against torch fp32 on the CPU).
+//
+// Weight blob (float32), in order:
+//   for layer l in 0..5:  w[3][3][Cin_l][Cout_l], b[Cout_l]       Cin/Cout = 9/64, 64/64, 64/128, 128/128, 128/256, 256/256
+//   attention: w[256], b[1]
+//   fc0: w[256][256] (in-major: w[i][o]), b[256];  fc1: w[256][128], b[128];  fc2: w[128][64], b[64];  fc3: w[64], b[1]
+#include "lg_internal.cuh"
+
+namespace {
+
+constexpr int CV_NT = 128;      // 16 pixel quads x 8 channel groups
+constexpr int CV_KC = 16;       // input channels per shared-memory stage
+constexpr int CV_CO = 64;       // output channels per CTA
+
+struct ConvArgs {
+    const float* in;
+    long long sn, sy, sx, sc;   // input strides in elements (n, y, x, channel)
+    int H, W, Cin, Cout;
+    const float* wt;            // [9][Cin][Cout]
+    const float* bias;
+    float* out;                 // NHWC, pooled when POOL
+};
+
+template <bool POOL>
+__global__ void __launch_bounds__(CV_NT) conv3x3_relu_kernel(ConvArgs A) {
+    __shared__ float s_in[CV_KC][10][12];            // 8x8 tile + halo, row padded to 12
+    __shared__ __align__(16) float s_w[9][CV_KC][CV_CO];
+    const int tid = threadIdx.x;
+    const int tiles_x = A.W / 8;
+    const int ty0 = (blockIdx.x / tiles_x) * 8, tx0 = (blockIdx.x % tiles_x) * 8;
+    const int co0 = blockIdx.y * CV_CO;
+    const int n = blockIdx.z;
+    const int quad = tid & 15, cg = tid >> 4;        // quad: 4x4 grid of 2x2 pixel quads; cg: 8 channels
+    const int qy = (quad >> 2) * 2, qx = (quad & 3) * 2;
+    float acc[4][8];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[p][k] = 0.f;
+    const float* inb = A.in + (long long)n * A.sn;
+    for (int c0 = 0; c0 < A.Cin; c0 += CV_KC) {
+        const int kc = min(CV_KC, A.Cin - c0);
+        __syncthreads();
+        for (int i = tid; i < CV_KC * 100; i += CV_NT) {
+            const int ci = i / 100, rem = i - ci * 100, ly = rem / 10, lx = rem - ly * 10;
+            const int y = ty0 - 1 + ly, x = tx0 - 1 + lx;
+            float v = 0.f;
+            if (ci < kc && y >= 0 && y < A.H && x >= 0 && x < A.W) v = inb[(long long)y * A.sy + (long long)x * A.sx + (long long)(c0 + ci) * A.sc];
+            s_in[ci][ly][lx] = v;
+        }
+        for (int i = tid; i < 9 * CV_KC * CV_CO; i += CV_NT) {
+            const int t = i / (CV_KC * CV_CO), rem = i - t * (CV_KC * CV_CO), ci = rem / CV_CO, co = rem - ci * CV_CO;
+            float v = 0.f;
+            if (ci < kc) v = A.wt[((long long)t * A.Cin + (c0 + ci)) * A.Cout + co0 + co];
+            s_w[t][ci][co] = v;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int t = 0; t < 9; ++t) {
+            const int ky = t / 3, kx = t - ky * 3;
+#pragma unroll 4
+            for (int ci = 0; ci < CV_KC; ++ci) {
+                const float i00 = s_in[ci][qy + ky][qx + kx], i01 = s_in[ci][qy + ky][qx + kx + 1];
+                const float i10 = s_in[ci][qy + ky + 1][qx + kx], i11 = s_in[ci][qy + ky + 1][qx + kx + 1];
+                const float4 w0 = *reinterpret_cast<const float4*>(&s_w[t][ci][cg * 8]);
+                const float4 w1 = *reinterpret_cast<const float4*>(&s_w[t][ci][cg * 8 + 4]);
+                const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    acc[0][k] = fmaf(i00, w[k], acc[0][k]);
+                    acc[1][k] = fmaf(i01, w[k], acc[1][k]);
+                    acc[2][k] = fmaf(i10, w[k], acc[2][k]);
+                    acc[3][k] = fmaf(i11, w[k], acc[3][k]);
+                }
+            }
+        }
+    }
+    const int co = co0 + cg * 8;
+    if (POOL) {
+        const int Ho = A.H / 2, Wo = A.W / 2;
+        const int oy = (ty0 + qy) / 2, ox = (tx0 + qx) / 2;
+        float* o = A.out + (((long long)n * Ho + oy) * Wo + ox) * A.Cout + co;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float bsv = A.bias[co + k];
+            float m = fmaxf(fmaxf(acc[0][k], acc[1][k]), fmaxf(acc[2][k], acc[3][k]));
+            o[k] = fmaxf(m + bsv, 0.f);
+        }
+    } else {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int y = ty0 + qy + (p >> 1), x = tx0 + qx + (p & 1);
+            float* o = A.out + (((long long)n * A.H + y) * A.W + x) * A.Cout + co;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = fmaxf(acc[p][k] + A.bias[co + k], 0.f);
+        }
+    }
+}
+
+// attention + global average + MLP; one CTA per patch.  in: NHWC [n][4][4][256]
+constexpr int TL_NT = 256;
+__global__ void __launch_bounds__(TL_NT) cnn_tail_kernel(const float* __restrict__ feat, const float* __restrict__ blob_tail,
+                                                          float* __restrict__ logits) {
+    __shared__ float s_f[16][256];
+    __shared__ float s_att[16];
+    __shared__ float s_a[256], s_b[256];
+    const int n = blockIdx.x, tid = threadIdx.x;
+    const float* f = feat + (size_t)n * 16 * 256;
+    for (int i = tid; i < 16 * 256; i += TL_NT) s_f[i >> 8][i & 255] = f[i];
+    __syncthreads();
+    const float* aw = blob_tail;              // 256
+    const float* ab = aw + 256;               // 1
+    const float* w0 = ab + 1;                 // 256x256
+    const float* b0 = w0 + 256 * 256;
+    const float* w1 = b0 + 256;               // 256x128
+    const float* b1 = w1 + 256 * 128;
+    const float* w2 = b1 + 128;               // 128x64
+    const float* b2 = w2 + 128 * 64;
+    const float* w3 = b2 + 64;                // 64
+    const float* b3 = w3 + 64;
+    {   // attention logit per pixel: 16 pixels x 256 channels, 16 threads per pixel
+        const int p = tid >> 4, l = tid & 15;
+        float s = 0.f;
+        for (int ch = l; ch < 256; ch += 16) s = fmaf(s_f[p][ch], aw[ch], s);
+#pragma unroll
+        for (int d = 8; d > 0; d >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, d);
+        if (l == 0) s_att[p] = 1.f / (1.f + expf(-(s + ab[0])));
+    }
+    __syncthreads();
+    {
+        float s = 0.f;
+#pragma unroll
+        for (int p = 0; p < 16; ++p) s = fmaf(s_f[p][tid], s_att[p], s);
+        s_a[tid] = s * (1.f / 16.f);
+    }
+    __syncthreads();
+    {
+        float s = b0[tid];
+        for (int i = 0; i < 256; ++i) s = fmaf(s_a[i], w0[i * 256 + tid], s);
+        s_b[tid] = fmaxf(s, 0.f);
+    }
+    __syncthreads();
+    if (tid < 128) {
+        float s = b1[tid];
+        for (int i = 0; i < 256; ++i) s = fmaf(s_b[i], w1[i * 128 + tid], s);
+        s_a[tid] = fmaxf(s, 0.f);
+    }
+    __syncthreads();
+    if (tid < 64) {
+        float s = b2[tid];
+        for (int i = 0; i < 128; ++i) s = fmaf(s_a[i], w2[i * 64 + tid], s);
+        s_b[tid] = fmaxf(s, 0.f);
+    }
+    __syncthreads();
+    if (tid < 32) {
+        float s = s_b[tid] * w3[tid] + s_b[tid + 32] * w3[tid + 32];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, d);
+        if (tid == 0) logits[n] = s + b3[0];
+    }
+}
+
+const int kCin[6] = {9, 64, 64, 128, 128, 256};
+const int kCout[6] = {64, 64, 128, 128, 256, 256};
+const int kHW[6] = {32, 32, 16, 16, 8, 8};
+
+}  // namespace
+
+uint64_t lg_cnn_blob_floats() {
+    uint64_t n = 0;
+    for (int l = 0; l < 6; ++l) n += 9ull * kCin[l] * kCout[l] + kCout[l];
+    n += 256 + 1 + 256 * 256 + 256 + 256 * 128 + 128 + 128 * 64 + 64 + 64 + 1;
+    return n;
+}
+
+int lg_run_cnn_bf16(lg_context* c, const float* patches, int n, float* logits, cudaStream_t st);
+
+int lg_run_cnn(lg_context* c, const float* patches, int n, float* logits, int use_bf16, cudaStream_t st) {
+    if (!c->cnn.loaded) {
+        lg_set_error("lg_cnn_forward: no weights loaded (lg_set_cnn_weights)");
+        return LG_E_ARG;
+    }
+    if (use_bf16) return lg_run_cnn_bf16(c, patches, n, logits, st);
+    const float* blob = c->cnn.blob;
+    for (int done = 0; done < n; done += c->cnn_cap) {
+        const int m = min(c->cnn_cap, n - done);
+        const float* in = patches + (size_t)done * LG_CHANNELS * LG_PATCH * LG_PATCH;
+        float* a0 = (float*)c->cnn_act0;
+        float* a1 = (float*)c->cnn_act1;
+        const float* w = blob;
+        for (int l = 0; l < 6; ++l) {
+            ConvArgs A;
+            const int hw = kHW[l];
+            if (l == 0) { A.in = in; A.sn = 9 * 32 * 32; A.sc = 32 * 32; A.sy = 32; A.sx = 1; }
+            else { A.in = (l & 1) ? a0 : a1; A.sn = (long long)hw * hw * kCin[l]; A.sy = (long long)hw * kCin[l]; A.sx = kCin[l]; A.sc = 1; }
+            A.H = hw; A.W = hw; A.Cin = kCin[l]; A.Cout = kCout[l]; A.wt = w; A.bias = w + 9ull * kCin[l] * kCout[l];
+            A.out = (l & 1) ? a1 : a0;
+            dim3 grid((hw / 8) * (hw / 8), kCout[l] / CV_CO, m);
+            if (l & 1) conv3x3_relu_kernel<true><<<grid, CV_NT, 0, st>>>(A);
+            else conv3x3_relu_kernel<false><<<grid, CV_NT, 0, st>>>(A);
+            LG_LAUNCH_CHECK();
+            w += 9ull * kCin[l] * kCout[l] + kCout[l];
+        }
+        cnn_tail_kernel<<<m, TL_NT, 0, st>>>(a1, w, logits + done);
+        LG_LAUNCH_CHECK();
+    }
+    return LG_OK;
+}

@@ -1,0 +1,139 @@
+// Internal declarations shared by the translation units of liblgb200.so (not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/leafgrasp.h"
+
+#define LG_NUM_SM_HINT 148
+
+// OpenCV DIST_L2 5x5 chamfer weights in Q16 and its saturation value (oracle: chamfer5_q16)
+#define LG_CH_A 65536
+#define LG_CH_B 91750
+#define LG_CH_C 143976
+#define LG_CH_DIST_MAX (0xFFFFFFFFu - 143976u)
+#define LG_CH_INF (1 << 30)
+
+#define LG_MIN_LEAF_AREA 10000u
+#define LG_NMS_REACH 20  // two +-10 marks overlap  <=>  Chebyshev distance <= 20
+#define LG_REGION_PAD 16 // score maps are produced on the leaf bbox grown by half a patch
+#define LG_SE_STEM 30
+#define LG_SE_PRE 31
+
+struct LgRegion {
+    int x0, y0, x1, y1;  // bounding box of the chosen leaf, exclusive upper bounds
+    int ok;              // 0: frame has no chosen leaf -> every stage-2 kernel skips it
+    int sx0, sy0, sx1, sy1;  // rectangle the score maps are written on (bbox +- LG_REGION_PAD, or full frame)
+};
+
+// Where "is this pixel part of the leaf" comes from: the label image + the chosen id, or a u8 mask.
+struct LgMaskSrc {
+    const int16_t* labels;
+    const uint8_t* mask;
+    const int32_t* leaf_id;  // [frames], used with labels
+    __device__ __forceinline__ int id(int b) const { return labels ? leaf_id[b] : 1; }
+    __device__ __forceinline__ bool at(size_t frame_off, size_t idx, int id_) const {
+        return labels ? (labels[frame_off + idx] == (int16_t)id_) : (mask[frame_off + idx] != 0);
+    }
+};
+
+struct LgOrient {
+    double angle;      // rad, after the +90 rule; NaN when there is no contour
+    double cos_a, sin_a;
+    double major, minor, cx, cy;
+    int has_angle;
+    int n_hull;
+    unsigned status;
+    unsigned pad;
+};
+
+// Folded CNN weights on the device (see cnn.py:pack_weights for the blob layout)
+struct LgCnn {
+    float* blob;        // fp32 blob
+    uint64_t n_floats;
+    void* bf16_blob;    // bf16 copy of conv weights, tensor-core layout
+    int loaded;
+};
+
+struct lg_context {
+    int B, H, W, L;
+    size_t P;
+    uint64_t bytes;
+    // ---- stage 1 tables, [B][L] unless noted
+    uint32_t* cnt;
+    unsigned long long *sx, *sy, *sdep, *sdist;
+    uint32_t *bx0, *bx1, *by0, *by1, *border;
+    uint32_t* first_leaf;          // [B] flat index of the first pixel with label >= 1
+    uint32_t* seg_off;             // [B][L+1]
+    uint32_t* seg_cur;             // [B][L]
+    float* seg;                    // [B][P] depth values grouped by label
+    float* median;                 // [B][L]
+    uint16_t* edt_g;               // [B][P] column distances
+    unsigned long long* edt_best;  // [B] packed (d2 << 32 | ~index)
+    int32_t* leaf_id;              // [B]
+    lg_leaf_record* records;       // [B][L]
+    uint32_t* status;              // [B]
+    LgRegion* region;              // [B]
+    // ---- stage 2
+    int32_t* dt_fwd;               // [2][B][P] forward-pass scratch of the two chamfer transforms
+    float* di;                     // [B][P] distance inside (distance_map)
+    uint32_t* dt_max;              // [B][2] max Q16 of (inside, outside)
+    uint32_t* bits;                // [B][bits_stride] leaf bitmask on bbox+1 ring
+    size_t bits_stride;
+    int run_cap;
+    uint16_t *run_x0, *run_x1, *run_y;   // [B][run_cap]
+    int32_t* run_parent;                 // [B][run_cap]
+    int32_t* row_first;                  // [B][H+3] first run index of each region row
+    int32_t* hull;                       // [B][2*(H+2)][2]
+    LgOrient* orient;                    // [B]
+    double *m_sdf, *m_app, *m_acc, *m_trad;  // [B][P]
+    float *m_flat, *m_stem;                  // [B][P]
+    uint8_t* m_valid;                        // [B][P]
+    double* list_key;                        // [B][P] compacted positive keys
+    uint32_t* list_idx;                      // [B][P]
+    uint32_t* list_n;                        // [B]
+    float* patches;                          // [B*20][9][32][32]
+    float* logits;                           // [B*20]
+    lg_frame_result* results;                // [B]
+    // CNN scratch
+    void* cnn_act0;
+    void* cnn_act1;
+    size_t cnn_act_bytes;
+    int cnn_cap;                             // patches the activation scratch holds
+    LgCnn cnn;
+    // staging for the *_host entry point
+    int16_t* in_labels;
+    float* in_depth;
+    // constants
+    float gauss[25];
+    int se30_a[LG_SE_STEM], se30_b[LG_SE_STEM];   // per structuring-element row: first / last+1 column
+    int se31_a[LG_SE_PRE], se31_b[LG_SE_PRE];
+};
+
+void lg_set_error(const char* fmt, ...);
+#define LG_CUDA(expr)                                                                       \
+    do {                                                                                    \
+        cudaError_t e__ = (expr);                                                           \
+        if (e__ != cudaSuccess) {                                                           \
+            lg_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+            return LG_E_CUDA;                                                               \
+        }                                                                                   \
+    } while (0)
+#define LG_LAUNCH_CHECK() LG_CUDA(cudaGetLastError())
+
+// stage launchers (defined across the .cu files); all asynchronous on `st`
+int lg_run_stage1(lg_context* c, const int16_t* labels, const float* depth, int n, lg_camera cam, cudaStream_t st);
+int lg_run_select(lg_context* c, int n, lg_camera cam, int32_t* leaf_out, lg_leaf_record* rec_out, cudaStream_t st);
+int lg_run_edt_union(lg_context* c, const int16_t* labels, int n, cudaStream_t st);
+int lg_run_chamfer(lg_context* c, LgMaskSrc src, int n, int rect_mode, int invert_base, int nvar,
+                   float* out0, uint32_t* q0, uint32_t* out_max, cudaStream_t st);
+int lg_run_orientation(lg_context* c, LgMaskSrc src, int n, cudaStream_t st);
+int lg_run_scores(lg_context* c, LgMaskSrc src, const float* depth, int n, lg_camera cam, int full,
+                  double* iso_out, cudaStream_t st);
+int lg_run_nms(lg_context* c, int n, cudaStream_t st);
+int lg_run_gather(lg_context* c, LgMaskSrc src, const float* depth, int n, lg_camera cam, cudaStream_t st);
+int lg_run_cnn(lg_context* c, const float* patches, int n, float* logits, int use_bf16, cudaStream_t st);
+int lg_run_fuse(lg_context* c, LgMaskSrc src, const float* depth, int n, lg_camera cam, int have_ml,
+                lg_frame_result* out, cudaStream_t st);
+int lg_run_mask_regions(lg_context* c, const uint8_t* mask, int n, int full, cudaStream_t st);

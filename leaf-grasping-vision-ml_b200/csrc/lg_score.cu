@@ -1,0 +1,574 @@
+// Stage 2 - per-pixel grasp scoring, candidates, patches and the CV/ML fusion
+// (reference scripts/utils/grasp_point_selector.py).  Compile with -fmad=false: the reference combines
+// float64 / float32 terms with separately rounded products and sums, and candidate indices only stay
+// identical if this file does the same.
+//
+//   score_kernel   one pass over the leaf rectangle: masked depth tile -> 5x5 Gaussian -> Sobel ->
+//                  flatness; closed-form approach / accessibility; sdf_score from the chamfer field;
+//                  stem penalty from the leaf bitmask; traditional score; valid mask; compaction of the
+//                  positive keys for the candidate search                     (:256-288, 502-701)
+//   nms_kernel     top-20 greedy pick with the +-10 px mark                      (:447-482)
+//   gather_kernel  9 x 32 x 32 patch tensor written in the CNN's input layout    (:59-127, 392-445)
+//   fuse_kernel    ML rescale + confidence weighting + 3-D / pre-grasp points    (:133-136, 205-249, 152-180, 754-826)
+#include <math_constants.h>
+
+#include "lg_internal.cuh"
+
+namespace {
+
+constexpr int SC_TW = 32, SC_TH = 8;
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * n - 2 - i;
+    return i;
+}
+
+// any leaf pixel on local bitmask row ly within local columns [xa, xb) ?
+__device__ __forceinline__ bool bits_any(const uint32_t* bits, int wpr, int bw, int bh, int ly, int xa, int xb) {
+    if (ly < 0 || ly >= bh) return false;
+    xa = max(xa, 0); xb = min(xb, bw);
+    if (xa >= xb) return false;
+    const uint32_t* row = bits + ly * wpr;
+    int wa = xa >> 5, wb = (xb - 1) >> 5;
+    for (int wi = wa; wi <= wb; ++wi) {
+        uint32_t m = row[wi];
+        if (wi == wa) m &= 0xFFFFFFFFu << (xa & 31);
+        if (wi == wb) { int hi = xb - (wb << 5); if (hi < 32) m &= (1u << hi) - 1u; }
+        if (m) return true;
+    }
+    return false;
+}
+
+__device__ __forceinline__ float exp32(float x) { return (float)exp((double)x); }
+
+__global__ void __launch_bounds__(SC_TW * SC_TH) score_kernel(lg_context c, LgMaskSrc src, const float* __restrict__ depth,
+                                                               lg_camera cam, int full, double* iso_out) {
+    const int b = blockIdx.z;
+    const LgRegion r = c.region[b];
+    if (!r.ok && !full) return;
+    const int W = c.W, H = c.H;
+    const int tx0 = r.sx0 + blockIdx.x * SC_TW, ty0 = r.sy0 + blockIdx.y * SC_TH;
+    if (tx0 >= r.sx1 || ty0 >= r.sy1) return;
+    __shared__ float zt[SC_TH + 6][SC_TW + 6];
+    __shared__ float st[SC_TH + 2][SC_TW + 2];
+    const int tid = threadIdx.x;
+    const size_t fo = (size_t)b * c.P;
+    const int id = src.id(b);
+    // masked depth tile with reflect-101 borders (image_processor.py:60-61)
+    for (int i = tid; i < (SC_TH + 6) * (SC_TW + 6); i += SC_TW * SC_TH) {
+        const int ly = i / (SC_TW + 6), lx = i - ly * (SC_TW + 6);
+        const int y = reflect101(ty0 - 3 + ly, H), x = reflect101(tx0 - 3 + lx, W);
+        const size_t p = (size_t)y * W + x;
+        const float m = src.at(fo, p, id) ? 1.f : 0.f;
+        zt[ly][lx] = __fmul_rn(depth[fo + p], m);
+    }
+    __syncthreads();
+    // Gaussian 5x5 at in-image positions of the (tile + 1) ring
+    for (int i = tid; i < (SC_TH + 2) * (SC_TW + 2); i += SC_TW * SC_TH) {
+        const int ly = i / (SC_TW + 2), lx = i - ly * (SC_TW + 2);
+        const int y = ty0 - 1 + ly, x = tx0 - 1 + lx;
+        if (y >= 0 && y < H && x >= 0 && x < W) {
+            float acc = __fmul_rn(c.gauss[0], zt[ly][lx]);
+#pragma unroll
+            for (int k = 1; k < 25; ++k) acc = __fadd_rn(acc, __fmul_rn(c.gauss[k], zt[ly + k / 5][lx + k % 5]));
+            st[ly][lx] = acc;
+        }
+    }
+    __syncthreads();
+    // reflect-101 padding of the smoothed image (grasp_point_selector.py:648)
+    for (int i = tid; i < (SC_TH + 2) * (SC_TW + 2); i += SC_TW * SC_TH) {
+        const int ly = i / (SC_TW + 2), lx = i - ly * (SC_TW + 2);
+        const int y = ty0 - 1 + ly, x = tx0 - 1 + lx;
+        if (!(y >= 0 && y < H && x >= 0 && x < W)) {
+            const int ry = reflect101(y, H) - (ty0 - 1), rx = reflect101(x, W) - (tx0 - 1);
+            float v = 0.f;
+            if (ry >= 0 && ry < SC_TH + 2 && rx >= 0 && rx < SC_TW + 2) v = st[ry][rx];
+            st[ly][lx] = v;
+        }
+    }
+    __syncthreads();
+    const int lx = tid % SC_TW, ly = tid / SC_TW;
+    const int x = tx0 + lx, y = ty0 + ly;
+    bool want = false;
+    double trad = 0.0;
+    if (x < r.sx1 && y < r.sy1) {
+        const size_t p = (size_t)y * W + x;
+        const bool M = src.at(fo, p, id);
+        // flatness (:650-655)
+        const float s00 = st[ly][lx], s01 = st[ly][lx + 1], s02 = st[ly][lx + 2];
+        const float s10 = st[ly + 1][lx], s12 = st[ly + 1][lx + 2];
+        const float s20 = st[ly + 2][lx], s21 = st[ly + 2][lx + 1], s22 = st[ly + 2][lx + 2];
+        float gx = -s00;
+        gx = __fadd_rn(gx, s02);
+        gx = __fadd_rn(gx, __fmul_rn(-2.f, s10));
+        gx = __fadd_rn(gx, __fmul_rn(2.f, s12));
+        gx = __fadd_rn(gx, -s20);
+        gx = __fadd_rn(gx, s22);
+        float gy = -s00;
+        gy = __fadd_rn(gy, __fmul_rn(-2.f, s01));
+        gy = __fadd_rn(gy, -s02);
+        gy = __fadd_rn(gy, s20);
+        gy = __fadd_rn(gy, __fmul_rn(2.f, s21));
+        gy = __fadd_rn(gy, s22);
+        const float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)));
+        const float flat = exp32(__fmul_rn(-mag, 5.f));
+        double sdf_score = 0.0, approach = 0.0, access = 0.0;
+        float stem = 0.f;
+        float di = 0.f;
+        if (M) {
+            di = c.di[fo + p];
+            const uint32_t* mx = c.dt_max + (size_t)b * 2;
+            const float sdf_max = __fmul_rn((float)max(mx[0], mx[1]), 1.0f / 65536.0f);
+            const LgOrient o = c.orient[b];
+            // sdf_score (:526-567)
+            const float dm = __fsub_rn(di, 20.f);
+            const float interior = exp32(__fdiv_rn(-__fmul_rn(dm, dm), 800.f));
+            const float sdf = __fdiv_rn(di, sdf_max);
+            const double dx = (double)x - cam.cx, dy = (double)y - cam.cy;
+            const double r2 = dx * dx + dy * dy;
+            double nrm = sqrt(r2);
+            const double rr = nrm;
+            if (nrm == 0.0) nrm = 1.0;
+            double align = 1.0;
+            if (o.has_angle) align = fabs((dx / nrm) * o.sin_a - (dy / nrm) * o.cos_a);
+            sdf_score = ((double)__fmul_rn(0.4f, interior) + 0.4 * align) + (double)__fmul_rn(0.2f, sdf);
+            // approach (:569-593)
+            approach = fabs(cam.f / sqrt(r2 + cam.f * cam.f));
+            // accessibility (:502-524)
+            const double diag = sqrt((double)((long long)W * W + (long long)H * H));
+            const double fwd = (rr == 0.0) ? 1.0 : dx / rr;
+            access = 0.7 * (1.0 - rr / diag) + 0.3 * fwd;
+            // stem penalty (:688-701): dilation of (leaf AND bottom third) by the 30x30 ellipse, AND leaf
+            const int h3 = H - H / 3;
+            if (y + (LG_SE_STEM - 1 - LG_SE_STEM / 2) >= h3) {
+                const uint32_t* bits = c.bits + (size_t)b * c.bits_stride;
+                const int ox = r.x0 - 1, oy = r.y0 - 1;
+                const int bw = r.x1 - r.x0 + 2, bh = r.y1 - r.y0 + 2, wpr = (bw + 31) >> 5;
+                for (int j = 0; j < LG_SE_STEM; ++j) {
+                    const int yy = y + j - LG_SE_STEM / 2;
+                    if (yy < h3 || yy >= H) continue;
+                    if (bits_any(bits, wpr, bw, bh, yy - oy, x + c.se30_a[j] - LG_SE_STEM / 2 - ox,
+                                 x + c.se30_b[j] - LG_SE_STEM / 2 - ox)) { stem = 1.f; break; }
+                }
+            }
+        }
+        // combination (:272-277); evaluated for every pixel like the reference (flatness is not masked)
+        trad = (((0.4 * approach + 0.3 * sdf_score) + (double)__fmul_rn(0.2f, flat)) + 0.1 * access) *
+               (double)__fsub_rn(1.f, stem);
+        const bool valid = (di > 20.f) && M && (stem < 0.8f);
+        c.m_sdf[fo + p] = sdf_score; c.m_app[fo + p] = approach; c.m_acc[fo + p] = access; c.m_trad[fo + p] = trad;
+        c.m_flat[fo + p] = flat; c.m_stem[fo + p] = stem; c.m_valid[fo + p] = valid ? 1 : 0;
+        if (iso_out) {
+            double iso = 0.0;
+            if (M) iso = (y == H - 1) ? 0.2 : ((double)y * ((0.2 - 1.0) / (double)(H - 1)) + 1.0);
+            iso_out[fo + p] = iso;
+        }
+        want = valid && trad > 0.0;
+    }
+    // warp-aggregated append of the positive keys
+    const unsigned ball = __ballot_sync(0xFFFFFFFFu, want);
+    if (ball) {
+        const int lane = tid & 31;
+        unsigned base = 0;
+        if (lane == (__ffs(ball) - 1)) base = atomicAdd(&c.list_n[b], __popc(ball));
+        base = __shfl_sync(0xFFFFFFFFu, base, __ffs(ball) - 1);
+        if (want) {
+            const unsigned pos = base + __popc(ball & ((1u << lane) - 1u));
+            c.list_key[fo + pos] = trad;
+            c.list_idx[fo + pos] = (unsigned)((size_t)y * W + x);
+        }
+    }
+}
+
+// fill the per-frame maps with their analytic values outside the score rectangle (full mode only needs
+// nothing: the rectangle is the frame).  Not needed in region mode: consumers special-case the outside.
+
+constexpr int NMS_NT = 256;
+__global__ void __launch_bounds__(NMS_NT) nms_kernel(lg_context c, const double* ext_score, const uint8_t* ext_valid,
+                                                      int32_t* ext_xy, int32_t* ext_count) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int W = c.W;
+    const size_t fo = (size_t)b * c.P;
+    lg_frame_result* res = &c.results[b];
+    __shared__ int px[LG_TOP_K], py[LG_TOP_K];
+    __shared__ double wk[NMS_NT / 32];
+    __shared__ unsigned wi[NMS_NT / 32];
+    __shared__ int s_found;
+    const LgRegion r = c.region[b];
+    if (!ext_score && !r.ok) {
+        if (tid == 0) { res->n_candidates = 0; res->n_positive = 0; }
+        return;
+    }
+    const unsigned n = c.list_n[b];
+    double* key = c.list_key + fo;
+    const unsigned* idx = c.list_idx + fo;
+    int cnt = 0;
+    for (int it = 0; it < LG_TOP_K; ++it) {
+        double bk = -1.0;
+        unsigned bi = 0;
+        for (unsigned i = tid; i < n; i += NMS_NT) {
+            double k = key[i];
+            if (!(k > 0.0)) continue;
+            const unsigned id = idx[i];
+            if (it > 0) {
+                const int x = (int)(id % W), y = (int)(id / W);
+                if (abs(x - px[it - 1]) <= LG_NMS_REACH && abs(y - py[it - 1]) <= LG_NMS_REACH) { key[i] = -1.0; continue; }
+            }
+            if (k > bk || (k == bk && id > bi)) { bk = k; bi = id; }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            double ok = __shfl_xor_sync(0xFFFFFFFFu, bk, d);
+            unsigned oi = __shfl_xor_sync(0xFFFFFFFFu, bi, d);
+            if (ok > bk || (ok == bk && oi > bi)) { bk = ok; bi = oi; }
+        }
+        if ((tid & 31) == 0) { wk[tid >> 5] = bk; wi[tid >> 5] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < NMS_NT / 32; ++w)
+                if (wk[w] > bk || (wk[w] == bk && wi[w] > bi)) { bk = wk[w]; bi = wi[w]; }
+            s_found = bk > 0.0;
+            if (s_found) {
+                px[it] = (int)(bi % W); py[it] = (int)(bi / W);
+                res->cand_x[it] = px[it]; res->cand_y[it] = py[it]; res->trad[it] = bk;
+            }
+        }
+        __syncthreads();
+        if (!s_found) break;
+        ++cnt;
+    }
+    if (tid == 0) {
+        const int n_pos = cnt;
+        // zero-key fill: every positive key is picked or suppressed by now, so the remaining picks are
+        // the non-suppressed pixels in descending flat index (oracle: candidate_points)
+        long long i = (long long)c.P - 1;
+        while (cnt < LG_TOP_K && i >= 0) {
+            const int x = (int)(i % W), y = (int)(i / W);
+            int hit = -1;
+            for (int k = 0; k < cnt; ++k)
+                if (abs(x - px[k]) <= LG_NMS_REACH && abs(y - py[k]) <= LG_NMS_REACH) { hit = k; break; }
+            if (hit >= 0) {
+                const int nx = px[hit] - LG_NMS_REACH - 1;
+                i = (nx >= 0) ? (long long)y * W + nx : (long long)y * W - 1;
+                continue;
+            }
+            px[cnt] = x; py[cnt] = y;
+            res->cand_x[cnt] = x; res->cand_y[cnt] = y;
+            double t;
+            if (ext_score) t = ext_score[fo + i];
+            else if (x >= r.sx0 && x < r.sx1 && y >= r.sy0 && y < r.sy1) t = c.m_trad[fo + i];
+            else t = (double)0.2f;   // outside the leaf rectangle only the (unmasked) flatness term is left, and it is 1
+            res->trad[cnt] = t;
+            ++cnt;
+            --i;
+        }
+        res->n_candidates = cnt;
+        res->n_positive = n_pos;
+        if (cnt == 0) atomicOr(&c.status[b], LG_ST_NO_CANDIDATE);
+        if (ext_xy) {
+            for (int k = 0; k < LG_TOP_K; ++k) {
+                ext_xy[(b * LG_TOP_K + k) * 2] = k < cnt ? px[k] : -1;
+                ext_xy[(b * LG_TOP_K + k) * 2 + 1] = k < cnt ? py[k] : -1;
+            }
+            ext_count[b] = cnt;
+        }
+    }
+}
+
+// build the positive-key list from caller-supplied maps (entry for lg_candidate_points)
+__global__ void list_from_maps_kernel(lg_context c, const double* score, const uint8_t* valid) {
+    const int b = blockIdx.y;
+    const size_t fo = (size_t)b * c.P;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool want = false;
+    double k = 0.0;
+    if (i < c.P) { k = score[fo + i] * (double)(valid[fo + i] ? 1 : 0); want = k > 0.0; }
+    const unsigned ball = __ballot_sync(0xFFFFFFFFu, want);
+    if (ball) {
+        const int lane = threadIdx.x & 31;
+        unsigned base = 0;
+        if (lane == (__ffs(ball) - 1)) base = atomicAdd(&c.list_n[b], __popc(ball));
+        base = __shfl_sync(0xFFFFFFFFu, base, __ffs(ball) - 1);
+        if (want) {
+            const unsigned pos = base + __popc(ball & ((1u << lane) - 1u));
+            c.list_key[fo + pos] = k;
+            c.list_idx[fo + pos] = (unsigned)i;
+        }
+    }
+}
+
+__global__ void clear_list_kernel(lg_context c, int n) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < n) { c.list_n[b] = 0; c.status[b] = 0; }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// patches
+// ---------------------------------------------------------------------------------------------------
+constexpr int GA_NT = 256;
+__global__ void __launch_bounds__(GA_NT) gather_kernel(lg_context c, LgMaskSrc src, const float* __restrict__ depth) {
+    const int k = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    lg_frame_result* res = &c.results[b];
+    float* out = c.patches + ((size_t)b * LG_TOP_K + k) * (LG_CHANNELS * LG_PATCH * LG_PATCH);
+    const LgRegion r = c.region[b];
+    const int W = c.W, H = c.H;
+    __shared__ float smn[GA_NT / 32][LG_CHANNELS], smx[GA_NT / 32][LG_CHANNELS];
+    __shared__ float fmn[LG_CHANNELS], fmx[LG_CHANNELS];
+    const int ncand = r.ok ? res->n_candidates : 0;
+    const int cx = (k < ncand) ? res->cand_x[k] : -1000, cy = (k < ncand) ? res->cand_y[k] : -1000;
+    // the reference only gets an ML score when the window needs no padding (bool replicate-pad raises)
+    const bool ok = (k < ncand) && cx - 16 >= 0 && cy - 16 >= 0 && cx + 16 <= W && cy + 16 <= H;
+    if (tid == 0) res->ml_valid[k] = ok ? 1 : 0;
+    if (!ok) {
+        for (int i = tid; i < LG_CHANNELS * LG_PATCH * LG_PATCH; i += GA_NT) out[i] = 0.f;
+        return;
+    }
+    const size_t fo = (size_t)b * c.P;
+    const int id = src.id(b);
+    float v[LG_CHANNELS][4];
+    float mn[LG_CHANNELS], mx[LG_CHANNELS];
+#pragma unroll
+    for (int ch = 0; ch < LG_CHANNELS; ++ch) { mn[ch] = CUDART_INF_F; mx[ch] = -CUDART_INF_F; }
+    const double step = (0.2 - 1.0) / (double)(H - 1);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int pi = tid + q * GA_NT;
+        const int y = min(max(cy - 16 + (pi >> 5), 0), H - 1), x = min(max(cx - 16 + (pi & 31), 0), W - 1);
+        const size_t p = (size_t)y * W + x;
+        const bool M = src.at(fo, p, id);
+        const bool in = x >= r.sx0 && x < r.sx1 && y >= r.sy0 && y < r.sy1;
+        v[0][q] = depth[fo + p];
+        v[1][q] = M ? 1.f : 0.f;
+        v[2][q] = in ? (float)c.m_sdf[fo + p] : 0.f;
+        v[3][q] = in ? (float)c.m_app[fo + p] : 0.f;
+        v[4][q] = in ? c.m_flat[fo + p] : 1.f;
+        v[5][q] = M ? (float)((y == H - 1) ? 0.2 : ((double)y * step + 1.0)) : 0.f;
+        v[6][q] = M ? c.di[fo + p] : 0.f;
+        v[7][q] = in ? (float)c.m_acc[fo + p] : 0.f;
+        v[8][q] = in ? c.m_stem[fo + p] : 0.f;
+#pragma unroll
+        for (int ch = 0; ch < LG_CHANNELS; ++ch) { mn[ch] = fminf(mn[ch], v[ch][q]); mx[ch] = fmaxf(mx[ch], v[ch][q]); }
+    }
+#pragma unroll
+    for (int ch = 0; ch < LG_CHANNELS; ++ch) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            mn[ch] = fminf(mn[ch], __shfl_xor_sync(0xFFFFFFFFu, mn[ch], d));
+            mx[ch] = fmaxf(mx[ch], __shfl_xor_sync(0xFFFFFFFFu, mx[ch], d));
+        }
+        if ((tid & 31) == 0) { smn[tid >> 5][ch] = mn[ch]; smx[tid >> 5][ch] = mx[ch]; }
+    }
+    __syncthreads();
+    if (tid < LG_CHANNELS) {
+        float a = smn[0][tid], z = smx[0][tid];
+        for (int w = 1; w < GA_NT / 32; ++w) { a = fminf(a, smn[w][tid]); z = fmaxf(z, smx[w][tid]); }
+        fmn[tid] = a; fmx[tid] = z;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ch = 0; ch < LG_CHANNELS; ++ch) {
+        const float lo = fmn[ch], hi = fmx[ch];
+        const bool norm = (ch != 1) && (hi > lo);
+        const float den = __fsub_rn(hi, lo);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float val = v[ch][q];
+            if (norm) val = __fdiv_rn(__fsub_rn(val, lo), den);
+            out[ch * (LG_PATCH * LG_PATCH) + tid + q * GA_NT] = val;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fusion + 3-D points
+// ---------------------------------------------------------------------------------------------------
+__global__ void fuse_kernel(lg_context c, LgMaskSrc src, const float* __restrict__ depth, lg_camera cam, int have_ml, int n) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    lg_frame_result* res = &c.results[b];
+    const LgRegion r = c.region[b];
+    const int W = c.W, H = c.H;
+    const size_t fo = (size_t)b * c.P;
+    res->status = c.status[b];
+    res->leaf_id = c.leaf_id[b];
+    res->region[0] = r.x0; res->region[1] = r.y0; res->region[2] = r.x1; res->region[3] = r.y1;
+    const LgOrient o = c.orient[b];
+    res->angle = o.angle;
+    const uint32_t* mxq = c.dt_max + (size_t)b * 2;
+    res->sdf_max = __fmul_rn((float)max(mxq[0], mxq[1]), 1.0f / 65536.0f);
+    res->best_index = -1; res->ml_used = 0; res->best_score = 0.0;
+    res->grasp_x = -1; res->grasp_y = -1;
+    for (int k = 0; k < 3; ++k) { res->grasp_3d[k] = CUDART_NAN; res->pre_grasp[k] = CUDART_NAN; }
+    const int nc = r.ok ? res->n_candidates : 0;
+    if (!r.ok) { res->n_candidates = 0; res->n_positive = 0; }
+    for (int k = 0; k < LG_TOP_K; ++k) {
+        const bool mlk = have_ml && nc > 1 && k < nc && res->ml_valid[k];
+        if (mlk) {
+            const float lg = c.logits[(size_t)b * LG_TOP_K + k];
+            res->logit[k] = lg;
+            const float s = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-lg)));
+            res->ml[k] = tanh((double)s * 3.0) * 0.5 + 0.5;
+        } else {
+            res->logit[k] = CUDART_NAN_F; res->ml[k] = CUDART_NAN; res->ml_valid[k] = 0;
+        }
+    }
+    if (nc == 0) return;
+    int best = 0;
+    double best_score = res->trad[0];
+    int ml_used = 0;
+    if (have_ml && nc > 1) {
+        for (int k = 0; k < nc; ++k) {
+            if (!res->ml_valid[k]) continue;
+            const double ml = res->ml[k];
+            const double conf = 1.0 - fabs(ml - 0.5) * 2.0;
+            const double w = fmin(0.3, conf * 0.6);
+            const double comb = (1.0 - w) * res->trad[k] + w * ml;
+            if (comb > best_score) { best_score = comb; best = k; ml_used = 1; }
+        }
+    }
+    res->best_index = best; res->best_score = best_score; res->ml_used = ml_used;
+    const int u = res->cand_x[best], v = res->cand_y[best];
+    res->grasp_x = u; res->grasp_y = v;
+    const double z = (double)depth[fo + (size_t)v * W + u];
+    const double X = (z * ((double)u - cam.cx)) / cam.f, Y = (z * ((double)v - cam.cy)) / cam.f;
+    res->grasp_3d[0] = X; res->grasp_3d[1] = Y; res->grasp_3d[2] = z;
+    // pre-grasp (:754-819)
+    const double nrm = sqrt(X * X + Y * Y + z * z);
+    const double d0 = X / nrm, d1 = Y / nrm;
+    const uint32_t* bits = c.bits + (size_t)b * c.bits_stride;
+    const int ox = r.x0 - 1, oy = r.y0 - 1, bw = r.x1 - r.x0 + 2, bh = r.y1 - r.y0 + 2, wpr = (bw + 31) >> 5;
+    bool found = false;
+    for (int i = 0; i < 5 && !found; ++i) {
+        const double dist = 0.05 + (double)i * 0.01;
+        const double t0 = X - d0 * dist, t1 = Y - d1 * dist;
+        const int pu = (int)((t0 * cam.f / z) + cam.cx), pv = (int)((t1 * cam.f / z) + cam.cy);
+        if (!(pu >= 0 && pu < W && pv >= 0 && pv < H)) continue;
+        bool blocked = false;
+        for (int j = 0; j < LG_SE_PRE && !blocked; ++j)
+            blocked = bits_any(bits, wpr, bw, bh, pv + j - LG_SE_PRE / 2 - oy, pu + c.se31_a[j] - LG_SE_PRE / 2 - ox,
+                               pu + c.se31_b[j] - LG_SE_PRE / 2 - ox);
+        if (!blocked) {
+            const double e0 = t0 - X, e1 = t1 - Y;
+            if (sqrt(e0 * e0 + e1 * e1 + 0.0) >= 0.05) {
+                res->pre_grasp[0] = t0; res->pre_grasp[1] = t1; res->pre_grasp[2] = z;
+                found = true;
+            }
+        }
+    }
+    if (!found) {
+        res->pre_grasp[0] = X - d0 * 0.10; res->pre_grasp[1] = Y - d1 * 0.10; res->pre_grasp[2] = z;
+    }
+}
+
+// copy the internal maps out in the reference's dtypes (standalone score-map API)
+__global__ void export_maps_kernel(lg_context c, int n, double* sdf, double* app, float* flat, float* dist, double* acc,
+                                   float* stem, double* trad, uint8_t* valid, double* angle) {
+    const size_t total = (size_t)n * c.P;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        if (sdf) sdf[i] = c.m_sdf[i];
+        if (app) app[i] = c.m_app[i];
+        if (flat) flat[i] = c.m_flat[i];
+        if (dist) dist[i] = c.di[i];
+        if (acc) acc[i] = c.m_acc[i];
+        if (stem) stem[i] = c.m_stem[i];
+        if (trad) trad[i] = c.m_trad[i];
+        if (valid) valid[i] = c.m_valid[i];
+    }
+    if (angle)
+        for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < n; b += gridDim.x * blockDim.x) angle[b] = c.orient[b].angle;
+}
+
+__global__ void export_orient_kernel(lg_context c, int n, double* out5) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    const LgOrient o = c.orient[b];
+    out5[b * 5] = o.has_angle ? o.angle : CUDART_NAN;
+    out5[b * 5 + 1] = o.major; out5[b * 5 + 2] = o.minor; out5[b * 5 + 3] = o.cx; out5[b * 5 + 4] = o.cy;
+}
+
+// per-patch min-max normalisation of caller-built raw patches (get_ml_score, :83-123): every channel but the mask
+__global__ void __launch_bounds__(256) normalize_patches_kernel(const float* __restrict__ raw, float* __restrict__ out) {
+    const int ch = blockIdx.x, n = blockIdx.y, tid = threadIdx.x;
+    const float* src = raw + ((size_t)n * LG_CHANNELS + ch) * (LG_PATCH * LG_PATCH);
+    float* dst = out + ((size_t)n * LG_CHANNELS + ch) * (LG_PATCH * LG_PATCH);
+    __shared__ float smn[8], smx[8];
+    float v[4], mn = CUDART_INF_F, mx = -CUDART_INF_F;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { v[q] = src[tid + q * 256]; mn = fminf(mn, v[q]); mx = fmaxf(mx, v[q]); }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, d));
+        mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, d));
+    }
+    if ((tid & 31) == 0) { smn[tid >> 5] = mn; smx[tid >> 5] = mx; }
+    __syncthreads();
+    mn = smn[0]; mx = smx[0];
+    for (int w = 1; w < 8; ++w) { mn = fminf(mn, smn[w]); mx = fmaxf(mx, smx[w]); }
+    const bool norm = ch != 1 && mx > mn;
+    const float den = __fsub_rn(mx, mn);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dst[tid + q * 256] = norm ? __fdiv_rn(__fsub_rn(v[q], mn), den) : v[q];
+}
+
+}  // namespace
+
+int lg_run_scores(lg_context* c, LgMaskSrc src, const float* depth, int n, lg_camera cam, int full, double* iso_out,
+                  cudaStream_t st) {
+    dim3 grid((c->W + SC_TW - 1) / SC_TW + 1, (c->H + SC_TH - 1) / SC_TH + 1, n);
+    score_kernel<<<grid, SC_TW * SC_TH, 0, st>>>(*c, src, depth, cam, full, iso_out);
+    LG_LAUNCH_CHECK();
+    return LG_OK;
+}
+
+int lg_run_nms(lg_context* c, int n, cudaStream_t st) {
+    nms_kernel<<<n, NMS_NT, 0, st>>>(*c, nullptr, nullptr, nullptr, nullptr);
+    LG_LAUNCH_CHECK();
+    return LG_OK;
+}
+
+int lg_run_gather(lg_context* c, LgMaskSrc src, const float* depth, int n, lg_camera cam, cudaStream_t st) {
+    (void)cam;
+    gather_kernel<<<dim3(LG_TOP_K, n), GA_NT, 0, st>>>(*c, src, depth);
+    LG_LAUNCH_CHECK();
+    return LG_OK;
+}
+
+int lg_run_fuse(lg_context* c, LgMaskSrc src, const float* depth, int n, lg_camera cam, int have_ml, lg_frame_result* out,
+                cudaStream_t st) {
+    fuse_kernel<<<(n + 63) / 64, 64, 0, st>>>(*c, src, depth, cam, have_ml, n);
+    LG_LAUNCH_CHECK();
+    if (out && out != c->results)
+        LG_CUDA(cudaMemcpyAsync(out, c->results, sizeof(lg_frame_result) * n, cudaMemcpyDeviceToDevice, st));
+    return LG_OK;
+}
+
+int lg_run_export_maps(lg_context* c, int n, double* sdf, double* app, float* flat, float* dist, double* acc, float* stem,
+                       double* trad, uint8_t* valid, double* angle, cudaStream_t st) {
+    export_maps_kernel<<<LG_NUM_SM_HINT * 8, 256, 0, st>>>(*c, n, sdf, app, flat, dist, acc, stem, trad, valid, angle);
+    LG_LAUNCH_CHECK();
+    return LG_OK;
+}
+
+int lg_run_candidates_from_maps(lg_context* c, const double* score, const uint8_t* valid, int n, int32_t* xy, int32_t* count,
+                                cudaStream_t st) {
+    clear_list_kernel<<<(n + 63) / 64, 64, 0, st>>>(*c, n);
+    LG_LAUNCH_CHECK();
+    list_from_maps_kernel<<<dim3((unsigned)((c->P + 255) / 256), n), 256, 0, st>>>(*c, score, valid);
+    LG_LAUNCH_CHECK();
+    nms_kernel<<<n, NMS_NT, 0, st>>>(*c, score, valid, xy, count);
+    LG_LAUNCH_CHECK();
+    return LG_OK;
+}
+
+int lg_run_export_orient(lg_context* c, int n, double* out5, cudaStream_t st) {
+    export_orient_kernel<<<(n + 63) / 64, 64, 0, st>>>(*c, n, out5);
+    LG_LAUNCH_CHECK();
+    return LG_OK;
+}
+
+int lg_run_normalize_patches(const float* raw, int n, float* out, cudaStream_t st) {
+    normalize_patches_kernel<<<dim3(LG_CHANNELS, n), 256, 0, st>>>(raw, out);
+    LG_LAUNCH_CHECK();
+    return LG_OK;
+}

@@ -1,0 +1,545 @@
+// Stage 1 - optimal-leaf selection (reference scripts/utils/leaf_scorer.py:25-203, 277-306).
+//
+// Kernels (all batched over frames, no host synchronisation):
+//   leaf_stats_kernel    one pass over labels+depth: per-label pixel count, coordinate sums, depth sum,
+//                        sum of ray lengths, bounding box, border contact; first leaf pixel of the frame
+//   leaf_offsets_kernel  exclusive scan of the counts -> where each label's depth values go
+//   leaf_scatter_kernel  groups the depth values by label (order inside a group is irrelevant)
+//   leaf_median_kernel   exact np.median per label by radix selection on the grouped values
+//   edt_col_kernel / edt_row_kernel   exact squared Euclidean distance transform (two passes); used on
+//                        (labels >= 1) to find the background pixel farthest from every leaf
+//   select_leaf_kernel   the per-leaf scores, tall-leaf rule, Pareto front and weighted pick
+//
+// Integer sums are exact and order independent, so results do not depend on scheduling: coordinate
+// sums are 64-bit integers, depth and ray-length sums are fixed point (2^-28 m and 2^-36).
+#include <math_constants.h>
+
+#include "lg_internal.cuh"
+
+namespace {
+
+constexpr int ST_NT = 256;
+constexpr int ST_PX = 8;
+constexpr double DEP_SCALE = 268435456.0;       // 2^28
+constexpr double DIST_SCALE = 68719476736.0;    // 2^36
+
+struct SmemLeaf {
+    unsigned cnt, sx, sy, bx0, bx1, by0, by1, border;
+    unsigned long long sdep, sdist;
+};
+
+__global__ void clear_tables_kernel(lg_context c, int n) {
+    size_t total = (size_t)n * c.L;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        c.cnt[i] = 0; c.sx[i] = 0; c.sy[i] = 0; c.sdep[i] = 0; c.sdist[i] = 0;
+        c.bx0[i] = 0xFFFFFFFFu; c.by0[i] = 0xFFFFFFFFu; c.bx1[i] = 0; c.by1[i] = 0; c.border[i] = 0;
+        c.seg_cur[i] = 0;
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        c.first_leaf[i] = 0xFFFFFFFFu; c.edt_best[i] = 0ull; c.status[i] = 0; c.list_n[i] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(ST_NT) leaf_stats_kernel(lg_context c, const int16_t* __restrict__ labels,
+                                                            const float* __restrict__ depth, lg_camera cam) {
+    extern __shared__ SmemLeaf tab[];
+    __shared__ unsigned s_first, s_bad;
+    const int L = c.L, W = c.W, H = c.H;
+    const size_t P = c.P;
+    const int b = blockIdx.y;
+    for (int l = threadIdx.x; l < L; l += ST_NT) {
+        SmemLeaf z;
+        z.cnt = 0; z.sx = 0; z.sy = 0; z.bx0 = 0xFFFFFFFFu; z.by0 = 0xFFFFFFFFu; z.bx1 = 0; z.by1 = 0;
+        z.border = 0; z.sdep = 0; z.sdist = 0;
+        tab[l] = z;
+    }
+    if (threadIdx.x == 0) { s_first = 0xFFFFFFFFu; s_bad = 0; }
+    __syncthreads();
+
+    const size_t base = ((size_t)blockIdx.x * ST_NT + threadIdx.x) * ST_PX;
+    if (base < P) {
+        const int16_t* lp = labels + (size_t)b * P;
+        const float* dp = depth + (size_t)b * P;
+        int y = (int)(base / W), x = (int)(base % W);
+        const double inv_f2 = 1.0 / (cam.f * cam.f);
+        int cur = -1;
+        unsigned rc = 0, rsx = 0, rsy = 0, rx0 = 0, rx1 = 0, ry0 = 0, ry1 = 0, rb = 0;
+        long long rdep = 0;
+        unsigned long long rdist = 0;
+        auto flush = [&]() {
+            if (cur >= 0 && rc) {
+                SmemLeaf* t = &tab[cur];
+                atomicAdd(&t->cnt, rc);
+                if (cur > 0) {
+                    atomicAdd(&t->sx, rsx); atomicAdd(&t->sy, rsy);
+                    atomicMin(&t->bx0, rx0); atomicMax(&t->bx1, rx1);
+                    atomicMin(&t->by0, ry0); atomicMax(&t->by1, ry1);
+                    if (rb) atomicOr(&t->border, 1u);
+                    atomicAdd(&t->sdep, (unsigned long long)rdep);
+                    atomicAdd(&t->sdist, rdist);
+                }
+            }
+        };
+#pragma unroll
+        for (int i = 0; i < ST_PX; ++i) {
+            size_t idx = base + i;
+            if (idx >= P) break;
+            int l = lp[idx];
+            if (l < 0 || l >= L) { s_bad = 1; l = -1; }
+            if (l != cur) {
+                flush();
+                cur = l; rc = 0; rsx = 0; rsy = 0; rx0 = x; rx1 = x; ry0 = y; ry1 = y; rb = 0; rdep = 0; rdist = 0;
+                if (l >= 1) atomicMin(&s_first, (unsigned)idx);
+            }
+            if (l >= 0) {
+                rc++;
+                if (l > 0) {
+                    rsx += x; rsy += y;
+                    rx0 = min(rx0, (unsigned)x); rx1 = max(rx1, (unsigned)x);
+                    ry0 = min(ry0, (unsigned)y); ry1 = max(ry1, (unsigned)y);
+                    rb |= (x == 0) | (y == 0) | (x == W - 1) | (y == H - 1);
+                    float d = dp[idx];
+                    double dd = fmin(fmax((double)d, -2048.0), 2048.0);
+                    rdep += __double2ll_rn(dd * DEP_SCALE);
+                    double ddx = (double)x - cam.cx, ddy = (double)y - cam.cy;
+                    double s = sqrt((ddx * ddx + ddy * ddy) * inv_f2 + 1.0);
+                    rdist += (unsigned long long)__double2ll_rn(s * DIST_SCALE);
+                }
+            }
+            if (++x == W) { x = 0; ++y; }
+        }
+        flush();
+    }
+    __syncthreads();
+    for (int l = threadIdx.x; l < L; l += ST_NT) {
+        SmemLeaf t = tab[l];
+        if (t.cnt) {
+            size_t o = (size_t)b * L + l;
+            atomicAdd(&c.cnt[o], t.cnt);
+            if (l > 0) {
+                atomicAdd(&c.sx[o], (unsigned long long)t.sx);
+                atomicAdd(&c.sy[o], (unsigned long long)t.sy);
+                atomicAdd(&c.sdep[o], t.sdep);
+                atomicAdd(&c.sdist[o], t.sdist);
+                atomicMin(&c.bx0[o], t.bx0); atomicMax(&c.bx1[o], t.bx1);
+                atomicMin(&c.by0[o], t.by0); atomicMax(&c.by1[o], t.by1);
+                if (t.border) atomicOr(&c.border[o], 1u);
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        if (s_first != 0xFFFFFFFFu) atomicMin(&c.first_leaf[b], s_first);
+        if (s_bad) atomicOr(&c.status[b], LG_ST_LABEL_RANGE);
+    }
+}
+
+// background id = smallest id present (torch.unique(mask)[1:], leaf_scorer.py:32)
+__device__ __forceinline__ int background_id(const uint32_t* cnt, int L) {
+    for (int l = 0; l < L; ++l)
+        if (cnt[l]) return l;
+    return -1;
+}
+
+__global__ void leaf_offsets_kernel(lg_context c, int n) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    const uint32_t* cnt = c.cnt + (size_t)b * c.L;
+    uint32_t* off = c.seg_off + (size_t)b * (c.L + 1);
+    int bg = background_id(cnt, c.L);
+    uint32_t o = 0;
+    for (int l = 0; l < c.L; ++l) {
+        off[l] = o;
+        if (cnt[l] && l != bg) o += cnt[l];
+    }
+    off[c.L] = o;
+}
+
+__global__ void __launch_bounds__(ST_NT) leaf_scatter_kernel(lg_context c, const int16_t* __restrict__ labels,
+                                                              const float* __restrict__ depth) {
+    const int L = c.L;
+    const size_t P = c.P;
+    const int b = blockIdx.y;
+    const size_t base = ((size_t)blockIdx.x * ST_NT + threadIdx.x) * ST_PX;
+    const uint32_t* cnt = c.cnt + (size_t)b * L;
+    __shared__ int s_bg;
+    if (threadIdx.x == 0) s_bg = background_id(cnt, L);
+    __syncthreads();
+    if (base >= P) return;
+    const int bg = s_bg;
+    const int16_t* lp = labels + (size_t)b * P;
+    const float* dp = depth + (size_t)b * P;
+    const uint32_t* off = c.seg_off + (size_t)b * (L + 1);
+    float* seg = c.seg + (size_t)b * P;
+    int i = 0;
+    while (i < ST_PX && base + i < P) {
+        int l = lp[base + i];
+        int j = i + 1;
+        while (j < ST_PX && base + j < P && lp[base + j] == l) ++j;
+        if (l >= 0 && l < L && l != bg) {
+            uint32_t pos = atomicAdd(&c.seg_cur[(size_t)b * L + l], (uint32_t)(j - i));
+            float* dst = seg + off[l] + pos;
+            for (int k = i; k < j; ++k) dst[k - i] = dp[base + k];
+        }
+        i = j;
+    }
+}
+
+__device__ __forceinline__ unsigned f2key(float f) {
+    unsigned u = __float_as_uint(f);
+    return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float key2f(unsigned k) {
+    unsigned u = (k & 0x80000000u) ? (k ^ 0x80000000u) : ~k;
+    return __uint_as_float(u);
+}
+
+template <int NT>
+__device__ __forceinline__ void block_sum3(unsigned& a, unsigned& b, unsigned& c, unsigned* sm) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        a += __shfl_xor_sync(0xFFFFFFFFu, a, d);
+        b += __shfl_xor_sync(0xFFFFFFFFu, b, d);
+        c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
+    }
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) { sm[w * 3] = a; sm[w * 3 + 1] = b; sm[w * 3 + 2] = c; }
+    __syncthreads();
+    a = 0; b = 0; c = 0;
+#pragma unroll
+    for (int k = 0; k < NT / 32; ++k) { a += sm[k * 3]; b += sm[k * 3 + 1]; c += sm[k * 3 + 2]; }
+}
+
+constexpr int MED_NT = 256;
+// np.median(depth[labels == l]) for every label of every frame (leaf_scorer.py:41-47):
+// radix selection, two key bits per pass, on the values grouped by leaf_scatter_kernel.
+__global__ void __launch_bounds__(MED_NT) leaf_median_kernel(lg_context c) {
+    const int l = blockIdx.x, b = blockIdx.y, L = c.L;
+    const uint32_t* cnt = c.cnt + (size_t)b * L;
+    __shared__ unsigned sm[MED_NT / 32 * 3];
+    __shared__ int s_bg;
+    if (threadIdx.x == 0) s_bg = background_id(cnt, L);
+    __syncthreads();
+    const unsigned n = cnt[l];
+    if (n == 0 || l == s_bg) {
+        if (threadIdx.x == 0) c.median[(size_t)b * L + l] = CUDART_NAN_F;
+        return;
+    }
+    const float* v = c.seg + (size_t)b * c.P + c.seg_off[(size_t)b * (L + 1) + l];
+    unsigned k = (n & 1) ? n / 2 : n / 2 - 1;   // rank of the lower middle
+    unsigned prefix = 0, pmask = 0;
+    for (int shift = 30; shift >= 0; shift -= 2) {
+        unsigned c0 = 0, c1 = 0, c2 = 0;
+        for (unsigned i = threadIdx.x; i < n; i += MED_NT) {
+            unsigned key = f2key(v[i]);
+            if ((key & pmask) == prefix) {
+                unsigned d = (key >> shift) & 3u;
+                c0 += (d == 0); c1 += (d == 1); c2 += (d == 2);
+            }
+        }
+        block_sum3<MED_NT>(c0, c1, c2, sm);
+        unsigned d;
+        if (k < c0) d = 0;
+        else if (k < c0 + c1) { d = 1; k -= c0; }
+        else if (k < c0 + c1 + c2) { d = 2; k -= c0 + c1; }
+        else { d = 3; k -= c0 + c1 + c2; }
+        prefix |= d << shift;
+        pmask |= 3u << shift;
+    }
+    const unsigned klo = prefix;
+    float med = key2f(klo);
+    if (!(n & 1)) {
+        // upper middle: same value if enough elements are <= it, else the smallest larger key
+        unsigned le = 0, dummy1 = 0, dummy2 = 0, mn = 0xFFFFFFFFu;
+        for (unsigned i = threadIdx.x; i < n; i += MED_NT) {
+            unsigned key = f2key(v[i]);
+            if (key <= klo) le++;
+            else mn = min(mn, key);
+        }
+        block_sum3<MED_NT>(le, dummy1, dummy2, sm);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, d));
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mn;
+        __syncthreads();
+        mn = 0xFFFFFFFFu;
+        for (int w = 0; w < MED_NT / 32; ++w) mn = min(mn, sm[w]);
+        float hi = (le > n / 2) ? med : key2f(mn);
+        med = __fmul_rn(__fadd_rn(med, hi), 0.5f);   // float32 mean of the two middles
+    }
+    if (threadIdx.x == 0) c.median[(size_t)b * L + l] = med;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// exact squared Euclidean distance transform
+// ---------------------------------------------------------------------------------------------------
+struct EdtSrc {
+    const int16_t* labels;   // source (distance 0) where labels >= 1
+    const uint8_t* mask;     // source where mask == 0
+    __device__ __forceinline__ bool is_source(size_t i) const { return labels ? (labels[i] >= 1) : (mask[i] == 0); }
+};
+
+// pass 1: per column, distance (in rows) to the nearest source pixel in that column; 0xFFFF = none
+__global__ void edt_col_kernel(EdtSrc src, uint16_t* __restrict__ g, int H, int W, size_t P) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
+    const size_t fo = (size_t)blockIdx.y * P;
+    uint16_t* gp = g + fo;
+    unsigned d = 0xFFFFu;
+    for (int y = 0; y < H; ++y) {
+        size_t i = (size_t)y * W + x;
+        d = src.is_source(fo + i) ? 0u : min(d + 1u, 0xFFFFu);
+        gp[i] = (uint16_t)d;
+    }
+    d = 0xFFFFu;
+    for (int y = H - 1; y >= 0; --y) {
+        size_t i = (size_t)y * W + x;
+        unsigned cur = gp[i];
+        d = min(cur, min(d + 1u, 0xFFFFu));
+        gp[i] = (uint16_t)d;
+    }
+}
+
+constexpr int EDT_NT = 256;
+// pass 2: per row, d2(x) = min over x' of (x - x')^2 + g(x')^2.  The search around x stops as soon
+// as the horizontal offset alone exceeds the best distance found (Meijster's lower-envelope bound).
+__global__ void __launch_bounds__(EDT_NT) edt_row_kernel(const uint16_t* __restrict__ g, uint32_t* __restrict__ d2out,
+                                                          unsigned long long* __restrict__ best, int H, int W, size_t P) {
+    extern __shared__ unsigned srow[];   // g squared, 0xFFFFFFFF = no source in that column
+    __shared__ unsigned long long sbest[EDT_NT / 32];
+    __shared__ int s_any;
+    const int y = blockIdx.x, b = blockIdx.y;
+    const uint16_t* gp = g + (size_t)b * P + (size_t)y * W;
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
+    int any = 0;
+    for (int x = threadIdx.x; x < W; x += EDT_NT) {
+        unsigned v = gp[x];
+        srow[x] = (v == 0xFFFFu) ? 0xFFFFFFFFu : v * v;
+        any |= (v != 0xFFFFu);
+    }
+    if (any) s_any = 1;
+    __syncthreads();
+    unsigned long long mybest = 0;
+    if (s_any) {
+        for (int x = threadIdx.x; x < W; x += EDT_NT) {
+            unsigned bestd = srow[x];
+            for (unsigned k = 1; k * k < bestd; ++k) {
+                int xl = x - (int)k, xr = x + (int)k;
+                if (xl < 0 && xr >= W) break;
+                unsigned kk = k * k;
+                if (xl >= 0) { unsigned s = srow[xl]; if (s != 0xFFFFFFFFu) bestd = min(bestd, s + kk); }
+                if (xr < W) { unsigned s = srow[xr]; if (s != 0xFFFFFFFFu) bestd = min(bestd, s + kk); }
+            }
+            size_t idx = (size_t)y * W + x;
+            if (d2out) d2out[(size_t)b * P + idx] = bestd;
+            unsigned long long key = ((unsigned long long)bestd << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)idx);
+            mybest = max(mybest, key);
+        }
+    } else if (d2out) {
+        for (int x = threadIdx.x; x < W; x += EDT_NT) d2out[(size_t)b * P + (size_t)y * W + x] = 0xFFFFFFFFu;
+    }
+    if (best) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) mybest = max(mybest, __shfl_xor_sync(0xFFFFFFFFu, mybest, d));
+        if ((threadIdx.x & 31) == 0) sbest[threadIdx.x >> 5] = mybest;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < EDT_NT / 32; ++w) mybest = max(mybest, sbest[w]);
+            if (mybest) atomicMax(&best[b], mybest);
+        }
+    }
+}
+
+__global__ void edt_argmax_out_kernel(const unsigned long long* best, int32_t* argmax, int n) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < n) argmax[b] = (int32_t)(0xFFFFFFFFu - (unsigned)(best[b] & 0xFFFFFFFFull));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the pick
+// ---------------------------------------------------------------------------------------------------
+// numpy's pairwise float32 summation (np.mean of the medians, leaf_scorer.py:53-54)
+__device__ float np_pairwise_sum_f32(const float* a, int n) {
+    if (n < 8) {
+        float r = 0.f;
+        for (int i = 0; i < n; ++i) r = __fadd_rn(r, a[i]);
+        return r;
+    }
+    if (n <= 128) {
+        float r[8];
+        for (int j = 0; j < 8; ++j) r[j] = a[j];
+        int i;
+        for (i = 8; i < n - (n % 8); i += 8)
+            for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], a[i + j]);
+        float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                              __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+        for (; i < n; ++i) res = __fadd_rn(res, a[i]);
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return __fadd_rn(np_pairwise_sum_f32(a, n2), np_pairwise_sum_f32(a + n2, n - n2));
+}
+
+struct SelScratch {   // per label, in shared memory
+    double s0, s1, s2;
+    float med;
+    int id;
+    int tall;
+    int cand;
+};
+
+__global__ void select_leaf_kernel(lg_context c, lg_camera cam, int32_t* leaf_out, lg_leaf_record* rec_out) {
+    extern __shared__ unsigned char sraw[];
+    const int b = blockIdx.x, L = c.L, W = c.W, H = c.H;
+    if (threadIdx.x != 0) return;
+    SelScratch* s = reinterpret_cast<SelScratch*>(sraw);
+    float* meds = reinterpret_cast<float*>(sraw + sizeof(SelScratch) * L);
+    const size_t o = (size_t)b * L;
+    const uint32_t* cnt = c.cnt + o;
+    LgRegion reg;
+    reg.x0 = reg.y0 = reg.x1 = reg.y1 = 0; reg.ok = 0; reg.sx0 = reg.sy0 = reg.sx1 = reg.sy1 = 0;
+    int best_id = -1;
+    const int bg = background_id(cnt, L);
+    int n_ids = 0;
+    for (int l = 0; l < L; ++l) {
+        if (rec_out) {
+            lg_leaf_record r;
+            memset(&r, 0, sizeof(r));
+            r.leaf_id = l;
+            rec_out[o + l] = r;
+        }
+        if (cnt[l] && l != bg) {
+            s[n_ids].id = l;
+            s[n_ids].med = c.median[o + l];
+            meds[n_ids] = s[n_ids].med;
+            ++n_ids;
+        }
+    }
+    if (n_ids > 0 && !(c.status[b] & LG_ST_LABEL_RANGE)) {
+        const float mean_med = __fdiv_rn(np_pairwise_sum_f32(meds, n_ids), (float)n_ids);
+        const unsigned fl = c.first_leaf[b];
+        const double pmin_x = (double)(fl % W), pmin_y = (double)(fl / W);
+        const unsigned far = 0xFFFFFFFFu - (unsigned)(c.edt_best[b] & 0xFFFFFFFFull);
+        const double pmax_x = (double)(far % W), pmax_y = (double)(far / W);
+        int n_tall_c = 0, n_c = 0;
+        for (int k = 0; k < n_ids; ++k) {
+            const int l = s[k].id;
+            s[k].tall = s[k].med < mean_med;
+            s[k].cand = 0;
+            const unsigned area = cnt[l];
+            lg_leaf_record r;
+            memset(&r, 0, sizeof(r));
+            r.leaf_id = l; r.area = area; r.median_depth = s[k].med; r.is_tall = s[k].tall;
+            const double n = (double)area;
+            const double cx = (double)c.sx[o + l] / n, cy = (double)c.sy[o + l] / n;
+            r.centroid_x = cx; r.centroid_y = cy;
+            const float md = (float)(((double)(long long)c.sdep[o + l] / DEP_SCALE) / n);
+            r.mean_depth = md;
+            if (area >= LG_MIN_LEAF_AREA) {
+                const double dmin = sqrt((cx - pmin_x) * (cx - pmin_x) + (cy - pmin_y) * (cy - pmin_y));
+                const double dmax = sqrt((cx - pmax_x) * (cx - pmax_x) + (cy - pmax_y) * (cy - pmax_y));
+                const double tot = dmin + dmax;
+                const double clutter = tot > 0 ? dmin / tot : 0.0;
+                const double mean_dist = (double)md * (((double)c.sdist[o + l] / DIST_SCALE) / n);
+                const double dist_score = exp(-mean_dist / 0.3);
+                double vis = 0.0;
+                if (!c.border[o + l]) {
+                    const double hw = W / 2.0, hh = H / 2.0;
+                    vis = 1.0 - sqrt((cx - hw) * (cx - hw) + (cy - hh) * (cy - hh)) / sqrt(hw * hw + hh * hh);
+                }
+                s[k].s0 = clutter; s[k].s1 = dist_score; s[k].s2 = vis; s[k].cand = 1;
+                r.clutter = clutter; r.distance = dist_score; r.visibility = vis; r.mean_distance = mean_dist;
+                r.is_candidate = 1;
+                ++n_c;
+                if (s[k].tall) ++n_tall_c;
+            }
+            if (rec_out) rec_out[o + l] = r;
+        }
+        if (n_c > 0) {
+            const int want_tall = n_tall_c > 0;
+            const double scale = want_tall ? 1.1 : 1.0;
+            double best_score = -CUDART_INF;
+            for (int i = 0; i < n_ids; ++i) {
+                if (!s[i].cand || (want_tall && !s[i].tall)) continue;
+                const double a0 = s[i].s0 * scale, a1 = s[i].s1 * scale, a2 = s[i].s2 * scale;
+                bool dominated = false;
+                for (int j = 0; j < n_ids && !dominated; ++j) {
+                    if (j == i || !s[j].cand || (want_tall && !s[j].tall)) continue;
+                    const double b0 = s[j].s0 * scale, b1 = s[j].s1 * scale, b2 = s[j].s2 * scale;
+                    const bool ge = b0 >= a0 && b1 >= a1 && b2 >= a2;
+                    const bool gt = b0 > a0 || b1 > a1 || b2 > a2;
+                    if (ge && (gt || j < i)) dominated = true;
+                }
+                if (dominated) continue;
+                const double w = ((0.0 + 0.35 * s[i].s0) + 0.35 * s[i].s1) + 0.3 * s[i].s2;
+                if (w > best_score) { best_score = w; best_id = s[i].id; }
+            }
+        }
+    }
+    if (best_id >= 0) {
+        reg.x0 = (int)c.bx0[o + best_id]; reg.x1 = (int)c.bx1[o + best_id] + 1;
+        reg.y0 = (int)c.by0[o + best_id]; reg.y1 = (int)c.by1[o + best_id] + 1;
+        reg.ok = 1;
+        reg.sx0 = max(0, reg.x0 - LG_REGION_PAD); reg.sy0 = max(0, reg.y0 - LG_REGION_PAD);
+        reg.sx1 = min(W, reg.x1 + LG_REGION_PAD); reg.sy1 = min(H, reg.y1 + LG_REGION_PAD);
+    } else {
+        atomicOr(&c.status[b], LG_ST_NO_LEAF);
+    }
+    c.leaf_id[b] = best_id;
+    c.region[b] = reg;
+    if (leaf_out) leaf_out[b] = best_id;
+}
+
+}  // namespace
+
+int lg_run_edt_union(lg_context* c, const int16_t* labels, int n, cudaStream_t st) {
+    EdtSrc src{labels, nullptr};
+    edt_col_kernel<<<dim3((c->W + 127) / 128, n), 128, 0, st>>>(src, c->edt_g, c->H, c->W, c->P);
+    LG_LAUNCH_CHECK();
+    edt_row_kernel<<<dim3(c->H, n), EDT_NT, c->W * sizeof(unsigned), st>>>(c->edt_g, nullptr, c->edt_best, c->H, c->W, c->P);
+    LG_LAUNCH_CHECK();
+    return LG_OK;
+}
+
+int lg_run_stage1(lg_context* c, const int16_t* labels, const float* depth, int n, lg_camera cam, cudaStream_t st) {
+    clear_tables_kernel<<<64, 256, 0, st>>>(*c, n);
+    LG_LAUNCH_CHECK();
+    const int tiles = (int)((c->P + ST_NT * ST_PX - 1) / (ST_NT * ST_PX));
+    leaf_stats_kernel<<<dim3(tiles, n), ST_NT, c->L * sizeof(SmemLeaf), st>>>(*c, labels, depth, cam);
+    LG_LAUNCH_CHECK();
+    leaf_offsets_kernel<<<(n + 63) / 64, 64, 0, st>>>(*c, n);
+    LG_LAUNCH_CHECK();
+    leaf_scatter_kernel<<<dim3(tiles, n), ST_NT, 0, st>>>(*c, labels, depth);
+    LG_LAUNCH_CHECK();
+    leaf_median_kernel<<<dim3(c->L, n), MED_NT, 0, st>>>(*c);
+    LG_LAUNCH_CHECK();
+    int rc = lg_run_edt_union(c, labels, n, st);
+    if (rc) return rc;
+    return LG_OK;
+}
+
+int lg_run_select(lg_context* c, int n, lg_camera cam, int32_t* leaf_out, lg_leaf_record* rec_out, cudaStream_t st) {
+    size_t sm = (sizeof(SelScratch) + sizeof(float)) * c->L;
+    select_leaf_kernel<<<n, 32, sm, st>>>(*c, cam, leaf_out, rec_out);
+    LG_LAUNCH_CHECK();
+    return LG_OK;
+}
+
+extern "C" int lg_edt_squared(lg_context* c, const uint8_t* mask, int n, uint32_t* d2, int32_t* argmax, void* stream) {
+    if (!c || !mask || n < 1) return LG_E_ARG;
+    if (n > c->B) return LG_E_CAPACITY;
+    cudaStream_t st = (cudaStream_t)stream;
+    LG_CUDA(cudaMemsetAsync(c->edt_best, 0, sizeof(unsigned long long) * n, st));
+    EdtSrc src{nullptr, mask};
+    edt_col_kernel<<<dim3((c->W + 127) / 128, n), 128, 0, st>>>(src, c->edt_g, c->H, c->W, c->P);
+    LG_LAUNCH_CHECK();
+    edt_row_kernel<<<dim3(c->H, n), EDT_NT, c->W * sizeof(unsigned), st>>>(c->edt_g, d2, c->edt_best, c->H, c->W, c->P);
+    LG_LAUNCH_CHECK();
+    if (argmax) {
+        edt_argmax_out_kernel<<<(n + 63) / 64, 64, 0, st>>>(c->edt_best, argmax, n);
+        LG_LAUNCH_CHECK();
+    }
+    return LG_OK;
+}

@@ -1,0 +1,42 @@
+"""Multi-GPU plumbing: frames are independent, so a batch is split into contiguous
+per-rank ranges, every rank runs the whole path on its range, and the only exchange is one all-gather of
+fixed-size candidate records for the aggregate result.  torch.distributed (NCCL on GPUs, gloo in the CPU
+tests) carries it; there is no data-path collective to fuse with."""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+RECORD_FIELDS = 4   # x, y, traditional score, ml score  (320 B per frame at 20 candidates)
+
+
+def shard_range(n_frames: int, rank: int, world: int):
+    """Contiguous block [lo, hi) of frame indices owned by `rank`; sizes differ by at most one."""
+    base, rem = divmod(n_frames, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def records_from_results(res, device) -> torch.Tensor:
+    """Structured FRAME_RESULT array -> float32 tensor [frames, 20, 4] (x, y, trad, ml)."""
+    import numpy as np
+    rec = np.stack([res["cand_x"].astype(np.float32), res["cand_y"].astype(np.float32),
+                    res["trad"].astype(np.float32), np.nan_to_num(res["ml"]).astype(np.float32)], axis=-1)
+    return torch.from_numpy(rec).to(device)
+
+
+def gather_candidate_records(local: torch.Tensor, n_frames: int) -> torch.Tensor:
+    """All-gather of the per-rank record blocks into [n_frames, 20, 4] on every rank."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return local
+    world, rank = dist.get_world_size(), dist.get_rank()
+    per = (n_frames + world - 1) // world
+    pad = torch.zeros(per, *local.shape[1:], dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = torch.empty(world * per, *local.shape[1:], dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad)
+    parts = []
+    for r in range(world):
+        lo, hi = shard_range(n_frames, r, world)
+        parts.append(out[r * per: r * per + (hi - lo)])
+    return torch.cat(parts, dim=0)

@@ -1,0 +1,209 @@
+"""GraspEngine: one device context of the native library + thin tensor-in / record-out calls.
+
+torch is used for device memory, streams and (in dist.py) the NCCL plumbing only; every computation
+happens inside liblgb200.so.  All calls run on the current torch CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def camera_from_projection(P) -> N.Camera:
+    """f = P[0,0], cx = P[0,2], cy = P[1,2] (grasp_point_selector.py:145-150)."""
+    P = np.asarray(P, dtype=np.float64)
+    return N.Camera(float(P[0, 0]), float(P[0, 2]), float(P[1, 2]))
+
+
+class GraspEngine:
+    def __init__(self, max_frames: int, height: int, width: int, max_labels: int = 128, device=None):
+        if not torch.cuda.is_available():
+            raise N.NativeError("GraspEngine needs a CUDA device; this package has no CPU fallback")
+        self.lib = N.lib()
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.B, self.H, self.W, self.L = int(max_frames), int(height), int(width), int(max_labels)
+        self._ctx = C.c_void_p(0)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.lg_create(C.byref(self._ctx), self.B, self.H, self.W, self.L), "lg_create")
+        self.has_cnn = False
+
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            with torch.cuda.device(self.device):
+                torch.cuda.synchronize()
+                self.lib.lg_destroy(self._ctx)
+            self._ctx = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def context_bytes(self) -> int:
+        return int(self.lib.lg_context_bytes(self._ctx))
+
+    # ---- helpers ---------------------------------------------------------------------------------
+    def _frames(self, t, dtype, name):
+        if t.dim() == 2:
+            t = t.unsqueeze(0)
+        if t.shape[-2:] != (self.H, self.W):
+            raise ValueError(f"{name}: expected [..., {self.H}, {self.W}], got {tuple(t.shape)}")
+        return t.to(self.device, dtype, non_blocking=True).contiguous()
+
+    def _new_results(self, n):
+        return torch.empty(n * N.FRAME_RESULT.itemsize, dtype=torch.uint8, device=self.device)
+
+    @staticmethod
+    def _records(buf, dtype):
+        return np.frombuffer(buf.cpu().numpy().tobytes(), dtype=dtype)
+
+    # ---- CNN ----------------------------------------------------------------------------------------
+    def set_cnn_weights(self, blob):
+        with torch.cuda.device(self.device):
+            if blob is None:
+                N.check(self.lib.lg_set_cnn_weights(self._ctx, None, 0), "lg_set_cnn_weights")
+                self.has_cnn = False
+                return
+            blob = np.ascontiguousarray(blob, dtype=np.float32)
+            N.check(self.lib.lg_set_cnn_weights(self._ctx, blob.ctypes.data_as(C.c_void_p), blob.size), "lg_set_cnn_weights")
+            self.has_cnn = True
+
+    def cnn_forward(self, patches: torch.Tensor, use_bf16: bool = False) -> torch.Tensor:
+        patches = patches.to(self.device, torch.float32).contiguous()
+        n = patches.shape[0]
+        out = torch.empty(n, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.lg_cnn_forward(self._ctx, _ptr(patches), n, _ptr(out), int(use_bf16), _stream()), "lg_cnn_forward")
+        return out
+
+    def normalize_patches(self, raw: torch.Tensor) -> torch.Tensor:
+        raw = raw.to(self.device, torch.float32).contiguous()
+        out = torch.empty_like(raw)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.lg_normalize_patches(self._ctx, _ptr(raw), raw.shape[0], _ptr(out), _stream()), "lg_normalize_patches")
+        return out
+
+    # ---- whole path ----------------------------------------------------------------------------------
+    def process_batch(self, labels, depth, cam: N.Camera, use_bf16: bool = False, sync: bool = True):
+        """labels int16 / depth float32 device tensors [n,H,W] -> structured ndarray (or the raw device
+        buffer when sync=False)."""
+        labels = self._frames(labels, torch.int16, "labels")
+        depth = self._frames(depth, torch.float32, "depth")
+        n = labels.shape[0]
+        res = self._new_results(n)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.lg_process_batch(self._ctx, _ptr(labels), _ptr(depth), n, C.byref(cam), _ptr(res),
+                                              int(use_bf16), _stream()), "lg_process_batch")
+        return self._records(res, N.FRAME_RESULT) if sync else res
+
+    def process_batch_host(self, labels_host, depth_host, cam: N.Camera, use_bf16: bool = False):
+        """Pinned (or plain) HOST tensors in, structured ndarray out; copies are inside the call."""
+        n = labels_host.shape[0]
+        out = np.empty(n, dtype=N.FRAME_RESULT)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.lg_process_batch_host(self._ctx, _ptr(labels_host), _ptr(depth_host), n, C.byref(cam),
+                                                   out.ctypes.data_as(C.c_void_p), int(use_bf16), _stream()),
+                    "lg_process_batch_host")
+        return out
+
+    def select_leaf(self, labels, depth, cam: N.Camera):
+        labels = self._frames(labels, torch.int16, "labels")
+        depth = self._frames(depth, torch.float32, "depth")
+        n = labels.shape[0]
+        ids = torch.empty(n, dtype=torch.int32, device=self.device)
+        rec = torch.empty(n * self.L * N.LEAF_RECORD.itemsize, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.lg_select_leaf(self._ctx, _ptr(labels), _ptr(depth), n, C.byref(cam), _ptr(ids), _ptr(rec),
+                                            _stream()), "lg_select_leaf")
+        return ids.cpu().numpy(), self._records(rec, N.LEAF_RECORD).reshape(n, self.L)
+
+    def select_grasp_point(self, mask, depth, cam: N.Camera, use_bf16: bool = False):
+        mask = self._frames(mask, torch.uint8, "mask")
+        depth = self._frames(depth, torch.float32, "depth")
+        n = mask.shape[0]
+        res = self._new_results(n)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.lg_select_grasp_point(self._ctx, _ptr(mask), _ptr(depth), n, C.byref(cam), _ptr(res),
+                                                   int(use_bf16), _stream()), "lg_select_grasp_point")
+        return self._records(res, N.FRAME_RESULT)
+
+    def last_patches(self, n: int) -> torch.Tensor:
+        out = torch.empty(n, N.TOP_K, N.CHANNELS, N.PATCH, N.PATCH, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.lg_patches(self._ctx, _ptr(out), n, _stream()), "lg_patches")
+        return out
+
+    # ---- stages ----------------------------------------------------------------------------------------
+    def chamfer(self, mask, invert: bool = False, want_q16: bool = True):
+        mask = self._frames(mask, torch.uint8, "mask")
+        n = mask.shape[0]
+        dist = torch.empty(n, self.H, self.W, dtype=torch.float32, device=self.device)
+        q16 = torch.empty(n, self.H, self.W, dtype=torch.int32, device=self.device) if want_q16 else None
+        mx = torch.empty(n, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.lg_chamfer_transform(self._ctx, _ptr(mask), n, int(invert), _ptr(dist), _ptr(q16), _ptr(mx),
+                                                  _stream()), "lg_chamfer_transform")
+        return dist, q16, mx
+
+    def edt_squared(self, mask):
+        mask = self._frames(mask, torch.uint8, "mask")
+        n = mask.shape[0]
+        d2 = torch.empty(n, self.H, self.W, dtype=torch.int32, device=self.device)
+        am = torch.empty(n, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.lg_edt_squared(self._ctx, _ptr(mask), n, _ptr(d2), _ptr(am), _stream()), "lg_edt_squared")
+        return d2, am
+
+    def score_maps(self, mask, depth, cam: N.Camera):
+        """Full-frame maps with the reference's names and dtypes (device tensors) + 'valid' + 'angle'."""
+        mask = self._frames(mask, torch.uint8, "mask")
+        depth = self._frames(depth, torch.float32, "depth")
+        n = mask.shape[0]
+        f64 = lambda: torch.empty(n, self.H, self.W, dtype=torch.float64, device=self.device)
+        f32 = lambda: torch.empty(n, self.H, self.W, dtype=torch.float32, device=self.device)
+        out = {"sdf_score": f64(), "approach_score": f64(), "flatness_map": f32(), "isolation_map": f64(),
+               "distance_map": f32(), "accessibility_map": f64(), "stem_penalty": f32(), "traditional_score": f64()}
+        valid = torch.empty(n, self.H, self.W, dtype=torch.uint8, device=self.device)
+        angle = torch.empty(n, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.lg_score_maps(
+                self._ctx, _ptr(mask), _ptr(depth), n, C.byref(cam), _ptr(out["sdf_score"]), _ptr(out["approach_score"]),
+                _ptr(out["flatness_map"]), _ptr(out["isolation_map"]), _ptr(out["distance_map"]),
+                _ptr(out["accessibility_map"]), _ptr(out["stem_penalty"]), _ptr(out["traditional_score"]), _ptr(valid),
+                _ptr(angle), _stream()), "lg_score_maps")
+        out["valid"] = valid
+        out["angle"] = angle
+        return out
+
+    def candidate_points(self, score, valid):
+        score = self._frames(score, torch.float64, "score")
+        valid = self._frames(valid, torch.uint8, "valid")
+        n = score.shape[0]
+        xy = torch.empty(n, N.TOP_K, 2, dtype=torch.int32, device=self.device)
+        cnt = torch.empty(n, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.lg_candidate_points(self._ctx, _ptr(score), _ptr(valid), n, _ptr(xy), _ptr(cnt), _stream()),
+                    "lg_candidate_points")
+        return xy, cnt
+
+    def leaf_orientation(self, mask):
+        mask = self._frames(mask, torch.uint8, "mask")
+        n = mask.shape[0]
+        out = torch.empty(n, 5, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.lg_leaf_orientation(self._ctx, _ptr(mask), n, _ptr(out), _stream()), "lg_leaf_orientation")
+        return out

@@ -198,6 +198,162 @@ def leaf_orientation(mask_u8: np.ndarray):
     return np.deg2rad(ang), max(w, h), min(w, h), (cx, cy)
 
 
+def hull_from_points(pts: np.ndarray) -> np.ndarray:
+    """Strictly convex hull of integer pixel coordinates, in the order cv2.convexHull(contour, clockwise=True)
+    gives for a contour that starts at its raster-first pixel: start at the top-left pixel, down the left
+    side, along the bottom, up the right side.  Built from the per-row extents with two monotone chains."""
+    pts = np.asarray(pts, dtype=np.int64).reshape(-1, 2)
+    ys = np.unique(pts[:, 1])
+    lo = {int(y): int(pts[pts[:, 1] == y, 0].min()) for y in ys}
+    hi = {int(y): int(pts[pts[:, 1] == y, 0].max()) for y in ys}
+
+    def cross(a, b, c):
+        return (b[0] - a[0]) * (c[1] - b[1]) - (b[1] - a[1]) * (c[0] - b[0])
+
+    h = []
+    for y in ys:
+        p = (lo[int(y)], int(y))
+        while len(h) >= 2 and cross(h[-2], h[-1], p) >= 0:
+            h.pop()
+        h.append(p)
+    base = len(h)
+    for y in ys[::-1]:
+        p = (hi[int(y)], int(y))
+        if h and h[-1] == p:
+            continue
+        while len(h) >= base + 1 and len(h) >= 2 and cross(h[-2], h[-1], p) >= 0:
+            h.pop()
+        h.append(p)
+    if len(h) > 1 and h[-1] == h[0]:
+        h.pop()
+    while len(h) >= 3 and cross(h[-2], h[-1], h[0]) >= 0:
+        h.pop()
+    return np.array(h, dtype=np.int64)
+
+
+def min_area_rect_restated(hull: np.ndarray):
+    """OpenCV's rotatingCalipers(CALIPERS_MINAREARECT) and the tail of cv::minAreaRect restated in float32
+    without fused multiply-add (strict-mode definition; cv2 4.13 agrees to the last bit on most inputs and to
+    1-2 ulp on the rest).  Returns ((cx, cy), (w, h), angle_deg) as float32."""
+    f32, f64 = np.float32, np.float64
+    pts = np.asarray(hull, dtype=np.float32)
+    n = len(pts)
+    if n == 1:
+        return (pts[0, 0], pts[0, 1]), (f32(0), f32(0)), f32(0)
+    if n == 2:
+        dx, dy = f64(pts[1, 0]) - f64(pts[0, 0]), f64(pts[1, 1]) - f64(pts[0, 1])
+        return ((pts[0, 0] + pts[1, 0]) * f32(0.5), (pts[0, 1] + pts[1, 1]) * f32(0.5)), \
+               (f32(np.sqrt(dx * dx + dy * dy)), f32(0)), f32(np.arctan2(dy, dx) * 180.0 / np.pi)
+    vect = np.zeros((n, 2), f32)
+    inv = np.zeros(n, f32)
+    left = bottom = right = top = 0
+    pt0 = pts[0].copy()
+    left_x = right_x = pt0[0]
+    top_y = bottom_y = pt0[1]
+    for i in range(n):
+        if pt0[0] < left_x:
+            left_x, left = pt0[0], i
+        if pt0[0] > right_x:
+            right_x, right = pt0[0], i
+        if pt0[1] > top_y:
+            top_y, top = pt0[1], i
+        if pt0[1] < bottom_y:
+            bottom_y, bottom = pt0[1], i
+        pt = pts[(i + 1) % n]
+        dx, dy = f64(pt[0]) - f64(pt0[0]), f64(pt[1]) - f64(pt0[1])
+        vect[i] = (f32(dx), f32(dy))
+        inv[i] = f32(1.0 / np.sqrt(dx * dx + dy * dy))
+        pt0 = pt.copy()
+    orientation = f32(0)
+    ax, ay = f64(vect[n - 1, 0]), f64(vect[n - 1, 1])
+    for i in range(n):
+        bx, by = f64(vect[i, 0]), f64(vect[i, 1])
+        conv = ax * by - ay * bx
+        if conv != 0:
+            orientation = f32(1) if conv > 0 else f32(-1)
+            break
+        ax, ay = bx, by
+    base_a, base_b = orientation, f32(0)
+    seq = [bottom, right, top, left]
+    minarea = f32(3.4028235e38)
+    best = None
+    for _ in range(n):
+        dp = [base_a * vect[seq[0], 0] + base_b * vect[seq[0], 1],
+              -base_b * vect[seq[1], 0] + base_a * vect[seq[1], 1],
+              -base_a * vect[seq[2], 0] - base_b * vect[seq[2], 1],
+              base_b * vect[seq[3], 0] - base_a * vect[seq[3], 1]]
+        maxcos, main = dp[0] * inv[seq[0]], 0
+        for i in range(1, 4):
+            c = dp[i] * inv[seq[i]]
+            if c > maxcos:
+                main, maxcos = i, c
+        p = seq[main]
+        lx, ly = vect[p, 0] * inv[p], vect[p, 1] * inv[p]
+        base_a, base_b = ((lx, ly), (ly, -lx), (-lx, -ly), (-ly, lx))[main]
+        seq[main] = (seq[main] + 1) % n
+        dx, dy = pts[seq[1], 0] - pts[seq[3], 0], pts[seq[1], 1] - pts[seq[3], 1]
+        width = dx * base_a + dy * base_b
+        dx, dy = pts[seq[2], 0] - pts[seq[0], 0], pts[seq[2], 1] - pts[seq[0], 1]
+        height = -dx * base_b + dy * base_a
+        area = width * height
+        if area <= minarea:
+            minarea = area
+            best = (seq[3], base_a, width, base_b, height, seq[0])
+    l, A1, w, B1, h, b = best
+    A2, B2 = -B1, A1
+    C1 = A1 * pts[l, 0] + pts[l, 1] * B1
+    C2 = A2 * pts[b, 0] + pts[b, 1] * B2
+    idet = f32(1) / (A1 * B2 - A2 * B1)
+    px, py = (C1 * B2 - C2 * B1) * idet, (A1 * C2 - A2 * C1) * idet
+    o2, o3, o4, o5 = A1 * w, B1 * w, A2 * h, B2 * h
+    cx, cy = px + (o2 + o4) * f32(0.5), py + (o3 + o5) * f32(0.5)
+    ww = f32(np.sqrt(f64(o2) * f64(o2) + f64(o3) * f64(o3)))
+    hh = f32(np.sqrt(f64(o4) * f64(o4) + f64(o5) * f64(o5)))
+    ang = f32(np.arctan2(f64(o3), f64(o2)) * 180.0 / np.pi)
+    return (cx, cy), (ww, hh), ang
+
+
+def leaf_orientation_restated(mask_u8: np.ndarray):
+    """Strict-mode orientation: cv2 picks the outer contour of largest polygon area; its hull and the
+    rectangle come from the restatements above."""
+    contours, _ = cv2.findContours(np.ascontiguousarray(mask_u8, dtype=np.uint8),
+                                   cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_NONE)
+    if not contours:
+        return None, None, None, None
+    contour = max(contours, key=cv2.contourArea)
+    (cx, cy), (w, h), ang = min_area_rect_restated(hull_from_points(contour.reshape(-1, 2)))
+    ang = float(ang)
+    if w < h:
+        ang = ang + 90
+    return np.deg2rad(ang), float(max(w, h)), float(min(w, h)), (float(cx), float(cy))
+
+
+def moore_contour_area(mask_u8: np.ndarray, sx: int, sy: int) -> float:
+    """cv2.contourArea of the outer border of the 8-connected component whose raster-first pixel is
+    (sx, sy), by Moore-neighbour tracing and the shoelace formula (the rule csrc/lg_orient.cu uses)."""
+    DX = (1, 1, 0, -1, -1, -1, 0, 1)
+    DY = (0, 1, 1, 1, 0, -1, -1, -1)
+    H, W = mask_u8.shape
+    bit = lambda x, y: 0 <= x < W and 0 <= y < H and mask_u8[y, x] != 0
+    cx, cy, db, first, a00 = sx, sy, 4, -1, 0
+    while True:
+        d = -1
+        for k in range(1, 9):
+            dd = (db + k) % 8
+            if bit(cx + DX[dd], cy + DY[dd]):
+                d = dd
+                break
+        if d < 0 or (cx == sx and cy == sy and first >= 0 and d == first):
+            break
+        if first < 0:
+            first = d
+        nx, ny = cx + DX[d], cy + DY[d]
+        a00 += cx * ny - nx * cy
+        cx, cy = nx, ny
+        db = (d + (5 if d % 2 else 6)) % 8
+    return abs(a00) * 0.5
+
+
 # ----------------------------------------------------------------------------------------------
 # stage 1: optimal leaf            (leaf_scorer.py:25-203, 277-306)
 # ----------------------------------------------------------------------------------------------
@@ -386,7 +542,7 @@ def sdf_score_map(mask_u8, cx, cy, arith="reference", use_cv2=True, want_parts=F
     nrm[nrm == 0] = 1
     vx = vx / nrm
     vy = vy / nrm
-    angle, _, _, _ = leaf_orientation(mask_u8)
+    angle, _, _, _ = leaf_orientation(mask_u8) if arith == "reference" else leaf_orientation_restated(mask_u8)
     if angle is not None:
         ca, sa = np.cos(angle), np.sin(angle)
         align = np.abs(vx * sa - vy * ca)

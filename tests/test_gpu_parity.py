@@ -1,0 +1,379 @@
+"""GPU parity tests (run with ``-m gpu`` on the B200 box): every stage of the CUDA path, called through
+the C-ABI, against oracle/leafgrasp_oracle.py on the same seeded inputs, and against the golden vectors
+the reference itself produced (tests/golden/).  Nothing here reads /root/reference.
+
+Bars (BASELINE.json north_star): distance transforms, masks and candidate indices bit-exact; score maps
+within 1e-5 relative (they are in fact held to a few ulp); CNN logits within 1e-4 in fp32 / 1e-2 in bf16.
+"""
+import json
+import os
+
+import cv2
+import numpy as np
+import pytest
+import torch
+
+import leafgrasp_oracle as O
+from leafgrasp_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+META = json.load(open(os.path.join(GOLD, "golden_meta.json")))
+SEED = META["config_seed"]
+F64_MAPS = ("sdf_score", "approach_score", "isolation_map", "accessibility_map", "traditional_score")
+
+
+def _engine(frames, H, W, labels=128):
+    from leafgrasp_b200 import GraspEngine
+    return GraspEngine(frames, H, W, labels)
+
+
+def _cam(spec):
+    from leafgrasp_b200 import camera_from_projection
+    return camera_from_projection(synth.projection_matrix(spec))
+
+
+def _blobs(rng, H, W, n):
+    m = np.zeros((H, W), np.uint8)
+    for _ in range(n):
+        c = (int(rng.integers(0, W)), int(rng.integers(0, H)))
+        ax = (int(rng.integers(2, max(3, W // 3))), int(rng.integers(2, max(3, H // 3))))
+        cv2.ellipse(m, c, ax, float(rng.uniform(0, 180)), 0, 360, 1, -1)
+    return m
+
+
+@pytest.fixture(scope="module")
+def state_dict():
+    return O.seeded_state_dict(META["cnn_seed"])
+
+
+@pytest.fixture(scope="module")
+def blob(state_dict):
+    from leafgrasp_b200 import pack_weights
+    return pack_weights(state_dict)
+
+
+# ------------------------------------------------------------------------------------------------------
+# distance transforms
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(8, 8), (9, 700), (40, 57), (97, 131), (360, 480), (1080, 1440)])
+def test_chamfer_bit_exact(shape):
+    H, W = shape
+    rng = np.random.default_rng(H * 7 + W)
+    masks = [_blobs(rng, H, W, k + 1) for k in range(3)]
+    masks.append(np.ones((H, W), np.uint8))                  # no source at all: OpenCV's saturation value
+    m1 = np.ones((H, W), np.uint8)
+    m1[H // 2, W // 3] = 0
+    masks.append(m1)                                         # single far source
+    m = np.stack(masks)
+    eng = _engine(len(masks), H, W, 2)
+    for invert in (False, True):
+        dist, q16, mx = eng.chamfer(torch.from_numpy(m), invert=invert)
+        dist, q16, mx = dist.cpu().numpy(), q16.cpu().numpy().view(np.uint32), mx.cpu().numpy().view(np.uint32)
+        for k in range(len(masks)):
+            src = (1 - m[k]) if invert else m[k]
+            ref = cv2.distanceTransform(np.ascontiguousarray(src), cv2.DIST_L2, 5)
+            np.testing.assert_array_equal(dist[k], ref, err_msg=f"mask {k} invert {invert}")
+            if H * W <= 200 * 300:
+                np.testing.assert_array_equal(q16[k], O.chamfer5_q16(src))
+            assert mx[k] == q16[k].max()
+    eng.close()
+
+
+@pytest.mark.parametrize("shape", [(17, 23), (64, 96), (360, 480), (1080, 1440)])
+def test_edt_squared_exact(shape):
+    H, W = shape
+    rng = np.random.default_rng(H + W)
+    masks = np.stack([1 - _blobs(rng, H, W, k + 1) for k in range(3)])   # zeros (sources) = blobs
+    eng = _engine(3, H, W, 2)
+    d2, am = eng.edt_squared(torch.from_numpy(masks))
+    d2, am = d2.cpu().numpy().view(np.uint32), am.cpu().numpy()
+    for k in range(3):
+        ref = O.edt_squared(masks[k])
+        if (masks[k] == 0).any():
+            np.testing.assert_array_equal(d2[k].astype(np.int64), ref)
+            assert am[k] == int(ref.argmax())
+        if H * W <= 64 * 96:
+            np.testing.assert_array_equal(ref, O.edt_squared_bruteforce(masks[k]))
+    eng.close()
+
+
+# ------------------------------------------------------------------------------------------------------
+# stage 1
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("spec_name,count", [("SMALL", 4), ("CFG1", 1), ("CFG2", 2)])
+def test_select_leaf_against_oracle(spec_name, count):
+    spec = getattr(synth, spec_name)
+    P = synth.projection_matrix(spec)
+    lab, dep = synth.make_batch(spec, SEED, 0, count)
+    eng = _engine(count, spec.height, spec.width, 128)
+    ids, rec = eng.select_leaf(torch.from_numpy(lab), torch.from_numpy(dep), _cam(spec))
+    for i in range(count):
+        o = O.select_optimal_leaf(lab[i], dep[i], P[0, 0], P[0, 2], P[1, 2])
+        assert ids[i] == (o["leaf_id"] if o["leaf_id"] is not None else -1)
+        present = rec[i][rec[i]["area"] > 0]
+        assert [int(r["leaf_id"]) for r in present if r["is_tall"]] == o["tall"]
+        for r in present:
+            assert np.float32(r["median_depth"]) == np.float32(o["medians"][int(r["leaf_id"])])   # bit-exact median
+        by_id = {c["leaf_id"]: c for c in o["candidates"]}
+        for r in present:
+            if not r["is_candidate"]:
+                assert int(r["leaf_id"]) not in by_id
+                continue
+            c = by_id[int(r["leaf_id"])]
+            assert r["area"] == c["area"]
+            assert r["centroid_x"] == c["centroid"][0] and r["centroid_y"] == c["centroid"][1]
+            np.testing.assert_allclose([r["clutter"], r["distance"], r["visibility"]], c["scores"], rtol=1e-6, atol=1e-12)
+            np.testing.assert_allclose(r["mean_depth"], c["mean_depth"], rtol=3e-7)
+    eng.close()
+
+
+def test_select_leaf_matches_reference_golden():
+    for f in META["frames"]:
+        spec = getattr(synth, f["spec"])
+        lab, dep = synth.make_frame(spec, SEED, f["index"])
+        g = np.load(os.path.join(GOLD, f["file"]))
+        eng = _engine(1, spec.height, spec.width, 128)
+        ids, rec = eng.select_leaf(torch.from_numpy(lab), torch.from_numpy(dep), _cam(spec))
+        assert ids[0] == int(g["leaf_id"])
+        tall = [int(r["leaf_id"]) for r in rec[0] if r["area"] > 0 and r["is_tall"]]
+        assert tall == g["tall"].tolist()
+        eng.close()
+
+
+# ------------------------------------------------------------------------------------------------------
+# stage 2
+# ------------------------------------------------------------------------------------------------------
+def _ulp_diff32(a, b):
+    ai = a.astype(np.float32).view(np.int32).astype(np.int64)
+    bi = b.astype(np.float32).view(np.int32).astype(np.int64)
+    return np.abs(ai - bi)
+
+
+@pytest.mark.parametrize("spec_name,idx", [("SMALL", 0), ("SMALL", 1), ("SMALL", 3), ("CFG2", 0)])
+def test_score_maps_against_strict_oracle(spec_name, idx):
+    spec = getattr(synth, spec_name)
+    P = synth.projection_matrix(spec)
+    lab, dep = synth.make_frame(spec, SEED, idx)
+    leaf = O.select_optimal_leaf(lab, dep, P[0, 0], P[0, 2], P[1, 2])["leaf_id"]
+    mask = (lab == leaf).astype(np.uint8)
+    eng = _engine(1, spec.height, spec.width, 2)
+    got = eng.score_maps(torch.from_numpy(mask), torch.from_numpy(dep), _cam(spec))
+    ref = O.score_maps(mask, dep, P[0, 0], P[0, 2], P[1, 2], "strict")
+    # integer / mask results: bit-exact
+    np.testing.assert_array_equal(got["distance_map"][0].cpu().numpy(), ref["distance_map"])
+    np.testing.assert_array_equal(got["stem_penalty"][0].cpu().numpy(), ref["stem_penalty"])
+    np.testing.assert_array_equal(got["valid"][0].cpu().numpy().astype(bool), O.valid_regions(mask, ref))
+    # the restated orientation: same float32 arithmetic on both sides
+    assert abs(float(got["angle"][0]) - ref["_parts"]["angle"]) <= 1e-15
+    # flatness: float32, every op correctly rounded except exp -> at most 1 ulp, and rarely
+    fl = got["flatness_map"][0].cpu().numpy()
+    ulp = _ulp_diff32(fl, ref["flatness_map"])
+    assert ulp.max() <= 1 and (ulp > 0).mean() < 1e-3
+    for k in F64_MAPS:
+        np.testing.assert_allclose(got[k][0].cpu().numpy(), ref[k], rtol=1e-9, atol=1e-12, err_msg=k)
+    # and within the north-star tolerance of the reference-arithmetic maps
+    rr = O.score_maps(mask, dep, P[0, 0], P[0, 2], P[1, 2], "reference")
+    for k in F64_MAPS + ("flatness_map",):
+        np.testing.assert_allclose(got[k][0].cpu().numpy(), rr[k], rtol=1e-5, atol=1e-6, err_msg=k)
+    eng.close()
+
+
+def test_candidate_points_exact():
+    rng = np.random.default_rng(3)
+    H, W = 240, 320
+    eng = _engine(3, H, W, 2)
+    score = rng.random((3, H, W))
+    valid = np.ones((3, H, W), np.uint8)
+    valid[1] = 0
+    valid[1, 100:140, 100:150] = 1          # few positives -> zero-key fill
+    valid[2, :, :] = 0                      # nothing valid at all
+    xy, cnt = eng.candidate_points(torch.from_numpy(score), torch.from_numpy(valid))
+    xy, cnt = xy.cpu().numpy(), cnt.cpu().numpy()
+    for k in range(3):
+        ref = O.candidate_points(score[k], valid[k].astype(bool))
+        assert cnt[k] == len(ref)
+        assert [tuple(p) for p in xy[k, :cnt[k]].tolist()] == ref
+    eng.close()
+
+
+def test_orientation_against_opencv():
+    rng = np.random.default_rng(0)
+    H, W = 300, 400
+    masks = []
+    for t in range(24):
+        m = np.zeros((H, W), np.uint8)
+        for _ in range(int(rng.integers(1, 4))):
+            cv2.ellipse(m, (int(rng.integers(60, 340)), int(rng.integers(50, 250))),
+                        (int(rng.integers(15, 90)), int(rng.integers(8, 60))), float(rng.uniform(0, 180)), 0, 360, 1, -1)
+        if t % 3 == 0:   # occluder splits the leaf into components
+            cv2.ellipse(m, (int(rng.integers(60, 340)), int(rng.integers(50, 250))), (120, 6), float(rng.uniform(0, 180)), 0, 360, 0, -1)
+        masks.append(m)
+    masks = np.stack(masks)
+    eng = _engine(len(masks), H, W, 2)
+    out = eng.leaf_orientation(torch.from_numpy(masks)).cpu().numpy()
+    for k, m in enumerate(masks):
+        ang_cv = O.leaf_orientation(m)
+        ang_re = O.leaf_orientation_restated(m)
+        assert out[k, 0] == ang_re[0], (k, out[k, 0], ang_re[0])                 # same restated arithmetic
+        assert abs(out[k, 0] - ang_cv[0]) < 1e-6                                 # OpenCV within float32 noise
+        np.testing.assert_allclose(out[k, 1:3], [ang_re[1], ang_re[2]], rtol=1e-6)
+    eng.close()
+
+
+# ------------------------------------------------------------------------------------------------------
+# CNN
+# ------------------------------------------------------------------------------------------------------
+def test_cnn_fp32_against_reference_logits(blob):
+    g = np.load(os.path.join(GOLD, "cnn_patches.npz"))
+    eng = _engine(1, 64, 64, 2)
+    eng.set_cnn_weights(blob)
+    y = eng.cnn_forward(torch.from_numpy(g["x"])).cpu().numpy()
+    np.testing.assert_allclose(y, g["logits"], atol=1e-4, rtol=1e-4)
+    eng.close()
+
+
+def test_cnn_dropin_module(state_dict):
+    from leafgrasp_b200 import GraspPointCNN
+    g = np.load(os.path.join(GOLD, "cnn_patches.npz"))
+    net = GraspPointCNN(in_channels=9)
+    net.load_state_dict(state_dict)
+    net.eval()
+    with torch.no_grad():
+        y = net(torch.from_numpy(g["x"]).cuda())
+    assert y.shape == (16, 1)
+    np.testing.assert_allclose(y.reshape(-1).cpu().numpy(), g["logits"], atol=1e-4, rtol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------------
+# whole path
+# ------------------------------------------------------------------------------------------------------
+def _check_frame(r, lab, dep, P, sd, patches=None):
+    o = O.process_frame(lab, dep, P, sd, arith="strict")
+    assert r["leaf_id"] == (o["leaf_id"] if o["leaf_id"] is not None else -1)
+    if o["leaf_id"] is None:
+        return o
+    d = o["debug"]
+    n = len(d["picks"])
+    assert r["n_candidates"] == n
+    got = list(zip(r["cand_x"][:n].tolist(), r["cand_y"][:n].tolist()))
+    assert got == d["picks"], "candidate pixels differ from the strict oracle"
+    np.testing.assert_allclose(r["trad"][:n], d["trad_at"], rtol=1e-9)
+    for k in range(n):
+        has = d["logits"][k] is not None
+        assert bool(r["ml_valid"][k]) == has
+        if has:
+            assert abs(r["logit"][k] - d["logits"][k]) < 2e-4
+            assert abs(r["ml"][k] - d["ml"][k]) < 1e-4
+            if patches is not None:
+                ref_patch = O.patch_tensor((lab == o["leaf_id"]).astype(np.uint8), dep, d["scores"], *d["picks"][k])
+                np.testing.assert_allclose(patches[k], ref_patch, rtol=1e-5, atol=2e-6)
+    best, p3, pre = o["grasp"]
+    assert (int(r["grasp_x"]), int(r["grasp_y"])) == tuple(best)
+    np.testing.assert_allclose(r["grasp_3d"], np.array(p3, dtype=np.float64), rtol=1e-12)
+    np.testing.assert_allclose(r["pre_grasp"], np.array(pre, dtype=np.float64), rtol=1e-9)
+    return o
+
+
+@pytest.mark.parametrize("spec_name,count", [("SMALL", 4), ("CFG1", 1), ("CFG2", 3)])
+def test_process_batch_against_strict_oracle(spec_name, count, state_dict, blob):
+    spec = getattr(synth, spec_name)
+    P = synth.projection_matrix(spec)
+    lab, dep = synth.make_batch(spec, SEED, 0, count)
+    eng = _engine(count, spec.height, spec.width, 128)
+    eng.set_cnn_weights(blob)
+    res = eng.process_batch(torch.from_numpy(lab).cuda(), torch.from_numpy(dep).cuda(), _cam(spec))
+    patches = eng.last_patches(count).cpu().numpy()
+    for i in range(count):
+        _check_frame(res[i], lab[i], dep[i], P, state_dict, patches[i])
+    # host-buffer entry point gives the same records
+    res_h = eng.process_batch_host(torch.from_numpy(lab).pin_memory(), torch.from_numpy(dep).pin_memory(), _cam(spec))
+    for name in ("leaf_id", "n_candidates", "cand_x", "cand_y", "grasp_x", "grasp_y"):
+        np.testing.assert_array_equal(res[name], res_h[name])
+    eng.close()
+
+
+def test_process_batch_against_reference_golden(blob):
+    """The reference's own outputs: every candidate whose key is positive, the fused pick and the 3-D points."""
+    for f in META["frames"]:
+        spec = getattr(synth, f["spec"])
+        lab, dep = synth.make_frame(spec, SEED, f["index"])
+        g = np.load(os.path.join(GOLD, f["file"]))
+        eng = _engine(1, spec.height, spec.width, 128)
+        eng.set_cnn_weights(blob)
+        r = eng.process_batch(torch.from_numpy(lab)[None].cuda(), torch.from_numpy(dep)[None].cuda(), _cam(spec))[0]
+        assert r["leaf_id"] == int(g["leaf_id"])
+        n_pos = int(g["n_positive"])
+        assert r["n_positive"] == n_pos
+        got = np.stack([r["cand_x"][:n_pos], r["cand_y"][:n_pos]], axis=1)
+        np.testing.assert_array_equal(got, g["candidates"][:n_pos])
+        np.testing.assert_allclose(r["trad"][:n_pos], g["trad_at"][:n_pos], rtol=1e-5)
+        assert abs(r["angle"] - float(g["angle"])) < 1e-6
+        assert (int(r["grasp_x"]), int(r["grasp_y"])) == tuple(g["grasp_2d"].tolist())
+        np.testing.assert_allclose(r["grasp_3d"], g["grasp_3d"], rtol=1e-12)
+        np.testing.assert_allclose(r["pre_grasp"], g["pre_grasp"], rtol=1e-9)
+        eng.close()
+
+
+def test_empty_and_degenerate_frames(blob):
+    spec = synth.SMALL
+    H, W = spec.height, spec.width
+    lab = np.zeros((3, H, W), np.int16)
+    dep = np.full((3, H, W), 0.5, np.float32)
+    lab[1, 10:60, 10:60] = 3          # one leaf, too small (2500 px < 10000)
+    lab[2, :, :] = 5                  # a single id everywhere: it is the "background" (smallest id dropped)
+    eng = _engine(3, H, W, 16)
+    eng.set_cnn_weights(blob)
+    res = eng.process_batch(torch.from_numpy(lab).cuda(), torch.from_numpy(dep).cuda(), _cam(spec))
+    P = synth.projection_matrix(spec)
+    for i in range(3):
+        o = O.select_optimal_leaf(lab[i], dep[i], P[0, 0], P[0, 2], P[1, 2])
+        assert o["leaf_id"] is None
+        assert res[i]["leaf_id"] == -1 and res[i]["n_candidates"] == 0
+        assert res[i]["status"] & 1
+    eng.close()
+
+
+def test_dropin_classes_match_reference_golden(state_dict):
+    """The call sequence of leaf_grasp_node_v3.py:110-119 through the drop-in classes."""
+    from leafgrasp_b200 import GraspPointCNN, GraspPointSelector, ImageProcessor, OptimalLeafSelector
+    spec = synth.SMALL
+    P = synth.projection_matrix(spec)
+    g = np.load(os.path.join(GOLD, "frame_small_2.npz"))
+    lab, dep = synth.make_frame(spec, SEED, 2)
+    dev = torch.device("cuda")
+    scorer = OptimalLeafSelector(dev)
+    scorer.set_camera_params(P)
+    sel = GraspPointSelector(dev)
+    sel.set_camera_params(P)
+    net = GraspPointCNN(in_channels=9)
+    net.load_state_dict(state_dict)
+    net.eval()
+    sel.ml_predictor = net
+    ip = ImageProcessor(spec.height, spec.width, 21, 5)
+    mask_t, depth_t = torch.from_numpy(lab).to(dev), torch.from_numpy(dep).to(dev)
+    leaf = scorer.select_optimal_leaf(mask_t, depth_t)
+    assert leaf == int(g["leaf_id"])
+    assert scorer.get_tall_leaves() == g["tall"].tolist()
+    g2, g3, pre = sel.select_grasp_point(mask_t == leaf, depth_t, ip)
+    assert tuple(g2) == tuple(g["grasp_2d"].tolist())
+    np.testing.assert_allclose(g3, g["grasp_3d"], rtol=1e-12)
+    np.testing.assert_allclose(pre, g["pre_grasp"], rtol=1e-9)
+    mask_np = (lab == leaf).astype(np.uint8)
+    scores = sel._calculate_all_scores(mask_np, depth_t, ip)
+    yx = g["sample_yx"]
+    for k in ("sdf_score", "approach_score", "flatness_map", "isolation_map", "distance_map", "accessibility_map",
+              "stem_penalty", "traditional_score"):
+        np.testing.assert_allclose(scores[k][yx[:, 0], yx[:, 1]].astype(np.float64), g["sample_" + k], rtol=1e-5, atol=1e-6)
+    valid = sel._get_valid_regions(mask_np, scores)
+    assert int(valid.sum()) == int(g["valid_count"])
+    cands = sel._get_candidate_points(scores["traditional_score"], valid, top_k=20, min_distance=10)
+    n_pos = int(g["n_positive"])
+    assert cands[:n_pos] == [tuple(p) for p in g["candidates"][:n_pos].tolist()]
+    ang = sel.estimate_leaf_orientation(mask_np)
+    assert abs(ang[0] - float(g["angle"])) < 1e-6
+    ml = sel.get_ml_score(mask_t == leaf, depth_t, scores, cands[0])
+    assert ml is not None and 0.5 <= ml <= 1.0
+    # error convention: no camera -> (None, None, None), no exception
+    bare = GraspPointSelector(dev)
+    assert bare.select_grasp_point(mask_t == leaf, depth_t, ip) == (None, None, None)

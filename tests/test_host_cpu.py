@@ -1,0 +1,135 @@
+"""CPU tests of the host side: the C-ABI library loads and exports everything the header declares, struct
+layouts agree, BatchNorm folding / weight packing is right, the drop-in module keeps the reference's
+state_dict keys, and frame sharding + record gathering work across 2 gloo ranks."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import leafgrasp_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from leafgrasp_b200 import _native as N
+    h = N.lib()
+    header = open(os.path.join(ROOT, "include", "leafgrasp.h")).read()
+    declared = set(re.findall(r"\b(lg_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(N.SYMBOLS), declared ^ set(N.SYMBOLS)
+    for name in declared:
+        assert hasattr(h, name)
+    assert h.lg_sizeof_frame_result() == N.FRAME_RESULT.itemsize
+    assert h.lg_sizeof_leaf_record() == N.LEAF_RECORD.itemsize
+
+
+def test_no_cpu_fallback():
+    """Without a GPU every compute entry point must refuse, not fall back."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from leafgrasp_b200 import GraspEngine, GraspPointCNN, _native as N
+    with pytest.raises(N.NativeError):
+        GraspEngine(1, 64, 64, 2)
+    net = GraspPointCNN().eval()
+    with pytest.raises(N.NativeError):
+        net(torch.zeros(1, 9, 32, 32))
+
+
+def test_product_package_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "leaf-grasping-vision-ml_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert "leafgrasp_oracle" not in src and "import oracle" not in src, fn
+
+
+def test_state_dict_keys_match_reference_layout():
+    from leafgrasp_b200 import GraspPointCNN, pack_weights, _native as N
+    sd = O.seeded_state_dict(1)
+    net = GraspPointCNN(in_channels=9)
+    assert set(net.state_dict().keys()) == set(sd.keys())
+    net.load_state_dict(sd)
+    assert pack_weights(net.state_dict()).size == N.lib().lg_cnn_weight_floats()
+    with pytest.raises(NotImplementedError):
+        GraspPointCNN(attention_type="channel")
+
+
+def test_batchnorm_folding_is_exact_enough():
+    """Run the folded weights through plain torch ops and compare with the unfolded oracle forward."""
+    from leafgrasp_b200 import fold_batchnorm
+    sd = O.seeded_state_dict(5)
+    folded = fold_batchnorm(sd)
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(4, 9, 32, 32, generator=g)
+    y = x.double()
+    for l in range(6):
+        w, b = folded[l]
+        y = F.relu(F.conv2d(y, torch.from_numpy(w), torch.from_numpy(b), padding=1))
+        if l % 2 == 1:
+            y = F.max_pool2d(y, 2)
+    aw, ab = folded[6]
+    att = torch.sigmoid(F.conv2d(y, torch.from_numpy(aw), torch.from_numpy(ab)))
+    y = (y * att).mean(dim=(2, 3))
+    for k in range(7, 11):
+        w, b = folded[k]
+        y = F.linear(y, torch.from_numpy(w), torch.from_numpy(b))
+        if k != 10:
+            y = F.relu(y)
+    ref = O.cnn_forward(sd, x)
+    np.testing.assert_allclose(y.float().numpy(), ref.numpy(), atol=2e-5, rtol=1e-5)
+
+
+def test_ellipse_rows_restated_equals_opencv():
+    """csrc/lg_api.cu:ellipse_rows restates cv2.getStructuringElement(MORPH_ELLIPSE); same formula here."""
+    import cv2
+    for n in (30, 31):
+        se = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (n, n))
+        r = c = n // 2
+        for i in range(n):
+            dy = i - r
+            dx = int(np.rint(c * np.sqrt((r * r - dy * dy) / (r * r))))
+            a, b = max(c - dx, 0), min(c + dx + 1, n)
+            row = np.zeros(n, np.uint8)
+            row[a:b] = 1
+            np.testing.assert_array_equal(row, se[i])
+
+
+def _dist_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from leafgrasp_b200 import dist as lgd
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = lgd.shard_range(10, rank, world)
+    rec = torch.zeros(hi - lo, 20, 4)
+    rec[:, :, 0] = torch.arange(lo, hi).float()[:, None]
+    allrec = lgd.gather_candidate_records(rec, 10)
+    if rank == 0:
+        out.put(allrec[:, 0, 0].tolist())
+    dist.destroy_process_group()
+
+
+def test_frame_sharding_and_gather_two_ranks():
+    import torch.multiprocessing as mp
+    from leafgrasp_b200 import dist as lgd
+    assert lgd.shard_range(10, 0, 2) == (0, 5) and lgd.shard_range(10, 1, 2) == (5, 10)
+    assert lgd.shard_range(7, 0, 3) == (0, 3) and lgd.shard_range(7, 2, 3) == (5, 7)
+    covered = []
+    for r in range(8):
+        lo, hi = lgd.shard_range(8192, r, 8)
+        covered += list(range(lo, hi))
+    assert covered == list(range(8192))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_dist_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got == [float(i) for i in range(10)]
