@@ -181,6 +181,17 @@ int lg_patches(lg_context* ctx, float* patches_out, int frames, void* stream);
  * patches float32 [n][9][32][32] (channel 1, the mask, is passed through). */
 int lg_normalize_patches(lg_context* ctx, const float* raw, int n, float* out, void* stream);
 
+/* ---- measurement hooks (bench.py) ------------------------------------------------------------------ */
+
+/* Record a CUDA event on the launch stream after every stage of lg_process_batch. */
+int lg_set_profiling(lg_context* ctx, int on);
+/* ms[14]: device milliseconds of each stage of the last lg_process_batch call, in the order
+ * [unused, leaf_stats, scatter, median, edt_columns, edt_rows, select, chamfer, orientation, score_maps,
+ *  candidates, patches, cnn, fuse].  Synchronises on the last recorded event. */
+int lg_stage_times(lg_context* ctx, float* ms, int n);
+/* Number of kernels this library has launched in this process so far. */
+uint64_t lg_launch_count(void);
+
 /* ---- ABI self-description (the Python binding checks its struct layouts against these) ---------- */
 uint64_t lg_sizeof_frame_result(void);
 uint64_t lg_sizeof_leaf_record(void);

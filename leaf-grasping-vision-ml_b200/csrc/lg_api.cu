@@ -18,6 +18,7 @@ int lg_run_export_orient(lg_context* c, int n, double* out5, cudaStream_t st);
 int lg_run_normalize_patches(const float* raw, int n, float* out, cudaStream_t st);
 
 static thread_local char g_err[512] = "";
+unsigned long long g_lg_launches = 0;
 
 void lg_set_error(const char* fmt, ...) {
     va_list ap;
@@ -167,8 +168,11 @@ static int run_stage2(lg_context* c, LgMaskSrc src, const float* depth, int n, l
                       cudaStream_t st) {
     // inside transform on the leaf rectangle (+ its distance map), outside transform on the whole frame (max only)
     TRY(lg_run_chamfer(c, src, n, full ? 0 : 1, 0, 2, c->di, nullptr, c->dt_max, st));
+    lg_mark(c, LG_M_CHAMFER, st);
     TRY(lg_run_orientation(c, src, n, st));
+    lg_mark(c, LG_M_ORIENT, st);
     TRY(lg_run_scores(c, src, depth, n, cam, full, iso_out, st));
+    lg_mark(c, LG_M_SCORE, st);
     return LG_OK;
 }
 
@@ -177,17 +181,23 @@ extern "C" int lg_process_batch(lg_context* c, const int16_t* labels, const floa
     TRY(check_batch(c, labels, depth, frames));
     if (!cam) return LG_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
+    if (c->prof_on) memset(c->prof_seen, 0, sizeof(c->prof_seen));
+    lg_mark(c, LG_M_START, st);
     TRY(lg_run_stage1(c, labels, depth, frames, *cam, st));
     TRY(lg_run_select(c, frames, *cam, nullptr, c->records, st));
     LgMaskSrc src{labels, nullptr, c->leaf_id};
     TRY(run_stage2(c, src, depth, frames, *cam, 0, nullptr, st));
     TRY(lg_run_nms(c, frames, st));
+    lg_mark(c, LG_M_NMS, st);
     const int have_ml = c->cnn.loaded;
     if (have_ml) {
         TRY(lg_run_gather(c, src, depth, frames, *cam, st));
+        lg_mark(c, LG_M_GATHER, st);
         TRY(lg_run_cnn(c, c->patches, frames * LG_TOP_K, c->logits, use_bf16_cnn, st));
+        lg_mark(c, LG_M_CNN, st);
     }
     TRY(lg_run_fuse(c, src, depth, frames, *cam, have_ml, results, st));
+    lg_mark(c, LG_M_FUSE, st);
     return LG_OK;
 }
 
@@ -275,3 +285,32 @@ extern "C" int lg_normalize_patches(lg_context* c, const float* raw, int n, floa
 extern "C" uint64_t lg_sizeof_frame_result(void) { return sizeof(lg_frame_result); }
 extern "C" uint64_t lg_sizeof_leaf_record(void) { return sizeof(lg_leaf_record); }
 extern "C" uint64_t lg_cnn_weight_floats(void) { return lg_cnn_blob_floats(); }
+
+extern "C" int lg_set_profiling(lg_context* c, int on) {
+    if (!c) return LG_E_ARG;
+    if (on && !c->prof_ev[0]) {
+        for (int i = 0; i < LG_PROF_MARKS; ++i) LG_CUDA(cudaEventCreate(&c->prof_ev[i]));
+    }
+    c->prof_on = on ? 1 : 0;
+    memset(c->prof_seen, 0, sizeof(c->prof_seen));
+    return LG_OK;
+}
+
+/* ms[i] = device time between mark i and the previous recorded mark of the last lg_process_batch call
+ * (LG_M_* order: stats, scatter, median, edt_col, edt_row, select, chamfer, orient, score, nms, gather,
+ * cnn, fuse); 0 for stages that did not run.  Synchronises on the last event. */
+extern "C" int lg_stage_times(lg_context* c, float* ms, int n) {
+    if (!c || !ms || n < LG_M_COUNT) return LG_E_ARG;
+    for (int i = 0; i < n; ++i) ms[i] = 0.f;
+    if (!c->prof_on || !c->prof_seen[LG_M_START]) return LG_OK;
+    int prev = LG_M_START;
+    for (int i = 1; i < LG_M_COUNT; ++i) {
+        if (!c->prof_seen[i]) continue;
+        LG_CUDA(cudaEventSynchronize(c->prof_ev[i]));
+        LG_CUDA(cudaEventElapsedTime(&ms[i], c->prof_ev[prev], c->prof_ev[i]));
+        prev = i;
+    }
+    return LG_OK;
+}
+
+extern "C" uint64_t lg_launch_count(void) { return g_lg_launches; }

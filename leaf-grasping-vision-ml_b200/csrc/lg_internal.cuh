@@ -20,6 +20,9 @@
 #define LG_REGION_PAD 16 // score maps are produced on the leaf bbox grown by half a patch
 #define LG_SE_STEM 30
 #define LG_SE_PRE 31
+#define LG_PROF_MARKS 16
+enum LgMark { LG_M_START = 0, LG_M_STATS, LG_M_SCATTER, LG_M_MEDIAN, LG_M_EDT_COL, LG_M_EDT_ROW, LG_M_SELECT, LG_M_CHAMFER,
+              LG_M_ORIENT, LG_M_SCORE, LG_M_NMS, LG_M_GATHER, LG_M_CNN, LG_M_FUSE, LG_M_COUNT };
 
 struct LgRegion {
     int x0, y0, x1, y1;  // bounding box of the chosen leaf, exclusive upper bounds
@@ -105,6 +108,10 @@ struct lg_context {
     // staging for the *_host entry point
     int16_t* in_labels;
     float* in_depth;
+    // optional per-stage timing (lg_set_profiling): events recorded on the launch stream
+    int prof_on;
+    cudaEvent_t prof_ev[LG_PROF_MARKS];
+    int prof_seen[LG_PROF_MARKS];
     // constants
     float gauss[25];
     int se30_a[LG_SE_STEM], se30_b[LG_SE_STEM];   // per structuring-element row: first / last+1 column
@@ -120,7 +127,15 @@ void lg_set_error(const char* fmt, ...);
             return LG_E_CUDA;                                                               \
         }                                                                                   \
     } while (0)
-#define LG_LAUNCH_CHECK() LG_CUDA(cudaGetLastError())
+extern unsigned long long g_lg_launches;
+#define LG_LAUNCH_CHECK()            \
+    do {                             \
+        ++g_lg_launches;             \
+        LG_CUDA(cudaGetLastError()); \
+    } while (0)
+static inline void lg_mark(lg_context* c, int id, cudaStream_t st) {
+    if (c->prof_on) { cudaEventRecord(c->prof_ev[id], st); c->prof_seen[id] = 1; }
+}
 
 // stage launchers (defined across the .cu files); all asynchronous on `st`
 int lg_run_stage1(lg_context* c, const int16_t* labels, const float* depth, int n, lg_camera cam, cudaStream_t st);

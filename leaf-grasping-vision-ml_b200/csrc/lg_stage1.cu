@@ -498,8 +498,10 @@ int lg_run_edt_union(lg_context* c, const int16_t* labels, int n, cudaStream_t s
     EdtSrc src{labels, nullptr};
     edt_col_kernel<<<dim3((c->W + 127) / 128, n), 128, 0, st>>>(src, c->edt_g, c->H, c->W, c->P);
     LG_LAUNCH_CHECK();
+    lg_mark(c, LG_M_EDT_COL, st);
     edt_row_kernel<<<dim3(c->H, n), EDT_NT, c->W * sizeof(unsigned), st>>>(c->edt_g, nullptr, c->edt_best, c->H, c->W, c->P);
     LG_LAUNCH_CHECK();
+    lg_mark(c, LG_M_EDT_ROW, st);
     return LG_OK;
 }
 
@@ -509,12 +511,15 @@ int lg_run_stage1(lg_context* c, const int16_t* labels, const float* depth, int 
     const int tiles = (int)((c->P + ST_NT * ST_PX - 1) / (ST_NT * ST_PX));
     leaf_stats_kernel<<<dim3(tiles, n), ST_NT, c->L * sizeof(SmemLeaf), st>>>(*c, labels, depth, cam);
     LG_LAUNCH_CHECK();
+    lg_mark(c, LG_M_STATS, st);
     leaf_offsets_kernel<<<(n + 63) / 64, 64, 0, st>>>(*c, n);
     LG_LAUNCH_CHECK();
     leaf_scatter_kernel<<<dim3(tiles, n), ST_NT, 0, st>>>(*c, labels, depth);
     LG_LAUNCH_CHECK();
+    lg_mark(c, LG_M_SCATTER, st);
     leaf_median_kernel<<<dim3(c->L, n), MED_NT, 0, st>>>(*c);
     LG_LAUNCH_CHECK();
+    lg_mark(c, LG_M_MEDIAN, st);
     int rc = lg_run_edt_union(c, labels, n, st);
     if (rc) return rc;
     return LG_OK;
@@ -524,6 +529,7 @@ int lg_run_select(lg_context* c, int n, lg_camera cam, int32_t* leaf_out, lg_lea
     size_t sm = (sizeof(SelScratch) + sizeof(float)) * c->L;
     select_leaf_kernel<<<n, 32, sm, st>>>(*c, cam, leaf_out, rec_out);
     LG_LAUNCH_CHECK();
+    lg_mark(c, LG_M_SELECT, st);
     return LG_OK;
 }
 

@@ -81,8 +81,8 @@ def make_frame(spec: FrameSpec, config_seed: int, frame_index: int):
     rng = np.random.default_rng(frame_seed(config_seed, frame_index))
     labels = np.zeros((H, W), dtype=np.int16)
     depth = np.full((H, W), 0.8, dtype=np.float64)
-    yy, xx = np.mgrid[0:H, 0:W]
     slope = 2e-4 / spec.scale
+    stamp = np.zeros((H, W), dtype=np.uint8)
     for leaf in range(1, N + 1):
         cx = rng.uniform(margin, W - margin)
         cy = rng.uniform(margin, H - margin)
@@ -92,13 +92,18 @@ def make_frame(spec: FrameSpec, config_seed: int, frame_index: int):
         z0 = rng.uniform(0.3, 0.6)
         sx = rng.uniform(-slope, slope)
         sy = rng.uniform(-slope, slope)
-        stamp = np.zeros((H, W), dtype=np.uint8)
+        # paint into a window that certainly contains the ellipse (same pixels as a full-frame stamp)
+        reach = int(round(a)) + 2
+        x0, x1 = max(0, int(round(cx)) - reach), min(W, int(round(cx)) + reach + 1)
+        y0, y1 = max(0, int(round(cy)) - reach), min(H, int(round(cy)) + reach + 1)
+        stamp[y0:y1, x0:x1] = 0
         cv2.ellipse(stamp, (int(round(cx)), int(round(cy))), (int(round(a)), int(round(b))),
                     float(ang), 0.0, 360.0, 1, -1)
-        sel = stamp.astype(bool)
-        labels[sel] = leaf
+        sel = stamp[y0:y1, x0:x1].astype(bool)
+        yy, xx = np.mgrid[y0:y1, x0:x1]
+        labels[y0:y1, x0:x1][sel] = leaf
         plane = z0 + sx * (xx - cx) + sy * (yy - cy)
-        depth[sel] = plane[sel]
+        depth[y0:y1, x0:x1][sel] = plane[sel]
     depth += rng.normal(0.0, 1e-3, size=(H, W))
     return labels, depth.astype(np.float32)
 
