@@ -161,6 +161,12 @@ int lg_candidate_points(lg_context* ctx, const double* score, const uint8_t* val
 /* patches float32 [n][9][32][32] -> logits float32 [n].  Needs lg_set_cnn_weights first. */
 int lg_cnn_forward(lg_context* ctx, const float* patches, int n, float* logits, int use_bf16, void* stream);
 
+/* The bf16 tensor-core path stopped after conv layer `layer` (0..5; the 2x2 max-pool of model.py:25-28 applied
+ * after layers 1, 3 and 5): features float32 [n][C][S][S] with (C, S) = (64,32) (64,16) (128,16) (128,8) (256,8)
+ * for layers 0..4 and float32 [n][4][4][256] (channels last) for layer 5.  n must fit one activation chunk
+ * (>= 2048 patches).  Used by the per-layer parity tests. */
+int lg_cnn_bf16_features(lg_context* ctx, const float* patches, int n, int layer, float* features, void* stream);
+
 /* ---- stage 2 on a caller-supplied leaf mask --------------------------------------------------- */
 
 /* GraspPointSelector.select_grasp_point (grasp_point_selector.py:184-253) for one binary leaf mask per

@@ -52,6 +52,7 @@ SYMBOLS = {
     "lg_score_maps": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(Camera)] + [_P] * 10 + [_P]),
     "lg_candidate_points": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P]),
     "lg_cnn_forward": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P]),
+    "lg_cnn_bf16_features": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
     "lg_select_grasp_point": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(Camera), _P, C.c_int, _P]),
     "lg_leaf_orientation": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "lg_patches": (C.c_int, [_P, _P, C.c_int, _P]),

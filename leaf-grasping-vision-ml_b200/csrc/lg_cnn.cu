@@ -182,6 +182,13 @@ uint64_t lg_cnn_blob_floats() {
 
 int lg_run_cnn_bf16(lg_context* c, const float* patches, int n, float* logits, cudaStream_t st);
 
+// attention + average + MLP on fp32 NHWC [n][4][4][256] features (shared by the fp32 and the bf16 conv paths)
+int lg_launch_cnn_tail(const float* feat, const float* blob_tail, float* logits, int n, cudaStream_t st) {
+    cnn_tail_kernel<<<n, TL_NT, 0, st>>>(feat, blob_tail, logits);
+    LG_LAUNCH_CHECK();
+    return LG_OK;
+}
+
 int lg_run_cnn(lg_context* c, const float* patches, int n, float* logits, int use_bf16, cudaStream_t st) {
     if (!c->cnn.loaded) {
         lg_set_error("lg_cnn_forward: no weights loaded (lg_set_cnn_weights)");

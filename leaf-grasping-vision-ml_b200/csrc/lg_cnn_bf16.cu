@@ -1,10 +1,555 @@
-// bf16 tensor-core GraspPointCNN path (placeholder until the implicit-GEMM kernels land).
+// GraspPointCNN forward on the 5th-generation tensor cores (reference scripts/utils/ml_grasp_optimizer/model.py:102-128).
+//
+// The six 3x3 convolutions run as bf16 implicit GEMMs: tcgen05.mma (cta_group::1, kind::f16, M=128) issued by
+// one thread, fp32 accumulators in TMEM, operands brought to shared memory by cp.async.bulk + mbarrier, epilogue
+// (bias + ReLU + bf16 pack) from TMEM with tcgen05.ld.  Attention / average / MLP tail: cnn_tail_kernel (fp32).
+//
+// Activation layout ("plane-major, shared-halo flat"): a feature map of C channels on S x S pixels for n patches is
+// C/8 planes; plane p holds, for every flat position, the 8 channels 8p..8p+7 as one 16-byte unit.  Positions are
+//     q = patch * PP + r * pitch + c,     pitch = S + 1,  PP = (S + 1)^2,  pixel (y, x) sits at (r, c) = (y + 1, x + 1)
+// Row 0 and column 0 of every patch are zero; they are the left/top halo of that patch and, because the layout is
+// flat, also the right halo of the previous row and the bottom halo of the previous patch.  A 3x3 convolution is
+// then out[q] = sum_taps W[tap] . in[q + (ky-1)*pitch + (kx-1)] for EVERY q - a 1-D stencil over the flat array -
+// so an output tile of 128 consecutive positions needs, for tap (ky, kx), the 128 consecutive input rows starting
+// ky*pitch + kx further on.  With the unswizzled K-major UMMA layout (8 rows x 16 B core matrices, rows 16 B
+// apart, SBO = 128 B, LBO = plane stride) that is the same shared-memory tile with the descriptor start address
+// moved by 16 B per position: the input tile is loaded ONCE per 64 channels and reused by all nine taps.
+// Outputs at halo positions are computed and discarded (6 % / 11 % / 21 % of the rows at 32 / 16 / 8 px) and
+// written as zeros, which makes the output directly the next layer's input.  LEAD zero rows precede position 0.
+//
+// Weights: bf16, BatchNorm folded, packed [n_split][Cin/64][tap][8 planes][NC][8] so that the B operand of one
+// (channel chunk, tap) stage is one contiguous bulk copy, again unswizzled K-major (LBO = NC * 16 B).
+#include <cuda_bf16.h>
+
+#include <vector>
+
 #include "lg_internal.cuh"
 
-int lg_cnn_prepare_bf16(lg_context* c) { (void)c; return LG_OK; }
+namespace {
+
+constexpr int LEAD = 64;        // zero rows in front of every plane (>= pitch + 1)
+constexpr int TILE_M = 512;     // positions per work item: 4 UMMA tiles of 128 rows
+constexpr int UMMA_T = 4;
+constexpr int NB_STAGES = 4;    // weight stages in flight
+constexpr int CONV_THREADS = 192;   // warp 0 producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue
+
+struct UmmaConvArgs {
+    const uint4* in;      // [Cin/8 planes][R]
+    uint4* out;           // [Cout/8 planes][R]
+    const uint4* wt;      // packed weights
+    const float* bias;    // [Cout]
+    long long R;          // rows per plane
+    int pitch, PP;
+    long long Q;          // n_patches * PP
+    int n_tiles;          // ceil((Q + pitch + 1) / TILE_M)
+    int KC;               // input channel chunks (of KP planes)
+    int n_split;          // Cout / NC
+    int rows;             // shared-memory rows per plane of the A stage: TILE_M + 2 * pitch + 2, rounded up to 8
+    int cout;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// unswizzled K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// One work item = TILE_M consecutive output positions x NC output channels.  KP = planes (8 channels each) per
+// input-channel chunk: 8 for the 64-channel chunks of layers 1-5, 2 for the 9 (padded to 16) channels of layer 0.
+template <int KP, int NC>
+__global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvArgs A) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int ACC_STAGES = 512 / (UMMA_T * NC);          // 2 (NC = 64) or 1 (NC = 128) accumulator sets in TMEM
+    constexpr uint32_t B_STAGE = KP * NC * 16;
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NC >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t a_stage_bytes = (uint32_t)KP * A.rows * 16;
+    unsigned char* sA = smem;
+    unsigned char* sB = smem + 2 * a_stage_bytes;
+    float* s_bias = reinterpret_cast<float*>(sB + NB_STAGES * B_STAGE);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 256);
+    // barrier indices
+    uint64_t* a_full = bars;            // [2]
+    uint64_t* a_empty = bars + 2;       // [2]
+    uint64_t* b_full = bars + 4;        // [NB]
+    uint64_t* b_empty = bars + 4 + NB_STAGES;
+    uint64_t* acc_full = bars + 4 + 2 * NB_STAGES;   // [2]
+    uint64_t* acc_empty = acc_full + 2;              // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_items = A.n_tiles * A.n_split;
+
+    for (int i = threadIdx.x; i < A.cout; i += CONV_THREADS) s_bias[i] = A.bias[i];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&a_full[i]), 1); mbar_init(smem_u32(&a_empty[i]), 1); }
+        for (int i = 0; i < NB_STAGES; ++i) { mbar_init(smem_u32(&b_full[i]), 1); mbar_init(smem_u32(&b_empty[i]), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== producer: bulk copies of the input tile (once per channel chunk) and of the per-tap weights =====
+        if (lane == 0) {
+            int a_st = 0, a_ph = 0, b_st = 0, b_ph = 0;
+            auto issue_a = [&](int item, int kc) {
+                const int tile = item / A.n_split;
+                mbar_wait(smem_u32(&a_empty[a_st]), a_ph ^ 1);
+                const uint32_t bar = smem_u32(&a_full[a_st]);
+                mbar_expect_tx(bar, a_stage_bytes);
+                const long long rho0 = LEAD + (long long)tile * TILE_M - A.pitch - 1;
+                const uint32_t dst = smem_u32(sA + (size_t)a_st * a_stage_bytes);
+#pragma unroll 1
+                for (int p = 0; p < KP; ++p)
+                    bulk_g2s(dst + p * A.rows * 16, A.in + ((long long)(kc * KP + p) * A.R + rho0), A.rows * 16, bar);
+                a_st ^= 1;
+                if (a_st == 0) a_ph ^= 1;
+            };
+            const int first = blockIdx.x;
+            if (first < n_items) issue_a(first, 0);
+            for (int item = first; item < n_items; item += gridDim.x) {
+                const int half = item % A.n_split;
+                for (int kc = 0; kc < A.KC; ++kc) {
+#pragma unroll 1
+                    for (int tap = 0; tap < 9; ++tap) {
+                        if (tap == 1) {   // prefetch the next input stage behind the first weight stage
+                            if (kc + 1 < A.KC) issue_a(item, kc + 1);
+                            else if (item + (int)gridDim.x < n_items) issue_a(item + gridDim.x, 0);
+                        }
+                        mbar_wait(smem_u32(&b_empty[b_st]), b_ph ^ 1);
+                        const uint32_t bar = smem_u32(&b_full[b_st]);
+                        mbar_expect_tx(bar, B_STAGE);
+                        const uint4* src = A.wt + ((size_t)(half * A.KC + kc) * 9 + tap) * (KP * NC);
+                        bulk_g2s(smem_u32(sB + (size_t)b_st * B_STAGE), src, B_STAGE, bar);
+                        if (++b_st == NB_STAGES) { b_st = 0; b_ph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        int a_st = 0, a_ph = 0, b_st = 0, b_ph = 0, acc_st = 0, acc_ph = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            mbar_wait(smem_u32(&acc_empty[acc_st]), acc_ph ^ 1);
+            tc_fence_after();
+            for (int kc = 0; kc < A.KC; ++kc) {
+                mbar_wait(smem_u32(&a_full[a_st]), a_ph);
+                const uint32_t a_base = smem_u32(sA + (size_t)a_st * a_stage_bytes);
+#pragma unroll 1
+                for (int tap = 0; tap < 9; ++tap) {
+                    mbar_wait(smem_u32(&b_full[b_st]), b_ph);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const int ky = tap / 3, kx = tap - ky * 3;
+                        const uint32_t b_base = smem_u32(sB + (size_t)b_st * B_STAGE);
+                        const uint32_t a_tap = a_base + (uint32_t)(ky * A.pitch + kx) * 16;
+#pragma unroll
+                        for (int t = 0; t < UMMA_T; ++t) {
+#pragma unroll
+                            for (int j = 0; j < KP / 2; ++j) {
+                                const uint64_t ad = umma_desc(a_tap + (uint32_t)(2 * j * A.rows + t * 128) * 16, A.rows * 16, 128);
+                                const uint64_t bd = umma_desc(b_base + (uint32_t)(2 * j * NC) * 16, NC * 16, 128);
+                                umma_bf16(tmem_base + (uint32_t)((acc_st * UMMA_T + t) * NC), ad, bd, IDESC,
+                                          (uint32_t)((kc | tap | j) != 0));
+                            }
+                        }
+                        tc_commit(smem_u32(&b_empty[b_st]));
+                    }
+                    __syncwarp();
+                    if (++b_st == NB_STAGES) { b_st = 0; b_ph ^= 1; }
+                }
+                if (lane == 0) tc_commit(smem_u32(&a_empty[a_st]));
+                __syncwarp();
+                a_st ^= 1;
+                if (a_st == 0) a_ph ^= 1;
+            }
+            if (lane == 0) tc_commit(smem_u32(&acc_full[acc_st]));
+            __syncwarp();
+            if (++acc_st == ACC_STAGES) { acc_st = 0; acc_ph ^= 1; }
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> bias + ReLU -> bf16 -> global (plane-major) =====
+        const int wq = warp & 3;     // TMEM lane quarter this warp may read
+        if (blockIdx.x == 0) {       // zero rows in front of position 0 of every output plane
+            const int et = threadIdx.x - 64;
+            const int planes = A.cout / 8;
+            for (int i = et; i < planes * LEAD; i += 128) A.out[(long long)(i / LEAD) * A.R + (i % LEAD)] = make_uint4(0, 0, 0, 0);
+        }
+        int acc_st = 0, acc_ph = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int tile = item / A.n_split, half = item % A.n_split;
+            mbar_wait(smem_u32(&acc_full[acc_st]), acc_ph);
+            tc_fence_after();
+#pragma unroll 1
+            for (int t = 0; t < UMMA_T; ++t) {
+                const long long q = (long long)tile * TILE_M + t * 128 + wq * 32 + lane;
+                bool data = q < A.Q;
+                if (data) {
+                    const int ql = (int)(q % A.PP);
+                    const int r = ql / A.pitch, cc = ql - r * A.pitch;
+                    data = (r >= 1) && (cc >= 1);
+                }
+#pragma unroll 1
+                for (int ch = 0; ch < NC / 32; ++ch) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((acc_st * UMMA_T + t) * NC + ch * 32), v);
+                    const float* bs = s_bias + half * NC + ch * 32;
+                    uint4* o = A.out + (long long)((half * NC + ch * 32) / 8) * A.R + LEAD + q;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        uint4 w = make_uint4(0, 0, 0, 0);
+                        if (data) {
+                            float f[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) f[e] = fmaxf(__uint_as_float(v[g * 8 + e]) + bs[g * 8 + e], 0.f);
+                            w.x = pack_bf16x2(f[0], f[1]); w.y = pack_bf16x2(f[2], f[3]);
+                            w.z = pack_bf16x2(f[4], f[5]); w.w = pack_bf16x2(f[6], f[7]);
+                        }
+                        o[(long long)g * A.R] = w;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&acc_empty[acc_st]));
+            if (++acc_st == ACC_STAGES) { acc_st = 0; acc_ph ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// fp32 patches [n][9][32][32] -> layer-0 input: 2 planes (channels 0-7 | 8 + zeros), pitch 33
+__global__ void pack_input_kernel(const float* __restrict__ patches, uint4* __restrict__ out, long long R, int n) {
+    const int pitch = 33, PP = 33 * 33;
+    const long long total = (long long)n * PP + pitch + 1 + LEAD;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long q = i - LEAD;
+        uint4 w0 = make_uint4(0, 0, 0, 0), w1 = w0;
+        if (q >= 0 && q < (long long)n * PP) {
+            const int pn = (int)(q / PP), ql = (int)(q - (long long)pn * PP);
+            const int r = ql / pitch, c = ql - r * pitch;
+            if (r >= 1 && c >= 1) {
+                const float* p = patches + (size_t)pn * 9 * 1024 + (r - 1) * 32 + (c - 1);
+                float f[9];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) f[k] = p[k * 1024];
+                w0.x = pack_bf16x2(f[0], f[1]); w0.y = pack_bf16x2(f[2], f[3]);
+                w0.z = pack_bf16x2(f[4], f[5]); w0.w = pack_bf16x2(f[6], f[7]);
+                w1.x = pack_bf16x2(f[8], 0.f);
+            }
+        }
+        out[i] = w0;
+        out[R + i] = w1;
+    }
+}
+
+__device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
+    uint4 r;
+    const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+    __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+    return r;
+}
+
+// 2x2 max pool between two shared-halo layouts (S -> S/2).  FINAL: write fp32 NHWC [n][S/2][S/2][C] instead
+// (the input of cnn_tail_kernel).
+template <bool FINAL>
+__global__ void pool2x2_kernel(const uint4* __restrict__ in, long long Rin, int S, void* __restrict__ outp, long long Rout,
+                               int planes, int n) {
+    const int pin = S + 1, PPin = pin * pin, So = S / 2, po = So + 1, PPo = po * po;
+    if (FINAL) {
+        float* out = reinterpret_cast<float*>(outp);
+        const long long total = (long long)n * So * So * planes;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+            const int p = (int)(i % planes);
+            const long long pix = i / planes;
+            const int x = (int)(pix % So), y = (int)((pix / So) % So);
+            const long long pn = pix / (So * So);
+            const uint4* src = in + (long long)p * Rin + LEAD + pn * PPin + (2 * y + 1) * pin + 2 * x + 1;
+            uint4 m = bf16x8_max(bf16x8_max(src[0], src[1]), bf16x8_max(src[pin], src[pin + 1]));
+            const __nv_bfloat162* pm = reinterpret_cast<const __nv_bfloat162*>(&m);
+            float4 lo, hi;
+            float2 t;
+            t = __bfloat1622float2(pm[0]); lo.x = t.x; lo.y = t.y;
+            t = __bfloat1622float2(pm[1]); lo.z = t.x; lo.w = t.y;
+            t = __bfloat1622float2(pm[2]); hi.x = t.x; hi.y = t.y;
+            t = __bfloat1622float2(pm[3]); hi.z = t.x; hi.w = t.y;
+            float4* dst = reinterpret_cast<float4*>(out + (pix * planes + p) * 8);
+            dst[0] = lo; dst[1] = hi;
+        }
+    } else {
+        uint4* out = reinterpret_cast<uint4*>(outp);
+        const long long per_plane = (long long)n * PPo + po + 1 + LEAD;
+        const long long total = per_plane * planes;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+            const int p = (int)(i / per_plane);
+            const long long rho = i - (long long)p * per_plane;
+            const long long q = rho - LEAD;
+            uint4 m = make_uint4(0, 0, 0, 0);
+            if (q >= 0 && q < (long long)n * PPo) {
+                const long long pn = q / PPo;
+                const int ql = (int)(q - pn * PPo);
+                const int r = ql / po, c = ql - r * po;
+                if (r >= 1 && c >= 1) {
+                    const uint4* src = in + (long long)p * Rin + LEAD + pn * PPin + (2 * (r - 1) + 1) * pin + 2 * (c - 1) + 1;
+                    m = bf16x8_max(bf16x8_max(src[0], src[1]), bf16x8_max(src[pin], src[pin + 1]));
+                }
+            }
+            out[(long long)p * Rout + rho] = m;
+        }
+    }
+}
+
+// plane-major bf16 activations -> fp32 NCHW [n][C][S][S] (parity tests: lg_cnn_bf16_features)
+__global__ void unpack_features_kernel(const uint4* __restrict__ in, long long R, int S, int C, int n, float* __restrict__ out) {
+    const int pitch = S + 1, PP = pitch * pitch;
+    const long long total = (long long)n * C * S * S;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % S), y = (int)((i / S) % S), ch = (int)((i / ((long long)S * S)) % C);
+        const long long pn = i / ((long long)S * S * C);
+        const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(in + (long long)(ch / 8) * R + LEAD + pn * PP + (y + 1) * pitch + x + 1);
+        out[i] = __bfloat162float(src[ch % 8]);
+    }
+}
+
+struct LayerCfg { int cin, cout, S, KP, KC, NC; };
+const LayerCfg kLayers[6] = {{9, 64, 32, 2, 1, 64},   {64, 64, 32, 8, 1, 64},   {64, 128, 16, 8, 1, 128},
+                             {128, 128, 16, 8, 2, 128}, {128, 256, 8, 8, 2, 128}, {256, 256, 8, 8, 4, 128}};
+
+inline long long rows_per_plane(int S, long long n) {
+    const long long pitch = S + 1, Q = n * pitch * pitch;
+    const long long tiles = (Q + pitch + 1 + TILE_M - 1) / TILE_M;
+    return LEAD + tiles * TILE_M + 64;
+}
+inline int a_rows(int S) { return (TILE_M + 2 * (S + 1) + 2 + 7) / 8 * 8; }
+
+template <int KP, int NC>
+size_t conv_smem(int S) {
+    return 2 * (size_t)KP * a_rows(S) * 16 + (size_t)NB_STAGES * KP * NC * 16 + 256 * sizeof(float) + 16 * sizeof(uint64_t) + 16;
+}
+
+uint16_t f2bf(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7FFFFFFFu) > 0x7F800000u) return (uint16_t)((u >> 16) | 0x40);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+
+// packed bf16 weight offsets (in uint4 units) of every layer inside cnn.bf16_blob
+size_t layer_w_units(const LayerCfg& l) { return (size_t)(l.cout / l.NC) * l.KC * 9 * l.KP * l.NC; }
+
+template <int KP, int NC>
+int launch_conv(const UmmaConvArgs& A, int S, int sms, cudaStream_t st) {
+    static bool attr_set = false;
+    const size_t smem = conv_smem<KP, NC>(32);   // one attribute value covers every spatial size
+    if (!attr_set) {
+        LG_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<KP, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const int items = A.n_tiles * A.n_split;
+    const int grid = items < sms ? items : sms;
+    conv3x3_umma_kernel<KP, NC><<<grid, CONV_THREADS, conv_smem<KP, NC>(S), st>>>(A);
+    LG_LAUNCH_CHECK();
+    return LG_OK;
+}
+
+}  // namespace
+
+uint64_t lg_cnn_blob_floats();
+int lg_launch_cnn_tail(const float* feat, const float* blob_tail, float* logits, int n, cudaStream_t st);
+
+// Pack the folded fp32 weights (cnn.py:pack_weights layout) into the bf16 operand layout; synchronous.
+int lg_cnn_prepare_bf16(lg_context* c) {
+    std::vector<float> blob(c->cnn.n_floats);
+    LG_CUDA(cudaMemcpy(blob.data(), c->cnn.blob, blob.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    size_t units = 0;
+    for (const LayerCfg& l : kLayers) units += layer_w_units(l);
+    std::vector<uint16_t> packed(units * 8, 0);
+    const float* w = blob.data();
+    size_t off = 0;
+    for (const LayerCfg& l : kLayers) {
+        const int n_split = l.cout / l.NC;
+        for (int half = 0; half < n_split; ++half)
+            for (int kc = 0; kc < l.KC; ++kc)
+                for (int tap = 0; tap < 9; ++tap)
+                    for (int p = 0; p < l.KP; ++p)
+                        for (int n = 0; n < l.NC; ++n)
+                            for (int e = 0; e < 8; ++e) {
+                                const int ci = kc * l.KP * 8 + p * 8 + e, co = half * l.NC + n;
+                                const float v = ci < l.cin ? w[((size_t)tap * l.cin + ci) * l.cout + co] : 0.f;
+                                packed[(off + ((((size_t)(half * l.KC + kc) * 9 + tap) * l.KP + p) * l.NC + n)) * 8 + e] = f2bf(v);
+                            }
+        off += layer_w_units(l);
+        w += 9ull * l.cin * l.cout + l.cout;
+    }
+    if (!c->cnn.bf16_blob) LG_CUDA(cudaMalloc(&c->cnn.bf16_blob, packed.size() * sizeof(uint16_t)));
+    LG_CUDA(cudaMemcpy(c->cnn.bf16_blob, packed.data(), packed.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    return LG_OK;
+}
+
+static int run_cnn_bf16(lg_context* c, const float* patches, int n, float* logits, int stop_layer, float* feat_out,
+                        cudaStream_t st);
 
 int lg_run_cnn_bf16(lg_context* c, const float* patches, int n, float* logits, cudaStream_t st) {
-    (void)c; (void)patches; (void)n; (void)logits; (void)st;
-    lg_set_error("bf16 CNN path is not built");
-    return LG_E_ARG;
+    return run_cnn_bf16(c, patches, n, logits, -1, nullptr, st);
+}
+
+extern "C" int lg_cnn_bf16_features(lg_context* c, const float* patches, int n, int layer, float* features, void* stream) {
+    if (!c || !patches || !features || n < 1 || layer < 0 || layer > 5) return LG_E_ARG;
+    if (!c->cnn.loaded) { lg_set_error("lg_cnn_bf16_features: no weights loaded"); return LG_E_ARG; }
+    if (n > c->cnn_cap) return LG_E_CAPACITY;
+    return run_cnn_bf16(c, patches, n, nullptr, layer, features, (cudaStream_t)stream);
+}
+
+static int run_cnn_bf16(lg_context* c, const float* patches, int n, float* logits, int stop_layer, float* feat_out,
+                        cudaStream_t st) {
+    if (!c->cnn.bf16_blob) { lg_set_error("bf16 CNN weights are not prepared"); return LG_E_ARG; }
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        LG_CUDA(cudaGetDevice(&dev));
+        LG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    // bias pointers inside the fp32 blob; bf16 weights inside bf16_blob
+    const float* bias[6];
+    const uint4* wts[6];
+    {
+        const float* w = c->cnn.blob;
+        const uint4* pw = reinterpret_cast<const uint4*>(c->cnn.bf16_blob);
+        for (int l = 0; l < 6; ++l) {
+            bias[l] = w + 9ull * kLayers[l].cin * kLayers[l].cout;
+            w += 9ull * kLayers[l].cin * kLayers[l].cout + kLayers[l].cout;
+            wts[l] = pw;
+            pw += layer_w_units(kLayers[l]);
+        }
+    }
+    const float* tail = c->cnn.blob + (lg_cnn_blob_floats() - (256 + 1 + 256 * 256 + 256 + 256 * 128 + 128 + 128 * 64 + 64 + 64 + 1));
+    for (int done = 0; done < n; done += c->cnn_cap) {
+        const int m = n - done < c->cnn_cap ? n - done : c->cnn_cap;
+        uint4* buf[2] = {reinterpret_cast<uint4*>(c->cnn_act0), reinterpret_cast<uint4*>(c->cnn_act1)};
+        int cur = 0;   // buffer holding the current layer's input
+        {
+            const long long R = rows_per_plane(32, m);
+            const long long total = (long long)m * 33 * 33 + 34 + LEAD;
+            const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+            pack_input_kernel<<<grid, 256, 0, st>>>(patches + (size_t)done * LG_CHANNELS * LG_PATCH * LG_PATCH, buf[0], R, m);
+            LG_LAUNCH_CHECK();
+        }
+        for (int l = 0; l < 6; ++l) {
+            const LayerCfg& L = kLayers[l];
+            UmmaConvArgs A;
+            A.in = buf[cur]; A.out = buf[cur ^ 1]; A.wt = wts[l]; A.bias = bias[l];
+            A.R = rows_per_plane(L.S, m);
+            A.pitch = L.S + 1; A.PP = A.pitch * A.pitch; A.Q = (long long)m * A.PP;
+            A.n_tiles = (int)((A.Q + A.pitch + 1 + TILE_M - 1) / TILE_M);
+            A.KC = L.KC; A.n_split = L.cout / L.NC; A.rows = a_rows(L.S); A.cout = L.cout;
+            int rc;
+            if (L.KP == 2) rc = launch_conv<2, 64>(A, L.S, sms, st);
+            else if (L.NC == 64) rc = launch_conv<8, 64>(A, L.S, sms, st);
+            else rc = launch_conv<8, 128>(A, L.S, sms, st);
+            if (rc) return rc;
+            cur ^= 1;
+            if (l & 1) {   // max-pool after the second conv of each block
+                const int planes = L.cout / 8;
+                if (l == 5) {
+                    const long long total = (long long)m * 16 * planes;
+                    const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+                    pool2x2_kernel<true><<<grid, 256, 0, st>>>(buf[cur], A.R, L.S, buf[cur ^ 1], 0, planes, m);
+                } else {
+                    const long long Rout = rows_per_plane(L.S / 2, m);
+                    const long long total = ((long long)m * (L.S / 2 + 1) * (L.S / 2 + 1) + L.S / 2 + 2 + LEAD) * planes;
+                    const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+                    pool2x2_kernel<false><<<grid, 256, 0, st>>>(buf[cur], A.R, L.S, buf[cur ^ 1], Rout, planes, m);
+                }
+                LG_LAUNCH_CHECK();
+                cur ^= 1;
+            }
+            if (l == stop_layer) {
+                if (l == 5) {   // pooled fp32 NHWC [m][4][4][256] -> NCHW
+                    LG_CUDA(cudaMemcpyAsync(feat_out, buf[cur], (size_t)m * 16 * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+                } else {
+                    const int So = (l & 1) ? L.S / 2 : L.S;
+                    unpack_features_kernel<<<148 * 8, 256, 0, st>>>(buf[cur], rows_per_plane(So, m), So, L.cout, m, feat_out);
+                    LG_LAUNCH_CHECK();
+                }
+                return LG_OK;
+            }
+        }
+        int rc = lg_launch_cnn_tail(reinterpret_cast<const float*>(buf[cur]), tail, logits + done, m, st);
+        if (rc) return rc;
+    }
+    return LG_OK;
 }

@@ -90,6 +90,17 @@ class GraspEngine:
             N.check(self.lib.lg_cnn_forward(self._ctx, _ptr(patches), n, _ptr(out), int(use_bf16), _stream()), "lg_cnn_forward")
         return out
 
+    def cnn_bf16_features(self, patches: torch.Tensor, layer: int) -> torch.Tensor:
+        """Activations of the bf16 tensor-core path after conv layer `layer` (see include/leafgrasp.h)."""
+        patches = patches.to(self.device, torch.float32).contiguous()
+        n = patches.shape[0]
+        shape = [(64, 32, 32), (64, 16, 16), (128, 16, 16), (128, 8, 8), (256, 8, 8), (4, 4, 256)][layer]
+        out = torch.empty((n,) + shape, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.lg_cnn_bf16_features(self._ctx, _ptr(patches), n, layer, _ptr(out), _stream()),
+                    "lg_cnn_bf16_features")
+        return out
+
     def normalize_patches(self, raw: torch.Tensor) -> torch.Tensor:
         raw = raw.to(self.device, torch.float32).contiguous()
         out = torch.empty_like(raw)

@@ -245,6 +245,64 @@ def test_cnn_dropin_module(state_dict):
     np.testing.assert_allclose(y.reshape(-1).cpu().numpy(), g["logits"], atol=1e-4, rtol=1e-4)
 
 
+def _torch_layer_features(sd, x, layer):
+    """fp32 torch activations after conv `layer` (BN + ReLU applied; pooled after layers 1, 3, 5)."""
+    import torch.nn.functional as F
+    k = 0
+    for b in range(3):
+        for conv, bn in ((0, 1), (3, 4)):
+            x = F.conv2d(x, sd[f"encoder.{b}.{conv}.weight"], sd[f"encoder.{b}.{conv}.bias"], padding=1)
+            x = F.batch_norm(x, sd[f"encoder.{b}.{bn}.running_mean"], sd[f"encoder.{b}.{bn}.running_var"],
+                             sd[f"encoder.{b}.{bn}.weight"], sd[f"encoder.{b}.{bn}.bias"], False, 0.0, 1e-5)
+            x = F.relu(x)
+            if conv == 3:
+                x = F.max_pool2d(x, 2)
+            if k == layer:
+                return x
+            k += 1
+    raise ValueError(layer)
+
+
+@pytest.mark.parametrize("layer", [0, 1, 2, 3, 4, 5])
+def test_cnn_bf16_layer_features(layer, state_dict, blob):
+    """Every tcgen05 conv layer against torch fp32 on the same patches: bf16 operands, fp32 accumulation."""
+    g = np.load(os.path.join(GOLD, "cnn_patches.npz"))
+    x = torch.from_numpy(g["x"])
+    rng = np.random.default_rng(5)
+    extra = torch.from_numpy(rng.random((45, 9, 32, 32), dtype=np.float32))   # 61 patches: several work items
+    extra[:, 1] = (extra[:, 1] > 0.5).float()
+    x = torch.cat([x, extra])
+    eng = _engine(1, 64, 64, 2)
+    eng.set_cnn_weights(blob)
+    got = eng.cnn_bf16_features(x, layer).cpu()
+    with torch.no_grad():
+        want = _torch_layer_features(state_dict, x, layer)
+    if layer == 5:
+        want = want.permute(0, 2, 3, 1).contiguous()
+    assert got.shape == want.shape
+    scale = float(want.abs().max())
+    err = float((got - want).abs().max())
+    assert err <= 2e-2 * scale, f"layer {layer}: max abs err {err} vs activation scale {scale}"
+    eng.close()
+
+
+def test_cnn_bf16_against_reference_logits(blob, state_dict):
+    """north_star: CNN logits within 1e-2 in bf16 (against the reference's fp32 logits, golden vectors)."""
+    g = np.load(os.path.join(GOLD, "cnn_patches.npz"))
+    eng = _engine(1, 64, 64, 2)
+    eng.set_cnn_weights(blob)
+    y = eng.cnn_forward(torch.from_numpy(g["x"]), use_bf16=True).cpu().numpy()
+    np.testing.assert_allclose(y, g["logits"], atol=1e-2, rtol=1e-2)
+    # a batch that spans several activation chunks agrees with the fp32 CUDA path
+    rng = np.random.default_rng(9)
+    x = torch.from_numpy(rng.random((2300, 9, 32, 32), dtype=np.float32))
+    x[:, 1] = (x[:, 1] > 0.5).float()
+    y16 = eng.cnn_forward(x, use_bf16=True).cpu().numpy()
+    y32 = eng.cnn_forward(x, use_bf16=False).cpu().numpy()
+    np.testing.assert_allclose(y16, y32, atol=1e-2, rtol=1e-2)
+    eng.close()
+
+
 # ------------------------------------------------------------------------------------------------------
 # whole path
 # ------------------------------------------------------------------------------------------------------
