@@ -318,7 +318,7 @@ def main():
     ap.add_argument("--frames", type=int, default=256, help="frames per GPU per step")
     ap.add_argument("--unique", type=int, default=32, help="distinct synthetic frames generated per rank")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cnn", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--cnn", default="bf16", choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-steps", type=int, default=2)
     args = ap.parse_args()

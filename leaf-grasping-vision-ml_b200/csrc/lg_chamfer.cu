@@ -30,6 +30,10 @@ struct ChamferArgs {
     size_t P;
 };
 
+// LPT = source / forward values each thread fetches per row (row width <= LPT * CH_NT), D = rows fetched ahead.
+// The fetches of row ly + 1 + D are issued D iterations before their values are stored to shared memory, so the
+// global-memory latency of the row stream is hidden behind D row steps instead of being paid once per row.
+template <int LPT, int D>
 __global__ void __launch_bounds__(CH_NT) chamfer_kernel(ChamferArgs A) {
     extern __shared__ int smem[];
     __shared__ int wtot[2][CH_NT / 32];
@@ -73,82 +77,108 @@ __global__ void __launch_bounds__(CH_NT) chamfer_kernel(ChamferArgs A) {
             int y = flip ? (ry1 - 1 - ly) : (ry0 + ly);
             return (size_t)y * W + x;
         };
-        auto load_row = [&](int ly, int* dst) {
-            for (int lx = tid; lx < w; lx += CH_NT) {
-                size_t p = phys(lx, ly);
-                if (pass == 0) {
-                    bool inside = A.src.at(fo, p, id) != invert;
-                    dst[lx] = inside ? 1 : 0;      // 0 = source pixel
-                } else {
-                    dst[lx] = fwd[p];
+        auto fetch = [&](int ly, int* dst) {       // global -> registers, all loads issued back to back
+#pragma unroll
+            for (int i = 0; i < LPT; ++i) {
+                const int lx = tid + i * CH_NT;
+                int v = 0;
+                if (lx < w && ly < h) {
+                    const size_t p = phys(lx, ly);
+                    if (pass == 0) v = (A.src.at(fo, p, id) != invert) ? 1 : 0;   // 0 = source pixel
+                    else v = fwd[p];
                 }
+                dst[i] = v;
+            }
+        };
+        auto commit = [&](const int* srcv, int* dst) {   // registers -> shared row
+#pragma unroll
+            for (int i = 0; i < LPT; ++i) {
+                const int lx = tid + i * CH_NT;
+                if (lx < w) dst[lx] = srcv[i];
             }
         };
         auto store_row = [&](int ly, const int* row) {   // row has the +2 border offset
-            for (int lx = tid; lx < w; lx += CH_NT) {
-                int t = row[lx + 2];
-                size_t p = phys(lx, ly);
-                if (pass == 0) {
-                    fwd[p] = t;
-                } else {
-                    unsigned q = (t >= LG_CH_INF) ? LG_CH_DIST_MAX : (unsigned)t;
-                    my_max = max(my_max, q);
-                    if (oq) oq[p] = q;
-                    if (of) of[p] = __fmul_rn((float)q, 1.0f / 65536.0f);
+#pragma unroll
+            for (int i = 0; i < LPT; ++i) {
+                const int lx = tid + i * CH_NT;
+                if (lx < w) {
+                    int t = row[lx + 2];
+                    size_t p = phys(lx, ly);
+                    if (pass == 0) {
+                        fwd[p] = t;
+                    } else {
+                        unsigned q = (t >= LG_CH_INF) ? LG_CH_DIST_MAX : (unsigned)t;
+                        my_max = max(my_max, q);
+                        if (oq) oq[p] = q;
+                        if (of) of[p] = __fmul_rn((float)q, 1.0f / 65536.0f);
+                    }
                 }
             }
         };
+        int pre[D][LPT];
         for (int i = tid; i < 3 * wpad; i += CH_NT) ring[i] = LG_CH_INF;
-        load_row(0, sbuf);
+        {
+            int first[LPT];
+            fetch(0, first);
+#pragma unroll
+            for (int d = 1; d <= D; ++d) fetch(d, pre[d % D]);
+            commit(first, sbuf);
+        }
         __syncthreads();
-        for (int ly = 0; ly < h; ++ly) {
-            int* cur = ring + (ly % 3) * wpad;
-            const int* p1 = ring + ((ly + 2) % 3) * wpad;
-            const int* p2 = ring + ((ly + 1) % 3) * wpad;
-            const int* sb = sbuf + (ly & 1) * w;
-            if (ly + 1 < h) load_row(ly + 1, sbuf + ((ly + 1) & 1) * w);
-            if (ly > 0) store_row(ly - 1, p1);
-            const int xb = tid * ipt;
-            int pv[CH_MAXI];
-            int run = 0x7FFFFFFF;
+        for (int ly0 = 0; ly0 < h; ly0 += D) {
 #pragma unroll
-            for (int i = 0; i < CH_MAXI; ++i) {
-                const int x = xb + i;
-                if (i < ipt && x < w) {
-                    const int s = sb[x];
-                    int m = min(p2[x + 1], p2[x + 3]) + LG_CH_C;
-                    m = min(m, min(p1[x], p1[x + 4]) + LG_CH_C);
-                    m = min(m, min(p1[x + 1], p1[x + 3]) + LG_CH_B);
-                    m = min(m, p1[x + 2] + LG_CH_A);
-                    int u;
-                    if (pass == 0) u = s ? min(m, LG_CH_INF) : 0;
-                    else u = min(s, m);
-                    run = min(run, u - LG_CH_A * x);
+            for (int dd = 0; dd < D; ++dd) {
+                const int ly = ly0 + dd;
+                if (ly >= h) break;
+                int* cur = ring + (ly % 3) * wpad;
+                const int* p1 = ring + ((ly + 2) % 3) * wpad;
+                const int* p2 = ring + ((ly + 1) % 3) * wpad;
+                const int* sb = sbuf + (ly & 1) * w;
+                if (ly + 1 < h) commit(pre[(dd + 1) % D], sbuf + ((ly + 1) & 1) * w);
+                fetch(ly + 1 + D, pre[(dd + 1) % D]);
+                if (ly > 0) store_row(ly - 1, p1);
+                const int xb = tid * ipt;
+                int pv[CH_MAXI];
+                int run = 0x7FFFFFFF;
+#pragma unroll
+                for (int i = 0; i < CH_MAXI; ++i) {
+                    const int x = xb + i;
+                    if (i < LPT && i < ipt && x < w) {
+                        const int s = sb[x];
+                        int m = min(p2[x + 1], p2[x + 3]) + LG_CH_C;
+                        m = min(m, min(p1[x], p1[x + 4]) + LG_CH_C);
+                        m = min(m, min(p1[x + 1], p1[x + 3]) + LG_CH_B);
+                        m = min(m, p1[x + 2] + LG_CH_A);
+                        int u;
+                        if (pass == 0) u = s ? min(m, LG_CH_INF) : 0;
+                        else u = min(s, m);
+                        run = min(run, u - LG_CH_A * x);
+                    }
+                    pv[i] = run;
                 }
-                pv[i] = run;
-            }
-            int incl = run;
+                int incl = run;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                int t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                if (lane >= d) incl = min(incl, t);
-            }
-            int excl = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
-            if (lane == 0) excl = 0x7FFFFFFF;
-            if (lane == 31) wtot[ly & 1][warp] = incl;
-            __syncthreads();
-            for (int k = 0; k < warp; ++k) excl = min(excl, wtot[ly & 1][k]);
-#pragma unroll
-            for (int i = 0; i < CH_MAXI; ++i) {
-                const int x = xb + i;
-                if (i < ipt && x < w) {
-                    int t = min(pv[i], excl);
-                    // t can only stay at the sentinel when nothing finite precedes x
-                    t = (t > LG_CH_INF) ? LG_CH_INF : min(t + LG_CH_A * x, LG_CH_INF);
-                    cur[x + 2] = t;
+                for (int d = 1; d < 32; d <<= 1) {
+                    int t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                    if (lane >= d) incl = min(incl, t);
                 }
+                int excl = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+                if (lane == 0) excl = 0x7FFFFFFF;
+                if (lane == 31) wtot[ly & 1][warp] = incl;
+                __syncthreads();
+                for (int k = 0; k < warp; ++k) excl = min(excl, wtot[ly & 1][k]);
+#pragma unroll
+                for (int i = 0; i < CH_MAXI; ++i) {
+                    const int x = xb + i;
+                    if (i < LPT && i < ipt && x < w) {
+                        int t = min(pv[i], excl);
+                        // t can only stay at the sentinel when nothing finite precedes x
+                        t = (t > LG_CH_INF) ? LG_CH_INF : min(t + LG_CH_A * x, LG_CH_INF);
+                        cur[x + 2] = t;
+                    }
+                }
+                __syncthreads();
             }
-            __syncthreads();
         }
         store_row(h - 1, ring + ((h - 1) % 3) * wpad);
         __syncthreads();
@@ -179,10 +209,12 @@ int lg_run_chamfer(lg_context* c, LgMaskSrc src, int n, int rect_mode, int inver
     size_t sm = (size_t)(3 * (c->W + 4) + 2 * c->W) * sizeof(int);
     static size_t configured = 0;
     if (sm > configured) {
-        LG_CUDA(cudaFuncSetAttribute(chamfer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        LG_CUDA(cudaFuncSetAttribute(chamfer_kernel<3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        LG_CUDA(cudaFuncSetAttribute(chamfer_kernel<CH_MAXI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         configured = sm;
     }
-    chamfer_kernel<<<dim3(n, nvar), CH_NT, sm, st>>>(A);
+    if (c->W <= 3 * CH_NT) chamfer_kernel<3, 4><<<dim3(n, nvar), CH_NT, sm, st>>>(A);
+    else chamfer_kernel<CH_MAXI, 2><<<dim3(n, nvar), CH_NT, sm, st>>>(A);
     LG_LAUNCH_CHECK();
     return LG_OK;
 }

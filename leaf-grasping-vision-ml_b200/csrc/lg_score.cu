@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(SC_TW * SC_TH) score_kernel(lg_context c, LgMa
 // fill the per-frame maps with their analytic values outside the score rectangle (full mode only needs
 // nothing: the rectangle is the frame).  Not needed in region mode: consumers special-case the outside.
 
-constexpr int NMS_NT = 256;
+constexpr int NMS_NT = 1024;
 __global__ void __launch_bounds__(NMS_NT) nms_kernel(lg_context c, const double* ext_score, const uint8_t* ext_valid,
                                                       int32_t* ext_xy, int32_t* ext_count) {
     const int b = blockIdx.x, tid = threadIdx.x;

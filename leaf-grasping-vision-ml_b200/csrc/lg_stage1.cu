@@ -154,8 +154,12 @@ __global__ void leaf_offsets_kernel(lg_context c, int n) {
     off[c.L] = o;
 }
 
+// Groups the depth values by label.  Global atomics are taken once per (CTA, label): the CTA counts its
+// pixels per label in shared memory, reserves one contiguous range per label in the frame's segment and
+// hands out positions inside it from shared-memory cursors.
 __global__ void __launch_bounds__(ST_NT) leaf_scatter_kernel(lg_context c, const int16_t* __restrict__ labels,
                                                               const float* __restrict__ depth) {
+    extern __shared__ unsigned s_cur[];   // [L] count, then absolute write cursor
     const int L = c.L;
     const size_t P = c.P;
     const int b = blockIdx.y;
@@ -163,24 +167,61 @@ __global__ void __launch_bounds__(ST_NT) leaf_scatter_kernel(lg_context c, const
     const uint32_t* cnt = c.cnt + (size_t)b * L;
     __shared__ int s_bg;
     if (threadIdx.x == 0) s_bg = background_id(cnt, L);
+    for (int l = threadIdx.x; l < L; l += ST_NT) s_cur[l] = 0;
     __syncthreads();
-    if (base >= P) return;
     const int bg = s_bg;
     const int16_t* lp = labels + (size_t)b * P;
     const float* dp = depth + (size_t)b * P;
-    const uint32_t* off = c.seg_off + (size_t)b * (L + 1);
-    float* seg = c.seg + (size_t)b * P;
-    int i = 0;
-    while (i < ST_PX && base + i < P) {
-        int l = lp[base + i];
-        int j = i + 1;
-        while (j < ST_PX && base + j < P && lp[base + j] == l) ++j;
-        if (l >= 0 && l < L && l != bg) {
-            uint32_t pos = atomicAdd(&c.seg_cur[(size_t)b * L + l], (uint32_t)(j - i));
-            float* dst = seg + off[l] + pos;
-            for (int k = i; k < j; ++k) dst[k - i] = dp[base + k];
+    int lab[ST_PX];
+    float val[ST_PX];
+    const int npx = base < P ? (int)min((size_t)ST_PX, P - base) : 0;
+    if (npx == ST_PX && ((reinterpret_cast<uintptr_t>(lp + base) | reinterpret_cast<uintptr_t>(dp + base)) & 15) == 0) {
+        const uint4 lv = *reinterpret_cast<const uint4*>(lp + base);
+        const float4 d0 = *reinterpret_cast<const float4*>(dp + base), d1 = *reinterpret_cast<const float4*>(dp + base + 4);
+        const unsigned w[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { lab[2 * k] = (int16_t)(w[k] & 0xFFFFu); lab[2 * k + 1] = (int16_t)(w[k] >> 16); }
+        val[0] = d0.x; val[1] = d0.y; val[2] = d0.z; val[3] = d0.w; val[4] = d1.x; val[5] = d1.y; val[6] = d1.z; val[7] = d1.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < ST_PX; ++k) {
+            lab[k] = k < npx ? (int)lp[base + k] : -1;
+            val[k] = k < npx ? dp[base + k] : 0.f;
         }
-        i = j;
+    }
+    // run starts: bit k set when pixel k opens a run; labels that are not scattered become -1
+    unsigned starts = 0;
+#pragma unroll
+    for (int k = 0; k < ST_PX; ++k) {
+        if (lab[k] < 0 || lab[k] >= L || lab[k] == bg) lab[k] = -1;
+        if (k == 0 || lab[k] != lab[k - 1]) starts |= 1u << k;
+    }
+#pragma unroll
+    for (int k = 0; k < ST_PX; ++k) {
+        if (((starts >> k) & 1u) && lab[k] >= 0) {
+            const unsigned rest = starts >> (k + 1);
+            const int len = rest ? __ffs(rest) : ST_PX - k;
+            atomicAdd(&s_cur[lab[k]], (unsigned)len);
+        }
+    }
+    __syncthreads();
+    for (int l = threadIdx.x; l < L; l += ST_NT) {
+        const unsigned n = s_cur[l];
+        if (n) s_cur[l] = c.seg_off[(size_t)b * (L + 1) + l] + atomicAdd(&c.seg_cur[(size_t)b * L + l], n);
+    }
+    __syncthreads();
+    float* seg = c.seg + (size_t)b * P;
+    unsigned pos = 0;
+#pragma unroll
+    for (int k = 0; k < ST_PX; ++k) {
+        if (lab[k] >= 0) {
+            if ((starts >> k) & 1u) {
+                const unsigned rest = starts >> (k + 1);
+                const int len = rest ? __ffs(rest) : ST_PX - k;
+                pos = atomicAdd(&s_cur[lab[k]], (unsigned)len);
+            }
+            seg[pos++] = val[k];
+        }
     }
 }
 
@@ -303,52 +344,91 @@ __global__ void edt_col_kernel(EdtSrc src, uint16_t* __restrict__ g, int H, int 
 constexpr int EDT_NT = 256;
 // pass 2: per row, d2(x) = min over x' of (x - x')^2 + g(x')^2.  The search around x stops as soon
 // as the horizontal offset alone exceeds the best distance found (Meijster's lower-envelope bound).
+//
+// When only the arg-max of the field is wanted (d2out == nullptr, the leaf-selection use) a pixel is
+// dropped as soon as its running upper bound falls below the largest exact distance found so far in
+// the frame (best[b], shared by all CTAs through atomicMax): such a pixel can neither be the maximum
+// nor tie with it, so the result is exactly the first maximum of the full field whatever the
+// scheduling.  CTAs walk rows `stride` apart (a permutation of the rows) so that the bound comes
+// from all over the frame early, and every CTA handles several rows to profit from it.
 __global__ void __launch_bounds__(EDT_NT) edt_row_kernel(const uint16_t* __restrict__ g, uint32_t* __restrict__ d2out,
-                                                          unsigned long long* __restrict__ best, int H, int W, size_t P) {
+                                                          unsigned long long* __restrict__ best, int H, int W, size_t P,
+                                                          int row_stride) {
     extern __shared__ unsigned srow[];   // g squared, 0xFFFFFFFF = no source in that column
     __shared__ unsigned long long sbest[EDT_NT / 32];
+    __shared__ unsigned s_lb;
     __shared__ int s_any;
-    const int y = blockIdx.x, b = blockIdx.y;
-    const uint16_t* gp = g + (size_t)b * P + (size_t)y * W;
-    if (threadIdx.x == 0) s_any = 0;
-    __syncthreads();
-    int any = 0;
-    for (int x = threadIdx.x; x < W; x += EDT_NT) {
-        unsigned v = gp[x];
-        srow[x] = (v == 0xFFFFu) ? 0xFFFFFFFFu : v * v;
-        any |= (v != 0xFFFFu);
-    }
-    if (any) s_any = 1;
-    __syncthreads();
+    const int b = blockIdx.x;
+    const bool prune = (d2out == nullptr) && (best != nullptr);
     unsigned long long mybest = 0;
-    if (s_any) {
-        for (int x = threadIdx.x; x < W; x += EDT_NT) {
-            unsigned bestd = srow[x];
-            for (unsigned k = 1; k * k < bestd; ++k) {
-                int xl = x - (int)k, xr = x + (int)k;
-                if (xl < 0 && xr >= W) break;
-                unsigned kk = k * k;
-                if (xl >= 0) { unsigned s = srow[xl]; if (s != 0xFFFFFFFFu) bestd = min(bestd, s + kk); }
-                if (xr < W) { unsigned s = srow[xr]; if (s != 0xFFFFFFFFu) bestd = min(bestd, s + kk); }
-            }
-            size_t idx = (size_t)y * W + x;
-            if (d2out) d2out[(size_t)b * P + idx] = bestd;
-            unsigned long long key = ((unsigned long long)bestd << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)idx);
-            mybest = max(mybest, key);
-        }
-    } else if (d2out) {
-        for (int x = threadIdx.x; x < W; x += EDT_NT) d2out[(size_t)b * P + (size_t)y * W + x] = 0xFFFFFFFFu;
-    }
-    if (best) {
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) mybest = max(mybest, __shfl_xor_sync(0xFFFFFFFFu, mybest, d));
-        if ((threadIdx.x & 31) == 0) sbest[threadIdx.x >> 5] = mybest;
-        __syncthreads();
+    for (int yi = blockIdx.y; yi < H; yi += gridDim.y) {
+        const int y = (int)(((long long)yi * row_stride) % H);
+        const uint16_t* gp = g + (size_t)b * P + (size_t)y * W;
+        __syncthreads();                 // previous row's readers of srow / s_lb are done
         if (threadIdx.x == 0) {
-            for (int w = 1; w < EDT_NT / 32; ++w) mybest = max(mybest, sbest[w]);
-            if (mybest) atomicMax(&best[b], mybest);
+            s_any = 0;
+            unsigned lb = 0;
+            if (prune) {
+                const unsigned long long gb = *reinterpret_cast<volatile unsigned long long*>(&best[b]);
+                lb = (unsigned)(max(gb, mybest) >> 32);
+            }
+            s_lb = lb;
+        }
+        __syncthreads();
+        int any = 0;
+        for (int x = threadIdx.x; x < W; x += EDT_NT) {
+            unsigned v = gp[x];
+            srow[x] = (v == 0xFFFFu) ? 0xFFFFFFFFu : v * v;
+            any |= (v != 0xFFFFu);
+        }
+        if (any) s_any = 1;
+        __syncthreads();
+        const unsigned lb = s_lb;
+        if (s_any) {
+            for (int x = threadIdx.x; x < W; x += EDT_NT) {
+                unsigned bestd = srow[x];
+                if (bestd < lb) continue;
+                for (unsigned k = 1; k * k < bestd; ++k) {
+                    int xl = x - (int)k, xr = x + (int)k;
+                    if (xl < 0 && xr >= W) break;
+                    unsigned kk = k * k;
+                    if (xl >= 0) { unsigned s = srow[xl]; if (s != 0xFFFFFFFFu) bestd = min(bestd, s + kk); }
+                    if (xr < W) { unsigned s = srow[xr]; if (s != 0xFFFFFFFFu) bestd = min(bestd, s + kk); }
+                    if (bestd < lb) break;
+                }
+                if (bestd < lb) continue;
+                size_t idx = (size_t)y * W + x;
+                if (d2out) d2out[(size_t)b * P + idx] = bestd;
+                unsigned long long key = ((unsigned long long)bestd << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)idx);
+                mybest = max(mybest, key);
+            }
+        } else if (d2out) {
+            for (int x = threadIdx.x; x < W; x += EDT_NT) d2out[(size_t)b * P + (size_t)y * W + x] = 0xFFFFFFFFu;
+        }
+        if (best) {   // publish after every row so that other CTAs of the frame can prune against it
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) mybest = max(mybest, __shfl_xor_sync(0xFFFFFFFFu, mybest, d));
+            if ((threadIdx.x & 31) == 0) sbest[threadIdx.x >> 5] = mybest;
+            __syncthreads();
+            for (int w = 0; w < EDT_NT / 32; ++w) mybest = max(mybest, sbest[w]);
+            if (threadIdx.x == 0 && mybest > *reinterpret_cast<volatile unsigned long long*>(&best[b])) atomicMax(&best[b], mybest);
         }
     }
+}
+
+// rows are visited in the order (i * stride) mod H: stride ~ 0.618 H, coprime with H
+static int edt_row_stride(int H) {
+    auto gcd = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
+    int s = (int)(H * 0.6180339887);
+    if (s < 1) s = 1;
+    while (gcd(s, H) != 1) ++s;
+    return s % H ? s % H : 1;
+}
+static dim3 edt_row_grid(int n, int H) {
+    int per_frame = (148 * 8 * 2 + n - 1) / n;     // ~two waves of 8 CTAs per SM over the whole batch
+    if (per_frame > H) per_frame = H;
+    if (per_frame < 1) per_frame = 1;
+    return dim3(n, per_frame);
 }
 
 __global__ void edt_argmax_out_kernel(const unsigned long long* best, int32_t* argmax, int n) {
@@ -499,7 +579,8 @@ int lg_run_edt_union(lg_context* c, const int16_t* labels, int n, cudaStream_t s
     edt_col_kernel<<<dim3((c->W + 127) / 128, n), 128, 0, st>>>(src, c->edt_g, c->H, c->W, c->P);
     LG_LAUNCH_CHECK();
     lg_mark(c, LG_M_EDT_COL, st);
-    edt_row_kernel<<<dim3(c->H, n), EDT_NT, c->W * sizeof(unsigned), st>>>(c->edt_g, nullptr, c->edt_best, c->H, c->W, c->P);
+    edt_row_kernel<<<edt_row_grid(n, c->H), EDT_NT, c->W * sizeof(unsigned), st>>>(c->edt_g, nullptr, c->edt_best, c->H, c->W, c->P,
+                                                                                   edt_row_stride(c->H));
     LG_LAUNCH_CHECK();
     lg_mark(c, LG_M_EDT_ROW, st);
     return LG_OK;
@@ -514,7 +595,7 @@ int lg_run_stage1(lg_context* c, const int16_t* labels, const float* depth, int 
     lg_mark(c, LG_M_STATS, st);
     leaf_offsets_kernel<<<(n + 63) / 64, 64, 0, st>>>(*c, n);
     LG_LAUNCH_CHECK();
-    leaf_scatter_kernel<<<dim3(tiles, n), ST_NT, 0, st>>>(*c, labels, depth);
+    leaf_scatter_kernel<<<dim3(tiles, n), ST_NT, c->L * sizeof(unsigned), st>>>(*c, labels, depth);
     LG_LAUNCH_CHECK();
     lg_mark(c, LG_M_SCATTER, st);
     leaf_median_kernel<<<dim3(c->L, n), MED_NT, 0, st>>>(*c);
@@ -541,7 +622,8 @@ extern "C" int lg_edt_squared(lg_context* c, const uint8_t* mask, int n, uint32_
     EdtSrc src{nullptr, mask};
     edt_col_kernel<<<dim3((c->W + 127) / 128, n), 128, 0, st>>>(src, c->edt_g, c->H, c->W, c->P);
     LG_LAUNCH_CHECK();
-    edt_row_kernel<<<dim3(c->H, n), EDT_NT, c->W * sizeof(unsigned), st>>>(c->edt_g, d2, c->edt_best, c->H, c->W, c->P);
+    edt_row_kernel<<<edt_row_grid(n, c->H), EDT_NT, c->W * sizeof(unsigned), st>>>(c->edt_g, d2, c->edt_best, c->H, c->W, c->P,
+                                                                                   edt_row_stride(c->H));
     LG_LAUNCH_CHECK();
     if (argmax) {
         edt_argmax_out_kernel<<<(n + 63) / 64, 64, 0, st>>>(c->edt_best, argmax, n);
