@@ -34,7 +34,7 @@ struct ChamferArgs {
 // The fetches of row ly + 1 + D are issued D iterations before their values are stored to shared memory, so the
 // global-memory latency of the row stream is hidden behind D row steps instead of being paid once per row.
 template <int LPT, int D>
-__global__ void __launch_bounds__(CH_NT) chamfer_kernel(ChamferArgs A) {
+__global__ void __launch_bounds__(CH_NT, LPT <= 3 ? 2 : 1) chamfer_kernel(ChamferArgs A) {
     extern __shared__ int smem[];
     __shared__ int wtot[2][CH_NT / 32];
     __shared__ unsigned smax[CH_NT / 32];
@@ -62,6 +62,14 @@ __global__ void __launch_bounds__(CH_NT) chamfer_kernel(ChamferArgs A) {
     const int wpad = w + 4;
     const int ipt = (w + CH_NT - 1) / CH_NT;
     const bool invert = ((A.invert_base ^ var) & 1) != 0;
+    // Rows above the first source row stay at the sentinel in the forward sweep; when the leaf's bounding box is
+    // known (pipeline mode) the outside transform starts its forward sweep there and the backward sweep reads
+    // the sentinel instead of the (unwritten) forward rows.
+    int fwd_first = 0;
+    if (A.rect_mode && var != 0 && invert) {
+        const LgRegion r = A.region[b];
+        if (r.ok) fwd_first = min(max(r.y0, 0), h - 1);
+    }
     int* ring = smem;              // 3 rows of wpad ints
     int* sbuf = smem + 3 * wpad;   // 2 rows of w ints: sources (pass 0) or forward values (pass 1)
     const size_t fo = (size_t)b * A.P;
@@ -72,42 +80,53 @@ __global__ void __launch_bounds__(CH_NT) chamfer_kernel(ChamferArgs A) {
 
     for (int pass = 0; pass < 2; ++pass) {
         const bool flip = pass == 1;
-        auto phys = [&](int lx, int ly) -> size_t {
-            int x = flip ? (rx1 - 1 - lx) : (rx0 + lx);
-            int y = flip ? (ry1 - 1 - ly) : (ry0 + ly);
-            return (size_t)y * W + x;
-        };
-        auto fetch = [&](int ly, int* dst) {       // global -> registers, all loads issued back to back
+        const int row_first = flip ? 0 : fwd_first;             // first logical row of this sweep
+        const int fwd_rows_valid = h - fwd_first;               // backward sweep: logical rows < this were written
+        int xcol[LPT];                                          // physical column of this thread's i-th element
+#pragma unroll
+        for (int i = 0; i < LPT; ++i) xcol[i] = flip ? (rx1 - 1 - (tid + i * CH_NT)) : (rx0 + tid + i * CH_NT);
+        auto rowoff = [&](int ly) -> size_t { return (size_t)(flip ? (ry1 - 1 - ly) : (ry0 + ly)) * W; };
+        // fetch only issues the loads (raw label / mask / forward value); nothing may consume them here, or the
+        // thread would wait for the memory round trip in every row.  commit() interprets them D rows later.
+        auto fetch = [&](int ly, int* dst) {
+            const bool row_ok = ly < h && !(flip && ly >= fwd_rows_valid);
+            const size_t ro = row_ok ? rowoff(ly) : 0;
 #pragma unroll
             for (int i = 0; i < LPT; ++i) {
-                const int lx = tid + i * CH_NT;
                 int v = 0;
-                if (lx < w && ly < h) {
-                    const size_t p = phys(lx, ly);
-                    if (pass == 0) v = (A.src.at(fo, p, id) != invert) ? 1 : 0;   // 0 = source pixel
-                    else v = fwd[p];
+                if (row_ok && tid + i * CH_NT < w) {
+                    const size_t p = fo + ro + xcol[i];
+                    if (pass == 0) v = A.src.labels ? (int)A.src.labels[p] : (int)A.src.mask[p];
+                    else v = fwd[p - fo];
                 }
                 dst[i] = v;
             }
         };
-        auto commit = [&](const int* srcv, int* dst) {   // registers -> shared row
-#pragma unroll
-            for (int i = 0; i < LPT; ++i) {
-                const int lx = tid + i * CH_NT;
-                if (lx < w) dst[lx] = srcv[i];
-            }
-        };
-        auto store_row = [&](int ly, const int* row) {   // row has the +2 border offset
+        auto commit = [&](int ly, const int* srcv, int* dst) {   // registers -> shared row
+            const bool unwritten = flip && ly >= fwd_rows_valid;
 #pragma unroll
             for (int i = 0; i < LPT; ++i) {
                 const int lx = tid + i * CH_NT;
                 if (lx < w) {
-                    int t = row[lx + 2];
-                    size_t p = phys(lx, ly);
+                    int v = srcv[i];
+                    if (pass == 0) v = ((A.src.labels ? (v == id) : (v != 0)) != invert) ? 1 : 0;   // 0 = source pixel
+                    else if (unwritten) v = LG_CH_INF;
+                    dst[lx] = v;
+                }
+            }
+        };
+        auto store_row = [&](int ly, const int* row) {   // row has the +2 border offset
+            const size_t ro = rowoff(ly);
+#pragma unroll
+            for (int i = 0; i < LPT; ++i) {
+                const int lx = tid + i * CH_NT;
+                if (lx < w) {
+                    const int t = row[lx + 2];
+                    const size_t p = ro + xcol[i];
                     if (pass == 0) {
                         fwd[p] = t;
                     } else {
-                        unsigned q = (t >= LG_CH_INF) ? LG_CH_DIST_MAX : (unsigned)t;
+                        const unsigned q = (t >= LG_CH_INF) ? LG_CH_DIST_MAX : (unsigned)t;
                         my_max = max(my_max, q);
                         if (oq) oq[p] = q;
                         if (of) of[p] = __fmul_rn((float)q, 1.0f / 65536.0f);
@@ -119,13 +138,14 @@ __global__ void __launch_bounds__(CH_NT) chamfer_kernel(ChamferArgs A) {
         for (int i = tid; i < 3 * wpad; i += CH_NT) ring[i] = LG_CH_INF;
         {
             int first[LPT];
-            fetch(0, first);
+            fetch(row_first, first);
 #pragma unroll
-            for (int d = 1; d <= D; ++d) fetch(d, pre[d % D]);
-            commit(first, sbuf);
+            for (int d = 1; d <= D; ++d) fetch(row_first + d, pre[d % D]);
+            commit(row_first, first, sbuf + (row_first & 1) * w);
         }
         __syncthreads();
-        for (int ly0 = 0; ly0 < h; ly0 += D) {
+        const int xb = tid * ipt;
+        for (int ly0 = row_first; ly0 < h; ly0 += D) {
 #pragma unroll
             for (int dd = 0; dd < D; ++dd) {
                 const int ly = ly0 + dd;
@@ -134,21 +154,26 @@ __global__ void __launch_bounds__(CH_NT) chamfer_kernel(ChamferArgs A) {
                 const int* p1 = ring + ((ly + 2) % 3) * wpad;
                 const int* p2 = ring + ((ly + 1) % 3) * wpad;
                 const int* sb = sbuf + (ly & 1) * w;
-                if (ly + 1 < h) commit(pre[(dd + 1) % D], sbuf + ((ly + 1) & 1) * w);
+                if (ly + 1 < h) commit(ly + 1, pre[(dd + 1) % D], sbuf + ((ly + 1) & 1) * w);
                 fetch(ly + 1 + D, pre[(dd + 1) % D]);
-                if (ly > 0) store_row(ly - 1, p1);
-                const int xb = tid * ipt;
-                int pv[CH_MAXI];
+                if (ly > row_first) store_row(ly - 1, p1);
+                // the thread's ipt consecutive pixels share their 5x5 neighbourhood loads
+                int a1[LPT + 4], a2[LPT + 2];
+#pragma unroll
+                for (int j = 0; j < LPT + 4; ++j) { const int xx = xb + j; a1[j] = xx < wpad ? p1[xx] : LG_CH_INF; }
+#pragma unroll
+                for (int j = 0; j < LPT + 2; ++j) { const int xx = xb + 1 + j; a2[j] = xx < wpad ? p2[xx] : LG_CH_INF; }
+                int pv[LPT];
                 int run = 0x7FFFFFFF;
 #pragma unroll
-                for (int i = 0; i < CH_MAXI; ++i) {
+                for (int i = 0; i < LPT; ++i) {
                     const int x = xb + i;
-                    if (i < LPT && i < ipt && x < w) {
+                    if (i < ipt && x < w) {
                         const int s = sb[x];
-                        int m = min(p2[x + 1], p2[x + 3]) + LG_CH_C;
-                        m = min(m, min(p1[x], p1[x + 4]) + LG_CH_C);
-                        m = min(m, min(p1[x + 1], p1[x + 3]) + LG_CH_B);
-                        m = min(m, p1[x + 2] + LG_CH_A);
+                        int m = min(a2[i], a2[i + 2]) + LG_CH_C;
+                        m = min(m, min(a1[i], a1[i + 4]) + LG_CH_C);
+                        m = min(m, min(a1[i + 1], a1[i + 3]) + LG_CH_B);
+                        m = min(m, a1[i + 2] + LG_CH_A);
                         int u;
                         if (pass == 0) u = s ? min(m, LG_CH_INF) : 0;
                         else u = min(s, m);
@@ -166,11 +191,16 @@ __global__ void __launch_bounds__(CH_NT) chamfer_kernel(ChamferArgs A) {
                 if (lane == 0) excl = 0x7FFFFFFF;
                 if (lane == 31) wtot[ly & 1][warp] = incl;
                 __syncthreads();
-                for (int k = 0; k < warp; ++k) excl = min(excl, wtot[ly & 1][k]);
+                {   // minimum over the preceding warps: one shuffle reduction instead of a serial chain
+                    int wv = (lane < warp && lane < CH_NT / 32) ? wtot[ly & 1][lane] : 0x7FFFFFFF;
 #pragma unroll
-                for (int i = 0; i < CH_MAXI; ++i) {
+                    for (int d = 16; d > 0; d >>= 1) wv = min(wv, __shfl_xor_sync(0xFFFFFFFFu, wv, d));
+                    excl = min(excl, wv);
+                }
+#pragma unroll
+                for (int i = 0; i < LPT; ++i) {
                     const int x = xb + i;
-                    if (i < LPT && i < ipt && x < w) {
+                    if (i < ipt && x < w) {
                         int t = min(pv[i], excl);
                         // t can only stay at the sentinel when nothing finite precedes x
                         t = (t > LG_CH_INF) ? LG_CH_INF : min(t + LG_CH_A * x, LG_CH_INF);

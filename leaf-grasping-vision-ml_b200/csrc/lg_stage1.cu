@@ -326,18 +326,32 @@ __global__ void edt_col_kernel(EdtSrc src, uint16_t* __restrict__ g, int H, int 
     if (x >= W) return;
     const size_t fo = (size_t)blockIdx.y * P;
     uint16_t* gp = g + fo;
+    constexpr int U = 8;    // rows whose loads are in flight together (the sweep itself is sequential)
     unsigned d = 0xFFFFu;
-    for (int y = 0; y < H; ++y) {
-        size_t i = (size_t)y * W + x;
-        d = src.is_source(fo + i) ? 0u : min(d + 1u, 0xFFFFu);
-        gp[i] = (uint16_t)d;
+    for (int y0 = 0; y0 < H; y0 += U) {
+        bool srcv[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) srcv[k] = (y0 + k < H) ? src.is_source(fo + (size_t)(y0 + k) * W + x) : false;
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            if (y0 + k < H) {
+                d = srcv[k] ? 0u : min(d + 1u, 0xFFFFu);
+                gp[(size_t)(y0 + k) * W + x] = (uint16_t)d;
+            }
+        }
     }
     d = 0xFFFFu;
-    for (int y = H - 1; y >= 0; --y) {
-        size_t i = (size_t)y * W + x;
-        unsigned cur = gp[i];
-        d = min(cur, min(d + 1u, 0xFFFFu));
-        gp[i] = (uint16_t)d;
+    for (int y0 = H - 1; y0 >= 0; y0 -= U) {
+        unsigned cur[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) cur[k] = (y0 - k >= 0) ? gp[(size_t)(y0 - k) * W + x] : 0xFFFFu;
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            if (y0 - k >= 0) {
+                d = min(cur[k], min(d + 1u, 0xFFFFu));
+                gp[(size_t)(y0 - k) * W + x] = (uint16_t)d;
+            }
+        }
     }
 }
 
@@ -353,7 +367,7 @@ constexpr int EDT_NT = 256;
 // from all over the frame early, and every CTA handles several rows to profit from it.
 __global__ void __launch_bounds__(EDT_NT) edt_row_kernel(const uint16_t* __restrict__ g, uint32_t* __restrict__ d2out,
                                                           unsigned long long* __restrict__ best, int H, int W, size_t P,
-                                                          int row_stride) {
+                                                          int row_stride, int yi_begin, int yi_end) {
     extern __shared__ unsigned srow[];   // g squared, 0xFFFFFFFF = no source in that column
     __shared__ unsigned long long sbest[EDT_NT / 32];
     __shared__ unsigned s_lb;
@@ -361,7 +375,7 @@ __global__ void __launch_bounds__(EDT_NT) edt_row_kernel(const uint16_t* __restr
     const int b = blockIdx.x;
     const bool prune = (d2out == nullptr) && (best != nullptr);
     unsigned long long mybest = 0;
-    for (int yi = blockIdx.y; yi < H; yi += gridDim.y) {
+    for (int yi = yi_begin + blockIdx.y; yi < yi_end; yi += gridDim.y) {
         const int y = (int)(((long long)yi * row_stride) % H);
         const uint16_t* gp = g + (size_t)b * P + (size_t)y * W;
         __syncthreads();                 // previous row's readers of srow / s_lb are done
@@ -388,6 +402,16 @@ __global__ void __launch_bounds__(EDT_NT) edt_row_kernel(const uint16_t* __restr
             for (int x = threadIdx.x; x < W; x += EDT_NT) {
                 unsigned bestd = srow[x];
                 if (bestd < lb) continue;
+                if (lb) {   // probes at doubling offsets: almost every pixel near a source drops below the bound here
+                    for (unsigned k = 1; k * k < bestd; k <<= 1) {
+                        const int xl = x - (int)k, xr = x + (int)k;
+                        if (xl < 0 && xr >= W) break;
+                        const unsigned kk = k * k;
+                        if (xl >= 0) { unsigned s = srow[xl]; if (s != 0xFFFFFFFFu) bestd = min(bestd, s + kk); }
+                        if (xr < W) { unsigned s = srow[xr]; if (s != 0xFFFFFFFFu) bestd = min(bestd, s + kk); }
+                    }
+                    if (bestd < lb) continue;
+                }
                 for (unsigned k = 1; k * k < bestd; ++k) {
                     int xl = x - (int)k, xr = x + (int)k;
                     if (xl < 0 && xr >= W) break;
@@ -574,14 +598,28 @@ __global__ void select_leaf_kernel(lg_context c, lg_camera cam, int32_t* leaf_ou
 
 }  // namespace
 
+// row pass for n frames; d2 == nullptr: arg-max only (pruned search, seeded by a few well spread rows)
+static int run_edt_rows(lg_context* c, int n, uint32_t* d2, cudaStream_t st) {
+    const int stride = edt_row_stride(c->H);
+    const size_t sm = c->W * sizeof(unsigned);
+    int seed = 0;
+    if (!d2 && c->H >= 64) {
+        seed = 16;
+        edt_row_kernel<<<dim3(n, seed), EDT_NT, sm, st>>>(c->edt_g, nullptr, c->edt_best, c->H, c->W, c->P, stride, 0, seed);
+        LG_LAUNCH_CHECK();
+    }
+    edt_row_kernel<<<edt_row_grid(n, c->H), EDT_NT, sm, st>>>(c->edt_g, d2, c->edt_best, c->H, c->W, c->P, stride, seed, c->H);
+    LG_LAUNCH_CHECK();
+    return LG_OK;
+}
+
 int lg_run_edt_union(lg_context* c, const int16_t* labels, int n, cudaStream_t st) {
     EdtSrc src{labels, nullptr};
     edt_col_kernel<<<dim3((c->W + 127) / 128, n), 128, 0, st>>>(src, c->edt_g, c->H, c->W, c->P);
     LG_LAUNCH_CHECK();
     lg_mark(c, LG_M_EDT_COL, st);
-    edt_row_kernel<<<edt_row_grid(n, c->H), EDT_NT, c->W * sizeof(unsigned), st>>>(c->edt_g, nullptr, c->edt_best, c->H, c->W, c->P,
-                                                                                   edt_row_stride(c->H));
-    LG_LAUNCH_CHECK();
+    int rc = run_edt_rows(c, n, nullptr, st);
+    if (rc) return rc;
     lg_mark(c, LG_M_EDT_ROW, st);
     return LG_OK;
 }
@@ -622,9 +660,8 @@ extern "C" int lg_edt_squared(lg_context* c, const uint8_t* mask, int n, uint32_
     EdtSrc src{nullptr, mask};
     edt_col_kernel<<<dim3((c->W + 127) / 128, n), 128, 0, st>>>(src, c->edt_g, c->H, c->W, c->P);
     LG_LAUNCH_CHECK();
-    edt_row_kernel<<<edt_row_grid(n, c->H), EDT_NT, c->W * sizeof(unsigned), st>>>(c->edt_g, d2, c->edt_best, c->H, c->W, c->P,
-                                                                                   edt_row_stride(c->H));
-    LG_LAUNCH_CHECK();
+    int rc = run_edt_rows(c, n, d2, st);
+    if (rc) return rc;
     if (argmax) {
         edt_argmax_out_kernel<<<(n + 63) / 64, 64, 0, st>>>(c->edt_best, argmax, n);
         LG_LAUNCH_CHECK();

@@ -170,10 +170,12 @@ class GraspEngine:
                                                   _stream()), "lg_chamfer_transform")
         return dist, q16, mx
 
-    def edt_squared(self, mask):
+    def edt_squared(self, mask, argmax_only: bool = False):
+        """Exact squared EDT and its first arg-max; argmax_only=True takes the pruned search the leaf-selection
+        stage uses (no field is written) and returns (None, argmax)."""
         mask = self._frames(mask, torch.uint8, "mask")
         n = mask.shape[0]
-        d2 = torch.empty(n, self.H, self.W, dtype=torch.int32, device=self.device)
+        d2 = None if argmax_only else torch.empty(n, self.H, self.W, dtype=torch.int32, device=self.device)
         am = torch.empty(n, dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):
             N.check(self.lib.lg_edt_squared(self._ctx, _ptr(mask), n, _ptr(d2), _ptr(am), _stream()), "lg_edt_squared")

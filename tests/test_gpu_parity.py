@@ -98,6 +98,25 @@ def test_edt_squared_exact(shape):
     eng.close()
 
 
+@pytest.mark.parametrize("shape,frames", [((70, 90), 5), ((360, 480), 12), ((1080, 1440), 40)])
+def test_edt_argmax_pruned_search(shape, frames):
+    """The arg-max-only path (rows pruned against the running frame maximum) returns the first maximum of the
+    exact field, for any scheduling: checked on batches large enough that every CTA walks several rows."""
+    H, W = shape
+    rng = np.random.default_rng(3 * H + W)
+    masks = np.stack([1 - _blobs(rng, H, W, 1 + k % 7) for k in range(frames)])
+    masks[0] = 1
+    masks[0, H // 3, W // 5] = 0          # a single source pixel: the maximum sits in a corner
+    eng = _engine(frames, H, W, 2)
+    for _ in range(2):
+        _, am = eng.edt_squared(torch.from_numpy(masks), argmax_only=True)
+        am = am.cpu().numpy()
+        for k in range(frames):
+            if (masks[k] == 0).any():
+                assert am[k] == int(O.edt_squared(masks[k]).argmax()), f"frame {k}"
+    eng.close()
+
+
 # ------------------------------------------------------------------------------------------------------
 # stage 1
 # ------------------------------------------------------------------------------------------------------
