@@ -87,6 +87,7 @@ extern "C" int lg_create(lg_context** out, int max_frames, int height, int width
     auto A = [&](auto pp, size_t count) { if (!rc) rc = dev_alloc(c, pp, count); };
     A(&c->cnt, B * L); A(&c->sx, B * L); A(&c->sy, B * L); A(&c->sdep, B * L); A(&c->sdist, B * L);
     A(&c->bx0, B * L); A(&c->bx1, B * L); A(&c->by0, B * L); A(&c->by1, B * L); A(&c->border, B * L);
+    A(&c->kmin, B * L); A(&c->kmax, B * L); A(&c->ray_tab, P);
     A(&c->first_leaf, B); A(&c->seg_off, B * (L + 1)); A(&c->seg_cur, B * L); A(&c->seg, B * P); A(&c->median, B * L);
     A(&c->edt_g, B * P); A(&c->edt_best, B); A(&c->leaf_id, B); A(&c->records, B * L); A(&c->status, B); A(&c->region, B);
     A(&c->dt_fwd, 2 * B * P); A(&c->di, B * P); A(&c->dt_max, B * 2);
@@ -105,8 +106,14 @@ extern "C" int lg_create(lg_context** out, int max_frames, int height, int width
     c->cnn_act_bytes = (size_t)c->cnn_cap * 32 * 32 * 64 * sizeof(float);
     if (!rc) { rc = dev_alloc(c, (unsigned char**)&c->cnn_act0, c->cnn_act_bytes); }
     if (!rc) { rc = dev_alloc(c, (unsigned char**)&c->cnn_act1, c->cnn_act_bytes); }
-    A(&c->in_labels, B * P); A(&c->in_depth, B * P);
+    A(&c->in_labels, B * P); A(&c->in_depth, B * P); A(&c->results_all, B);
     if (rc) { lg_destroy(c); return rc; }
+    {
+        cudaError_t e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+        for (int i = 0; i < LG_MAX_HOST_CHUNKS && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->copy_ev[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->copy_gate, cudaEventDisableTiming);
+        if (e != cudaSuccess) { lg_set_error("lg_create: %s", cudaGetErrorString(e)); lg_destroy(c); return LG_E_CUDA; }
+    }
     memcpy(c->gauss, kGaussBits, sizeof(kGaussBits));
     ellipse_rows(LG_SE_STEM, c->se30_a, c->se30_b);
     ellipse_rows(LG_SE_PRE, c->se31_a, c->se31_b);
@@ -120,14 +127,20 @@ extern "C" int lg_create(lg_context** out, int max_frames, int height, int width
 
 extern "C" void lg_destroy(lg_context* c) {
     if (!c) return;
-    void* ptrs[] = {c->cnt, c->sx, c->sy, c->sdep, c->sdist, c->bx0, c->bx1, c->by0, c->by1, c->border, c->first_leaf,
+    void* ptrs[] = {c->kmin, c->kmax, c->ray_tab, c->cnt, c->sx, c->sy, c->sdep, c->sdist, c->bx0, c->bx1, c->by0, c->by1, c->border, c->first_leaf,
                     c->seg_off, c->seg_cur, c->seg, c->median, c->edt_g, c->edt_best, c->leaf_id, c->records, c->status,
                     c->region, c->dt_fwd, c->di, c->dt_max, c->bits, c->run_x0, c->run_x1, c->run_y, c->run_parent,
                     c->row_first, c->hull, c->orient, c->m_sdf, c->m_app, c->m_acc, c->m_trad, c->m_flat, c->m_stem,
                     c->m_valid, c->list_key, c->list_idx, c->list_n, c->patches, c->logits, c->results, c->cnn_act0,
-                    c->cnn_act1, c->in_labels, c->in_depth, c->cnn.blob, c->cnn.bf16_blob};
+                    c->cnn_act1, c->in_labels, c->in_depth, c->results_all, c->cnn.blob, c->cnn.bf16_blob};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    for (int i = 0; i < LG_MAX_HOST_CHUNKS; ++i)
+        if (c->copy_ev[i]) cudaEventDestroy(c->copy_ev[i]);
+    if (c->copy_gate) cudaEventDestroy(c->copy_gate);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (int i = 0; i < LG_PROF_MARKS; ++i)
+        if (c->prof_ev[i]) cudaEventDestroy(c->prof_ev[i]);
     delete c;
 }
 
@@ -204,13 +217,29 @@ extern "C" int lg_process_batch(lg_context* c, const int16_t* labels, const floa
 extern "C" int lg_process_batch_host(lg_context* c, const int16_t* labels_host, const float* depth_host, int frames,
                                      const lg_camera* cam, lg_frame_result* results_host, int use_bf16_cnn, void* stream) {
     TRY(check_batch(c, labels_host, depth_host, frames));
-    if (!results_host) return LG_E_ARG;
+    if (!results_host || !cam) return LG_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t n = (size_t)frames * c->P;
-    LG_CUDA(cudaMemcpyAsync(c->in_labels, labels_host, n * sizeof(int16_t), cudaMemcpyHostToDevice, st));
-    LG_CUDA(cudaMemcpyAsync(c->in_depth, depth_host, n * sizeof(float), cudaMemcpyHostToDevice, st));
-    TRY(lg_process_batch(c, c->in_labels, c->in_depth, frames, cam, c->results, use_bf16_cnn, stream));
-    LG_CUDA(cudaMemcpyAsync(results_host, c->results, sizeof(lg_frame_result) * frames, cudaMemcpyDeviceToHost, st));
+    // Host-to-device copies run chunk by chunk on their own stream; chunk k is processed on the caller's stream
+    // as soon as it has landed, while chunk k+1 is still crossing PCIe (the copies are the longer leg).
+    int chunk = LG_HOST_CHUNK_FRAMES;
+    while ((frames + chunk - 1) / chunk > LG_MAX_HOST_CHUNKS) chunk *= 2;
+    const int n_chunks = (frames + chunk - 1) / chunk;
+    LG_CUDA(cudaEventRecord(c->copy_gate, st));                 // staging is free once earlier work on st is done
+    LG_CUDA(cudaStreamWaitEvent(c->copy_stream, c->copy_gate, 0));
+    for (int k = 0; k < n_chunks; ++k) {
+        const size_t off = (size_t)k * chunk * c->P;
+        const size_t n = (size_t)(frames - k * chunk < chunk ? frames - k * chunk : chunk) * c->P;
+        LG_CUDA(cudaMemcpyAsync(c->in_labels + off, labels_host + off, n * sizeof(int16_t), cudaMemcpyHostToDevice, c->copy_stream));
+        LG_CUDA(cudaMemcpyAsync(c->in_depth + off, depth_host + off, n * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
+        LG_CUDA(cudaEventRecord(c->copy_ev[k], c->copy_stream));
+    }
+    for (int k = 0; k < n_chunks; ++k) {
+        const size_t off = (size_t)k * chunk * c->P;
+        const int m = frames - k * chunk < chunk ? frames - k * chunk : chunk;
+        LG_CUDA(cudaStreamWaitEvent(st, c->copy_ev[k], 0));
+        TRY(lg_process_batch(c, c->in_labels + off, c->in_depth + off, m, cam, c->results_all + (size_t)k * chunk, use_bf16_cnn, stream));
+    }
+    LG_CUDA(cudaMemcpyAsync(results_host, c->results_all, sizeof(lg_frame_result) * frames, cudaMemcpyDeviceToHost, st));
     LG_CUDA(cudaStreamSynchronize(st));
     return LG_OK;
 }

@@ -21,6 +21,8 @@
 #define LG_SE_STEM 30
 #define LG_SE_PRE 31
 #define LG_PROF_MARKS 16
+#define LG_MAX_HOST_CHUNKS 64
+#define LG_HOST_CHUNK_FRAMES 32
 enum LgMark { LG_M_START = 0, LG_M_STATS, LG_M_SCATTER, LG_M_MEDIAN, LG_M_EDT_COL, LG_M_EDT_ROW, LG_M_SELECT, LG_M_CHAMFER,
               LG_M_ORIENT, LG_M_SCORE, LG_M_NMS, LG_M_GATHER, LG_M_CNN, LG_M_FUSE, LG_M_COUNT };
 
@@ -67,6 +69,10 @@ struct lg_context {
     uint32_t* cnt;
     unsigned long long *sx, *sy, *sdep, *sdist;
     uint32_t *bx0, *bx1, *by0, *by1, *border;
+    uint32_t *kmin, *kmax;         // [B][L] smallest / largest depth key of the label (median search range)
+    unsigned long long* ray_tab;   // [P] viewing-ray length per unit depth, 2^36 fixed point, for ray_cam
+    lg_camera ray_cam;
+    int ray_valid;
     uint32_t* first_leaf;          // [B] flat index of the first pixel with label >= 1
     uint32_t* seg_off;             // [B][L+1]
     uint32_t* seg_cur;             // [B][L]
@@ -105,9 +111,14 @@ struct lg_context {
     size_t cnn_act_bytes;
     int cnn_cap;                             // patches the activation scratch holds
     LgCnn cnn;
-    // staging for the *_host entry point
+    // staging for the *_host entry point: inputs are copied chunk by chunk on copy_stream while the
+    // previous chunk is processed on the caller's stream
     int16_t* in_labels;
     float* in_depth;
+    lg_frame_result* results_all;            // [B] results of all chunks of one host call
+    cudaStream_t copy_stream;
+    cudaEvent_t copy_ev[LG_MAX_HOST_CHUNKS];
+    cudaEvent_t copy_gate;                   // the caller's stream reached the start of this host call
     // optional per-stage timing (lg_set_profiling): events recorded on the launch stream
     int prof_on;
     cudaEvent_t prof_ev[LG_PROF_MARKS];

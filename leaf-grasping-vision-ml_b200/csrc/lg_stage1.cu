@@ -24,15 +24,25 @@ constexpr double DEP_SCALE = 268435456.0;       // 2^28
 constexpr double DIST_SCALE = 68719476736.0;    // 2^36
 
 struct SmemLeaf {
-    unsigned cnt, sx, sy, bx0, bx1, by0, by1, border;
+    unsigned cnt, sx, sy, bx0, bx1, by0, by1, border, kmin, kmax;
     unsigned long long sdep, sdist;
 };
+
+__device__ __forceinline__ unsigned f2key(float f) {   // order-preserving float -> uint32 key
+    unsigned u = __float_as_uint(f);
+    return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float key2f(unsigned k) {
+    unsigned u = (k & 0x80000000u) ? (k ^ 0x80000000u) : ~k;
+    return __uint_as_float(u);
+}
 
 __global__ void clear_tables_kernel(lg_context c, int n) {
     size_t total = (size_t)n * c.L;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         c.cnt[i] = 0; c.sx[i] = 0; c.sy[i] = 0; c.sdep[i] = 0; c.sdist[i] = 0;
         c.bx0[i] = 0xFFFFFFFFu; c.by0[i] = 0xFFFFFFFFu; c.bx1[i] = 0; c.by1[i] = 0; c.border[i] = 0;
+        c.kmin[i] = 0xFFFFFFFFu; c.kmax[i] = 0;
         c.seg_cur[i] = 0;
     }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -40,8 +50,24 @@ __global__ void clear_tables_kernel(lg_context c, int n) {
     }
 }
 
+// ray_tab[y * W + x] = round(2^36 * sqrt(((x - cx)^2 + (y - cy)^2) / f^2 + 1)): the length of the viewing ray through
+// pixel (x, y) per unit depth (leaf_scorer.py:104-113 with X = md (x - cx) / f, Y = md (y - cy) / f, Z = md).  It depends
+// on the camera only, so it is built once per camera and read (L2-resident) by every frame.
+__global__ void ray_table_kernel(unsigned long long* __restrict__ tab, int H, int W, lg_camera cam) {
+    const size_t P = (size_t)H * W;
+    const double inv_f2 = 1.0 / (cam.f * cam.f);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (size_t)gridDim.x * blockDim.x) {
+        const double ddx = (double)(i % W) - cam.cx, ddy = (double)(i / W) - cam.cy;
+        const double sv = sqrt((ddx * ddx + ddy * ddy) * inv_f2 + 1.0);
+        tab[i] = (unsigned long long)__double2ll_rn(sv * DIST_SCALE);
+    }
+}
+
+// One pass over labels + depth.  Each thread owns ST_PX consecutive pixels.  A warp whose 256 pixels all carry the
+// same label (the common case) reduces its sums with REDUX and touches the CTA's shared-memory table once; mixed
+// warps fall back to one table update per run of equal labels.
 __global__ void __launch_bounds__(ST_NT) leaf_stats_kernel(lg_context c, const int16_t* __restrict__ labels,
-                                                            const float* __restrict__ depth, lg_camera cam) {
+                                                            const float* __restrict__ depth) {
     extern __shared__ SmemLeaf tab[];
     __shared__ unsigned s_first, s_bad;
     const int L = c.L, W = c.W, H = c.H;
@@ -50,20 +76,98 @@ __global__ void __launch_bounds__(ST_NT) leaf_stats_kernel(lg_context c, const i
     for (int l = threadIdx.x; l < L; l += ST_NT) {
         SmemLeaf z;
         z.cnt = 0; z.sx = 0; z.sy = 0; z.bx0 = 0xFFFFFFFFu; z.by0 = 0xFFFFFFFFu; z.bx1 = 0; z.by1 = 0;
-        z.border = 0; z.sdep = 0; z.sdist = 0;
+        z.border = 0; z.kmin = 0xFFFFFFFFu; z.kmax = 0; z.sdep = 0; z.sdist = 0;
         tab[l] = z;
     }
     if (threadIdx.x == 0) { s_first = 0xFFFFFFFFu; s_bad = 0; }
     __syncthreads();
 
     const size_t base = ((size_t)blockIdx.x * ST_NT + threadIdx.x) * ST_PX;
-    if (base < P) {
-        const int16_t* lp = labels + (size_t)b * P;
-        const float* dp = depth + (size_t)b * P;
-        int y = (int)(base / W), x = (int)(base % W);
-        const double inv_f2 = 1.0 / (cam.f * cam.f);
+    const int16_t* lp = labels + (size_t)b * P;
+    const float* dp = depth + (size_t)b * P;
+    const int npx = base < P ? (int)min((size_t)ST_PX, P - base) : 0;
+    int lab[ST_PX];
+    float val[ST_PX];
+    unsigned long long ray[ST_PX];
+    const bool vec = npx == ST_PX && ((reinterpret_cast<uintptr_t>(lp + base) | reinterpret_cast<uintptr_t>(dp + base)) & 15) == 0;
+    if (vec) {
+        const uint4 lv = *reinterpret_cast<const uint4*>(lp + base);
+        const unsigned w[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { lab[2 * k] = (int16_t)(w[k] & 0xFFFFu); lab[2 * k + 1] = (int16_t)(w[k] >> 16); }
+    } else {
+#pragma unroll
+        for (int k = 0; k < ST_PX; ++k) lab[k] = k < npx ? (int)lp[base + k] : -32768;
+    }
+    bool any_leaf = false, uni = npx == ST_PX;
+#pragma unroll
+    for (int k = 0; k < ST_PX; ++k) { any_leaf |= lab[k] > 0; uni &= lab[k] == lab[0]; }
+    if (any_leaf) {
+        if (vec) {
+            const float4 d0 = *reinterpret_cast<const float4*>(dp + base), d1 = *reinterpret_cast<const float4*>(dp + base + 4);
+            val[0] = d0.x; val[1] = d0.y; val[2] = d0.z; val[3] = d0.w; val[4] = d1.x; val[5] = d1.y; val[6] = d1.z; val[7] = d1.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < ST_PX; ++k) val[k] = k < npx ? dp[base + k] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < ST_PX; ++k) ray[k] = k < npx ? c.ray_tab[base + k] : 0ull;
+    } else {
+#pragma unroll
+        for (int k = 0; k < ST_PX; ++k) { val[k] = 0.f; ray[k] = 0ull; }
+    }
+    const int y0 = (int)(base / W), x0 = (int)(base % W);
+    const int l0 = lab[0];
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int l_first = __shfl_sync(FULL, l0, 0);      // outside the condition: every lane must take part in the shuffle
+    const bool warp_uni = __all_sync(FULL, uni && l0 == l_first && l0 >= 0 && l0 < L);
+    if (warp_uni) {
+        const int lane = threadIdx.x & 31;
+        if (l0 == 0) {
+            if (lane == 0) atomicAdd(&tab[0].cnt, 32u * ST_PX);
+        } else {
+            unsigned sx = 0, sy = 0, bx0 = 0xFFFFFFFFu, bx1 = 0, by0 = 0xFFFFFFFFu, by1 = 0, brd = 0, kmn = 0xFFFFFFFFu, kmx = 0;
+            long long rdep = 0;
+            unsigned long long rdist = 0;
+            int x = x0, y = y0;
+#pragma unroll
+            for (int k = 0; k < ST_PX; ++k) {
+                sx += x; sy += y;
+                bx0 = min(bx0, (unsigned)x); bx1 = max(bx1, (unsigned)x); by0 = min(by0, (unsigned)y); by1 = max(by1, (unsigned)y);
+                brd |= (x == 0) | (y == 0) | (x == W - 1) | (y == H - 1);
+                const double dd = fmin(fmax((double)val[k], -2048.0), 2048.0);
+                rdep += __double2ll_rn(dd * DEP_SCALE);
+                rdist += ray[k];
+                const unsigned key = f2key(val[k]);
+                kmn = min(kmn, key); kmx = max(kmx, key);
+                if (++x == W) { x = 0; ++y; }
+            }
+            sx = __reduce_add_sync(FULL, sx); sy = __reduce_add_sync(FULL, sy);
+            bx0 = __reduce_min_sync(FULL, bx0); bx1 = __reduce_max_sync(FULL, bx1);
+            by0 = __reduce_min_sync(FULL, by0); by1 = __reduce_max_sync(FULL, by1);
+            brd = __reduce_or_sync(FULL, brd);
+            kmn = __reduce_min_sync(FULL, kmn); kmx = __reduce_max_sync(FULL, kmx);
+            // 64-bit sums as (high part, low 24 bits): each half stays far below 2^31 over 32 lanes
+            const unsigned dep_lo = __reduce_add_sync(FULL, (unsigned)(rdep & 0xFFFFFF));
+            const int dep_hi = __reduce_add_sync(FULL, (int)(rdep >> 24));
+            const unsigned dist_lo = __reduce_add_sync(FULL, (unsigned)(rdist & 0xFFFFFF));
+            const unsigned dist_hi = __reduce_add_sync(FULL, (unsigned)(rdist >> 24));
+            if (lane == 0) {
+                SmemLeaf* t = &tab[l0];
+                atomicAdd(&t->cnt, 32u * ST_PX);
+                atomicAdd(&t->sx, sx); atomicAdd(&t->sy, sy);
+                atomicMin(&t->bx0, bx0); atomicMax(&t->bx1, bx1); atomicMin(&t->by0, by0); atomicMax(&t->by1, by1);
+                if (brd) atomicOr(&t->border, 1u);
+                atomicMin(&t->kmin, kmn); atomicMax(&t->kmax, kmx);
+                atomicAdd(&t->sdep, (unsigned long long)(((long long)dep_hi << 24) + (long long)dep_lo));
+                atomicAdd(&t->sdist, ((unsigned long long)dist_hi << 24) + dist_lo);
+                atomicMin(&s_first, (unsigned)base);
+            }
+        }
+    } else if (npx > 0) {
+        int x = x0, y = y0;
         int cur = -1;
-        unsigned rc = 0, rsx = 0, rsy = 0, rx0 = 0, rx1 = 0, ry0 = 0, ry1 = 0, rb = 0;
+        unsigned rc = 0, rsx = 0, rsy = 0, rx0 = 0, rx1 = 0, ry0 = 0, ry1 = 0, rb = 0, rkmn = 0xFFFFFFFFu, rkmx = 0;
         long long rdep = 0;
         unsigned long long rdist = 0;
         auto flush = [&]() {
@@ -75,6 +179,7 @@ __global__ void __launch_bounds__(ST_NT) leaf_stats_kernel(lg_context c, const i
                     atomicMin(&t->bx0, rx0); atomicMax(&t->bx1, rx1);
                     atomicMin(&t->by0, ry0); atomicMax(&t->by1, ry1);
                     if (rb) atomicOr(&t->border, 1u);
+                    atomicMin(&t->kmin, rkmn); atomicMax(&t->kmax, rkmx);
                     atomicAdd(&t->sdep, (unsigned long long)rdep);
                     atomicAdd(&t->sdist, rdist);
                 }
@@ -82,31 +187,31 @@ __global__ void __launch_bounds__(ST_NT) leaf_stats_kernel(lg_context c, const i
         };
 #pragma unroll
         for (int i = 0; i < ST_PX; ++i) {
-            size_t idx = base + i;
-            if (idx >= P) break;
-            int l = lp[idx];
-            if (l < 0 || l >= L) { s_bad = 1; l = -1; }
-            if (l != cur) {
-                flush();
-                cur = l; rc = 0; rsx = 0; rsy = 0; rx0 = x; rx1 = x; ry0 = y; ry1 = y; rb = 0; rdep = 0; rdist = 0;
-                if (l >= 1) atomicMin(&s_first, (unsigned)idx);
-            }
-            if (l >= 0) {
-                rc++;
-                if (l > 0) {
-                    rsx += x; rsy += y;
-                    rx0 = min(rx0, (unsigned)x); rx1 = max(rx1, (unsigned)x);
-                    ry0 = min(ry0, (unsigned)y); ry1 = max(ry1, (unsigned)y);
-                    rb |= (x == 0) | (y == 0) | (x == W - 1) | (y == H - 1);
-                    float d = dp[idx];
-                    double dd = fmin(fmax((double)d, -2048.0), 2048.0);
-                    rdep += __double2ll_rn(dd * DEP_SCALE);
-                    double ddx = (double)x - cam.cx, ddy = (double)y - cam.cy;
-                    double s = sqrt((ddx * ddx + ddy * ddy) * inv_f2 + 1.0);
-                    rdist += (unsigned long long)__double2ll_rn(s * DIST_SCALE);
+            if (i < npx) {
+                int l = lab[i];
+                if (l < 0 || l >= L) { s_bad = 1; l = -1; }
+                if (l != cur) {
+                    flush();
+                    cur = l; rc = 0; rsx = 0; rsy = 0; rx0 = x; rx1 = x; ry0 = y; ry1 = y; rb = 0; rdep = 0; rdist = 0;
+                    rkmn = 0xFFFFFFFFu; rkmx = 0;
+                    if (l >= 1) atomicMin(&s_first, (unsigned)(base + i));
                 }
+                if (l >= 0) {
+                    rc++;
+                    if (l > 0) {
+                        rsx += x; rsy += y;
+                        rx0 = min(rx0, (unsigned)x); rx1 = max(rx1, (unsigned)x);
+                        ry0 = min(ry0, (unsigned)y); ry1 = max(ry1, (unsigned)y);
+                        rb |= (x == 0) | (y == 0) | (x == W - 1) | (y == H - 1);
+                        const double dd = fmin(fmax((double)val[i], -2048.0), 2048.0);
+                        rdep += __double2ll_rn(dd * DEP_SCALE);
+                        rdist += ray[i];
+                        const unsigned key = f2key(val[i]);
+                        rkmn = min(rkmn, key); rkmx = max(rkmx, key);
+                    }
+                }
+                if (++x == W) { x = 0; ++y; }
             }
-            if (++x == W) { x = 0; ++y; }
         }
         flush();
     }
@@ -123,6 +228,7 @@ __global__ void __launch_bounds__(ST_NT) leaf_stats_kernel(lg_context c, const i
                 atomicAdd(&c.sdist[o], t.sdist);
                 atomicMin(&c.bx0[o], t.bx0); atomicMax(&c.bx1[o], t.bx1);
                 atomicMin(&c.by0[o], t.by0); atomicMax(&c.by1[o], t.by1);
+                atomicMin(&c.kmin[o], t.kmin); atomicMax(&c.kmax[o], t.kmax);
                 if (t.border) atomicOr(&c.border[o], 1u);
             }
         }
@@ -225,15 +331,6 @@ __global__ void __launch_bounds__(ST_NT) leaf_scatter_kernel(lg_context c, const
     }
 }
 
-__device__ __forceinline__ unsigned f2key(float f) {
-    unsigned u = __float_as_uint(f);
-    return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
-}
-__device__ __forceinline__ float key2f(unsigned k) {
-    unsigned u = (k & 0x80000000u) ? (k ^ 0x80000000u) : ~k;
-    return __uint_as_float(u);
-}
-
 template <int NT>
 __device__ __forceinline__ void block_sum3(unsigned& a, unsigned& b, unsigned& c, unsigned* sm) {
 #pragma unroll
@@ -252,14 +349,19 @@ __device__ __forceinline__ void block_sum3(unsigned& a, unsigned& b, unsigned& c
 }
 
 constexpr int MED_NT = 256;
-// np.median(depth[labels == l]) for every label of every frame (leaf_scorer.py:41-47):
-// radix selection, two key bits per pass, on the values grouped by leaf_scatter_kernel.
+constexpr int MED_CAP = 4096;    // candidate keys kept in shared memory once the search range is this small
+// np.median(depth[labels == l]) for every label of every frame (leaf_scorer.py:41-47): radix selection on the
+// values grouped by leaf_scatter_kernel, two key bits per pass.  The passes start at the first bit in which the
+// label's smallest and largest key differ (leaf_stats_kernel), and as soon as the surviving candidates fit in
+// shared memory they are compacted there, so only the first two or three passes stream the whole segment.
 __global__ void __launch_bounds__(MED_NT) leaf_median_kernel(lg_context c) {
     const int l = blockIdx.x, b = blockIdx.y, L = c.L;
     const uint32_t* cnt = c.cnt + (size_t)b * L;
     __shared__ unsigned sm[MED_NT / 32 * 3];
+    __shared__ unsigned s_keys[MED_CAP];
+    __shared__ unsigned s_n;
     __shared__ int s_bg;
-    if (threadIdx.x == 0) s_bg = background_id(cnt, L);
+    if (threadIdx.x == 0) { s_bg = background_id(cnt, L); s_n = 0; }
     __syncthreads();
     const unsigned n = cnt[l];
     if (n == 0 || l == s_bg) {
@@ -267,45 +369,96 @@ __global__ void __launch_bounds__(MED_NT) leaf_median_kernel(lg_context c) {
         return;
     }
     const float* v = c.seg + (size_t)b * c.P + c.seg_off[(size_t)b * (L + 1) + l];
-    unsigned k = (n & 1) ? n / 2 : n / 2 - 1;   // rank of the lower middle
-    unsigned prefix = 0, pmask = 0;
-    for (int shift = 30; shift >= 0; shift -= 2) {
-        unsigned c0 = 0, c1 = 0, c2 = 0;
-        for (unsigned i = threadIdx.x; i < n; i += MED_NT) {
-            unsigned key = f2key(v[i]);
-            if ((key & pmask) == prefix) {
-                unsigned d = (key >> shift) & 3u;
-                c0 += (d == 0); c1 += (d == 1); c2 += (d == 2);
+    const unsigned kmin = c.kmin[(size_t)b * L + l], kmax = c.kmax[(size_t)b * L + l];
+    const unsigned k_lo = (n & 1) ? n / 2 : n / 2 - 1;   // rank of the lower middle
+    unsigned klo;            // key of rank k_lo
+    unsigned below = 0;      // elements whose key is smaller than every current candidate
+    unsigned m = n;          // current candidates
+    bool in_smem = false;
+    unsigned set_below = 0, set_m = 0;   // the compacted set: its size and the number of elements below it
+    const int lane = threadIdx.x & 31;
+    auto compact = [&](unsigned prefix, unsigned pmask) {   // candidates (key & pmask) == prefix -> s_keys
+        for (unsigned i0 = 0; i0 < n; i0 += MED_NT) {
+            const unsigned i = i0 + threadIdx.x;
+            unsigned key = 0;
+            bool hit = false;
+            if (i < n) { key = f2key(v[i]); hit = (key & pmask) == prefix; }
+            const unsigned ball = __ballot_sync(0xFFFFFFFFu, hit);
+            if (ball) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(&s_n, __popc(ball));
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (hit) s_keys[base + __popc(ball & ((1u << lane) - 1u))] = key;
             }
         }
-        block_sum3<MED_NT>(c0, c1, c2, sm);
-        unsigned d;
-        if (k < c0) d = 0;
-        else if (k < c0 + c1) { d = 1; k -= c0; }
-        else if (k < c0 + c1 + c2) { d = 2; k -= c0 + c1; }
-        else { d = 3; k -= c0 + c1 + c2; }
-        prefix |= d << shift;
-        pmask |= 3u << shift;
+        __syncthreads();
+    };
+    if (kmin == kmax) {
+        klo = kmin;
+        below = 0; m = n;
+    } else {
+        const int top = 31 - __clz(kmin ^ kmax);          // highest differing bit
+        int shift = top & ~1;                              // the digit (shift+1, shift) contains it
+        unsigned pmask = shift >= 30 ? 0u : ~((4u << shift) - 1u);
+        unsigned prefix = kmin & pmask;
+        if (n <= MED_CAP) { compact(prefix, pmask); in_smem = true; set_below = 0; set_m = n; }
+        for (; shift >= 0; shift -= 2) {
+            unsigned c0 = 0, c1 = 0, c2 = 0;
+            if (in_smem) {
+                for (unsigned i = threadIdx.x; i < set_m; i += MED_NT) {
+                    const unsigned key = s_keys[i];
+                    if ((key & pmask) == prefix) {
+                        const unsigned d = (key >> shift) & 3u;
+                        c0 += (d == 0); c1 += (d == 1); c2 += (d == 2);
+                    }
+                }
+            } else {
+                for (unsigned i = threadIdx.x; i < n; i += MED_NT) {
+                    const unsigned key = f2key(v[i]);
+                    if ((key & pmask) == prefix) {
+                        const unsigned d = (key >> shift) & 3u;
+                        c0 += (d == 0); c1 += (d == 1); c2 += (d == 2);
+                    }
+                }
+            }
+            block_sum3<MED_NT>(c0, c1, c2, sm);
+            const unsigned kk = k_lo - below;
+            unsigned d;
+            if (kk < c0) { d = 0; m = c0; }
+            else if (kk < c0 + c1) { d = 1; below += c0; m = c1; }
+            else if (kk < c0 + c1 + c2) { d = 2; below += c0 + c1; m = c2; }
+            else { d = 3; below += c0 + c1 + c2; m = m - (c0 + c1 + c2); }
+            prefix |= d << shift;
+            pmask |= 3u << shift;
+            if (!in_smem && m <= MED_CAP && shift > 0) {
+                compact(prefix, pmask);
+                in_smem = true; set_below = below; set_m = m;
+            }
+        }
+        klo = prefix;
     }
-    const unsigned klo = prefix;
     float med = key2f(klo);
     if (!(n & 1)) {
-        // upper middle: same value if enough elements are <= it, else the smallest larger key
-        unsigned le = 0, dummy1 = 0, dummy2 = 0, mn = 0xFFFFFFFFu;
-        for (unsigned i = threadIdx.x; i < n; i += MED_NT) {
-            unsigned key = f2key(v[i]);
-            if (key <= klo) le++;
-            else mn = min(mn, key);
-        }
-        block_sum3<MED_NT>(le, dummy1, dummy2, sm);
+        // upper middle (rank k_lo + 1): klo again when enough elements are <= klo, else the smallest larger key
+        float hi;
+        if (below + m > k_lo + 1) {
+            hi = med;
+        } else {
+            unsigned mn = 0xFFFFFFFFu;
+            if (in_smem && k_lo + 1 < set_below + set_m) {
+                for (unsigned i = threadIdx.x; i < set_m; i += MED_NT) { const unsigned key = s_keys[i]; if (key > klo) mn = min(mn, key); }
+            } else {
+                for (unsigned i = threadIdx.x; i < n; i += MED_NT) { const unsigned key = f2key(v[i]); if (key > klo) mn = min(mn, key); }
+            }
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, d));
-        __syncthreads();
-        if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mn;
-        __syncthreads();
-        mn = 0xFFFFFFFFu;
-        for (int w = 0; w < MED_NT / 32; ++w) mn = min(mn, sm[w]);
-        float hi = (le > n / 2) ? med : key2f(mn);
+            for (int d = 16; d > 0; d >>= 1) mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, d));
+            __syncthreads();
+            if (lane == 0) sm[threadIdx.x >> 5] = mn;
+            __syncthreads();
+            mn = 0xFFFFFFFFu;
+            for (int w = 0; w < MED_NT / 32; ++w) mn = min(mn, sm[w]);
+            hi = key2f(mn);
+        }
         med = __fmul_rn(__fadd_rn(med, hi), 0.5f);   // float32 mean of the two middles
     }
     if (threadIdx.x == 0) c.median[(size_t)b * L + l] = med;
@@ -370,36 +523,80 @@ __global__ void __launch_bounds__(EDT_NT) edt_row_kernel(const uint16_t* __restr
                                                           int row_stride, int yi_begin, int yi_end) {
     extern __shared__ unsigned srow[];   // g squared, 0xFFFFFFFF = no source in that column
     __shared__ unsigned long long sbest[EDT_NT / 32];
-    __shared__ unsigned s_lb;
-    __shared__ int s_any;
+    __shared__ unsigned schunk[128];     // minimum of srow over each 32-column chunk (rows up to 4096 wide)
+    __shared__ unsigned s_lb;            // pruning bound of the current row
+    constexpr int MAXV = 16;             // row values per thread held in registers: rows up to 4096 wide
     const int b = blockIdx.x;
     const bool prune = (d2out == nullptr) && (best != nullptr);
-    unsigned long long mybest = 0;
+    unsigned long long mybest = 0;       // CTA-wide best so far (identical in every thread)
+    const int nv = (W + EDT_NT - 1) / EDT_NT;
+    // the next row's column distances are fetched while the current row is searched
+    unsigned short nxt[MAXV];
+    auto fetch = [&](int yi) {
+        if (yi < yi_end) {
+            const int y = (int)(((long long)yi * row_stride) % H);
+            const uint16_t* gp = g + (size_t)b * P + (size_t)y * W;
+#pragma unroll
+            for (int k = 0; k < MAXV; ++k) {
+                const int x = threadIdx.x + k * EDT_NT;
+                nxt[k] = (k < nv && x < W) ? gp[x] : (unsigned short)0xFFFFu;
+            }
+        }
+    };
+    fetch(yi_begin + blockIdx.y);
     for (int yi = yi_begin + blockIdx.y; yi < yi_end; yi += gridDim.y) {
         const int y = (int)(((long long)yi * row_stride) % H);
-        const uint16_t* gp = g + (size_t)b * P + (size_t)y * W;
-        __syncthreads();                 // previous row's readers of srow / s_lb are done
+        int any = 0;
+#pragma unroll
+        for (int k = 0; k < MAXV; ++k) {
+            const int x = threadIdx.x + k * EDT_NT;
+            if (k < nv && x < W) {
+                const unsigned v = nxt[k];
+                srow[x] = (v == 0xFFFFu) ? 0xFFFFFFFFu : v * v;
+                any |= (v != 0xFFFFu);
+            }
+        }
+        // one thread samples the frame's running maximum: the bound must be the same for the whole CTA (it steers
+        // barriers and warp shuffles below), and other CTAs raise best[b] concurrently
         if (threadIdx.x == 0) {
-            s_any = 0;
-            unsigned lb = 0;
+            unsigned v = 0;
             if (prune) {
                 const unsigned long long gb = *reinterpret_cast<volatile unsigned long long*>(&best[b]);
-                lb = (unsigned)(max(gb, mybest) >> 32);
+                v = (unsigned)(max(gb, mybest) >> 32);
             }
-            s_lb = lb;
+            s_lb = v;
         }
-        __syncthreads();
-        int any = 0;
-        for (int x = threadIdx.x; x < W; x += EDT_NT) {
-            unsigned v = gp[x];
-            srow[x] = (v == 0xFFFFu) ? 0xFFFFFFFFu : v * v;
-            any |= (v != 0xFFFFu);
-        }
-        if (any) s_any = 1;
-        __syncthreads();
+        any = __syncthreads_or(any);     // srow and s_lb complete; does the row see any source at all?
         const unsigned lb = s_lb;
-        if (s_any) {
-            for (int x = threadIdx.x; x < W; x += EDT_NT) {
+        fetch(yi + gridDim.y);
+        unsigned long long rowbest = 0;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int nchunks = (W + 31) >> 5;
+        if (any && lb) {   // minimum of every 32-column chunk: lets a warp discard a whole chunk at once
+            for (int j = warp; j < nchunks; j += EDT_NT / 32) {
+                const int x = (j << 5) + lane;
+                unsigned v = x < W ? srow[x] : 0xFFFFFFFFu;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) v = min(v, __shfl_xor_sync(0xFFFFFFFFu, v, d));
+                if (lane == 0) schunk[j] = v;
+            }
+            __syncthreads();
+        }
+        if (any) {
+            for (int j = warp; j < nchunks; j += EDT_NT / 32) {
+                if (lb) {
+                    // every pixel of chunk j is at most 31 + 32*dj columns away from the best column of chunk j +- dj
+                    unsigned long long ub = (unsigned long long)schunk[j] + 31ull * 31ull;
+                    for (int dj = 1; dj < nchunks; ++dj) {
+                        const unsigned long long off = (unsigned long long)(32 * dj + 31) * (32 * dj + 31);
+                        if (off >= lb || ub < lb) break;
+                        if (j - dj >= 0) ub = min(ub, (unsigned long long)schunk[j - dj] + off);
+                        if (j + dj < nchunks) ub = min(ub, (unsigned long long)schunk[j + dj] + off);
+                    }
+                    if (ub < lb) continue;
+                }
+                const int x = (j << 5) + lane;
+                if (x >= W) continue;
                 unsigned bestd = srow[x];
                 if (bestd < lb) continue;
                 if (lb) {   // probes at doubling offsets: almost every pixel near a source drops below the bound here
@@ -424,18 +621,22 @@ __global__ void __launch_bounds__(EDT_NT) edt_row_kernel(const uint16_t* __restr
                 size_t idx = (size_t)y * W + x;
                 if (d2out) d2out[(size_t)b * P + idx] = bestd;
                 unsigned long long key = ((unsigned long long)bestd << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)idx);
-                mybest = max(mybest, key);
+                rowbest = max(rowbest, key);
             }
         } else if (d2out) {
             for (int x = threadIdx.x; x < W; x += EDT_NT) d2out[(size_t)b * P + (size_t)y * W + x] = 0xFFFFFFFFu;
         }
-        if (best) {   // publish after every row so that other CTAs of the frame can prune against it
+        // the reduction only runs when some thread improved on the CTA's best (rare once the bound is tight);
+        // the barrier also protects srow against the next row's writers
+        const int improved = __syncthreads_or(best != nullptr && rowbest > mybest);
+        if (improved) {
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) mybest = max(mybest, __shfl_xor_sync(0xFFFFFFFFu, mybest, d));
-            if ((threadIdx.x & 31) == 0) sbest[threadIdx.x >> 5] = mybest;
+            for (int d = 16; d > 0; d >>= 1) rowbest = max(rowbest, __shfl_xor_sync(0xFFFFFFFFu, rowbest, d));
+            if ((threadIdx.x & 31) == 0) sbest[threadIdx.x >> 5] = rowbest;
             __syncthreads();
             for (int w = 0; w < EDT_NT / 32; ++w) mybest = max(mybest, sbest[w]);
             if (threadIdx.x == 0 && mybest > *reinterpret_cast<volatile unsigned long long*>(&best[b])) atomicMax(&best[b], mybest);
+            __syncthreads();             // sbest is reused by the next improving row
         }
     }
 }
@@ -628,7 +829,13 @@ int lg_run_stage1(lg_context* c, const int16_t* labels, const float* depth, int 
     clear_tables_kernel<<<64, 256, 0, st>>>(*c, n);
     LG_LAUNCH_CHECK();
     const int tiles = (int)((c->P + ST_NT * ST_PX - 1) / (ST_NT * ST_PX));
-    leaf_stats_kernel<<<dim3(tiles, n), ST_NT, c->L * sizeof(SmemLeaf), st>>>(*c, labels, depth, cam);
+    if (!c->ray_valid || c->ray_cam.f != cam.f || c->ray_cam.cx != cam.cx || c->ray_cam.cy != cam.cy) {
+        ray_table_kernel<<<LG_NUM_SM_HINT * 8, 256, 0, st>>>(c->ray_tab, c->H, c->W, cam);
+        LG_LAUNCH_CHECK();
+        c->ray_cam = cam;
+        c->ray_valid = 1;
+    }
+    leaf_stats_kernel<<<dim3(tiles, n), ST_NT, c->L * sizeof(SmemLeaf), st>>>(*c, labels, depth);
     LG_LAUNCH_CHECK();
     lg_mark(c, LG_M_STATS, st);
     leaf_offsets_kernel<<<(n + 63) / 64, 64, 0, st>>>(*c, n);
