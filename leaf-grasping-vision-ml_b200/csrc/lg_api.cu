@@ -2,6 +2,7 @@
 // per-stage calls the drop-in Python classes and the parity tests use.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -112,6 +113,13 @@ extern "C" int lg_create(lg_context** out, int max_frames, int height, int width
         cudaError_t e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
         for (int i = 0; i < LG_MAX_HOST_CHUNKS && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->copy_ev[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->copy_gate, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking);
+        for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+            e = cudaEventCreateWithFlags(&c->ev_fork[i], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
+        }
+        const char* no = getenv("LG_NO_OVERLAP");
+        c->overlap = !(no && no[0] == '1');
         if (e != cudaSuccess) { lg_set_error("lg_create: %s", cudaGetErrorString(e)); lg_destroy(c); return LG_E_CUDA; }
     }
     memcpy(c->gauss, kGaussBits, sizeof(kGaussBits));
@@ -139,6 +147,11 @@ extern "C" void lg_destroy(lg_context* c) {
         if (c->copy_ev[i]) cudaEventDestroy(c->copy_ev[i]);
     if (c->copy_gate) cudaEventDestroy(c->copy_gate);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (c->ev_fork[i]) cudaEventDestroy(c->ev_fork[i]);
+        if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+    }
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     for (int i = 0; i < LG_PROF_MARKS; ++i)
         if (c->prof_ev[i]) cudaEventDestroy(c->prof_ev[i]);
     delete c;
@@ -161,6 +174,23 @@ extern "C" int lg_set_cnn_weights(lg_context* c, const float* blob_host, uint64_
     return lg_cnn_prepare_bf16(c);
 }
 
+cudaStream_t lg_fork(lg_context* c, int k, cudaStream_t st) {
+    if (!c->overlap) return st;
+    if (cudaEventRecord(c->ev_fork[k], st) != cudaSuccess || cudaStreamWaitEvent(c->aux_stream, c->ev_fork[k], 0) != cudaSuccess)
+        return st;
+    lg_mark(c, k == 0 ? LG_M_FORK1 : LG_M_FORK2, c->aux_stream);
+    return c->aux_stream;
+}
+
+int lg_join(lg_context* c, int k, cudaStream_t aux, cudaStream_t st) {
+    if (aux != st) {
+        LG_CUDA(cudaEventRecord(c->ev_join[k], aux));
+        LG_CUDA(cudaStreamWaitEvent(st, c->ev_join[k], 0));
+    }
+    lg_mark(c, k == 0 ? LG_M_JOIN1 : LG_M_JOIN2, st);
+    return LG_OK;
+}
+
 static int check_batch(lg_context* c, const void* a, const void* b, int frames) {
     if (!c || !a || !b || frames < 1) { lg_set_error("null pointer or empty batch"); return LG_E_ARG; }
     if (frames > c->B) { lg_set_error("batch of %d frames exceeds context capacity %d", frames, c->B); return LG_E_CAPACITY; }
@@ -180,10 +210,12 @@ extern "C" int lg_select_leaf(lg_context* c, const int16_t* labels, const float*
 static int run_stage2(lg_context* c, LgMaskSrc src, const float* depth, int n, lg_camera cam, int full, double* iso_out,
                       cudaStream_t st) {
     // inside transform on the leaf rectangle (+ its distance map), outside transform on the whole frame (max only)
+    cudaStream_t aux = lg_fork(c, 1, st);          // orientation runs beside the two chamfer transforms
+    TRY(lg_run_orientation(c, src, n, aux));
+    lg_mark(c, LG_M_ORIENT, aux);
     TRY(lg_run_chamfer(c, src, n, full ? 0 : 1, 0, 2, c->di, nullptr, c->dt_max, st));
     lg_mark(c, LG_M_CHAMFER, st);
-    TRY(lg_run_orientation(c, src, n, st));
-    lg_mark(c, LG_M_ORIENT, st);
+    TRY(lg_join(c, 1, aux, st));
     TRY(lg_run_scores(c, src, depth, n, cam, full, iso_out, st));
     lg_mark(c, LG_M_SCORE, st);
     return LG_OK;
@@ -325,19 +357,33 @@ extern "C" int lg_set_profiling(lg_context* c, int on) {
     return LG_OK;
 }
 
-/* ms[i] = device time between mark i and the previous recorded mark of the last lg_process_batch call
- * (LG_M_* order: stats, scatter, median, edt_col, edt_row, select, chamfer, orient, score, nms, gather,
- * cnn, fuse); 0 for stages that did not run.  Synchronises on the last event. */
+/* ms[i] = device time of stage i of the last lg_process_batch call = time between the mark recorded after it and the
+ * mark that precedes it on the stream it ran on (stages on the auxiliary stream start at their fork mark, stages that
+ * follow a join start at the join mark); 0 for stages that did not run.  Stages on different streams overlap, so the
+ * sum can exceed the step time.  Synchronises on the recorded events. */
 extern "C" int lg_stage_times(lg_context* c, float* ms, int n) {
     if (!c || !ms || n < LG_M_COUNT) return LG_E_ARG;
     for (int i = 0; i < n; ++i) ms[i] = 0.f;
     if (!c->prof_on || !c->prof_seen[LG_M_START]) return LG_OK;
-    int prev = LG_M_START;
+    int pred[LG_PROF_MARKS];
+    for (int i = 0; i < LG_PROF_MARKS; ++i) pred[i] = i - 1;
+    pred[LG_M_START] = -1;
+    pred[LG_M_FORK1] = LG_M_START;   pred[LG_M_EDT_COL] = LG_M_FORK1;
+    pred[LG_M_JOIN1] = LG_M_EDT_ROW; pred[LG_M_SELECT] = LG_M_JOIN1;
+    pred[LG_M_FORK2] = LG_M_SELECT;  pred[LG_M_ORIENT] = LG_M_FORK2; pred[LG_M_CHAMFER] = LG_M_SELECT;
+    pred[LG_M_JOIN2] = LG_M_ORIENT;  pred[LG_M_SCORE] = LG_M_JOIN2;
+    if (!c->prof_seen[LG_M_FORK1]) {   // overlap off: EDT runs first on the caller's stream, then the statistics
+        pred[LG_M_EDT_COL] = LG_M_START; pred[LG_M_STATS] = LG_M_EDT_ROW; pred[LG_M_JOIN1] = LG_M_MEDIAN;
+    }
+    if (!c->prof_seen[LG_M_FORK2]) { pred[LG_M_ORIENT] = LG_M_SELECT; pred[LG_M_CHAMFER] = LG_M_ORIENT; pred[LG_M_JOIN2] = LG_M_CHAMFER; }
     for (int i = 1; i < LG_M_COUNT; ++i) {
         if (!c->prof_seen[i]) continue;
+        int p = pred[i];
+        while (p >= 0 && !c->prof_seen[p]) p = pred[p];
+        if (p < 0) continue;
         LG_CUDA(cudaEventSynchronize(c->prof_ev[i]));
-        LG_CUDA(cudaEventElapsedTime(&ms[i], c->prof_ev[prev], c->prof_ev[i]));
-        prev = i;
+        LG_CUDA(cudaEventSynchronize(c->prof_ev[p]));
+        LG_CUDA(cudaEventElapsedTime(&ms[i], c->prof_ev[p], c->prof_ev[i]));
     }
     return LG_OK;
 }

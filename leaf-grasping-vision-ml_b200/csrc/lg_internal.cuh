@@ -20,11 +20,13 @@
 #define LG_REGION_PAD 16 // score maps are produced on the leaf bbox grown by half a patch
 #define LG_SE_STEM 30
 #define LG_SE_PRE 31
-#define LG_PROF_MARKS 16
+#define LG_PROF_MARKS 20
 #define LG_MAX_HOST_CHUNKS 64
 #define LG_HOST_CHUNK_FRAMES 32
 enum LgMark { LG_M_START = 0, LG_M_STATS, LG_M_SCATTER, LG_M_MEDIAN, LG_M_EDT_COL, LG_M_EDT_ROW, LG_M_SELECT, LG_M_CHAMFER,
-              LG_M_ORIENT, LG_M_SCORE, LG_M_NMS, LG_M_GATHER, LG_M_CNN, LG_M_FUSE, LG_M_COUNT };
+              LG_M_ORIENT, LG_M_SCORE, LG_M_NMS, LG_M_GATHER, LG_M_CNN, LG_M_FUSE, LG_M_COUNT,
+              // fork / join points of the auxiliary stream (not stages): see lg_stage_times
+              LG_M_FORK1 = LG_M_COUNT, LG_M_JOIN1, LG_M_FORK2, LG_M_JOIN2 };
 
 struct LgRegion {
     int x0, y0, x1, y1;  // bounding box of the chosen leaf, exclusive upper bounds
@@ -119,7 +121,12 @@ struct lg_context {
     cudaStream_t copy_stream;
     cudaEvent_t copy_ev[LG_MAX_HOST_CHUNKS];
     cudaEvent_t copy_gate;                   // the caller's stream reached the start of this host call
-    // optional per-stage timing (lg_set_profiling): events recorded on the launch stream
+    // Independent branches run side by side: the distance transform of the leaf union next to the per-leaf
+    // statistics, the orientation next to the chamfer transforms.  aux_stream forks from and joins the caller's stream.
+    cudaStream_t aux_stream;
+    cudaEvent_t ev_fork[2], ev_join[2];
+    int overlap;
+    // optional per-stage timing (lg_set_profiling): events recorded on the stream the stage runs on
     int prof_on;
     cudaEvent_t prof_ev[LG_PROF_MARKS];
     int prof_seen[LG_PROF_MARKS];
@@ -152,6 +159,9 @@ static inline void lg_mark(lg_context* c, int id, cudaStream_t st) {
 int lg_run_stage1(lg_context* c, const int16_t* labels, const float* depth, int n, lg_camera cam, cudaStream_t st);
 int lg_run_select(lg_context* c, int n, lg_camera cam, int32_t* leaf_out, lg_leaf_record* rec_out, cudaStream_t st);
 int lg_run_edt_union(lg_context* c, const int16_t* labels, int n, cudaStream_t st);
+// aux = lg_fork(c, k, st): stream for the side branch (st itself when overlap is off); lg_join makes st wait for it
+cudaStream_t lg_fork(lg_context* c, int k, cudaStream_t st);
+int lg_join(lg_context* c, int k, cudaStream_t aux, cudaStream_t st);
 int lg_run_chamfer(lg_context* c, LgMaskSrc src, int n, int rect_mode, int invert_base, int nvar,
                    float* out0, uint32_t* q0, uint32_t* out_max, cudaStream_t st);
 int lg_run_orientation(lg_context* c, LgMaskSrc src, int n, cudaStream_t st);

@@ -63,179 +63,169 @@ __global__ void ray_table_kernel(unsigned long long* __restrict__ tab, int H, in
     }
 }
 
-// One pass over labels + depth.  Each thread owns ST_PX consecutive pixels.  A warp whose 256 pixels all carry the
-// same label (the common case) reduces its sums with REDUX and touches the CTA's shared-memory table once; mixed
-// warps fall back to one table update per run of equal labels.
-__global__ void __launch_bounds__(ST_NT) leaf_stats_kernel(lg_context c, const int16_t* __restrict__ labels,
-                                                            const float* __restrict__ depth) {
+// One pass over labels + depth.  A CTA owns one tile of ST_NT * ST_PX consecutive pixels and walks it through
+// ST_FR consecutive frames: the tile's viewing-ray lengths stay in registers, and the loads of frame f + 1 are in
+// flight while frame f is reduced.  Each thread owns ST_PX consecutive pixels.  A warp whose 256 pixels all carry
+// the same label (the common case) reduces its sums with REDUX and touches the CTA's shared-memory table once;
+// mixed warps fall back to one table update per run of equal labels.  The table is flushed to the frame's global
+// table (one atomic per touched field) after every frame.
+constexpr int ST_FR = 8;
+__global__ void __launch_bounds__(ST_NT, 3) leaf_stats_kernel(lg_context c, const int16_t* __restrict__ labels,
+                                                               const float* __restrict__ depth, int n_frames) {
     extern __shared__ SmemLeaf tab[];
     __shared__ unsigned s_first, s_bad;
     const int L = c.L, W = c.W, H = c.H;
     const size_t P = c.P;
-    const int b = blockIdx.y;
-    for (int l = threadIdx.x; l < L; l += ST_NT) {
-        SmemLeaf z;
+    auto reset = [&](SmemLeaf& z) {
         z.cnt = 0; z.sx = 0; z.sy = 0; z.bx0 = 0xFFFFFFFFu; z.by0 = 0xFFFFFFFFu; z.bx1 = 0; z.by1 = 0;
         z.border = 0; z.kmin = 0xFFFFFFFFu; z.kmax = 0; z.sdep = 0; z.sdist = 0;
-        tab[l] = z;
-    }
+    };
+    for (int l = threadIdx.x; l < L; l += ST_NT) reset(tab[l]);
     if (threadIdx.x == 0) { s_first = 0xFFFFFFFFu; s_bad = 0; }
-    __syncthreads();
 
     const size_t base = ((size_t)blockIdx.x * ST_NT + threadIdx.x) * ST_PX;
-    const int16_t* lp = labels + (size_t)b * P;
-    const float* dp = depth + (size_t)b * P;
     const int npx = base < P ? (int)min((size_t)ST_PX, P - base) : 0;
-    int lab[ST_PX];
-    float val[ST_PX];
-    unsigned long long ray[ST_PX];
-    const bool vec = npx == ST_PX && ((reinterpret_cast<uintptr_t>(lp + base) | reinterpret_cast<uintptr_t>(dp + base)) & 15) == 0;
-    if (vec) {
-        const uint4 lv = *reinterpret_cast<const uint4*>(lp + base);
-        const unsigned w[4] = {lv.x, lv.y, lv.z, lv.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { lab[2 * k] = (int16_t)(w[k] & 0xFFFFu); lab[2 * k + 1] = (int16_t)(w[k] >> 16); }
-    } else {
-#pragma unroll
-        for (int k = 0; k < ST_PX; ++k) lab[k] = k < npx ? (int)lp[base + k] : -32768;
-    }
-    bool any_leaf = false, uni = npx == ST_PX;
-#pragma unroll
-    for (int k = 0; k < ST_PX; ++k) { any_leaf |= lab[k] > 0; uni &= lab[k] == lab[0]; }
-    if (any_leaf) {
-        if (vec) {
-            const float4 d0 = *reinterpret_cast<const float4*>(dp + base), d1 = *reinterpret_cast<const float4*>(dp + base + 4);
-            val[0] = d0.x; val[1] = d0.y; val[2] = d0.z; val[3] = d0.w; val[4] = d1.x; val[5] = d1.y; val[6] = d1.z; val[7] = d1.w;
-        } else {
-#pragma unroll
-            for (int k = 0; k < ST_PX; ++k) val[k] = k < npx ? dp[base + k] : 0.f;
-        }
-#pragma unroll
-        for (int k = 0; k < ST_PX; ++k) ray[k] = k < npx ? c.ray_tab[base + k] : 0ull;
-    } else {
-#pragma unroll
-        for (int k = 0; k < ST_PX; ++k) { val[k] = 0.f; ray[k] = 0ull; }
-    }
     const int y0 = (int)(base / W), x0 = (int)(base % W);
-    const int l0 = lab[0];
     const unsigned FULL = 0xFFFFFFFFu;
-    const int l_first = __shfl_sync(FULL, l0, 0);      // outside the condition: every lane must take part in the shuffle
-    const bool warp_uni = __all_sync(FULL, uni && l0 == l_first && l0 >= 0 && l0 < L);
-    if (warp_uni) {
-        const int lane = threadIdx.x & 31;
-        if (l0 == 0) {
-            if (lane == 0) atomicAdd(&tab[0].cnt, 32u * ST_PX);
-        } else {
+    const int lane = threadIdx.x & 31;
+    unsigned ray[ST_PX];     // ray length in 2^-30 units (ray_tab >> 6; < 2^32 for rays up to 75 degrees off axis)
+#pragma unroll
+    for (int k = 0; k < ST_PX; ++k) ray[k] = k < npx ? (unsigned)min(c.ray_tab[base + k] >> 6, 0xFFFFFFFFull) : 0u;
+
+    const int f_begin = blockIdx.y * ST_FR, f_end = min(n_frames, f_begin + ST_FR);
+    // raw loads of one frame's tile (nothing is consumed here, see the prefetch below)
+    uint4 lraw = make_uint4(0, 0, 0, 0);
+    float4 draw0 = make_float4(0.f, 0.f, 0.f, 0.f), draw1 = draw0;
+    bool vec = false;
+    auto fetch = [&](int f) {
+        if (f >= f_end) return;
+        const int16_t* lp = labels + (size_t)f * P + base;
+        const float* dp = depth + (size_t)f * P + base;
+        vec = npx == ST_PX && ((reinterpret_cast<uintptr_t>(lp) | reinterpret_cast<uintptr_t>(dp)) & 15) == 0;
+        if (vec) {
+            lraw = *reinterpret_cast<const uint4*>(lp);
+            draw0 = *reinterpret_cast<const float4*>(dp);
+            draw1 = *reinterpret_cast<const float4*>(dp + 4);
+        }
+    };
+    fetch(f_begin);
+    __syncthreads();
+    for (int f = f_begin; f < f_end; ++f) {
+        int lab[ST_PX];
+        float val[ST_PX];
+        if (vec) {
+            const unsigned w[4] = {lraw.x, lraw.y, lraw.z, lraw.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { lab[2 * k] = (int16_t)(w[k] & 0xFFFFu); lab[2 * k + 1] = (int16_t)(w[k] >> 16); }
+            val[0] = draw0.x; val[1] = draw0.y; val[2] = draw0.z; val[3] = draw0.w;
+            val[4] = draw1.x; val[5] = draw1.y; val[6] = draw1.z; val[7] = draw1.w;
+        } else {     // tile tail or unaligned frame: plain loads, no prefetch
+            const int16_t* lp = labels + (size_t)f * P + base;
+            const float* dp = depth + (size_t)f * P + base;
+#pragma unroll
+            for (int k = 0; k < ST_PX; ++k) { lab[k] = k < npx ? (int)lp[k] : -32768; val[k] = k < npx ? dp[k] : 0.f; }
+        }
+        fetch(f + 1);
+        // Runs of equal labels inside the thread's ST_PX pixels (almost always one, two at a leaf edge).  Round r
+        // handles the r-th run of every lane: lanes are grouped by the run's label (labels are piecewise constant
+        // along a row, so a warp holds a handful of groups), each group reduces its sums with REDUX over its own
+        // member mask and its first lane updates the CTA's table - a few shared-memory atomics per warp instead of
+        // a dozen per thread, and no divergent slow path.
+        unsigned ridp = 0;      // run index of pixel k in bits [4k, 4k+4)
+        int nruns = 0;
+        {
+            int cur = 0;
+#pragma unroll
+            for (int k = 0; k < ST_PX; ++k) {
+                if (k > 0 && lab[k] != lab[k - 1]) ++cur;
+                ridp |= (unsigned)cur << (4 * k);
+                if (k < npx) nruns = cur + 1;
+            }
+        }
+        const int maxruns = __reduce_max_sync(FULL, nruns);
+        for (int r = 0; r < maxruns; ++r) {
+            int lr = -1, cnt = 0, firstk = ST_PX;
+#pragma unroll
+            for (int k = ST_PX - 1; k >= 0; --k)
+                if (k < npx && (int)((ridp >> (4 * k)) & 15u) == r) { lr = lab[k]; ++cnt; firstk = k; }
+            const bool has = cnt > 0;
+            const bool valid = has && lr >= 0 && lr < L;
+            if (has && !valid) s_bad = 1;
+            const unsigned grp = __match_any_sync(FULL, valid ? lr : (0x40000000 | lane));
+            if (!valid) continue;
+            const bool leader = (__ffs(grp) - 1) == lane;
+            const unsigned gcnt = __reduce_add_sync(grp, (unsigned)cnt);
+            if (lr == 0) {
+                if (leader) atomicAdd(&tab[0].cnt, gcnt);
+                continue;
+            }
             unsigned sx = 0, sy = 0, bx0 = 0xFFFFFFFFu, bx1 = 0, by0 = 0xFFFFFFFFu, by1 = 0, brd = 0, kmn = 0xFFFFFFFFu, kmx = 0;
             long long rdep = 0;
             unsigned long long rdist = 0;
-            int x = x0, y = y0;
 #pragma unroll
             for (int k = 0; k < ST_PX; ++k) {
-                sx += x; sy += y;
-                bx0 = min(bx0, (unsigned)x); bx1 = max(bx1, (unsigned)x); by0 = min(by0, (unsigned)y); by1 = max(by1, (unsigned)y);
-                brd |= (x == 0) | (y == 0) | (x == W - 1) | (y == H - 1);
-                const double dd = fmin(fmax((double)val[k], -2048.0), 2048.0);
-                rdep += __double2ll_rn(dd * DEP_SCALE);
-                rdist += ray[k];
-                const unsigned key = f2key(val[k]);
-                kmn = min(kmn, key); kmx = max(kmx, key);
-                if (++x == W) { x = 0; ++y; }
+                if (k < npx && (int)((ridp >> (4 * k)) & 15u) == r) {
+                    int x = x0 + k, y = y0;
+                    if (x >= W) { x -= W; ++y; }
+                    sx += x; sy += y;
+                    bx0 = min(bx0, (unsigned)x); bx1 = max(bx1, (unsigned)x); by0 = min(by0, (unsigned)y); by1 = max(by1, (unsigned)y);
+                    brd |= (x == 0) | (y == 0) | (x == W - 1) | (y == H - 1);
+                    const double dd = fmin(fmax((double)val[k], -2048.0), 2048.0);
+                    rdep += __double2ll_rn(dd * DEP_SCALE);
+                    rdist += ray[k];
+                    const unsigned key = f2key(val[k]);
+                    kmn = min(kmn, key); kmx = max(kmx, key);
+                }
             }
-            sx = __reduce_add_sync(FULL, sx); sy = __reduce_add_sync(FULL, sy);
-            bx0 = __reduce_min_sync(FULL, bx0); bx1 = __reduce_max_sync(FULL, bx1);
-            by0 = __reduce_min_sync(FULL, by0); by1 = __reduce_max_sync(FULL, by1);
-            brd = __reduce_or_sync(FULL, brd);
-            kmn = __reduce_min_sync(FULL, kmn); kmx = __reduce_max_sync(FULL, kmx);
+            sx = __reduce_add_sync(grp, sx); sy = __reduce_add_sync(grp, sy);
+            bx0 = __reduce_min_sync(grp, bx0); bx1 = __reduce_max_sync(grp, bx1);
+            by0 = __reduce_min_sync(grp, by0); by1 = __reduce_max_sync(grp, by1);
+            brd = __reduce_or_sync(grp, brd);
+            kmn = __reduce_min_sync(grp, kmn); kmx = __reduce_max_sync(grp, kmx);
+            const unsigned first = __reduce_min_sync(grp, (unsigned)(base + firstk));
             // 64-bit sums as (high part, low 24 bits): each half stays far below 2^31 over 32 lanes
-            const unsigned dep_lo = __reduce_add_sync(FULL, (unsigned)(rdep & 0xFFFFFF));
-            const int dep_hi = __reduce_add_sync(FULL, (int)(rdep >> 24));
-            const unsigned dist_lo = __reduce_add_sync(FULL, (unsigned)(rdist & 0xFFFFFF));
-            const unsigned dist_hi = __reduce_add_sync(FULL, (unsigned)(rdist >> 24));
-            if (lane == 0) {
-                SmemLeaf* t = &tab[l0];
-                atomicAdd(&t->cnt, 32u * ST_PX);
+            const unsigned dep_lo = __reduce_add_sync(grp, (unsigned)(rdep & 0xFFFFFF));
+            const int dep_hi = __reduce_add_sync(grp, (int)(rdep >> 24));
+            const unsigned dist_lo = __reduce_add_sync(grp, (unsigned)(rdist & 0xFFFFFF));
+            const unsigned dist_hi = __reduce_add_sync(grp, (unsigned)(rdist >> 24));
+            if (leader) {
+                SmemLeaf* t = &tab[lr];
+                atomicAdd(&t->cnt, gcnt);
                 atomicAdd(&t->sx, sx); atomicAdd(&t->sy, sy);
                 atomicMin(&t->bx0, bx0); atomicMax(&t->bx1, bx1); atomicMin(&t->by0, by0); atomicMax(&t->by1, by1);
                 if (brd) atomicOr(&t->border, 1u);
                 atomicMin(&t->kmin, kmn); atomicMax(&t->kmax, kmx);
                 atomicAdd(&t->sdep, (unsigned long long)(((long long)dep_hi << 24) + (long long)dep_lo));
-                atomicAdd(&t->sdist, ((unsigned long long)dist_hi << 24) + dist_lo);
-                atomicMin(&s_first, (unsigned)base);
+                atomicAdd(&t->sdist, (((unsigned long long)dist_hi << 24) + dist_lo) << 6);
+                atomicMin(&s_first, first);
             }
         }
-    } else if (npx > 0) {
-        int x = x0, y = y0;
-        int cur = -1;
-        unsigned rc = 0, rsx = 0, rsy = 0, rx0 = 0, rx1 = 0, ry0 = 0, ry1 = 0, rb = 0, rkmn = 0xFFFFFFFFu, rkmx = 0;
-        long long rdep = 0;
-        unsigned long long rdist = 0;
-        auto flush = [&]() {
-            if (cur >= 0 && rc) {
-                SmemLeaf* t = &tab[cur];
-                atomicAdd(&t->cnt, rc);
-                if (cur > 0) {
-                    atomicAdd(&t->sx, rsx); atomicAdd(&t->sy, rsy);
-                    atomicMin(&t->bx0, rx0); atomicMax(&t->bx1, rx1);
-                    atomicMin(&t->by0, ry0); atomicMax(&t->by1, ry1);
-                    if (rb) atomicOr(&t->border, 1u);
-                    atomicMin(&t->kmin, rkmn); atomicMax(&t->kmax, rkmx);
-                    atomicAdd(&t->sdep, (unsigned long long)rdep);
-                    atomicAdd(&t->sdist, rdist);
+        __syncthreads();
+        // flush the touched entries to frame f's global table and reset them for the next frame
+        for (int l = threadIdx.x; l < L; l += ST_NT) {
+            const SmemLeaf t = tab[l];
+            if (t.cnt) {
+                const size_t o = (size_t)f * L + l;
+                atomicAdd(&c.cnt[o], t.cnt);
+                if (l > 0) {
+                    atomicAdd(&c.sx[o], (unsigned long long)t.sx);
+                    atomicAdd(&c.sy[o], (unsigned long long)t.sy);
+                    atomicAdd(&c.sdep[o], t.sdep);
+                    atomicAdd(&c.sdist[o], t.sdist);
+                    atomicMin(&c.bx0[o], t.bx0); atomicMax(&c.bx1[o], t.bx1);
+                    atomicMin(&c.by0[o], t.by0); atomicMax(&c.by1[o], t.by1);
+                    atomicMin(&c.kmin[o], t.kmin); atomicMax(&c.kmax[o], t.kmax);
+                    if (t.border) atomicOr(&c.border[o], 1u);
                 }
-            }
-        };
-#pragma unroll
-        for (int i = 0; i < ST_PX; ++i) {
-            if (i < npx) {
-                int l = lab[i];
-                if (l < 0 || l >= L) { s_bad = 1; l = -1; }
-                if (l != cur) {
-                    flush();
-                    cur = l; rc = 0; rsx = 0; rsy = 0; rx0 = x; rx1 = x; ry0 = y; ry1 = y; rb = 0; rdep = 0; rdist = 0;
-                    rkmn = 0xFFFFFFFFu; rkmx = 0;
-                    if (l >= 1) atomicMin(&s_first, (unsigned)(base + i));
-                }
-                if (l >= 0) {
-                    rc++;
-                    if (l > 0) {
-                        rsx += x; rsy += y;
-                        rx0 = min(rx0, (unsigned)x); rx1 = max(rx1, (unsigned)x);
-                        ry0 = min(ry0, (unsigned)y); ry1 = max(ry1, (unsigned)y);
-                        rb |= (x == 0) | (y == 0) | (x == W - 1) | (y == H - 1);
-                        const double dd = fmin(fmax((double)val[i], -2048.0), 2048.0);
-                        rdep += __double2ll_rn(dd * DEP_SCALE);
-                        rdist += ray[i];
-                        const unsigned key = f2key(val[i]);
-                        rkmn = min(rkmn, key); rkmx = max(rkmx, key);
-                    }
-                }
-                if (++x == W) { x = 0; ++y; }
+                reset(tab[l]);
             }
         }
-        flush();
-    }
-    __syncthreads();
-    for (int l = threadIdx.x; l < L; l += ST_NT) {
-        SmemLeaf t = tab[l];
-        if (t.cnt) {
-            size_t o = (size_t)b * L + l;
-            atomicAdd(&c.cnt[o], t.cnt);
-            if (l > 0) {
-                atomicAdd(&c.sx[o], (unsigned long long)t.sx);
-                atomicAdd(&c.sy[o], (unsigned long long)t.sy);
-                atomicAdd(&c.sdep[o], t.sdep);
-                atomicAdd(&c.sdist[o], t.sdist);
-                atomicMin(&c.bx0[o], t.bx0); atomicMax(&c.bx1[o], t.bx1);
-                atomicMin(&c.by0[o], t.by0); atomicMax(&c.by1[o], t.by1);
-                atomicMin(&c.kmin[o], t.kmin); atomicMax(&c.kmax[o], t.kmax);
-                if (t.border) atomicOr(&c.border[o], 1u);
-            }
+        if (threadIdx.x == 0) {
+            if (s_first != 0xFFFFFFFFu) atomicMin(&c.first_leaf[f], s_first);
+            if (s_bad) atomicOr(&c.status[f], LG_ST_LABEL_RANGE);
+            s_first = 0xFFFFFFFFu; s_bad = 0;
         }
-    }
-    if (threadIdx.x == 0) {
-        if (s_first != 0xFFFFFFFFu) atomicMin(&c.first_leaf[b], s_first);
-        if (s_bad) atomicOr(&c.status[b], LG_ST_LABEL_RANGE);
+        __syncthreads();
     }
 }
 
@@ -828,6 +818,10 @@ int lg_run_edt_union(lg_context* c, const int16_t* labels, int n, cudaStream_t s
 int lg_run_stage1(lg_context* c, const int16_t* labels, const float* depth, int n, lg_camera cam, cudaStream_t st) {
     clear_tables_kernel<<<64, 256, 0, st>>>(*c, n);
     LG_LAUNCH_CHECK();
+    // the distance transform of the leaf union (arg-max only) is independent of the per-leaf statistics
+    cudaStream_t aux = lg_fork(c, 0, st);
+    int rc = lg_run_edt_union(c, labels, n, aux);
+    if (rc) return rc;
     const int tiles = (int)((c->P + ST_NT * ST_PX - 1) / (ST_NT * ST_PX));
     if (!c->ray_valid || c->ray_cam.f != cam.f || c->ray_cam.cx != cam.cx || c->ray_cam.cy != cam.cy) {
         ray_table_kernel<<<LG_NUM_SM_HINT * 8, 256, 0, st>>>(c->ray_tab, c->H, c->W, cam);
@@ -835,7 +829,7 @@ int lg_run_stage1(lg_context* c, const int16_t* labels, const float* depth, int 
         c->ray_cam = cam;
         c->ray_valid = 1;
     }
-    leaf_stats_kernel<<<dim3(tiles, n), ST_NT, c->L * sizeof(SmemLeaf), st>>>(*c, labels, depth);
+    leaf_stats_kernel<<<dim3(tiles, (n + ST_FR - 1) / ST_FR), ST_NT, c->L * sizeof(SmemLeaf), st>>>(*c, labels, depth, n);
     LG_LAUNCH_CHECK();
     lg_mark(c, LG_M_STATS, st);
     leaf_offsets_kernel<<<(n + 63) / 64, 64, 0, st>>>(*c, n);
@@ -846,9 +840,7 @@ int lg_run_stage1(lg_context* c, const int16_t* labels, const float* depth, int 
     leaf_median_kernel<<<dim3(c->L, n), MED_NT, 0, st>>>(*c);
     LG_LAUNCH_CHECK();
     lg_mark(c, LG_M_MEDIAN, st);
-    int rc = lg_run_edt_union(c, labels, n, st);
-    if (rc) return rc;
-    return LG_OK;
+    return lg_join(c, 0, aux, st);
 }
 
 int lg_run_select(lg_context* c, int n, lg_camera cam, int32_t* leaf_out, lg_leaf_record* rec_out, cudaStream_t st) {
