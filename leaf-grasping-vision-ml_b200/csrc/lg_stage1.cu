@@ -50,182 +50,135 @@ __global__ void clear_tables_kernel(lg_context c, int n) {
     }
 }
 
-// ray_tab[y * W + x] = round(2^36 * sqrt(((x - cx)^2 + (y - cy)^2) / f^2 + 1)): the length of the viewing ray through
-// pixel (x, y) per unit depth (leaf_scorer.py:104-113 with X = md (x - cx) / f, Y = md (y - cy) / f, Z = md).  It depends
-// on the camera only, so it is built once per camera and read (L2-resident) by every frame.
+// ray_tab[y * W + x] = sum over rows y' <= y of round(2^36 * sqrt(((x - cx)^2 + (y' - cy)^2) / f^2 + 1)): column-wise prefix
+// sums of the length of the viewing ray through a pixel per unit depth (leaf_scorer.py:104-113 with X = md (x - cx) / f,
+// Y = md (y - cy) / f, Z = md).  The sum over a vertical run of pixels is then a difference of two entries.  The table
+// depends on the camera only: it is built once per camera and read (L2-resident) by every frame.
 __global__ void ray_table_kernel(unsigned long long* __restrict__ tab, int H, int W, lg_camera cam) {
-    const size_t P = (size_t)H * W;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
     const double inv_f2 = 1.0 / (cam.f * cam.f);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (size_t)gridDim.x * blockDim.x) {
-        const double ddx = (double)(i % W) - cam.cx, ddy = (double)(i / W) - cam.cy;
+    const double ddx = (double)x - cam.cx;
+    unsigned long long acc = 0;
+    for (int y = 0; y < H; ++y) {
+        const double ddy = (double)y - cam.cy;
         const double sv = sqrt((ddx * ddx + ddy * ddy) * inv_f2 + 1.0);
-        tab[i] = (unsigned long long)__double2ll_rn(sv * DIST_SCALE);
+        acc += (unsigned long long)__double2ll_rn(sv * DIST_SCALE);
+        tab[(size_t)y * W + x] = acc;
     }
 }
 
-// One pass over labels + depth.  A CTA owns one tile of ST_NT * ST_PX consecutive pixels and walks it through
-// ST_FR consecutive frames: the tile's viewing-ray lengths stay in registers, and the loads of frame f + 1 are in
-// flight while frame f is reduced.  Each thread owns ST_PX consecutive pixels.  A warp whose 256 pixels all carry
-// the same label (the common case) reduces its sums with REDUX and touches the CTA's shared-memory table once;
-// mixed warps fall back to one table update per run of equal labels.  The table is flushed to the frame's global
-// table (one atomic per touched field) after every frame.
-constexpr int ST_FR = 8;
-__global__ void __launch_bounds__(ST_NT, 3) leaf_stats_kernel(lg_context c, const int16_t* __restrict__ labels,
-                                                               const float* __restrict__ depth, int n_frames) {
+// One pass over labels + depth.  A thread walks down one column: labels are piecewise constant along a column
+// (a leaf is ~100 rows tall), so the thread carries the sums of its current run in registers and updates the CTA's
+// shared-memory table only when the label changes - about ten updates per column instead of one per 8 pixels.
+// Everything that depends on the pixel position only has a closed form per run (count, coordinate sums, bounding
+// box, border contact) or is a difference of two ray_tab entries; per pixel only the depth is accumulated (2^-28
+// fixed point, exact and order independent) and its key range tracked.  Loads run ST_U rows ahead.
+constexpr int ST_U = 8;
+constexpr int STC_NT = 128;   // columns per CTA
+__global__ void __launch_bounds__(STC_NT) leaf_stats_kernel(lg_context c, const int16_t* __restrict__ labels,
+                                                            const float* __restrict__ depth) {
     extern __shared__ SmemLeaf tab[];
     __shared__ unsigned s_first, s_bad;
     const int L = c.L, W = c.W, H = c.H;
     const size_t P = c.P;
-    auto reset = [&](SmemLeaf& z) {
+    const int b = blockIdx.y;
+    for (int l = threadIdx.x; l < L; l += STC_NT) {
+        SmemLeaf z;
         z.cnt = 0; z.sx = 0; z.sy = 0; z.bx0 = 0xFFFFFFFFu; z.by0 = 0xFFFFFFFFu; z.bx1 = 0; z.by1 = 0;
         z.border = 0; z.kmin = 0xFFFFFFFFu; z.kmax = 0; z.sdep = 0; z.sdist = 0;
-    };
-    for (int l = threadIdx.x; l < L; l += ST_NT) reset(tab[l]);
+        tab[l] = z;
+    }
     if (threadIdx.x == 0) { s_first = 0xFFFFFFFFu; s_bad = 0; }
-
-    const size_t base = ((size_t)blockIdx.x * ST_NT + threadIdx.x) * ST_PX;
-    const int npx = base < P ? (int)min((size_t)ST_PX, P - base) : 0;
-    const int y0 = (int)(base / W), x0 = (int)(base % W);
-    const unsigned FULL = 0xFFFFFFFFu;
-    const int lane = threadIdx.x & 31;
-    unsigned ray[ST_PX];     // ray length in 2^-30 units (ray_tab >> 6; < 2^32 for rays up to 75 degrees off axis)
-#pragma unroll
-    for (int k = 0; k < ST_PX; ++k) ray[k] = k < npx ? (unsigned)min(c.ray_tab[base + k] >> 6, 0xFFFFFFFFull) : 0u;
-
-    const int f_begin = blockIdx.y * ST_FR, f_end = min(n_frames, f_begin + ST_FR);
-    // raw loads of one frame's tile (nothing is consumed here, see the prefetch below)
-    uint4 lraw = make_uint4(0, 0, 0, 0);
-    float4 draw0 = make_float4(0.f, 0.f, 0.f, 0.f), draw1 = draw0;
-    bool vec = false;
-    auto fetch = [&](int f) {
-        if (f >= f_end) return;
-        const int16_t* lp = labels + (size_t)f * P + base;
-        const float* dp = depth + (size_t)f * P + base;
-        vec = npx == ST_PX && ((reinterpret_cast<uintptr_t>(lp) | reinterpret_cast<uintptr_t>(dp)) & 15) == 0;
-        if (vec) {
-            lraw = *reinterpret_cast<const uint4*>(lp);
-            draw0 = *reinterpret_cast<const float4*>(dp);
-            draw1 = *reinterpret_cast<const float4*>(dp + 4);
-        }
-    };
-    fetch(f_begin);
     __syncthreads();
-    for (int f = f_begin; f < f_end; ++f) {
-        int lab[ST_PX];
-        float val[ST_PX];
-        if (vec) {
-            const unsigned w[4] = {lraw.x, lraw.y, lraw.z, lraw.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { lab[2 * k] = (int16_t)(w[k] & 0xFFFFu); lab[2 * k + 1] = (int16_t)(w[k] >> 16); }
-            val[0] = draw0.x; val[1] = draw0.y; val[2] = draw0.z; val[3] = draw0.w;
-            val[4] = draw1.x; val[5] = draw1.y; val[6] = draw1.z; val[7] = draw1.w;
-        } else {     // tile tail or unaligned frame: plain loads, no prefetch
-            const int16_t* lp = labels + (size_t)f * P + base;
-            const float* dp = depth + (size_t)f * P + base;
-#pragma unroll
-            for (int k = 0; k < ST_PX; ++k) { lab[k] = k < npx ? (int)lp[k] : -32768; val[k] = k < npx ? dp[k] : 0.f; }
-        }
-        fetch(f + 1);
-        // Runs of equal labels inside the thread's ST_PX pixels (almost always one, two at a leaf edge).  Round r
-        // handles the r-th run of every lane: lanes are grouped by the run's label (labels are piecewise constant
-        // along a row, so a warp holds a handful of groups), each group reduces its sums with REDUX over its own
-        // member mask and its first lane updates the CTA's table - a few shared-memory atomics per warp instead of
-        // a dozen per thread, and no divergent slow path.
-        unsigned ridp = 0;      // run index of pixel k in bits [4k, 4k+4)
-        int nruns = 0;
-        {
-            int cur = 0;
-#pragma unroll
-            for (int k = 0; k < ST_PX; ++k) {
-                if (k > 0 && lab[k] != lab[k - 1]) ++cur;
-                ridp |= (unsigned)cur << (4 * k);
-                if (k < npx) nruns = cur + 1;
-            }
-        }
-        const int maxruns = __reduce_max_sync(FULL, nruns);
-        for (int r = 0; r < maxruns; ++r) {
-            int lr = -1, cnt = 0, firstk = ST_PX;
-#pragma unroll
-            for (int k = ST_PX - 1; k >= 0; --k)
-                if (k < npx && (int)((ridp >> (4 * k)) & 15u) == r) { lr = lab[k]; ++cnt; firstk = k; }
-            const bool has = cnt > 0;
-            const bool valid = has && lr >= 0 && lr < L;
-            if (has && !valid) s_bad = 1;
-            const unsigned grp = __match_any_sync(FULL, valid ? lr : (0x40000000 | lane));
-            if (!valid) continue;
-            const bool leader = (__ffs(grp) - 1) == lane;
-            const unsigned gcnt = __reduce_add_sync(grp, (unsigned)cnt);
-            if (lr == 0) {
-                if (leader) atomicAdd(&tab[0].cnt, gcnt);
-                continue;
-            }
-            unsigned sx = 0, sy = 0, bx0 = 0xFFFFFFFFu, bx1 = 0, by0 = 0xFFFFFFFFu, by1 = 0, brd = 0, kmn = 0xFFFFFFFFu, kmx = 0;
-            long long rdep = 0;
-            unsigned long long rdist = 0;
-#pragma unroll
-            for (int k = 0; k < ST_PX; ++k) {
-                if (k < npx && (int)((ridp >> (4 * k)) & 15u) == r) {
-                    int x = x0 + k, y = y0;
-                    if (x >= W) { x -= W; ++y; }
-                    sx += x; sy += y;
-                    bx0 = min(bx0, (unsigned)x); bx1 = max(bx1, (unsigned)x); by0 = min(by0, (unsigned)y); by1 = max(by1, (unsigned)y);
-                    brd |= (x == 0) | (y == 0) | (x == W - 1) | (y == H - 1);
-                    const double dd = fmin(fmax((double)val[k], -2048.0), 2048.0);
-                    rdep += __double2ll_rn(dd * DEP_SCALE);
-                    rdist += ray[k];
-                    const unsigned key = f2key(val[k]);
-                    kmn = min(kmn, key); kmx = max(kmx, key);
-                }
-            }
-            sx = __reduce_add_sync(grp, sx); sy = __reduce_add_sync(grp, sy);
-            bx0 = __reduce_min_sync(grp, bx0); bx1 = __reduce_max_sync(grp, bx1);
-            by0 = __reduce_min_sync(grp, by0); by1 = __reduce_max_sync(grp, by1);
-            brd = __reduce_or_sync(grp, brd);
-            kmn = __reduce_min_sync(grp, kmn); kmx = __reduce_max_sync(grp, kmx);
-            const unsigned first = __reduce_min_sync(grp, (unsigned)(base + firstk));
-            // 64-bit sums as (high part, low 24 bits): each half stays far below 2^31 over 32 lanes
-            const unsigned dep_lo = __reduce_add_sync(grp, (unsigned)(rdep & 0xFFFFFF));
-            const int dep_hi = __reduce_add_sync(grp, (int)(rdep >> 24));
-            const unsigned dist_lo = __reduce_add_sync(grp, (unsigned)(rdist & 0xFFFFFF));
-            const unsigned dist_hi = __reduce_add_sync(grp, (unsigned)(rdist >> 24));
-            if (leader) {
-                SmemLeaf* t = &tab[lr];
-                atomicAdd(&t->cnt, gcnt);
-                atomicAdd(&t->sx, sx); atomicAdd(&t->sy, sy);
-                atomicMin(&t->bx0, bx0); atomicMax(&t->bx1, bx1); atomicMin(&t->by0, by0); atomicMax(&t->by1, by1);
-                if (brd) atomicOr(&t->border, 1u);
+    const int x = blockIdx.x * STC_NT + threadIdx.x;
+    if (x < W) {
+        const int16_t* lp = labels + (size_t)b * P + x;
+        const float* dp = depth + (size_t)b * P + x;
+        const unsigned long long* rt = c.ray_tab + x;
+        int cur = -1, ya = 0;
+        bool seen_leaf = false;
+        long long sdep = 0;
+        unsigned kmn = 0xFFFFFFFFu, kmx = 0;
+        auto flush = [&](int yb) {     // run [ya, yb] of label cur ends
+            if (cur < 0) return;
+            SmemLeaf* t = &tab[cur];
+            const unsigned len = (unsigned)(yb - ya + 1);
+            atomicAdd(&t->cnt, len);
+            if (cur > 0) {
+                atomicAdd(&t->sx, (unsigned)x * len);
+                atomicAdd(&t->sy, (unsigned)(ya + yb) * len / 2u);
+                atomicMin(&t->bx0, (unsigned)x); atomicMax(&t->bx1, (unsigned)x);
+                atomicMin(&t->by0, (unsigned)ya); atomicMax(&t->by1, (unsigned)yb);
+                if (x == 0 || x == W - 1 || ya == 0 || yb == H - 1) atomicOr(&t->border, 1u);
                 atomicMin(&t->kmin, kmn); atomicMax(&t->kmax, kmx);
-                atomicAdd(&t->sdep, (unsigned long long)(((long long)dep_hi << 24) + (long long)dep_lo));
-                atomicAdd(&t->sdist, (((unsigned long long)dist_hi << 24) + dist_lo) << 6);
-                atomicMin(&s_first, first);
+                atomicAdd(&t->sdep, (unsigned long long)sdep);
+                const unsigned long long hi = rt[(size_t)yb * W], lo = ya > 0 ? rt[(size_t)(ya - 1) * W] : 0ull;
+                atomicAdd(&t->sdist, hi - lo);
             }
+        };
+        int nl[ST_U];
+        float nd[ST_U];
+#pragma unroll
+        for (int k = 0; k < ST_U; ++k) {
+            nl[k] = k < H ? (int)lp[(size_t)k * W] : 0;
+            nd[k] = k < H ? dp[(size_t)k * W] : 0.f;
         }
-        __syncthreads();
-        // flush the touched entries to frame f's global table and reset them for the next frame
-        for (int l = threadIdx.x; l < L; l += ST_NT) {
-            const SmemLeaf t = tab[l];
-            if (t.cnt) {
-                const size_t o = (size_t)f * L + l;
-                atomicAdd(&c.cnt[o], t.cnt);
-                if (l > 0) {
-                    atomicAdd(&c.sx[o], (unsigned long long)t.sx);
-                    atomicAdd(&c.sy[o], (unsigned long long)t.sy);
-                    atomicAdd(&c.sdep[o], t.sdep);
-                    atomicAdd(&c.sdist[o], t.sdist);
-                    atomicMin(&c.bx0[o], t.bx0); atomicMax(&c.bx1[o], t.bx1);
-                    atomicMin(&c.by0[o], t.by0); atomicMax(&c.by1[o], t.by1);
-                    atomicMin(&c.kmin[o], t.kmin); atomicMax(&c.kmax[o], t.kmax);
-                    if (t.border) atomicOr(&c.border[o], 1u);
+        for (int y0 = 0; y0 < H; y0 += ST_U) {
+            int cl[ST_U];
+            float cd[ST_U];
+#pragma unroll
+            for (int k = 0; k < ST_U; ++k) { cl[k] = nl[k]; cd[k] = nd[k]; }
+#pragma unroll
+            for (int k = 0; k < ST_U; ++k) {        // next batch in flight while this one is reduced
+                const int y = y0 + ST_U + k;
+                nl[k] = y < H ? (int)lp[(size_t)y * W] : 0;
+                nd[k] = y < H ? dp[(size_t)y * W] : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < ST_U; ++k) {
+                const int y = y0 + k;
+                if (y < H) {
+                    int l = cl[k];
+                    if (l < 0 || l >= L) { s_bad = 1; l = -1; }
+                    if (l != cur) {
+                        flush(y - 1);
+                        cur = l; ya = y; sdep = 0; kmn = 0xFFFFFFFFu; kmx = 0;
+                        if (l >= 1 && !seen_leaf) { atomicMin(&s_first, (unsigned)((size_t)y * W + x)); seen_leaf = true; }
+                    }
+                    if (l > 0) {
+                        // 2^28 * depth is exact in float32 (power-of-two scale), so this equals the float64 formulation
+                        const float dd = fminf(fmaxf(cd[k], -2048.f), 2048.f);
+                        sdep += __float2ll_rn(dd * 268435456.f);
+                        const unsigned key = f2key(cd[k]);
+                        kmn = min(kmn, key); kmx = max(kmx, key);
+                    }
                 }
-                reset(tab[l]);
             }
         }
-        if (threadIdx.x == 0) {
-            if (s_first != 0xFFFFFFFFu) atomicMin(&c.first_leaf[f], s_first);
-            if (s_bad) atomicOr(&c.status[f], LG_ST_LABEL_RANGE);
-            s_first = 0xFFFFFFFFu; s_bad = 0;
+        flush(H - 1);
+    }
+    __syncthreads();
+    for (int l = threadIdx.x; l < L; l += STC_NT) {
+        const SmemLeaf t = tab[l];
+        if (t.cnt) {
+            const size_t o = (size_t)b * L + l;
+            atomicAdd(&c.cnt[o], t.cnt);
+            if (l > 0) {
+                atomicAdd(&c.sx[o], (unsigned long long)t.sx);
+                atomicAdd(&c.sy[o], (unsigned long long)t.sy);
+                atomicAdd(&c.sdep[o], t.sdep);
+                atomicAdd(&c.sdist[o], t.sdist);
+                atomicMin(&c.bx0[o], t.bx0); atomicMax(&c.bx1[o], t.bx1);
+                atomicMin(&c.by0[o], t.by0); atomicMax(&c.by1[o], t.by1);
+                atomicMin(&c.kmin[o], t.kmin); atomicMax(&c.kmax[o], t.kmax);
+                if (t.border) atomicOr(&c.border[o], 1u);
+            }
         }
-        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (s_first != 0xFFFFFFFFu) atomicMin(&c.first_leaf[b], s_first);
+        if (s_bad) atomicOr(&c.status[b], LG_ST_LABEL_RANGE);
     }
 }
 
@@ -824,12 +777,12 @@ int lg_run_stage1(lg_context* c, const int16_t* labels, const float* depth, int 
     if (rc) return rc;
     const int tiles = (int)((c->P + ST_NT * ST_PX - 1) / (ST_NT * ST_PX));
     if (!c->ray_valid || c->ray_cam.f != cam.f || c->ray_cam.cx != cam.cx || c->ray_cam.cy != cam.cy) {
-        ray_table_kernel<<<LG_NUM_SM_HINT * 8, 256, 0, st>>>(c->ray_tab, c->H, c->W, cam);
+        ray_table_kernel<<<(c->W + 127) / 128, 128, 0, st>>>(c->ray_tab, c->H, c->W, cam);
         LG_LAUNCH_CHECK();
         c->ray_cam = cam;
         c->ray_valid = 1;
     }
-    leaf_stats_kernel<<<dim3(tiles, (n + ST_FR - 1) / ST_FR), ST_NT, c->L * sizeof(SmemLeaf), st>>>(*c, labels, depth, n);
+    leaf_stats_kernel<<<dim3((c->W + STC_NT - 1) / STC_NT, n), STC_NT, c->L * sizeof(SmemLeaf), st>>>(*c, labels, depth);
     LG_LAUNCH_CHECK();
     lg_mark(c, LG_M_STATS, st);
     leaf_offsets_kernel<<<(n + 63) / 64, 64, 0, st>>>(*c, n);
