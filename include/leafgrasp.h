@@ -193,8 +193,13 @@ int lg_normalize_patches(lg_context* ctx, const float* raw, int n, float* out, v
 int lg_set_profiling(lg_context* ctx, int on);
 /* ms[14]: device milliseconds of each stage of the last lg_process_batch call, in the order
  * [unused, leaf_stats, scatter, median, edt_columns, edt_rows, select, chamfer, orientation, score_maps,
- *  candidates, patches, cnn, fuse].  Synchronises on the last recorded event. */
+ *  candidates, patches, cnn, fuse].  A stage's time runs from the previous mark on the stream it ran on; stages on the
+ * internal stream overlap the others, so the sum can exceed the step time.  Synchronises on the recorded events. */
 int lg_stage_times(lg_context* ctx, float* ms, int n);
+/* Independent stages (union distance transform | per-leaf statistics, orientation | chamfer transforms) run side by
+ * side on an internal stream that forks from and joins `stream`; on = 0 serialises them on `stream` (clean per-stage
+ * times).  Default: on, unless the environment has LG_NO_OVERLAP=1.  Results are identical either way. */
+int lg_set_overlap(lg_context* ctx, int on);
 /* Number of kernels this library has launched in this process so far. */
 uint64_t lg_launch_count(void);
 

@@ -389,3 +389,9 @@ extern "C" int lg_stage_times(lg_context* c, float* ms, int n) {
 }
 
 extern "C" uint64_t lg_launch_count(void) { return g_lg_launches; }
+
+extern "C" int lg_set_overlap(lg_context* c, int on) {
+    if (!c) return LG_E_ARG;
+    c->overlap = on ? 1 : 0;
+    return LG_OK;
+}

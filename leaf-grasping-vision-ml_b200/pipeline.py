@@ -52,6 +52,10 @@ class GraspEngine:
         except Exception:
             pass
 
+    def set_overlap(self, on: bool):
+        """Run independent stages side by side on the library's internal stream (default) or serialised."""
+        N.check(self.lib.lg_set_overlap(self._ctx, int(bool(on))), "lg_set_overlap")
+
     @property
     def context_bytes(self) -> int:
         return int(self.lib.lg_context_bytes(self._ctx))

@@ -392,6 +392,84 @@ def test_process_batch_against_reference_golden(blob):
         eng.close()
 
 
+def test_cfg3_4k_dense_clutter_frame(state_dict, blob):
+    """BASELINE config[2]: one 3840x2160 frame with 100 overlapping leaves against the strict oracle."""
+    spec = synth.CFG3
+    P = synth.projection_matrix(spec)
+    lab, dep = synth.make_batch(spec, SEED, 0, 1)
+    eng = _engine(1, spec.height, spec.width, 128)
+    eng.set_cnn_weights(blob)
+    res = eng.process_batch(torch.from_numpy(lab).cuda(), torch.from_numpy(dep).cuda(), _cam(spec))
+    _check_frame(res[0], lab[0], dep[0], P, state_dict)
+    eng.close()
+
+
+_EXACT_FIELDS = ("status", "leaf_id", "n_candidates", "n_positive", "cand_x", "cand_y", "trad", "ml_valid", "best_index",
+                 "ml_used", "grasp_x", "grasp_y", "grasp_3d", "pre_grasp", "angle", "sdf_max", "region")
+
+
+def test_batch_invariance_and_scheduling_independence(blob):
+    """Size-independent properties at the benchmark's frame size: a frame's record does not depend on the batch it
+    travels in, on its position in the batch, on stage overlap (side stream on/off), or on the run (atomics and
+    pruning make the schedule vary; results may not).  fp32 CNN, so logits are bit-identical too."""
+    spec = synth.CFG2
+    n = 24
+    lab, dep = synth.make_batch(spec, SEED, 100, 6)
+    idx = np.arange(n) % 6
+    labs, deps = torch.from_numpy(lab[idx]).cuda(), torch.from_numpy(dep[idx]).cuda()
+    eng = _engine(n, spec.height, spec.width, 128)
+    eng.set_cnn_weights(blob)
+    a = eng.process_batch(labs, deps, _cam(spec))
+    b = eng.process_batch(labs, deps, _cam(spec))                     # idempotence
+    eng.set_overlap(False)
+    c = eng.process_batch(labs, deps, _cam(spec))                     # serialised stages
+    eng.set_overlap(True)
+    single = eng.process_batch(labs[:1], deps[:1], _cam(spec))        # batch of one
+    for name in _EXACT_FIELDS + ("logit",):
+        np.testing.assert_array_equal(a[name], b[name], err_msg=name)
+        np.testing.assert_array_equal(a[name], c[name], err_msg=name)
+        np.testing.assert_array_equal(a[name][:1], single[name], err_msg=name)
+        for k in range(6, n):                                          # same frame, other slot
+            np.testing.assert_array_equal(a[name][k], a[name][k % 6], err_msg=name)
+    assert (a["leaf_id"] > 0).all() and (a["n_candidates"] == 20).all()
+    eng.close()
+
+
+@pytest.mark.parametrize("shape", [(203, 317), (360, 484), (97, 1000)])
+def test_odd_sizes_take_the_generic_kernels(shape, state_dict, blob):
+    """Widths that are not multiples of 8 (no vector loads, generic chamfer kernel) against the strict oracle."""
+    H, W = shape
+    spec = synth.FrameSpec(height=H, width=W, n_leaves=3, a_range=(70.0, 90.0), b_range=(45.0, 60.0), margin=min(H, W) * 0.3)
+    P = synth.projection_matrix(spec)
+    lab, dep = synth.make_batch(spec, SEED, 7, 2)
+    eng = _engine(2, H, W, 16)
+    eng.set_cnn_weights(blob)
+    res = eng.process_batch(torch.from_numpy(lab).cuda(), torch.from_numpy(dep).cuda(), _cam(spec))
+    for i in range(2):
+        _check_frame(res[i], lab[i], dep[i], P, state_dict)
+    eng.close()
+
+
+def test_bf16_pipeline_matches_fp32_picks(blob):
+    """The tensor-core CNN inside the whole path: same candidates, logits within the bf16 bar, and the fused pick
+    agrees wherever the fp32 decision has a margin larger than the bf16 error."""
+    spec = synth.CFG2
+    lab, dep = synth.make_batch(spec, SEED, 200, 8)
+    eng = _engine(8, spec.height, spec.width, 128)
+    eng.set_cnn_weights(blob)
+    labs, deps = torch.from_numpy(lab).cuda(), torch.from_numpy(dep).cuda()
+    r32 = eng.process_batch(labs, deps, _cam(spec), use_bf16=False)
+    r16 = eng.process_batch(labs, deps, _cam(spec), use_bf16=True)
+    for name in ("leaf_id", "n_candidates", "cand_x", "cand_y", "trad", "ml_valid"):
+        np.testing.assert_array_equal(r32[name], r16[name], err_msg=name)
+    ok = r32["ml_valid"] > 0
+    np.testing.assert_allclose(r16["logit"][ok], r32["logit"][ok], atol=1e-2, rtol=1e-2)
+    np.testing.assert_allclose(r16["ml"][ok], r32["ml"][ok], atol=5e-3)
+    same = (r16["best_index"] == r32["best_index"]).mean()
+    assert same >= 0.75, f"fused pick agreement {same}"
+    eng.close()
+
+
 def test_empty_and_degenerate_frames(blob):
     spec = synth.SMALL
     H, W = spec.height, spec.width
