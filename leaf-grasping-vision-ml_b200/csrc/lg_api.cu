@@ -90,7 +90,8 @@ extern "C" int lg_create(lg_context** out, int max_frames, int height, int width
     A(&c->bx0, B * L); A(&c->bx1, B * L); A(&c->by0, B * L); A(&c->by1, B * L); A(&c->border, B * L);
     A(&c->kmin, B * L); A(&c->kmax, B * L); A(&c->ray_tab, P);
     A(&c->first_leaf, B); A(&c->seg_off, B * (L + 1)); A(&c->seg_cur, B * L); A(&c->seg, B * P); A(&c->median, B * L);
-    A(&c->edt_g, B * P); A(&c->edt_best, B); A(&c->leaf_id, B); A(&c->records, B * L); A(&c->status, B); A(&c->region, B);
+    c->edt_nchunks = (width + 31) / 32;
+    A(&c->edt_g, B * P); A(&c->edt_gmin, B * (size_t)height * c->edt_nchunks); A(&c->edt_best, B); A(&c->leaf_id, B); A(&c->records, B * L); A(&c->status, B); A(&c->region, B);
     A(&c->dt_fwd, 2 * B * P); A(&c->di, B * P); A(&c->dt_max, B * 2);
     c->bits_stride = (size_t)((width + 2 + 31) / 32) * (height + 2);
     A(&c->bits, B * c->bits_stride);
@@ -135,7 +136,7 @@ extern "C" int lg_create(lg_context** out, int max_frames, int height, int width
 
 extern "C" void lg_destroy(lg_context* c) {
     if (!c) return;
-    void* ptrs[] = {c->kmin, c->kmax, c->ray_tab, c->cnt, c->sx, c->sy, c->sdep, c->sdist, c->bx0, c->bx1, c->by0, c->by1, c->border, c->first_leaf,
+    void* ptrs[] = {c->edt_gmin, c->kmin, c->kmax, c->ray_tab, c->cnt, c->sx, c->sy, c->sdep, c->sdist, c->bx0, c->bx1, c->by0, c->by1, c->border, c->first_leaf,
                     c->seg_off, c->seg_cur, c->seg, c->median, c->edt_g, c->edt_best, c->leaf_id, c->records, c->status,
                     c->region, c->dt_fwd, c->di, c->dt_max, c->bits, c->run_x0, c->run_x1, c->run_y, c->run_parent,
                     c->row_first, c->hull, c->orient, c->m_sdf, c->m_app, c->m_acc, c->m_trad, c->m_flat, c->m_stem,

@@ -81,6 +81,8 @@ struct lg_context {
     float* seg;                    // [B][P] depth values grouped by label
     float* median;                 // [B][L]
     uint16_t* edt_g;               // [B][P] column distances
+    uint16_t* edt_gmin;            // [B][H][edt_nchunks] minimum of edt_g over each chunk of 32 columns
+    int edt_nchunks;
     unsigned long long* edt_best;  // [B] packed (d2 << 32 | ~index)
     int32_t* leaf_id;              // [B]
     lg_leaf_record* records;       // [B][L]

@@ -416,10 +416,14 @@ struct EdtSrc {
     __device__ __forceinline__ bool is_source(size_t i) const { return labels ? (labels[i] >= 1) : (mask[i] == 0); }
 };
 
-// pass 1: per column, distance (in rows) to the nearest source pixel in that column; 0xFFFF = none
-__global__ void edt_col_kernel(EdtSrc src, uint16_t* __restrict__ g, int H, int W, size_t P) {
+// pass 1: per column, distance (in rows) to the nearest source pixel in that column; 0xFFFF = none.
+// gmin (optional): for every row the minimum of g over each chunk of 32 columns (one warp), [H][nchunks] per frame -
+// the arg-max search reads these instead of the rows themselves.
+__global__ void edt_col_kernel(EdtSrc src, uint16_t* __restrict__ g, uint16_t* __restrict__ gmin, int nchunks, int H, int W,
+                               size_t P) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= W) return;
+    const bool in = x < W;
+    const int xc = in ? x : W - 1;             // out-of-range lanes shadow the last column and store nothing
     const size_t fo = (size_t)blockIdx.y * P;
     uint16_t* gp = g + fo;
     constexpr int U = 8;    // rows whose loads are in flight together (the sweep itself is sequential)
@@ -427,25 +431,31 @@ __global__ void edt_col_kernel(EdtSrc src, uint16_t* __restrict__ g, int H, int 
     for (int y0 = 0; y0 < H; y0 += U) {
         bool srcv[U];
 #pragma unroll
-        for (int k = 0; k < U; ++k) srcv[k] = (y0 + k < H) ? src.is_source(fo + (size_t)(y0 + k) * W + x) : false;
+        for (int k = 0; k < U; ++k) srcv[k] = (y0 + k < H) ? src.is_source(fo + (size_t)(y0 + k) * W + xc) : false;
 #pragma unroll
         for (int k = 0; k < U; ++k) {
             if (y0 + k < H) {
                 d = srcv[k] ? 0u : min(d + 1u, 0xFFFFu);
-                gp[(size_t)(y0 + k) * W + x] = (uint16_t)d;
+                if (in) gp[(size_t)(y0 + k) * W + x] = (uint16_t)d;
             }
         }
     }
     d = 0xFFFFu;
+    const int chunk = x >> 5, lane = threadIdx.x & 31;
+    uint16_t* gm = gmin ? gmin + (size_t)blockIdx.y * H * nchunks : nullptr;
     for (int y0 = H - 1; y0 >= 0; y0 -= U) {
         unsigned cur[U];
 #pragma unroll
-        for (int k = 0; k < U; ++k) cur[k] = (y0 - k >= 0) ? gp[(size_t)(y0 - k) * W + x] : 0xFFFFu;
+        for (int k = 0; k < U; ++k) cur[k] = (y0 - k >= 0) ? gp[(size_t)(y0 - k) * W + xc] : 0xFFFFu;
 #pragma unroll
         for (int k = 0; k < U; ++k) {
             if (y0 - k >= 0) {
                 d = min(cur[k], min(d + 1u, 0xFFFFu));
-                gp[(size_t)(y0 - k) * W + x] = (uint16_t)d;
+                if (in) gp[(size_t)(y0 - k) * W + x] = (uint16_t)d;
+                if (gm) {
+                    const unsigned m = __reduce_min_sync(0xFFFFFFFFu, in ? d : 0xFFFFu);
+                    if (lane == 0 && chunk < nchunks) gm[(size_t)(y0 - k) * nchunks + chunk] = (uint16_t)m;
+                }
             }
         }
     }
@@ -580,6 +590,108 @@ __global__ void __launch_bounds__(EDT_NT) edt_row_kernel(const uint16_t* __restr
             for (int w = 0; w < EDT_NT / 32; ++w) mybest = max(mybest, sbest[w]);
             if (threadIdx.x == 0 && mybest > *reinterpret_cast<volatile unsigned long long*>(&best[b])) atomicMax(&best[b], mybest);
             __syncthreads();             // sbest is reused by the next improving row
+        }
+    }
+}
+
+// Arg-max search, main part: ONE WARP PER ROW.  A row is first judged by its chunk minima alone (gmin, 1/32 of the
+// data): chunk j cannot hold the maximum if min over j' of gmin(j')^2 + (32 |j - j'| + 31)^2 is below the frame's
+// running maximum.  Only rows with a surviving chunk load their column distances (into the warp's shared-memory
+// row) and run the exact search, for the surviving chunks only.  Exactness argument as for edt_row_kernel: a pixel
+// is only dropped when an upper bound of its distance is below an exact distance found elsewhere in the frame.
+constexpr int EDTW_NT = 256;
+__global__ void __launch_bounds__(EDTW_NT) edt_rowmax_kernel(const uint16_t* __restrict__ g, const uint16_t* __restrict__ gmin,
+                                                              unsigned long long* __restrict__ best, int nchunks, int H, int W,
+                                                              size_t P, int row_stride, int yi_begin, int yi_end) {
+    extern __shared__ unsigned sm_rows[];            // per warp: W squared column distances, then 128 chunk minima
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned* srow = sm_rows + (size_t)warp * (W + 128);
+    unsigned* mrow = srow + W;
+    const uint16_t* gmf = gmin + (size_t)b * H * nchunks;
+    unsigned long long mybest = 0;                   // this warp's best (identical in all lanes)
+    const int rows_per_pass = gridDim.y * (EDTW_NT / 32);
+    for (int yi = yi_begin + blockIdx.y * (EDTW_NT / 32) + warp; yi < yi_end; yi += rows_per_pass) {
+        const int y = (int)(((long long)yi * row_stride) % H);
+        unsigned long long gb = 0;
+        if (lane == 0) gb = *reinterpret_cast<volatile unsigned long long*>(&best[b]);
+        gb = __shfl_sync(0xFFFFFFFFu, gb, 0);
+        const unsigned lb = (unsigned)(max(gb, mybest) >> 32);
+        __syncwarp();
+        bool has_source = false;
+        for (int j = lane; j < nchunks; j += 32) {
+            const unsigned v = gmf[(size_t)y * nchunks + j];
+            mrow[j] = (v == 0xFFFFu) ? 0xFFFFFFFFu : v * v;
+            has_source |= v != 0xFFFFu;
+        }
+        if (!__any_sync(0xFFFFFFFFu, has_source)) continue;      // no source in any column of this row: nothing to rank
+        __syncwarp();
+        // chunks that may still hold a pixel at distance >= lb
+        unsigned alive[4] = {0u, 0u, 0u, 0u};        // bit `lane` of alive[k]: chunk 32 k + lane survives
+        bool any_alive = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int j = 32 * k + lane;
+            bool keep = false;
+            if (j < nchunks) {
+                unsigned long long ub = (unsigned long long)mrow[j] + 31ull * 31ull;
+                for (int dj = 1; dj < nchunks && ub >= lb; ++dj) {
+                    const unsigned long long off = (unsigned long long)(32 * dj + 31) * (32 * dj + 31);
+                    if (off >= lb) break;
+                    if (j - dj >= 0) ub = min(ub, (unsigned long long)mrow[j - dj] + off);
+                    if (j + dj < nchunks) ub = min(ub, (unsigned long long)mrow[j + dj] + off);
+                }
+                keep = ub >= lb;
+            }
+            alive[k] = __ballot_sync(0xFFFFFFFFu, keep);
+            any_alive |= alive[k] != 0u;
+        }
+        if (!any_alive) continue;
+        // exact search on the surviving chunks
+        const uint16_t* gp = g + (size_t)b * P + (size_t)y * W;
+        for (int x = lane; x < W; x += 32) {
+            const unsigned v = gp[x];
+            srow[x] = (v == 0xFFFFu) ? 0xFFFFFFFFu : v * v;
+        }
+        __syncwarp();
+        unsigned long long rowbest = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            unsigned rem = alive[k];
+            while (rem) {
+                const int j = 32 * k + (__ffs(rem) - 1);
+                rem &= rem - 1;
+                const int x = (j << 5) + lane;
+                if (x >= W) continue;
+                unsigned bestd = srow[x];
+                if (bestd < lb) continue;
+                if (lb) {
+                    for (unsigned kk = 1; kk * kk < bestd; kk <<= 1) {
+                        const int xl = x - (int)kk, xr = x + (int)kk;
+                        if (xl < 0 && xr >= W) break;
+                        const unsigned q = kk * kk;
+                        if (xl >= 0) { const unsigned t = srow[xl]; if (t != 0xFFFFFFFFu) bestd = min(bestd, t + q); }
+                        if (xr < W) { const unsigned t = srow[xr]; if (t != 0xFFFFFFFFu) bestd = min(bestd, t + q); }
+                    }
+                    if (bestd < lb) continue;
+                }
+                for (unsigned kk = 1; kk * kk < bestd; ++kk) {
+                    const int xl = x - (int)kk, xr = x + (int)kk;
+                    if (xl < 0 && xr >= W) break;
+                    const unsigned q = kk * kk;
+                    if (xl >= 0) { const unsigned t = srow[xl]; if (t != 0xFFFFFFFFu) bestd = min(bestd, t + q); }
+                    if (xr < W) { const unsigned t = srow[xr]; if (t != 0xFFFFFFFFu) bestd = min(bestd, t + q); }
+                    if (bestd < lb) break;
+                }
+                if (bestd < lb) continue;
+                const unsigned idx = (unsigned)((size_t)y * W + x);
+                rowbest = max(rowbest, ((unsigned long long)bestd << 32) | (unsigned long long)(0xFFFFFFFFu - idx));
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) rowbest = max(rowbest, __shfl_xor_sync(0xFFFFFFFFu, rowbest, d));
+        if (rowbest > mybest) {
+            mybest = rowbest;
+            if (lane == 0 && mybest > *reinterpret_cast<volatile unsigned long long*>(&best[b])) atomicMax(&best[b], mybest);
         }
     }
 }
@@ -742,24 +854,40 @@ __global__ void select_leaf_kernel(lg_context c, lg_camera cam, int32_t* leaf_ou
 
 }  // namespace
 
-// row pass for n frames; d2 == nullptr: arg-max only (pruned search, seeded by a few well spread rows)
+// row pass for n frames; d2 == nullptr: arg-max only (pruned search).  The arg-max search first runs a few well
+// spread rows per frame one after the other (edt_row_kernel, one CTA per frame: the first row is searched in full,
+// the following ones against the bound it leaves), then all remaining rows with one warp per row.
 static int run_edt_rows(lg_context* c, int n, uint32_t* d2, cudaStream_t st) {
     const int stride = edt_row_stride(c->H);
     const size_t sm = c->W * sizeof(unsigned);
-    int seed = 0;
-    if (!d2 && c->H >= 64) {
-        seed = 16;
-        edt_row_kernel<<<dim3(n, seed), EDT_NT, sm, st>>>(c->edt_g, nullptr, c->edt_best, c->H, c->W, c->P, stride, 0, seed);
+    if (d2 || c->H < 64) {
+        edt_row_kernel<<<edt_row_grid(n, c->H), EDT_NT, sm, st>>>(c->edt_g, d2, c->edt_best, c->H, c->W, c->P, stride, 0, c->H);
         LG_LAUNCH_CHECK();
+        return LG_OK;
     }
-    edt_row_kernel<<<edt_row_grid(n, c->H), EDT_NT, sm, st>>>(c->edt_g, d2, c->edt_best, c->H, c->W, c->P, stride, seed, c->H);
+    const int seed = 16;
+    int seed_ctas = 296 / n;                         // small batches: spread the seed rows over a few CTAs per frame
+    seed_ctas = seed_ctas < 1 ? 1 : (seed_ctas > seed ? seed : seed_ctas);
+    edt_row_kernel<<<dim3(n, seed_ctas), EDT_NT, sm, st>>>(c->edt_g, nullptr, c->edt_best, c->H, c->W, c->P, stride, 0, seed);
+    LG_LAUNCH_CHECK();
+    const size_t smw = (size_t)(EDTW_NT / 32) * (c->W + 128) * sizeof(unsigned);
+    static size_t configured = 0;
+    if (smw > configured) {
+        LG_CUDA(cudaFuncSetAttribute(edt_rowmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw));
+        configured = smw;
+    }
+    int per_frame = (148 * 4 * 2 + n - 1) / n;       // about two waves of CTAs over the batch
+    const int max_ctas = (c->H - seed + EDTW_NT / 32 - 1) / (EDTW_NT / 32);
+    per_frame = per_frame < 1 ? 1 : (per_frame > max_ctas ? max_ctas : per_frame);
+    edt_rowmax_kernel<<<dim3(n, per_frame), EDTW_NT, smw, st>>>(c->edt_g, c->edt_gmin, c->edt_best, c->edt_nchunks, c->H, c->W,
+                                                                 c->P, stride, seed, c->H);
     LG_LAUNCH_CHECK();
     return LG_OK;
 }
 
 int lg_run_edt_union(lg_context* c, const int16_t* labels, int n, cudaStream_t st) {
     EdtSrc src{labels, nullptr};
-    edt_col_kernel<<<dim3((c->W + 127) / 128, n), 128, 0, st>>>(src, c->edt_g, c->H, c->W, c->P);
+    edt_col_kernel<<<dim3((c->W + 127) / 128, n), 128, 0, st>>>(src, c->edt_g, c->edt_gmin, c->edt_nchunks, c->H, c->W, c->P);
     LG_LAUNCH_CHECK();
     lg_mark(c, LG_M_EDT_COL, st);
     int rc = run_edt_rows(c, n, nullptr, st);
@@ -810,7 +938,8 @@ extern "C" int lg_edt_squared(lg_context* c, const uint8_t* mask, int n, uint32_
     cudaStream_t st = (cudaStream_t)stream;
     LG_CUDA(cudaMemsetAsync(c->edt_best, 0, sizeof(unsigned long long) * n, st));
     EdtSrc src{nullptr, mask};
-    edt_col_kernel<<<dim3((c->W + 127) / 128, n), 128, 0, st>>>(src, c->edt_g, c->H, c->W, c->P);
+    edt_col_kernel<<<dim3((c->W + 127) / 128, n), 128, 0, st>>>(src, c->edt_g, d2 ? nullptr : c->edt_gmin, c->edt_nchunks, c->H, c->W,
+                                                                c->P);
     LG_LAUNCH_CHECK();
     int rc = run_edt_rows(c, n, d2, st);
     if (rc) return rc;
