@@ -279,7 +279,8 @@ def run_ours(args):
     leaf_px = float(np.mean((lab_u > 0).sum(axis=(1, 2))))
     n_patches = float(np.mean(records["ml_valid"].sum(axis=1)))
     alg_bytes = {   # per frame, compulsory traffic: inputs once + outputs once
-        "leaf_stats": 6 * P, "scatter": 6 * P + 4 * leaf_px, "median": 4 * leaf_px, "edt_columns": 4 * P,
+        # leaf_stats also carries the column pass of the union distance transform (writes 2 B/px of column distances)
+        "leaf_stats": 8 * P, "scatter": 6 * P + 4 * leaf_px, "median": 4 * leaf_px, "edt_columns": 0,
         "edt_rows": 2 * P, "select": 0, "chamfer": 2 * P + 6 * bbox_px, "orientation": 2 * bbox_px,
         "score_maps": (2 + 4 + 4 + 45) * rect_px, "candidates": 12 * 20000, "patches": 20 * 9 * 1024 * 8, "fuse": 760}
     top = int(np.argmax(serial_ms))
@@ -304,7 +305,7 @@ def run_ours(args):
     roof["stage_ms"] = {STAGES[i]: round(float(stage_ms[i]), 4) for i in range(1, len(STAGES))}
     roof["stage_ms_serial"] = {STAGES[i]: round(float(serial_ms[i]), 4) for i in range(1, len(STAGES))}
     roof["stage_gbs"] = {k: round(alg_bytes[k] * B / (serial_ms[STAGES.index(k)] * 1e-3) / 1e9, 1)
-                         for k in alg_bytes if serial_ms[STAGES.index(k)] > 0}
+                         for k in alg_bytes if serial_ms[STAGES.index(k)] > 0 and alg_bytes[k] > 0}
     roof["cnn_tflops"] = round(312.83e6 * n_patches * B / (serial_ms[STAGES.index("cnn")] * 1e-3) / 1e12, 1) \
         if serial_ms[STAGES.index("cnn")] > 0 else None
     roof["whole_step_gbs"] = round((45 * P) * B / (ms / args.steps * 1e-3) / 1e9, 1)   # 45 B/px, SURVEY.md 8d

@@ -193,7 +193,8 @@ int lg_normalize_patches(lg_context* ctx, const float* raw, int n, float* out, v
 int lg_set_profiling(lg_context* ctx, int on);
 /* ms[14]: device milliseconds of each stage of the last lg_process_batch call, in the order
  * [unused, leaf_stats, scatter, median, edt_columns, edt_rows, select, chamfer, orientation, score_maps,
- *  candidates, patches, cnn, fuse].  A stage's time runs from the previous mark on the stream it ran on; stages on the
+ *  candidates, patches, cnn, fuse] (edt_columns is ~0 in lg_process_batch: the column pass of the union distance
+ *  transform is fused into leaf_stats).  A stage's time runs from the previous mark on the stream it ran on; stages on the
  * internal stream overlap the others, so the sum can exceed the step time.  Synchronises on the recorded events. */
 int lg_stage_times(lg_context* ctx, float* ms, int n);
 /* Independent stages (union distance transform | per-leaf statistics, orientation | chamfer transforms) run side by

@@ -369,12 +369,12 @@ extern "C" int lg_stage_times(lg_context* c, float* ms, int n) {
     int pred[LG_PROF_MARKS];
     for (int i = 0; i < LG_PROF_MARKS; ++i) pred[i] = i - 1;
     pred[LG_M_START] = -1;
-    pred[LG_M_FORK1] = LG_M_START;   pred[LG_M_EDT_COL] = LG_M_FORK1;
+    pred[LG_M_FORK1] = LG_M_STATS;   pred[LG_M_EDT_COL] = LG_M_FORK1;
     pred[LG_M_JOIN1] = LG_M_EDT_ROW; pred[LG_M_SELECT] = LG_M_JOIN1;
     pred[LG_M_FORK2] = LG_M_SELECT;  pred[LG_M_ORIENT] = LG_M_FORK2; pred[LG_M_CHAMFER] = LG_M_SELECT;
     pred[LG_M_JOIN2] = LG_M_ORIENT;  pred[LG_M_SCORE] = LG_M_JOIN2;
-    if (!c->prof_seen[LG_M_FORK1]) {   // overlap off: EDT runs first on the caller's stream, then the statistics
-        pred[LG_M_EDT_COL] = LG_M_START; pred[LG_M_STATS] = LG_M_EDT_ROW; pred[LG_M_JOIN1] = LG_M_MEDIAN;
+    if (!c->prof_seen[LG_M_FORK1]) {   // overlap off: stats (+ column pass), row pass, scatter, median on the caller's stream
+        pred[LG_M_EDT_COL] = LG_M_STATS; pred[LG_M_SCATTER] = LG_M_EDT_ROW; pred[LG_M_JOIN1] = LG_M_MEDIAN;
     }
     if (!c->prof_seen[LG_M_FORK2]) { pred[LG_M_ORIENT] = LG_M_SELECT; pred[LG_M_CHAMFER] = LG_M_ORIENT; pred[LG_M_JOIN2] = LG_M_CHAMFER; }
     for (int i = 1; i < LG_M_COUNT; ++i) {

@@ -160,7 +160,6 @@ static inline void lg_mark(lg_context* c, int id, cudaStream_t st) {
 // stage launchers (defined across the .cu files); all asynchronous on `st`
 int lg_run_stage1(lg_context* c, const int16_t* labels, const float* depth, int n, lg_camera cam, cudaStream_t st);
 int lg_run_select(lg_context* c, int n, lg_camera cam, int32_t* leaf_out, lg_leaf_record* rec_out, cudaStream_t st);
-int lg_run_edt_union(lg_context* c, const int16_t* labels, int n, cudaStream_t st);
 // aux = lg_fork(c, k, st): stream for the side branch (st itself when overlap is off); lg_join makes st wait for it
 cudaStream_t lg_fork(lg_context* c, int k, cudaStream_t st);
 int lg_join(lg_context* c, int k, cudaStream_t aux, cudaStream_t st);

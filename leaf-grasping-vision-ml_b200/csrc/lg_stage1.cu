@@ -76,6 +76,8 @@ __global__ void ray_table_kernel(unsigned long long* __restrict__ tab, int H, in
 // fixed point, exact and order independent) and its key range tracked.  Loads run ST_U rows ahead.
 constexpr int ST_U = 8;
 constexpr int STC_NT = 128;   // columns per CTA
+// The same walk is the column pass of the union distance transform (edt_col_kernel with source = label >= 1): the
+// kernel also writes the column distances c.edt_g and, on the way back up, their chunk minima c.edt_gmin.
 __global__ void __launch_bounds__(STC_NT) leaf_stats_kernel(lg_context c, const int16_t* __restrict__ labels,
                                                             const float* __restrict__ depth) {
     extern __shared__ SmemLeaf tab[];
@@ -98,6 +100,8 @@ __global__ void __launch_bounds__(STC_NT) leaf_stats_kernel(lg_context c, const 
         const unsigned long long* rt = c.ray_tab + x;
         int cur = -1, ya = 0;
         bool seen_leaf = false;
+        unsigned dcol = 0xFFFFu;                   // rows since the last leaf pixel of this column (EDT)
+        uint16_t* gcol = c.edt_g + (size_t)b * P + x;
         long long sdep = 0;
         unsigned kmn = 0xFFFFFFFFu, kmx = 0;
         auto flush = [&](int yb) {     // run [ya, yb] of label cur ends
@@ -140,6 +144,8 @@ __global__ void __launch_bounds__(STC_NT) leaf_stats_kernel(lg_context c, const 
                 const int y = y0 + k;
                 if (y < H) {
                     int l = cl[k];
+                    dcol = l >= 1 ? 0u : min(dcol + 1u, 0xFFFFu);
+                    gcol[(size_t)y * W] = (uint16_t)dcol;
                     if (l < 0 || l >= L) { s_bad = 1; l = -1; }
                     if (l != cur) {
                         flush(y - 1);
@@ -179,6 +185,28 @@ __global__ void __launch_bounds__(STC_NT) leaf_stats_kernel(lg_context c, const 
     if (threadIdx.x == 0) {
         if (s_first != 0xFFFFFFFFu) atomicMin(&c.first_leaf[b], s_first);
         if (s_bad) atomicOr(&c.status[b], LG_ST_LABEL_RANGE);
+    }
+    {   // backward sweep of the column distances + chunk minima (whole warps: the reduction needs every lane)
+        const bool in = x < W;
+        const int xc = in ? x : W - 1;
+        uint16_t* gp = c.edt_g + (size_t)b * P;
+        uint16_t* gm = c.edt_gmin + (size_t)b * H * c.edt_nchunks;
+        const int chunk = x >> 5, lane = threadIdx.x & 31, nchunks = c.edt_nchunks;
+        unsigned d = 0xFFFFu;
+        for (int y0 = H - 1; y0 >= 0; y0 -= ST_U) {
+            unsigned curv[ST_U];
+#pragma unroll
+            for (int k = 0; k < ST_U; ++k) curv[k] = (y0 - k >= 0) ? gp[(size_t)(y0 - k) * W + xc] : 0xFFFFu;
+#pragma unroll
+            for (int k = 0; k < ST_U; ++k) {
+                if (y0 - k >= 0) {
+                    d = min(curv[k], min(d + 1u, 0xFFFFu));
+                    if (in) gp[(size_t)(y0 - k) * W + x] = (uint16_t)d;
+                    const unsigned m = __reduce_min_sync(0xFFFFFFFFu, in ? d : 0xFFFFu);
+                    if (lane == 0 && chunk < nchunks) gm[(size_t)(y0 - k) * nchunks + chunk] = (uint16_t)m;
+                }
+            }
+        }
     }
 }
 
@@ -885,24 +913,9 @@ static int run_edt_rows(lg_context* c, int n, uint32_t* d2, cudaStream_t st) {
     return LG_OK;
 }
 
-int lg_run_edt_union(lg_context* c, const int16_t* labels, int n, cudaStream_t st) {
-    EdtSrc src{labels, nullptr};
-    edt_col_kernel<<<dim3((c->W + 127) / 128, n), 128, 0, st>>>(src, c->edt_g, c->edt_gmin, c->edt_nchunks, c->H, c->W, c->P);
-    LG_LAUNCH_CHECK();
-    lg_mark(c, LG_M_EDT_COL, st);
-    int rc = run_edt_rows(c, n, nullptr, st);
-    if (rc) return rc;
-    lg_mark(c, LG_M_EDT_ROW, st);
-    return LG_OK;
-}
-
 int lg_run_stage1(lg_context* c, const int16_t* labels, const float* depth, int n, lg_camera cam, cudaStream_t st) {
     clear_tables_kernel<<<64, 256, 0, st>>>(*c, n);
     LG_LAUNCH_CHECK();
-    // the distance transform of the leaf union (arg-max only) is independent of the per-leaf statistics
-    cudaStream_t aux = lg_fork(c, 0, st);
-    int rc = lg_run_edt_union(c, labels, n, aux);
-    if (rc) return rc;
     const int tiles = (int)((c->P + ST_NT * ST_PX - 1) / (ST_NT * ST_PX));
     if (!c->ray_valid || c->ray_cam.f != cam.f || c->ray_cam.cx != cam.cx || c->ray_cam.cy != cam.cy) {
         ray_table_kernel<<<(c->W + 127) / 128, 128, 0, st>>>(c->ray_tab, c->H, c->W, cam);
@@ -910,9 +923,16 @@ int lg_run_stage1(lg_context* c, const int16_t* labels, const float* depth, int 
         c->ray_cam = cam;
         c->ray_valid = 1;
     }
+    // per-leaf statistics + column pass of the union distance transform in one walk over the columns
     leaf_stats_kernel<<<dim3((c->W + STC_NT - 1) / STC_NT, n), STC_NT, c->L * sizeof(SmemLeaf), st>>>(*c, labels, depth);
     LG_LAUNCH_CHECK();
     lg_mark(c, LG_M_STATS, st);
+    // the row pass (arg-max only) is independent of the medians: it runs beside scatter + median
+    cudaStream_t aux = lg_fork(c, 0, st);
+    lg_mark(c, LG_M_EDT_COL, aux);
+    int rc = run_edt_rows(c, n, nullptr, aux);
+    if (rc) return rc;
+    lg_mark(c, LG_M_EDT_ROW, aux);
     leaf_offsets_kernel<<<(n + 63) / 64, 64, 0, st>>>(*c, n);
     LG_LAUNCH_CHECK();
     leaf_scatter_kernel<<<dim3(tiles, n), ST_NT, c->L * sizeof(unsigned), st>>>(*c, labels, depth);
