@@ -104,17 +104,18 @@ __global__ void __launch_bounds__(CV_NT) conv3x3_relu_kernel(ConvArgs A) {
     }
 }
 
-// attention + global average + MLP; one CTA per patch.  in: NHWC [n][4][4][256]
+// attention + global average + MLP.  in: NHWC [n][4][4][256].  One CTA handles TL_PB patches so that every MLP weight
+// fetched from L2 is used TL_PB times: the attention-pooled vectors of the patches are formed one after the other,
+// then the four linear layers run for all of them together.
 constexpr int TL_NT = 256;
+constexpr int TL_PB = 8;
 __global__ void __launch_bounds__(TL_NT) cnn_tail_kernel(const float* __restrict__ feat, const float* __restrict__ blob_tail,
-                                                          float* __restrict__ logits) {
+                                                          float* __restrict__ logits, int n) {
     __shared__ float s_f[16][256];
     __shared__ float s_att[16];
-    __shared__ float s_a[256], s_b[256];
-    const int n = blockIdx.x, tid = threadIdx.x;
-    const float* f = feat + (size_t)n * 16 * 256;
-    for (int i = tid; i < 16 * 256; i += TL_NT) s_f[i >> 8][i & 255] = f[i];
-    __syncthreads();
+    __shared__ float s_a[TL_PB][256], s_b[TL_PB][256];
+    const int n0 = blockIdx.x * TL_PB, tid = threadIdx.x;
+    const int np = min(TL_PB, n - n0);
     const float* aw = blob_tail;              // 256
     const float* ab = aw + 256;               // 1
     const float* w0 = ab + 1;                 // 256x256
@@ -125,45 +126,74 @@ __global__ void __launch_bounds__(TL_NT) cnn_tail_kernel(const float* __restrict
     const float* b2 = w2 + 128 * 64;
     const float* w3 = b2 + 64;                // 64
     const float* b3 = w3 + 64;
-    {   // attention logit per pixel: 16 pixels x 256 channels, 16 threads per pixel
-        const int p = tid >> 4, l = tid & 15;
-        float s = 0.f;
-        for (int ch = l; ch < 256; ch += 16) s = fmaf(s_f[p][ch], aw[ch], s);
+    for (int p = 0; p < TL_PB; ++p) {
+        if (p >= np) { s_a[p][tid] = 0.f; continue; }
+        const float* f = feat + (size_t)(n0 + p) * 16 * 256;
+        __syncthreads();
+        for (int i = tid; i < 16 * 256; i += TL_NT) s_f[i >> 8][i & 255] = f[i];
+        __syncthreads();
+        {   // attention logit per pixel: 16 pixels x 256 channels, 16 threads per pixel
+            const int px = tid >> 4, l = tid & 15;
+            float s = 0.f;
+            for (int ch = l; ch < 256; ch += 16) s = fmaf(s_f[px][ch], aw[ch], s);
 #pragma unroll
-        for (int d = 8; d > 0; d >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, d);
-        if (l == 0) s_att[p] = 1.f / (1.f + expf(-(s + ab[0])));
+            for (int d = 8; d > 0; d >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, d);
+            if (l == 0) s_att[px] = 1.f / (1.f + expf(-(s + ab[0])));
+        }
+        __syncthreads();
+        float s = 0.f;
+#pragma unroll
+        for (int px = 0; px < 16; ++px) s = fmaf(s_f[px][tid], s_att[px], s);
+        s_a[p][tid] = s * (1.f / 16.f);
     }
     __syncthreads();
     {
-        float s = 0.f;
+        float acc[TL_PB];
 #pragma unroll
-        for (int p = 0; p < 16; ++p) s = fmaf(s_f[p][tid], s_att[p], s);
-        s_a[tid] = s * (1.f / 16.f);
-    }
-    __syncthreads();
-    {
-        float s = b0[tid];
-        for (int i = 0; i < 256; ++i) s = fmaf(s_a[i], w0[i * 256 + tid], s);
-        s_b[tid] = fmaxf(s, 0.f);
+        for (int p = 0; p < TL_PB; ++p) acc[p] = b0[tid];
+        for (int i = 0; i < 256; ++i) {
+            const float w = w0[i * 256 + tid];
+#pragma unroll
+            for (int p = 0; p < TL_PB; ++p) acc[p] = fmaf(s_a[p][i], w, acc[p]);
+        }
+#pragma unroll
+        for (int p = 0; p < TL_PB; ++p) s_b[p][tid] = fmaxf(acc[p], 0.f);
     }
     __syncthreads();
     if (tid < 128) {
-        float s = b1[tid];
-        for (int i = 0; i < 256; ++i) s = fmaf(s_b[i], w1[i * 128 + tid], s);
-        s_a[tid] = fmaxf(s, 0.f);
+        float acc[TL_PB];
+#pragma unroll
+        for (int p = 0; p < TL_PB; ++p) acc[p] = b1[tid];
+        for (int i = 0; i < 256; ++i) {
+            const float w = w1[i * 128 + tid];
+#pragma unroll
+            for (int p = 0; p < TL_PB; ++p) acc[p] = fmaf(s_b[p][i], w, acc[p]);
+        }
+#pragma unroll
+        for (int p = 0; p < TL_PB; ++p) s_a[p][tid] = fmaxf(acc[p], 0.f);
     }
     __syncthreads();
     if (tid < 64) {
-        float s = b2[tid];
-        for (int i = 0; i < 128; ++i) s = fmaf(s_a[i], w2[i * 64 + tid], s);
-        s_b[tid] = fmaxf(s, 0.f);
+        float acc[TL_PB];
+#pragma unroll
+        for (int p = 0; p < TL_PB; ++p) acc[p] = b2[tid];
+        for (int i = 0; i < 128; ++i) {
+            const float w = w2[i * 64 + tid];
+#pragma unroll
+            for (int p = 0; p < TL_PB; ++p) acc[p] = fmaf(s_a[p][i], w, acc[p]);
+        }
+#pragma unroll
+        for (int p = 0; p < TL_PB; ++p) s_b[p][tid] = fmaxf(acc[p], 0.f);
     }
     __syncthreads();
-    if (tid < 32) {
-        float s = s_b[tid] * w3[tid] + s_b[tid + 32] * w3[tid + 32];
+    {   // final 64 -> 1: warp p handles patch p
+        const int p = tid >> 5, lane = tid & 31;
+        if (p < np) {
+            float s = s_b[p][lane] * w3[lane] + s_b[p][lane + 32] * w3[lane + 32];
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, d);
-        if (tid == 0) logits[n] = s + b3[0];
+            for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, d);
+            if (lane == 0) logits[n0 + p] = s + b3[0];
+        }
     }
 }
 
@@ -184,7 +214,7 @@ int lg_run_cnn_bf16(lg_context* c, const float* patches, int n, float* logits, c
 
 // attention + average + MLP on fp32 NHWC [n][4][4][256] features (shared by the fp32 and the bf16 conv paths)
 int lg_launch_cnn_tail(const float* feat, const float* blob_tail, float* logits, int n, cudaStream_t st) {
-    cnn_tail_kernel<<<n, TL_NT, 0, st>>>(feat, blob_tail, logits);
+    cnn_tail_kernel<<<(n + TL_PB - 1) / TL_PB, TL_NT, 0, st>>>(feat, blob_tail, logits, n);
     LG_LAUNCH_CHECK();
     return LG_OK;
 }
@@ -215,8 +245,8 @@ int lg_run_cnn(lg_context* c, const float* patches, int n, float* logits, int us
             LG_LAUNCH_CHECK();
             w += 9ull * kCin[l] * kCout[l] + kCout[l];
         }
-        cnn_tail_kernel<<<m, TL_NT, 0, st>>>(a1, w, logits + done);
-        LG_LAUNCH_CHECK();
+        int rc = lg_launch_cnn_tail(a1, w, logits + done, m, st);
+        if (rc) return rc;
     }
     return LG_OK;
 }

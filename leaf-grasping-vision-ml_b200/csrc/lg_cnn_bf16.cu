@@ -30,7 +30,7 @@ namespace {
 constexpr int LEAD = 64;        // zero rows in front of every plane (>= pitch + 1)
 constexpr int TILE_M = 512;     // positions per work item: 4 UMMA tiles of 128 rows
 constexpr int UMMA_T = 4;
-constexpr int NB_STAGES = 4;    // weight stages in flight
+__host__ __device__ constexpr int nb_stages(int nc) { return nc == 64 ? 8 : 5; }   // weight stages in flight (what shared memory allows)
 constexpr int CONV_THREADS = 192;   // warp 0 producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue
 
 struct UmmaConvArgs {
@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int ACC_STAGES = 512 / (UMMA_T * NC);          // 2 (NC = 64) or 1 (NC = 128) accumulator sets in TMEM
     constexpr uint32_t B_STAGE = KP * NC * 16;
+    constexpr int NB_STAGES = nb_stages(NC);
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NC >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t a_stage_bytes = (uint32_t)KP * A.rows * 16;
     unsigned char* sA = smem;
@@ -397,7 +398,7 @@ inline int a_rows(int S) { return (TILE_M + 2 * (S + 1) + 2 + 7) / 8 * 8; }
 
 template <int KP, int NC>
 size_t conv_smem(int S) {
-    return 2 * (size_t)KP * a_rows(S) * 16 + (size_t)NB_STAGES * KP * NC * 16 + 256 * sizeof(float) + 16 * sizeof(uint64_t) + 16;
+    return 2 * (size_t)KP * a_rows(S) * 16 + (size_t)nb_stages(NC) * KP * NC * 16 + 256 * sizeof(float) + 32 * sizeof(uint64_t) + 16;
 }
 
 uint16_t f2bf(float f) {
@@ -413,15 +414,15 @@ size_t layer_w_units(const LayerCfg& l) { return (size_t)(l.cout / l.NC) * l.KC 
 
 template <int KP, int NC>
 int launch_conv(const UmmaConvArgs& A, int S, int sms, cudaStream_t st) {
-    static bool attr_set = false;
-    const size_t smem = conv_smem<KP, NC>(32);   // one attribute value covers every spatial size
-    if (!attr_set) {
+    static size_t configured = 0;
+    const size_t smem = conv_smem<KP, NC>(S);
+    if (smem > configured) {
         LG_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<KP, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        configured = smem;
     }
     const int items = A.n_tiles * A.n_split;
     const int grid = items < sms ? items : sms;
-    conv3x3_umma_kernel<KP, NC><<<grid, CONV_THREADS, conv_smem<KP, NC>(S), st>>>(A);
+    conv3x3_umma_kernel<KP, NC><<<grid, CONV_THREADS, smem, st>>>(A);
     LG_LAUNCH_CHECK();
     return LG_OK;
 }
