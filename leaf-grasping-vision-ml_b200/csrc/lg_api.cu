@@ -93,6 +93,7 @@ extern "C" int lg_create(lg_context** out, int max_frames, int height, int width
     c->edt_nchunks = (width + 31) / 32;
     A(&c->edt_g, B * P); A(&c->edt_gmin, B * (size_t)height * c->edt_nchunks); A(&c->edt_best, B); A(&c->leaf_id, B); A(&c->records, B * L); A(&c->status, B); A(&c->region, B);
     A(&c->dt_fwd, 2 * B * P); A(&c->di, B * P); A(&c->dt_max, B * 2);
+    A(&c->bnd_list, B * (size_t)LG_BND_CAP); A(&c->bnd_count, B); A(&c->need_full, B);
     c->bits_stride = (size_t)((width + 2 + 31) / 32) * (height + 2);
     A(&c->bits, B * c->bits_stride);
     c->run_cap = 8 * (height + 2);
@@ -136,7 +137,7 @@ extern "C" int lg_create(lg_context** out, int max_frames, int height, int width
 
 extern "C" void lg_destroy(lg_context* c) {
     if (!c) return;
-    void* ptrs[] = {c->edt_gmin, c->kmin, c->kmax, c->ray_tab, c->cnt, c->sx, c->sy, c->sdep, c->sdist, c->bx0, c->bx1, c->by0, c->by1, c->border, c->first_leaf,
+    void* ptrs[] = {c->bnd_list, c->bnd_count, c->need_full, c->edt_gmin, c->kmin, c->kmax, c->ray_tab, c->cnt, c->sx, c->sy, c->sdep, c->sdist, c->bx0, c->bx1, c->by0, c->by1, c->border, c->first_leaf,
                     c->seg_off, c->seg_cur, c->seg, c->median, c->edt_g, c->edt_best, c->leaf_id, c->records, c->status,
                     c->region, c->dt_fwd, c->di, c->dt_max, c->bits, c->run_x0, c->run_x1, c->run_y, c->run_parent,
                     c->row_first, c->hull, c->orient, c->m_sdf, c->m_app, c->m_acc, c->m_trad, c->m_flat, c->m_stem,
@@ -214,7 +215,9 @@ static int run_stage2(lg_context* c, LgMaskSrc src, const float* depth, int n, l
     cudaStream_t aux = lg_fork(c, 1, st);          // orientation runs beside the two chamfer transforms
     TRY(lg_run_orientation(c, src, n, aux));
     lg_mark(c, LG_M_ORIENT, aux);
-    TRY(lg_run_chamfer(c, src, n, full ? 0 : 1, 0, 2, c->di, nullptr, c->dt_max, st));
+    // outside transform: only its maximum is used (sdf normalisation) -> branch and bound, sweeps only as fallback
+    TRY(lg_run_outside_max(c, src, n, st));
+    TRY(lg_run_chamfer(c, src, n, full ? 0 : 1, 0, 2, c->di, nullptr, c->dt_max, c->need_full, st));
     lg_mark(c, LG_M_CHAMFER, st);
     TRY(lg_join(c, 1, aux, st));
     TRY(lg_run_scores(c, src, depth, n, cam, full, iso_out, st));

@@ -29,6 +29,7 @@ struct ChamferArgs {
     float* out_f32;           // variant 0 only, [n][P] (may be null)
     uint32_t* out_q16;        // variant 0 only
     uint32_t* out_max;        // [n][nvar] (may be null)
+    const uint32_t* need_full; // [n] (may be null): variant 1 only runs for frames whose entry is non-zero
     size_t P;
 };
 
@@ -43,6 +44,7 @@ __global__ void __launch_bounds__(CH_NT, LPT <= 3 ? 2 : 1) chamfer_kernel(Chamfe
     const int b = blockIdx.x, var = blockIdx.y, nvar = gridDim.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = A.W, H = A.H;
+    if (var == 1 && A.need_full && A.need_full[b] == 0) return;   // outside_max_kernel already produced this frame's maximum
     int rx0 = 0, ry0 = 0, rx1 = W, ry1 = H;
     int id = 1;
     if (A.src.labels) {
@@ -244,6 +246,7 @@ __global__ void __launch_bounds__(512) chamfer8_kernel(ChamferArgs A) {
     const int b = blockIdx.x, var = blockIdx.y, nvar = gridDim.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int W = A.W, H = A.H;
+    if (var == 1 && A.need_full && A.need_full[b] == 0) return;   // outside_max_kernel already produced this frame's maximum
     int rx0 = 0, ry0 = 0, rx1 = W, ry1 = H;
     int id = 1;
     if (LABELS) {
@@ -431,10 +434,147 @@ __global__ void __launch_bounds__(512) chamfer8_kernel(ChamferArgs A) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Maximum of the OUTSIDE transform without running it.
+//
+// The two-sweep 5x5 chamfer transform computes, for every pixel p, min over source pixels q of the chamfer norm
+// N(p - q) (cost of the cheapest path of a/b/c moves; tests/test_oracle_golden.py holds the integer identity on
+// adversarial masks), and N satisfies the triangle inequality in integers.  The stage only needs max over p of that
+// distance to the leaf (the sdf normalisation, grasp_point_selector.py:531-532), so it is found by branch and bound:
+// the distance at the centre c of a cell is exact (minimum over the leaf's boundary pixels), every pixel of the
+// cell is at most d(c) + N(w/2, h/2) away, and cells whose bound cannot beat the best exact value seen so far are
+// dropped; survivors are split 4 x 4 until they are single pixels.  Exact by construction; ~10^6 norm evaluations
+// per frame instead of two sweeps over the whole frame with 2 H dependent row steps.  Frames whose boundary or
+// cell lists overflow fall back to the sweeps (need_full).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int BND_NT = 256;
+__global__ void __launch_bounds__(BND_NT) leaf_boundary_kernel(lg_context c, LgMaskSrc src) {
+    const int b = blockIdx.y;
+    const LgRegion r = c.region[b];
+    if (!r.ok) return;
+    const int W = c.W, H = c.H, id = src.id(b);
+    const size_t fo = (size_t)b * c.P;
+    const int lane = threadIdx.x & 31;
+    uint32_t* list = c.bnd_list + (size_t)b * LG_BND_CAP;
+    for (int y = r.y0 + blockIdx.x; y < r.y1; y += gridDim.x) {
+        for (int xb = r.x0; xb < r.x1; xb += BND_NT) {
+            const int x = xb + threadIdx.x;
+            bool hit = false;
+            if (x < r.x1 && src.at(fo, (size_t)y * W + x, id)) {
+#pragma unroll
+                for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        const int xx = x + dx, yy = y + dy;
+                        if ((dx | dy) != 0 && xx >= 0 && xx < W && yy >= 0 && yy < H && !src.at(fo, (size_t)yy * W + xx, id)) hit = true;
+                    }
+            }
+            const unsigned ball = __ballot_sync(0xFFFFFFFFu, hit);
+            if (ball) {
+                unsigned base = 0;
+                if (lane == (__ffs(ball) - 1)) base = atomicAdd(&c.bnd_count[b], __popc(ball));
+                base = __shfl_sync(0xFFFFFFFFu, base, __ffs(ball) - 1);
+                if (hit) {
+                    const unsigned pos = base + __popc(ball & ((1u << lane) - 1u));
+                    if (pos < LG_BND_CAP) list[pos] = (unsigned)x | ((unsigned)y << 16);
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ int chamfer_norm_q16(int dx, int dy) {
+    dx = abs(dx); dy = abs(dy);
+    const int mx = max(dx, dy), mn = min(dx, dy);
+    // the two linear pieces of the norm; it is convex, so it is their maximum
+    return max(LG_CH_A * mx + (LG_CH_C - 2 * LG_CH_A) * mn, (LG_CH_C - LG_CH_B) * mx + (2 * LG_CH_B - LG_CH_C) * mn);
+}
+
+constexpr int OM_NT = 512;
+constexpr int OM_CELLS = 1024;
+constexpr int OM_STAGE = 6144;
+__global__ void __launch_bounds__(OM_NT) outside_max_kernel(lg_context c) {
+    __shared__ unsigned s_bnd[OM_STAGE];
+    __shared__ unsigned s_cell[2][OM_CELLS][2];      // (x0 | y0 << 16, w | h << 16)
+    __shared__ int s_val[OM_CELLS];
+    __shared__ int s_cnt[2], s_lb, s_over;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const LgRegion r = c.region[b];
+    const unsigned Q = r.ok ? c.bnd_count[b] : 0u;
+    if (!r.ok || Q == 0u) {                          // no leaf, or the leaf covers the frame: the transform is zero
+        if (tid == 0) { c.dt_max[b * 2 + 1] = 0; c.need_full[b] = 0; }
+        return;
+    }
+    if (Q > (unsigned)OM_STAGE || Q > (unsigned)LG_BND_CAP) {
+        if (tid == 0) c.need_full[b] = 1;
+        return;
+    }
+    const int W = c.W, H = c.H;
+    const uint32_t* list = c.bnd_list + (size_t)b * LG_BND_CAP;
+    for (unsigned i = tid; i < Q; i += OM_NT) s_bnd[i] = list[i];
+    int G = 64;
+    while (((W + G - 1) / G) * ((H + G - 1) / G) > OM_CELLS / 2) G *= 2;
+    const int ncx = (W + G - 1) / G, ncy = (H + G - 1) / G;
+    for (int i = tid; i < ncx * ncy; i += OM_NT) {
+        const int x0 = (i % ncx) * G, y0 = (i / ncx) * G;
+        s_cell[0][i][0] = (unsigned)x0 | ((unsigned)y0 << 16);
+        s_cell[0][i][1] = (unsigned)min(G, W - x0) | ((unsigned)min(G, H - y0) << 16);
+    }
+    if (tid == 0) { s_cnt[0] = ncx * ncy; s_cnt[1] = 0; s_lb = 0; s_over = 0; }
+    __syncthreads();
+    int cur = 0;
+    while (true) {
+        const int ncell = s_cnt[cur];
+        // exact distance at every cell centre: one warp per cell, lanes over the boundary pixels
+        for (int i = warp; i < ncell; i += OM_NT / 32) {
+            const unsigned c0 = s_cell[cur][i][0], c1 = s_cell[cur][i][1];
+            const int cx = (int)(c0 & 0xFFFFu) + (int)(c1 & 0xFFFFu) / 2, cy = (int)(c0 >> 16) + (int)(c1 >> 16) / 2;
+            int dmin = 0x7FFFFFFF;
+            for (unsigned q = lane; q < Q; q += 32) {
+                const unsigned v = s_bnd[q];
+                dmin = min(dmin, chamfer_norm_q16(cx - (int)(v & 0xFFFFu), cy - (int)(v >> 16)));
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) dmin = min(dmin, __shfl_xor_sync(0xFFFFFFFFu, dmin, d));
+            if (lane == 0) { s_val[i] = dmin; atomicMax(&s_lb, dmin); }
+        }
+        __syncthreads();
+        const int lb = s_lb;
+        const int nxt = cur ^ 1;
+        for (int i = tid; i < ncell; i += OM_NT) {
+            const unsigned c0 = s_cell[cur][i][0], c1 = s_cell[cur][i][1];
+            const int x0 = (int)(c0 & 0xFFFFu), y0 = (int)(c0 >> 16), w = (int)(c1 & 0xFFFFu), h = (int)(c1 >> 16);
+            if (w == 1 && h == 1) continue;                                  // exact already
+            if (s_val[i] + chamfer_norm_q16(w / 2, h / 2) <= lb) continue;   // nothing in the cell can exceed the best
+            const int kx = min(4, w), ky = min(4, h);
+            const int pos = atomicAdd(&s_cnt[nxt], kx * ky);
+            if (pos + kx * ky > OM_CELLS) { s_over = 1; continue; }
+            for (int j = 0; j < ky; ++j)
+                for (int k = 0; k < kx; ++k) {
+                    const int xa = x0 + (w * k) / kx, xb = x0 + (w * (k + 1)) / kx;
+                    const int ya = y0 + (h * j) / ky, yb = y0 + (h * (j + 1)) / ky;
+                    s_cell[nxt][pos + j * kx + k][0] = (unsigned)xa | ((unsigned)ya << 16);
+                    s_cell[nxt][pos + j * kx + k][1] = (unsigned)(xb - xa) | ((unsigned)(yb - ya) << 16);
+                }
+        }
+        __syncthreads();
+        if (s_over) {
+            if (tid == 0) c.need_full[b] = 1;
+            return;
+        }
+        if (s_cnt[nxt] == 0) break;
+        __syncthreads();
+        if (tid == 0) s_cnt[cur] = 0;
+        cur = nxt;
+        __syncthreads();
+    }
+    if (tid == 0) { c.dt_max[b * 2 + 1] = (uint32_t)s_lb; c.need_full[b] = 0; }
+}
+
 }  // namespace
 
 int lg_run_chamfer(lg_context* c, LgMaskSrc src, int n, int rect_mode, int invert_base, int nvar,
-                   float* out0, uint32_t* q0, uint32_t* out_max, cudaStream_t st) {
+                   float* out0, uint32_t* q0, uint32_t* out_max, const uint32_t* need_full, cudaStream_t st) {
     if (c->W > CH_NT * CH_MAXI) {
         lg_set_error("chamfer transform supports widths up to %d", CH_NT * CH_MAXI);
         return LG_E_ARG;
@@ -442,6 +582,7 @@ int lg_run_chamfer(lg_context* c, LgMaskSrc src, int n, int rect_mode, int inver
     ChamferArgs A;
     A.src = src; A.region = c->region; A.n = n; A.H = c->H; A.W = c->W; A.rect_mode = rect_mode;
     A.invert_base = invert_base; A.fwd = c->dt_fwd; A.out_f32 = out0; A.out_q16 = q0; A.out_max = out_max; A.P = c->P;
+    A.need_full = need_full;
     // fast path: 8 pixels per thread, vector loads/stores -> needs 16-byte aligned rows
     const bool aligned = (c->W % 8 == 0) &&
                          ((reinterpret_cast<uintptr_t>(src.labels) | reinterpret_cast<uintptr_t>(src.mask) |
@@ -475,10 +616,21 @@ int lg_run_chamfer(lg_context* c, LgMaskSrc src, int n, int rect_mode, int inver
     return LG_OK;
 }
 
+// maximum of the outside transform by branch and bound (frames that overflow its lists are flagged in need_full
+// and handled by variant 1 of the sweep kernels)
+int lg_run_outside_max(lg_context* c, LgMaskSrc src, int n, cudaStream_t st) {
+    LG_CUDA(cudaMemsetAsync(c->bnd_count, 0, sizeof(uint32_t) * n, st));
+    leaf_boundary_kernel<<<dim3(16, n), BND_NT, 0, st>>>(*c, src);
+    LG_LAUNCH_CHECK();
+    outside_max_kernel<<<n, OM_NT, 0, st>>>(*c);
+    LG_LAUNCH_CHECK();
+    return LG_OK;
+}
+
 extern "C" int lg_chamfer_transform(lg_context* c, const uint8_t* mask, int n, int invert, float* dist,
                                     uint32_t* q16, uint32_t* max_q16, void* stream) {
     if (!c || !mask || n < 1) return LG_E_ARG;
     if (n > c->B) return LG_E_CAPACITY;
     LgMaskSrc src{nullptr, mask, nullptr};
-    return lg_run_chamfer(c, src, n, 0, invert ? 1 : 0, 1, dist, q16, max_q16, (cudaStream_t)stream);
+    return lg_run_chamfer(c, src, n, 0, invert ? 1 : 0, 1, dist, q16, max_q16, nullptr, (cudaStream_t)stream);
 }

@@ -21,6 +21,7 @@
 #define LG_SE_STEM 30
 #define LG_SE_PRE 31
 #define LG_PROF_MARKS 20
+#define LG_BND_CAP 16384
 #define LG_MAX_HOST_CHUNKS 64
 #define LG_HOST_CHUNK_FRAMES 32
 enum LgMark { LG_M_START = 0, LG_M_STATS, LG_M_SCATTER, LG_M_MEDIAN, LG_M_EDT_COL, LG_M_EDT_ROW, LG_M_SELECT, LG_M_CHAMFER,
@@ -92,6 +93,9 @@ struct lg_context {
     int32_t* dt_fwd;               // [2][B][P] forward-pass scratch of the two chamfer transforms
     float* di;                     // [B][P] distance inside (distance_map)
     uint32_t* dt_max;              // [B][2] max Q16 of (inside, outside)
+    uint32_t* bnd_list;            // [B][LG_BND_CAP] boundary pixels of the chosen leaf, x | y << 16
+    uint32_t* bnd_count;           // [B]
+    uint32_t* need_full;           // [B] 1: the outside maximum of this frame needs the full sweeps
     uint32_t* bits;                // [B][bits_stride] leaf bitmask on bbox+1 ring
     size_t bits_stride;
     int run_cap;
@@ -164,7 +168,8 @@ int lg_run_select(lg_context* c, int n, lg_camera cam, int32_t* leaf_out, lg_lea
 cudaStream_t lg_fork(lg_context* c, int k, cudaStream_t st);
 int lg_join(lg_context* c, int k, cudaStream_t aux, cudaStream_t st);
 int lg_run_chamfer(lg_context* c, LgMaskSrc src, int n, int rect_mode, int invert_base, int nvar,
-                   float* out0, uint32_t* q0, uint32_t* out_max, cudaStream_t st);
+                   float* out0, uint32_t* q0, uint32_t* out_max, const uint32_t* need_full, cudaStream_t st);
+int lg_run_outside_max(lg_context* c, LgMaskSrc src, int n, cudaStream_t st);
 int lg_run_orientation(lg_context* c, LgMaskSrc src, int n, cudaStream_t st);
 int lg_run_scores(lg_context* c, LgMaskSrc src, const float* depth, int n, lg_camera cam, int full,
                   double* iso_out, cudaStream_t st);

@@ -117,6 +117,34 @@ def test_edt_argmax_pruned_search(shape, frames):
     eng.close()
 
 
+def test_outside_maximum_branch_and_bound():
+    """sdf normalisation = max(inside, outside) chamfer distance (grasp_point_selector.py:531-532).  The outside
+    maximum comes from the branch-and-bound search (or from the sweeps when its lists overflow): checked against the
+    oracle's two-sweep transform on shapes chosen to break geometric shortcuts (rings, several components, thin
+    lines, a mask covering the frame, a comb with thousands of boundary pixels -> fallback)."""
+    H, W = 360, 480
+    rng = np.random.default_rng(21)
+    masks = []
+    for k in range(10):
+        masks.append(_blobs(rng, H, W, 1 + k % 4))
+    ring = np.zeros((H, W), np.uint8); cv2.circle(ring, (240, 180), 150, 1, 9); masks.append(ring)
+    two = np.zeros((H, W), np.uint8); cv2.circle(two, (30, 40), 25, 1, -1); cv2.circle(two, (450, 330), 22, 1, -1); masks.append(two)
+    lines = np.zeros((H, W), np.uint8); cv2.line(lines, (5, 350), (470, 8), 1, 2); cv2.line(lines, (0, 0), (100, 300), 1, 1); masks.append(lines)
+    masks.append(np.ones((H, W), np.uint8))
+    corner = np.zeros((H, W), np.uint8); corner[:40, :60] = 1; masks.append(corner)
+    comb = np.zeros((H, W), np.uint8); comb[40:300:2, 50:430] = 1; masks.append(comb)          # ~70k boundary pixels
+    masks = np.stack(masks)
+    dep = np.full(masks.shape, 0.5, np.float32)
+    eng = _engine(len(masks), H, W, 2)
+    res = eng.select_grasp_point(torch.from_numpy(masks), torch.from_numpy(dep), _cam(synth.SMALL))
+    for k, m in enumerate(masks):
+        di = O.chamfer5_q16(m).max()
+        do = O.chamfer5_q16(1 - m).max() if (m == 0).any() else 0
+        want = np.float32(max(int(di), int(do))) * np.float32(1.0 / 65536.0)
+        assert np.float32(res[k]["sdf_max"]) == want, f"mask {k}: {res[k]['sdf_max']} vs {want}"
+    eng.close()
+
+
 # ------------------------------------------------------------------------------------------------------
 # stage 1
 # ------------------------------------------------------------------------------------------------------

@@ -189,3 +189,38 @@ def test_pareto_front_matches_weighted_argmax():
         s = rng.random((12, 3))
         keep = O.pareto_front_max(s)
         assert keep[np.argmax(s @ w)]
+
+
+def test_chamfer_two_sweeps_equal_norm_minimum():
+    """The integer two-sweep chamfer transform equals min over source pixels of the closed-form chamfer norm, and the
+    norm obeys the triangle inequality in integers.  csrc/lg_chamfer.cu:outside_max_kernel (branch and bound for the
+    maximum of the outside transform) rests on exactly these two facts."""
+    N = O.chamfer_norm_q16
+    g = np.arange(-12, 13)
+    U = np.stack(np.meshgrid(g, g), -1).reshape(-1, 2)
+    nu = N(U[:, 0], U[:, 1])
+    for i in range(0, len(U), 5):
+        assert (N(U[:, 0] + U[i, 0], U[:, 1] + U[i, 1]) <= nu + nu[i]).all()
+    rng = np.random.default_rng(0)
+    for it in range(24):
+        H, W = int(rng.integers(8, 60)), int(rng.integers(8, 80))
+        m = np.zeros((H, W), np.uint8)
+        kind = it % 4
+        if kind == 0:
+            cv2.ellipse(m, (int(rng.integers(0, W)), int(rng.integers(0, H))), (int(rng.integers(2, max(3, W // 3))), int(rng.integers(2, max(3, H // 3)))),
+                        float(rng.uniform(0, 180)), 0, 360, 1, -1)
+        elif kind == 1:
+            cv2.line(m, (int(rng.integers(0, W)), int(rng.integers(0, H))), (int(rng.integers(0, W)), int(rng.integers(0, H))), 1, 1)
+            cv2.circle(m, (int(rng.integers(0, W)), int(rng.integers(0, H))), int(rng.integers(3, max(4, min(H, W) // 2))), 1, 1)
+        elif kind == 2:
+            m.flat[rng.integers(0, H * W, size=int(rng.integers(1, 9)))] = 1
+        else:
+            cv2.rectangle(m, (0, int(rng.integers(0, H // 2))), (int(rng.integers(2, W)), H - 1), 1, -1)
+            cv2.circle(m, (int(rng.integers(0, W)), int(rng.integers(0, H))), int(rng.integers(2, 7)), 0, -1)
+        if m.sum() == 0:
+            continue
+        two_sweeps = O.chamfer5_q16(1 - m).astype(np.int64)          # sources = the set pixels
+        qy, qx = np.nonzero(m)
+        yy, xx = np.mgrid[0:H, 0:W]
+        brute = N(xx[..., None] - qx, yy[..., None] - qy).min(-1)
+        np.testing.assert_array_equal(two_sweeps, brute)
