@@ -104,6 +104,7 @@ extern "C" int lg_create(lg_context** out, int max_frames, int height, int width
     A(&c->m_flat, B * P); A(&c->m_stem, B * P); A(&c->m_valid, B * P);
     A(&c->list_key, B * P); A(&c->list_idx, B * P); A(&c->list_n, B);
     A(&c->patches, B * LG_TOP_K * (size_t)(LG_CHANNELS * LG_PATCH * LG_PATCH)); A(&c->logits, B * LG_TOP_K);
+    A(&c->slot_map, B * LG_TOP_K); A(&c->cnn_count, 1);
     A(&c->results, B);
     c->cnn_cap = (int)(B * LG_TOP_K < 2048 ? 2048 : B * LG_TOP_K);
     c->cnn_act_bytes = (size_t)c->cnn_cap * 32 * 32 * 64 * sizeof(float);
@@ -137,7 +138,7 @@ extern "C" int lg_create(lg_context** out, int max_frames, int height, int width
 
 extern "C" void lg_destroy(lg_context* c) {
     if (!c) return;
-    void* ptrs[] = {c->bnd_list, c->bnd_count, c->need_full, c->edt_gmin, c->kmin, c->kmax, c->ray_tab, c->cnt, c->sx, c->sy, c->sdep, c->sdist, c->bx0, c->bx1, c->by0, c->by1, c->border, c->first_leaf,
+    void* ptrs[] = {c->slot_map, c->cnn_count, c->bnd_list, c->bnd_count, c->need_full, c->edt_gmin, c->kmin, c->kmax, c->ray_tab, c->cnt, c->sx, c->sy, c->sdep, c->sdist, c->bx0, c->bx1, c->by0, c->by1, c->border, c->first_leaf,
                     c->seg_off, c->seg_cur, c->seg, c->median, c->edt_g, c->edt_best, c->leaf_id, c->records, c->status,
                     c->region, c->dt_fwd, c->di, c->dt_max, c->bits, c->run_x0, c->run_x1, c->run_y, c->run_parent,
                     c->row_first, c->hull, c->orient, c->m_sdf, c->m_app, c->m_acc, c->m_trad, c->m_flat, c->m_stem,
@@ -242,7 +243,7 @@ extern "C" int lg_process_batch(lg_context* c, const int16_t* labels, const floa
     if (have_ml) {
         TRY(lg_run_gather(c, src, depth, frames, *cam, st));
         lg_mark(c, LG_M_GATHER, st);
-        TRY(lg_run_cnn(c, c->patches, frames * LG_TOP_K, c->logits, use_bf16_cnn, st));
+        TRY(lg_run_cnn(c, c->patches, frames * LG_TOP_K, c->cnn_count, c->logits, use_bf16_cnn, st));
         lg_mark(c, LG_M_CNN, st);
     }
     TRY(lg_run_fuse(c, src, depth, frames, *cam, have_ml, results, st));
@@ -304,7 +305,7 @@ extern "C" int lg_candidate_points(lg_context* c, const double* score, const uin
 
 extern "C" int lg_cnn_forward(lg_context* c, const float* patches, int n, float* logits, int use_bf16, void* stream) {
     if (!c || !patches || !logits || n < 1) return LG_E_ARG;
-    return lg_run_cnn(c, patches, n, logits, use_bf16, (cudaStream_t)stream);
+    return lg_run_cnn(c, patches, n, nullptr, logits, use_bf16, (cudaStream_t)stream);
 }
 
 extern "C" int lg_select_grasp_point(lg_context* c, const uint8_t* mask, const float* depth, int frames,
@@ -319,7 +320,7 @@ extern "C" int lg_select_grasp_point(lg_context* c, const uint8_t* mask, const f
     const int have_ml = c->cnn.loaded;
     if (have_ml) {
         TRY(lg_run_gather(c, src, depth, frames, *cam, st));
-        TRY(lg_run_cnn(c, c->patches, frames * LG_TOP_K, c->logits, use_bf16_cnn, st));
+        TRY(lg_run_cnn(c, c->patches, frames * LG_TOP_K, c->cnn_count, c->logits, use_bf16_cnn, st));
     }
     TRY(lg_run_fuse(c, src, depth, frames, *cam, have_ml, results, st));
     return LG_OK;
@@ -337,9 +338,7 @@ extern "C" int lg_leaf_orientation(lg_context* c, const uint8_t* mask, int frame
 
 extern "C" int lg_patches(lg_context* c, float* patches_out, int frames, void* stream) {
     if (!c || !patches_out || frames < 1 || frames > c->B) return LG_E_ARG;
-    LG_CUDA(cudaMemcpyAsync(patches_out, c->patches, sizeof(float) * (size_t)frames * LG_TOP_K * LG_CHANNELS * LG_PATCH * LG_PATCH,
-                            cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-    return LG_OK;
+    return lg_run_export_patches(c, patches_out, frames, (cudaStream_t)stream);
 }
 
 extern "C" int lg_normalize_patches(lg_context* c, const float* raw, int n, float* out, void* stream) {

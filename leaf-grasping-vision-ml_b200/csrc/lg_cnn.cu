@@ -110,7 +110,9 @@ __global__ void __launch_bounds__(CV_NT) conv3x3_relu_kernel(ConvArgs A) {
 constexpr int TL_NT = 256;
 constexpr int TL_PB = 8;
 __global__ void __launch_bounds__(TL_NT) cnn_tail_kernel(const float* __restrict__ feat, const float* __restrict__ blob_tail,
-                                                          float* __restrict__ logits, int n) {
+                                                          float* __restrict__ logits, int n_host, const int32_t* __restrict__ n_dev) {
+    const int n = n_dev ? min(*n_dev, n_host) : n_host;
+    if ((int)blockIdx.x * TL_PB >= n) return;
     __shared__ float s_f[16][256];
     __shared__ float s_att[16];
     __shared__ float s_a[TL_PB][256], s_b[TL_PB][256];
@@ -210,21 +212,22 @@ uint64_t lg_cnn_blob_floats() {
     return n;
 }
 
-int lg_run_cnn_bf16(lg_context* c, const float* patches, int n, float* logits, cudaStream_t st);
+int lg_run_cnn_bf16(lg_context* c, const float* patches, int n, const int32_t* n_dev, float* logits, cudaStream_t st);
 
 // attention + average + MLP on fp32 NHWC [n][4][4][256] features (shared by the fp32 and the bf16 conv paths)
-int lg_launch_cnn_tail(const float* feat, const float* blob_tail, float* logits, int n, cudaStream_t st) {
-    cnn_tail_kernel<<<(n + TL_PB - 1) / TL_PB, TL_NT, 0, st>>>(feat, blob_tail, logits, n);
+int lg_launch_cnn_tail(const float* feat, const float* blob_tail, float* logits, int n, const int32_t* n_dev, cudaStream_t st) {
+    cnn_tail_kernel<<<(n + TL_PB - 1) / TL_PB, TL_NT, 0, st>>>(feat, blob_tail, logits, n, n_dev);
     LG_LAUNCH_CHECK();
     return LG_OK;
 }
 
-int lg_run_cnn(lg_context* c, const float* patches, int n, float* logits, int use_bf16, cudaStream_t st) {
+int lg_run_cnn(lg_context* c, const float* patches, int n, const int32_t* n_dev, float* logits, int use_bf16, cudaStream_t st) {
     if (!c->cnn.loaded) {
         lg_set_error("lg_cnn_forward: no weights loaded (lg_set_cnn_weights)");
         return LG_E_ARG;
     }
-    if (use_bf16) return lg_run_cnn_bf16(c, patches, n, logits, st);
+    if (use_bf16) return lg_run_cnn_bf16(c, patches, n, n_dev, logits, st);
+    // the fp32 anchor path sizes its grids on the host: with a device-side count it simply runs all n slots
     const float* blob = c->cnn.blob;
     for (int done = 0; done < n; done += c->cnn_cap) {
         const int m = min(c->cnn_cap, n - done);
@@ -245,7 +248,7 @@ int lg_run_cnn(lg_context* c, const float* patches, int n, float* logits, int us
             LG_LAUNCH_CHECK();
             w += 9ull * kCin[l] * kCout[l] + kCout[l];
         }
-        int rc = lg_launch_cnn_tail(a1, w, logits + done, m, st);
+        int rc = lg_launch_cnn_tail(a1, w, logits + done, m, nullptr, st);
         if (rc) return rc;
     }
     return LG_OK;

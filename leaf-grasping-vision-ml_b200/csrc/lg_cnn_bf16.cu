@@ -40,8 +40,8 @@ struct UmmaConvArgs {
     const float* bias;    // [Cout]
     long long R;          // rows per plane
     int pitch, PP;
-    long long Q;          // n_patches * PP
-    int n_tiles;          // ceil((Q + pitch + 1) / TILE_M)
+    const int32_t* n_dev; // device-side patch count (may be null -> n_host)
+    int n_host;           // patches the launch was sized for (plane stride R, buffer sizes)
     int KC;               // input channel chunks (of KP planes)
     int n_split;          // Cout / NC
     int rows;             // shared-memory rows per plane of the A stage: TILE_M + 2 * pitch + 2, rounded up to 8
@@ -136,7 +136,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_items = A.n_tiles * A.n_split;
+    const int n_patches = A.n_dev ? min(*A.n_dev, A.n_host) : A.n_host;
+    const long long Q = (long long)n_patches * A.PP;                       // positions that carry data
+    const int n_tiles = (int)((Q + A.pitch + 1 + TILE_M - 1) / TILE_M);      // + the zero row behind the last patch
+    const int n_items = n_tiles * A.n_split;
 
     for (int i = threadIdx.x; i < A.cout; i += CONV_THREADS) s_bias[i] = A.bias[i];
     if (threadIdx.x == 0) {
@@ -249,7 +252,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
 #pragma unroll 1
             for (int t = 0; t < UMMA_T; ++t) {
                 const long long q = (long long)tile * TILE_M + t * 128 + wq * 32 + lane;
-                bool data = q < A.Q;
+                bool data = q < Q;
                 if (data) {
                     const int ql = (int)(q % A.PP);
                     const int r = ql / A.pitch, cc = ql - r * A.pitch;
@@ -290,7 +293,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
 }
 
 // fp32 patches [n][9][32][32] -> layer-0 input: 2 planes (channels 0-7 | 8 + zeros), pitch 33
-__global__ void pack_input_kernel(const float* __restrict__ patches, uint4* __restrict__ out, long long R, int n) {
+__global__ void pack_input_kernel(const float* __restrict__ patches, uint4* __restrict__ out, long long R, int n_host,
+                                  const int32_t* __restrict__ n_dev) {
+    const int n = n_dev ? min(*n_dev, n_host) : n_host;
     const int pitch = 33, PP = 33 * 33;
     const long long total = (long long)n * PP + pitch + 1 + LEAD;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -328,7 +333,8 @@ __device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
 // (the input of cnn_tail_kernel).
 template <bool FINAL>
 __global__ void pool2x2_kernel(const uint4* __restrict__ in, long long Rin, int S, void* __restrict__ outp, long long Rout,
-                               int planes, int n) {
+                               int planes, int n_host, const int32_t* __restrict__ n_dev) {
+    const int n = n_dev ? min(*n_dev, n_host) : n_host;
     const int pin = S + 1, PPin = pin * pin, So = S / 2, po = So + 1, PPo = po * po;
     if (FINAL) {
         float* out = reinterpret_cast<float*>(outp);
@@ -420,7 +426,8 @@ int launch_conv(const UmmaConvArgs& A, int S, int sms, cudaStream_t st) {
         LG_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<KP, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    const int items = A.n_tiles * A.n_split;
+    const long long Qmax = (long long)A.n_host * A.PP;
+    const int items = (int)((Qmax + A.pitch + 1 + TILE_M - 1) / TILE_M) * A.n_split;
     const int grid = items < sms ? items : sms;
     conv3x3_umma_kernel<KP, NC><<<grid, CONV_THREADS, smem, st>>>(A);
     LG_LAUNCH_CHECK();
@@ -430,7 +437,7 @@ int launch_conv(const UmmaConvArgs& A, int S, int sms, cudaStream_t st) {
 }  // namespace
 
 uint64_t lg_cnn_blob_floats();
-int lg_launch_cnn_tail(const float* feat, const float* blob_tail, float* logits, int n, cudaStream_t st);
+int lg_launch_cnn_tail(const float* feat, const float* blob_tail, float* logits, int n, const int32_t* n_dev, cudaStream_t st);
 
 // Pack the folded fp32 weights (cnn.py:pack_weights layout) into the bf16 operand layout; synchronous.
 int lg_cnn_prepare_bf16(lg_context* c) {
@@ -461,22 +468,23 @@ int lg_cnn_prepare_bf16(lg_context* c) {
     return LG_OK;
 }
 
-static int run_cnn_bf16(lg_context* c, const float* patches, int n, float* logits, int stop_layer, float* feat_out,
-                        cudaStream_t st);
+static int run_cnn_bf16(lg_context* c, const float* patches, int n, const int32_t* n_dev, float* logits, int stop_layer,
+                        float* feat_out, cudaStream_t st);
 
-int lg_run_cnn_bf16(lg_context* c, const float* patches, int n, float* logits, cudaStream_t st) {
-    return run_cnn_bf16(c, patches, n, logits, -1, nullptr, st);
+int lg_run_cnn_bf16(lg_context* c, const float* patches, int n, const int32_t* n_dev, float* logits, cudaStream_t st) {
+    if (n_dev && n > c->cnn_cap) { lg_set_error("device-side patch count needs n <= %d", c->cnn_cap); return LG_E_CAPACITY; }
+    return run_cnn_bf16(c, patches, n, n_dev, logits, -1, nullptr, st);
 }
 
 extern "C" int lg_cnn_bf16_features(lg_context* c, const float* patches, int n, int layer, float* features, void* stream) {
     if (!c || !patches || !features || n < 1 || layer < 0 || layer > 5) return LG_E_ARG;
     if (!c->cnn.loaded) { lg_set_error("lg_cnn_bf16_features: no weights loaded"); return LG_E_ARG; }
     if (n > c->cnn_cap) return LG_E_CAPACITY;
-    return run_cnn_bf16(c, patches, n, nullptr, layer, features, (cudaStream_t)stream);
+    return run_cnn_bf16(c, patches, n, nullptr, nullptr, layer, features, (cudaStream_t)stream);
 }
 
-static int run_cnn_bf16(lg_context* c, const float* patches, int n, float* logits, int stop_layer, float* feat_out,
-                        cudaStream_t st) {
+static int run_cnn_bf16(lg_context* c, const float* patches, int n, const int32_t* n_dev, float* logits, int stop_layer,
+                        float* feat_out, cudaStream_t st) {
     if (!c->cnn.bf16_blob) { lg_set_error("bf16 CNN weights are not prepared"); return LG_E_ARG; }
     static int sms = 0;
     if (!sms) {
@@ -506,7 +514,7 @@ static int run_cnn_bf16(lg_context* c, const float* patches, int n, float* logit
             const long long R = rows_per_plane(32, m);
             const long long total = (long long)m * 33 * 33 + 34 + LEAD;
             const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-            pack_input_kernel<<<grid, 256, 0, st>>>(patches + (size_t)done * LG_CHANNELS * LG_PATCH * LG_PATCH, buf[0], R, m);
+            pack_input_kernel<<<grid, 256, 0, st>>>(patches + (size_t)done * LG_CHANNELS * LG_PATCH * LG_PATCH, buf[0], R, m, n_dev);
             LG_LAUNCH_CHECK();
         }
         for (int l = 0; l < 6; ++l) {
@@ -514,8 +522,7 @@ static int run_cnn_bf16(lg_context* c, const float* patches, int n, float* logit
             UmmaConvArgs A;
             A.in = buf[cur]; A.out = buf[cur ^ 1]; A.wt = wts[l]; A.bias = bias[l];
             A.R = rows_per_plane(L.S, m);
-            A.pitch = L.S + 1; A.PP = A.pitch * A.pitch; A.Q = (long long)m * A.PP;
-            A.n_tiles = (int)((A.Q + A.pitch + 1 + TILE_M - 1) / TILE_M);
+            A.pitch = L.S + 1; A.PP = A.pitch * A.pitch; A.n_dev = n_dev; A.n_host = m;
             A.KC = L.KC; A.n_split = L.cout / L.NC; A.rows = a_rows(L.S); A.cout = L.cout;
             int rc;
             if (L.KP == 2) rc = launch_conv<2, 64>(A, L.S, sms, st);
@@ -528,12 +535,12 @@ static int run_cnn_bf16(lg_context* c, const float* patches, int n, float* logit
                 if (l == 5) {
                     const long long total = (long long)m * 16 * planes;
                     const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-                    pool2x2_kernel<true><<<grid, 256, 0, st>>>(buf[cur], A.R, L.S, buf[cur ^ 1], 0, planes, m);
+                    pool2x2_kernel<true><<<grid, 256, 0, st>>>(buf[cur], A.R, L.S, buf[cur ^ 1], 0, planes, m, n_dev);
                 } else {
                     const long long Rout = rows_per_plane(L.S / 2, m);
                     const long long total = ((long long)m * (L.S / 2 + 1) * (L.S / 2 + 1) + L.S / 2 + 2 + LEAD) * planes;
                     const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-                    pool2x2_kernel<false><<<grid, 256, 0, st>>>(buf[cur], A.R, L.S, buf[cur ^ 1], Rout, planes, m);
+                    pool2x2_kernel<false><<<grid, 256, 0, st>>>(buf[cur], A.R, L.S, buf[cur ^ 1], Rout, planes, m, n_dev);
                 }
                 LG_LAUNCH_CHECK();
                 cur ^= 1;
@@ -549,7 +556,7 @@ static int run_cnn_bf16(lg_context* c, const float* patches, int n, float* logit
                 return LG_OK;
             }
         }
-        int rc = lg_launch_cnn_tail(reinterpret_cast<const float*>(buf[cur]), tail, logits + done, m, st);
+        int rc = lg_launch_cnn_tail(reinterpret_cast<const float*>(buf[cur]), tail, logits + done, m, n_dev, st);
         if (rc) return rc;
     }
     return LG_OK;

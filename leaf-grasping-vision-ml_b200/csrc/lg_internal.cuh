@@ -111,7 +111,9 @@ struct lg_context {
     uint32_t* list_idx;                      // [B][P]
     uint32_t* list_n;                        // [B]
     float* patches;                          // [B*20][9][32][32]
-    float* logits;                           // [B*20]
+    float* logits;                           // [B*20], indexed by compact slot
+    int32_t* slot_map;                       // [B*20] compact patch index of every (frame, candidate), -1 = no ML score
+    int32_t* cnn_count;                      // [1] number of valid slots of the current batch
     lg_frame_result* results;                // [B]
     // CNN scratch
     void* cnn_act0;
@@ -175,7 +177,9 @@ int lg_run_scores(lg_context* c, LgMaskSrc src, const float* depth, int n, lg_ca
                   double* iso_out, cudaStream_t st);
 int lg_run_nms(lg_context* c, int n, cudaStream_t st);
 int lg_run_gather(lg_context* c, LgMaskSrc src, const float* depth, int n, lg_camera cam, cudaStream_t st);
-int lg_run_cnn(lg_context* c, const float* patches, int n, float* logits, int use_bf16, cudaStream_t st);
+// n patches; n_dev (device int, may be null) = the number actually present (<= n): the kernels read it on the device
+int lg_run_cnn(lg_context* c, const float* patches, int n, const int32_t* n_dev, float* logits, int use_bf16, cudaStream_t st);
+int lg_run_export_patches(lg_context* c, float* out, int n, cudaStream_t st);
 int lg_run_fuse(lg_context* c, LgMaskSrc src, const float* depth, int n, lg_camera cam, int have_ml,
                 lg_frame_result* out, cudaStream_t st);
 int lg_run_mask_regions(lg_context* c, const uint8_t* mask, int n, int full, cudaStream_t st);

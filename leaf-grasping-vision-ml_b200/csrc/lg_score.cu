@@ -306,24 +306,61 @@ __global__ void clear_list_kernel(lg_context c, int n) {
 // ---------------------------------------------------------------------------------------------------
 // patches
 // ---------------------------------------------------------------------------------------------------
+// Which of the n x 20 candidate slots get an ML score (the reference only scores windows that need no padding:
+// bool replicate-pad raises, grasp_point_selector.py:425-437), and where their patch goes: valid slots are numbered
+// consecutively so that the CNN runs on exactly that many patches (c.slot_map, c.cnn_count).  One CTA, block scan.
+constexpr int CS_NT = 1024;
+__global__ void __launch_bounds__(CS_NT) compact_slots_kernel(lg_context c, int n) {
+    __shared__ int s_warp[CS_NT / 32];
+    __shared__ int s_carry;
+    const int total = n * LG_TOP_K, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int W = c.W, H = c.H;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < total; base += CS_NT) {
+        const int i = base + tid;
+        int ok = 0;
+        if (i < total) {
+            const int b = i / LG_TOP_K, k = i - b * LG_TOP_K;
+            lg_frame_result* res = &c.results[b];
+            const int ncand = c.region[b].ok ? res->n_candidates : 0;
+            if (k < ncand) {
+                const int cx = res->cand_x[k], cy = res->cand_y[k];
+                ok = (cx - 16 >= 0 && cy - 16 >= 0 && cx + 16 <= W && cy + 16 <= H) ? 1 : 0;
+            }
+            res->ml_valid[k] = ok;
+        }
+        int incl = ok;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        int woff = 0;
+        for (int w = 0; w < warp; ++w) woff += s_warp[w];
+        const int carry = s_carry;
+        if (i < total) c.slot_map[i] = ok ? carry + woff + incl - 1 : -1;
+        __syncthreads();
+        if (tid == CS_NT - 1) s_carry = carry + woff + incl;
+        __syncthreads();
+    }
+    if (tid == 0) *c.cnn_count = s_carry;
+}
+
 constexpr int GA_NT = 256;
 __global__ void __launch_bounds__(GA_NT) gather_kernel(lg_context c, LgMaskSrc src, const float* __restrict__ depth) {
     const int k = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     lg_frame_result* res = &c.results[b];
-    float* out = c.patches + ((size_t)b * LG_TOP_K + k) * (LG_CHANNELS * LG_PATCH * LG_PATCH);
+    const int slot = c.slot_map[b * LG_TOP_K + k];
+    if (slot < 0) return;                      // no ML score for this candidate: nothing to build
+    float* out = c.patches + (size_t)slot * (LG_CHANNELS * LG_PATCH * LG_PATCH);
     const LgRegion r = c.region[b];
     const int W = c.W, H = c.H;
     __shared__ float smn[GA_NT / 32][LG_CHANNELS], smx[GA_NT / 32][LG_CHANNELS];
     __shared__ float fmn[LG_CHANNELS], fmx[LG_CHANNELS];
-    const int ncand = r.ok ? res->n_candidates : 0;
-    const int cx = (k < ncand) ? res->cand_x[k] : -1000, cy = (k < ncand) ? res->cand_y[k] : -1000;
-    // the reference only gets an ML score when the window needs no padding (bool replicate-pad raises)
-    const bool ok = (k < ncand) && cx - 16 >= 0 && cy - 16 >= 0 && cx + 16 <= W && cy + 16 <= H;
-    if (tid == 0) res->ml_valid[k] = ok ? 1 : 0;
-    if (!ok) {
-        for (int i = tid; i < LG_CHANNELS * LG_PATCH * LG_PATCH; i += GA_NT) out[i] = 0.f;
-        return;
-    }
+    const int cx = res->cand_x[k], cy = res->cand_y[k];
     const size_t fo = (size_t)b * c.P;
     const int id = src.id(b);
     float v[LG_CHANNELS][4];
@@ -380,6 +417,15 @@ __global__ void __launch_bounds__(GA_NT) gather_kernel(lg_context c, LgMaskSrc s
     }
 }
 
+__global__ void export_patches_kernel(lg_context c, float* __restrict__ out) {
+    const int k = blockIdx.x, b = blockIdx.y;
+    const int slot = c.slot_map[b * LG_TOP_K + k];
+    const size_t sz = LG_CHANNELS * LG_PATCH * LG_PATCH;
+    float* o = out + ((size_t)b * LG_TOP_K + k) * sz;
+    const float* src = slot >= 0 ? c.patches + (size_t)slot * sz : nullptr;
+    for (int i = threadIdx.x; i < (int)sz; i += blockDim.x) o[i] = src ? src[i] : 0.f;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // fusion + 3-D points
 // ---------------------------------------------------------------------------------------------------
@@ -405,7 +451,7 @@ __global__ void fuse_kernel(lg_context c, LgMaskSrc src, const float* __restrict
     for (int k = 0; k < LG_TOP_K; ++k) {
         const bool mlk = have_ml && nc > 1 && k < nc && res->ml_valid[k];
         if (mlk) {
-            const float lg = c.logits[(size_t)b * LG_TOP_K + k];
+            const float lg = c.logits[c.slot_map[b * LG_TOP_K + k]];
             res->logit[k] = lg;
             const float s = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-lg)));
             res->ml[k] = tanh((double)s * 3.0) * 0.5 + 0.5;
@@ -529,7 +575,16 @@ int lg_run_nms(lg_context* c, int n, cudaStream_t st) {
 
 int lg_run_gather(lg_context* c, LgMaskSrc src, const float* depth, int n, lg_camera cam, cudaStream_t st) {
     (void)cam;
+    compact_slots_kernel<<<1, CS_NT, 0, st>>>(*c, n);
+    LG_LAUNCH_CHECK();
     gather_kernel<<<dim3(LG_TOP_K, n), GA_NT, 0, st>>>(*c, src, depth);
+    LG_LAUNCH_CHECK();
+    return LG_OK;
+}
+
+// the patch tensor in the dense [frames][20][9][32][32] order of the API (zeros where no patch was built)
+int lg_run_export_patches(lg_context* c, float* out, int n, cudaStream_t st) {
+    export_patches_kernel<<<dim3(LG_TOP_K, n), 256, 0, st>>>(*c, out);
     LG_LAUNCH_CHECK();
     return LG_OK;
 }
