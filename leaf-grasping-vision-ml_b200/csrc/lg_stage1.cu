@@ -76,9 +76,28 @@ __global__ void ray_table_kernel(unsigned long long* __restrict__ tab, int H, in
 // fixed point, exact and order independent) and its key range tracked.  Loads run ST_U rows ahead.
 constexpr int ST_U = 8;
 constexpr int STC_NT = 128;   // columns per CTA
+
+// the vertical run [ya, yb] of label `cur` in column x ends: add its sums to the CTA's table (rare: ~10 per column)
+__device__ __noinline__ void stats_flush_run(SmemLeaf* tab, int cur, int x, int ya, int yb, int W, int H, unsigned kmn, unsigned kmx,
+                                             long long sdep, const unsigned long long* rt) {
+    SmemLeaf* t = &tab[cur];
+    const unsigned len = (unsigned)(yb - ya + 1);
+    atomicAdd(&t->cnt, len);
+    if (cur > 0) {
+        atomicAdd(&t->sx, (unsigned)x * len);
+        atomicAdd(&t->sy, (unsigned)(ya + yb) * len / 2u);
+        atomicMin(&t->bx0, (unsigned)x); atomicMax(&t->bx1, (unsigned)x);
+        atomicMin(&t->by0, (unsigned)ya); atomicMax(&t->by1, (unsigned)yb);
+        if (x == 0 || x == W - 1 || ya == 0 || yb == H - 1) atomicOr(&t->border, 1u);
+        atomicMin(&t->kmin, kmn); atomicMax(&t->kmax, kmx);
+        atomicAdd(&t->sdep, (unsigned long long)sdep);
+        const unsigned long long hi = rt[(size_t)yb * W], lo = ya > 0 ? rt[(size_t)(ya - 1) * W] : 0ull;
+        atomicAdd(&t->sdist, hi - lo);
+    }
+}
 // The same walk is the column pass of the union distance transform (edt_col_kernel with source = label >= 1): the
 // kernel also writes the column distances c.edt_g and, on the way back up, their chunk minima c.edt_gmin.
-__global__ void __launch_bounds__(STC_NT) leaf_stats_kernel(lg_context c, const int16_t* __restrict__ labels,
+__global__ void __launch_bounds__(STC_NT, 8) leaf_stats_kernel(lg_context c, const int16_t* __restrict__ labels,
                                                             const float* __restrict__ depth) {
     extern __shared__ SmemLeaf tab[];
     __shared__ unsigned s_first, s_bad;
@@ -104,21 +123,21 @@ __global__ void __launch_bounds__(STC_NT) leaf_stats_kernel(lg_context c, const 
         uint16_t* gcol = c.edt_g + (size_t)b * P + x;
         long long sdep = 0;
         unsigned kmn = 0xFFFFFFFFu, kmx = 0;
-        auto flush = [&](int yb) {     // run [ya, yb] of label cur ends
-            if (cur < 0) return;
-            SmemLeaf* t = &tab[cur];
-            const unsigned len = (unsigned)(yb - ya + 1);
-            atomicAdd(&t->cnt, len);
-            if (cur > 0) {
-                atomicAdd(&t->sx, (unsigned)x * len);
-                atomicAdd(&t->sy, (unsigned)(ya + yb) * len / 2u);
-                atomicMin(&t->bx0, (unsigned)x); atomicMax(&t->bx1, (unsigned)x);
-                atomicMin(&t->by0, (unsigned)ya); atomicMax(&t->by1, (unsigned)yb);
-                if (x == 0 || x == W - 1 || ya == 0 || yb == H - 1) atomicOr(&t->border, 1u);
-                atomicMin(&t->kmin, kmn); atomicMax(&t->kmax, kmx);
-                atomicAdd(&t->sdep, (unsigned long long)sdep);
-                const unsigned long long hi = rt[(size_t)yb * W], lo = ya > 0 ? rt[(size_t)(ya - 1) * W] : 0ull;
-                atomicAdd(&t->sdist, hi - lo);
+        auto step = [&](int y, int l, float dv, uint16_t* gdst) {     // one pixel of the downward walk
+            dcol = l >= 1 ? 0u : min(dcol + 1u, 0xFFFFu);
+            *gdst = (uint16_t)dcol;
+            if (l < 0 || l >= L) { s_bad = 1; l = -1; }
+            if (l != cur) {
+                if (cur >= 0) stats_flush_run(tab, cur, x, ya, y - 1, W, H, kmn, kmx, sdep, rt);
+                cur = l; ya = y; sdep = 0; kmn = 0xFFFFFFFFu; kmx = 0;
+                if (l >= 1 && !seen_leaf) { atomicMin(&s_first, (unsigned)((size_t)y * W + x)); seen_leaf = true; }
+            }
+            if (l > 0) {
+                // 2^28 * depth is exact in float32 (power-of-two scale), so this equals the float64 formulation
+                const float dd = fminf(fmaxf(dv, -2048.f), 2048.f);
+                sdep += __float2ll_rn(dd * 268435456.f);
+                const unsigned key = f2key(dv);
+                kmn = min(kmn, key); kmx = max(kmx, key);
             }
         };
         int nl[ST_U];
@@ -128,41 +147,35 @@ __global__ void __launch_bounds__(STC_NT) leaf_stats_kernel(lg_context c, const 
             nl[k] = k < H ? (int)lp[(size_t)k * W] : 0;
             nd[k] = k < H ? dp[(size_t)k * W] : 0.f;
         }
-        for (int y0 = 0; y0 < H; y0 += ST_U) {
+        const int16_t* lrow = lp;        // row y0 of this column
+        const float* drow = dp;
+        uint16_t* grow = gcol;
+        const size_t bump = (size_t)ST_U * W;
+        int y0 = 0;
+        for (; y0 + ST_U <= H; y0 += ST_U) {     // full batches: no bounds checks, running row pointers
             int cl[ST_U];
             float cd[ST_U];
 #pragma unroll
             for (int k = 0; k < ST_U; ++k) { cl[k] = nl[k]; cd[k] = nd[k]; }
+            if (y0 + 2 * ST_U <= H) {            // next batch in flight while this one is reduced
 #pragma unroll
-            for (int k = 0; k < ST_U; ++k) {        // next batch in flight while this one is reduced
-                const int y = y0 + ST_U + k;
-                nl[k] = y < H ? (int)lp[(size_t)y * W] : 0;
-                nd[k] = y < H ? dp[(size_t)y * W] : 0.f;
-            }
+                for (int k = 0; k < ST_U; ++k) { nl[k] = (int)lrow[bump + (size_t)k * W]; nd[k] = drow[bump + (size_t)k * W]; }
+            } else {
 #pragma unroll
-            for (int k = 0; k < ST_U; ++k) {
-                const int y = y0 + k;
-                if (y < H) {
-                    int l = cl[k];
-                    dcol = l >= 1 ? 0u : min(dcol + 1u, 0xFFFFu);
-                    gcol[(size_t)y * W] = (uint16_t)dcol;
-                    if (l < 0 || l >= L) { s_bad = 1; l = -1; }
-                    if (l != cur) {
-                        flush(y - 1);
-                        cur = l; ya = y; sdep = 0; kmn = 0xFFFFFFFFu; kmx = 0;
-                        if (l >= 1 && !seen_leaf) { atomicMin(&s_first, (unsigned)((size_t)y * W + x)); seen_leaf = true; }
-                    }
-                    if (l > 0) {
-                        // 2^28 * depth is exact in float32 (power-of-two scale), so this equals the float64 formulation
-                        const float dd = fminf(fmaxf(cd[k], -2048.f), 2048.f);
-                        sdep += __float2ll_rn(dd * 268435456.f);
-                        const unsigned key = f2key(cd[k]);
-                        kmn = min(kmn, key); kmx = max(kmx, key);
-                    }
+                for (int k = 0; k < ST_U; ++k) {
+                    const bool ok = y0 + ST_U + k < H;
+                    nl[k] = ok ? (int)lrow[bump + (size_t)k * W] : 0;
+                    nd[k] = ok ? drow[bump + (size_t)k * W] : 0.f;
                 }
             }
+#pragma unroll
+            for (int k = 0; k < ST_U; ++k) step(y0 + k, cl[k], cd[k], grow + (size_t)k * W);
+            lrow += bump; drow += bump; grow += bump;
         }
-        flush(H - 1);
+#pragma unroll
+        for (int k = 0; k < ST_U; ++k)           // the last H % ST_U rows (already fetched)
+            if (y0 + k < H) step(y0 + k, nl[k], nd[k], grow + (size_t)k * W);
+        if (cur >= 0) stats_flush_run(tab, cur, x, ya, H - 1, W, H, kmn, kmx, sdep, rt);
     }
     __syncthreads();
     for (int l = threadIdx.x; l < L; l += STC_NT) {
@@ -193,19 +206,29 @@ __global__ void __launch_bounds__(STC_NT) leaf_stats_kernel(lg_context c, const 
         uint16_t* gm = c.edt_gmin + (size_t)b * H * c.edt_nchunks;
         const int chunk = x >> 5, lane = threadIdx.x & 31, nchunks = c.edt_nchunks;
         unsigned d = 0xFFFFu;
-        for (int y0 = H - 1; y0 >= 0; y0 -= ST_U) {
+        uint16_t* grow = gp + (size_t)(H - 1) * W + xc;      // row y0 of this column, walking up
+        uint16_t* mrow = gm + (size_t)(H - 1) * nchunks + chunk;
+        const bool wr_min = lane == 0 && chunk < nchunks;
+        int y0 = H - 1;
+        for (; y0 - (ST_U - 1) >= 0; y0 -= ST_U) {           // full batches
             unsigned curv[ST_U];
 #pragma unroll
-            for (int k = 0; k < ST_U; ++k) curv[k] = (y0 - k >= 0) ? gp[(size_t)(y0 - k) * W + xc] : 0xFFFFu;
+            for (int k = 0; k < ST_U; ++k) curv[k] = *(grow - (size_t)k * W);
 #pragma unroll
             for (int k = 0; k < ST_U; ++k) {
-                if (y0 - k >= 0) {
-                    d = min(curv[k], min(d + 1u, 0xFFFFu));
-                    if (in) gp[(size_t)(y0 - k) * W + x] = (uint16_t)d;
-                    const unsigned m = __reduce_min_sync(0xFFFFFFFFu, in ? d : 0xFFFFu);
-                    if (lane == 0 && chunk < nchunks) gm[(size_t)(y0 - k) * nchunks + chunk] = (uint16_t)m;
-                }
+                d = min(curv[k], min(d + 1u, 0xFFFFu));
+                if (in) *(grow - (size_t)k * W) = (uint16_t)d;
+                const unsigned m = __reduce_min_sync(0xFFFFFFFFu, in ? d : 0xFFFFu);
+                if (wr_min) *(mrow - (size_t)k * nchunks) = (uint16_t)m;
             }
+            grow -= (size_t)ST_U * W; mrow -= (size_t)ST_U * nchunks;
+        }
+        for (; y0 >= 0; --y0) {                              // the first H % ST_U rows
+            d = min((unsigned)*grow, min(d + 1u, 0xFFFFu));
+            if (in) *grow = (uint16_t)d;
+            const unsigned m = __reduce_min_sync(0xFFFFFFFFu, in ? d : 0xFFFFu);
+            if (wr_min) *mrow = (uint16_t)m;
+            grow -= W; mrow -= nchunks;
         }
     }
 }
