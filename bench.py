@@ -203,9 +203,8 @@ def run_ours(args):
 
     def step_device():
         res = eng.process_batch(lab_d, dep_d, cam, use_bf16, sync=False)
-        if world > 1:       # aggregation of the candidate records, as north_star specifies
-            recs = np.frombuffer(res.cpu().numpy().tobytes(), dtype=N.FRAME_RESULT)
-            lgd.gather_candidate_records(lgd.records_from_results(recs, dev), B * world)
+        if world > 1:       # aggregation of the candidate records, as north_star specifies (stays on the device)
+            lgd.gather_candidate_records(lgd.records_from_result_buffer(res, B), B * world)
         return res
 
     for _ in range(args.warmup):

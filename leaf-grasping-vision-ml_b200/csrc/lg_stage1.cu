@@ -947,6 +947,14 @@ int lg_run_stage1(lg_context* c, const int16_t* labels, const float* depth, int 
         c->ray_valid = 1;
     }
     // per-leaf statistics + column pass of the union distance transform in one walk over the columns
+    {
+        static size_t configured = 48 * 1024;      // the per-label table grows past the default limit for L > ~850
+        const size_t need = c->L * sizeof(SmemLeaf);
+        if (need > configured) {
+            LG_CUDA(cudaFuncSetAttribute(leaf_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+            configured = need;
+        }
+    }
     leaf_stats_kernel<<<dim3((c->W + STC_NT - 1) / STC_NT, n), STC_NT, c->L * sizeof(SmemLeaf), st>>>(*c, labels, depth);
     LG_LAUNCH_CHECK();
     lg_mark(c, LG_M_STATS, st);

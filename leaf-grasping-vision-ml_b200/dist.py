@@ -25,6 +25,25 @@ def records_from_results(res, device) -> torch.Tensor:
     return torch.from_numpy(rec).to(device)
 
 
+def records_from_result_buffer(buf: torch.Tensor, n_frames: int) -> torch.Tensor:
+    """Same records, built from the raw lg_frame_result byte buffer WITHOUT leaving the device (no host sync):
+    buf is the uint8 tensor lg_process_batch filled (GraspEngine.process_batch(..., sync=False))."""
+    from . import _native as N
+    dt = N.FRAME_RESULT
+    rows = buf.reshape(n_frames, dt.itemsize)
+
+    def field(name, tdtype):
+        off = dt.fields[name][1]
+        nbytes = dt.fields[name][0].itemsize
+        return rows[:, off:off + nbytes].contiguous().view(tdtype)
+
+    x = field("cand_x", torch.int32).to(torch.float32)
+    y = field("cand_y", torch.int32).to(torch.float32)
+    trad = field("trad", torch.float64).to(torch.float32)
+    ml = torch.nan_to_num(field("ml", torch.float64)).to(torch.float32)
+    return torch.stack([x, y, trad, ml], dim=-1)
+
+
 def gather_candidate_records(local: torch.Tensor, n_frames: int) -> torch.Tensor:
     """All-gather of the per-rank record blocks into [n_frames, 20, 4] on every rank."""
     if not dist.is_initialized() or dist.get_world_size() == 1:

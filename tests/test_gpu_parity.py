@@ -498,6 +498,31 @@ def test_bf16_pipeline_matches_fp32_picks(blob):
     eng.close()
 
 
+def test_label_table_limits(state_dict, blob):
+    """Label ids: a table of the maximum size (1024 ids, shared-memory table above the default limit) gives the same
+    pick as a small one; an id outside the table is reported per frame (LG_ST_LABEL_RANGE) without disturbing the
+    other frames of the batch."""
+    spec = synth.SMALL
+    P = synth.projection_matrix(spec)
+    lab, dep = synth.make_batch(spec, SEED, 0, 2)
+    lab = lab.copy()
+    lab[0][lab[0] == 2] = 1000                    # a legal id near the top of the table
+    eng = _engine(2, spec.height, spec.width, 1024)
+    eng.set_cnn_weights(blob)
+    res = eng.process_batch(torch.from_numpy(lab).cuda(), torch.from_numpy(dep).cuda(), _cam(spec))
+    for i in range(2):
+        _check_frame(res[i], lab[i], dep[i], P, state_dict)
+    eng.close()
+    eng = _engine(2, spec.height, spec.width, 16)
+    eng.set_cnn_weights(blob)
+    bad = lab.copy()
+    bad[0][bad[0] == 1000] = 999                  # outside a 16-entry table
+    res = eng.process_batch(torch.from_numpy(bad).cuda(), torch.from_numpy(dep).cuda(), _cam(spec))
+    assert res[0]["status"] & 2 and res[0]["leaf_id"] == -1
+    _check_frame(res[1], lab[1], dep[1], P, state_dict)
+    eng.close()
+
+
 def test_empty_and_degenerate_frames(blob):
     spec = synth.SMALL
     H, W = spec.height, spec.width

@@ -98,6 +98,19 @@ def test_ellipse_rows_restated_equals_opencv():
             np.testing.assert_array_equal(row, se[i])
 
 
+def test_records_from_result_buffer_matches_numpy_view():
+    """The on-device record builder reads the same bytes as the NumPy structured view of lg_frame_result."""
+    from leafgrasp_b200 import _native as N, dist as lgd
+    rng = np.random.default_rng(3)
+    rec = np.zeros(5, dtype=N.FRAME_RESULT)
+    rec["cand_x"] = rng.integers(0, 1440, (5, 20)); rec["cand_y"] = rng.integers(0, 1080, (5, 20))
+    rec["trad"] = rng.random((5, 20)); rec["ml"] = rng.random((5, 20)); rec["ml"][2, 7:] = np.nan
+    buf = torch.from_numpy(np.frombuffer(rec.tobytes(), dtype=np.uint8).copy())
+    a = lgd.records_from_result_buffer(buf, 5)
+    b = lgd.records_from_results(rec, "cpu")
+    assert a.shape == (5, 20, 4) and torch.equal(a, b)
+
+
 def _dist_worker(rank, world, port, out):
     import torch.distributed as dist
     from leafgrasp_b200 import dist as lgd
