@@ -309,6 +309,16 @@ def run_ours(args):
         if serial_ms[STAGES.index("cnn")] > 0 else None
     roof["whole_step_gbs"] = round((45 * P) * B / (ms / args.steps * 1e-3) / 1e9, 1)   # 45 B/px, SURVEY.md 8d
 
+    # ---- in-run consistency check of the batch just timed (untimed): tensor-core CNN against the fp32 CUDA path --
+    check = None
+    if use_bf16:
+        r32 = np.frombuffer(eng.process_batch(lab_d, dep_d, cam, False, sync=False).cpu().numpy().tobytes(), dtype=N.FRAME_RESULT)
+        ok = (records["ml_valid"] > 0) & (r32["ml_valid"] > 0)
+        check = {"candidates_identical_to_fp32_path": bool(np.array_equal(records["cand_x"], r32["cand_x"]) and
+                                                            np.array_equal(records["cand_y"], r32["cand_y"])),
+                 "bf16_logit_max_abs_diff": float(np.abs(records["logit"][ok] - r32["logit"][ok]).max()) if ok.any() else 0.0,
+                 "fused_pick_agreement": float((records["best_index"] == r32["best_index"]).mean())}
+
     cpu = None
     if world == 1 and not args.no_cpu:
         r = cpu_arm(args.cpu_steps, 1)
@@ -326,7 +336,7 @@ def run_ours(args):
                    "picked": int((records["n_candidates"] > 0).sum())},
         "e2e": {"value": total_frames / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(B * P * 6),
                 "d2h_bytes_per_step": int(B * N.FRAME_RESULT.itemsize)},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "consistency": check,
     }
     print(json.dumps(line))
     if world > 1:

@@ -31,7 +31,19 @@ constexpr int LEAD = 64;        // zero rows in front of every plane (>= pitch +
 constexpr int TILE_M = 512;     // positions per work item: 4 UMMA tiles of 128 rows
 constexpr int UMMA_T = 4;
 __host__ __device__ constexpr int nb_stages(int nc) { return nc == 64 ? 8 : 5; }   // weight stages in flight (what shared memory allows)
-constexpr int CONV_THREADS = 192;   // warp 0 producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue
+constexpr int CONV_THREADS = 320;   // warp 0 producer, warp 1 MMA issuer + TMEM owner, warps 2-9 epilogue
+constexpr int EPI_WARPS = 8;        // two warps per TMEM lane quarter, each taking every other 32-column chunk
+
+// Optional pipeline timers (build with -DLG_CNN_TIMING): per CTA, cycles the MMA warp spent waiting for the
+// accumulators (0), the input stage (1), the weight stages (2), issuing (3), and the epilogue's wait (4) / work (5).
+#ifdef LG_CNN_TIMING
+__device__ unsigned long long g_cnn_timing[6][148][8];
+#define LG_T0(v) const long long v = clock64()
+#define LG_TACC(slot, v) t_acc[slot] += clock64() - (v)
+#else
+#define LG_T0(v)
+#define LG_TACC(slot, v)
+#endif
 
 struct UmmaConvArgs {
     const uint4* in;      // [Cin/8 planes][R]
@@ -46,6 +58,7 @@ struct UmmaConvArgs {
     int n_split;          // Cout / NC
     int rows;             // shared-memory rows per plane of the A stage: TILE_M + 2 * pitch + 2, rounded up to 8
     int cout;
+    int layer;            // 0..5 (timers only)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -105,8 +118,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
           "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
           "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
@@ -145,7 +158,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&a_full[i]), 1); mbar_init(smem_u32(&a_empty[i]), 1); }
         for (int i = 0; i < NB_STAGES; ++i) { mbar_init(smem_u32(&b_full[i]), 1); mbar_init(smem_u32(&b_empty[i]), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -198,16 +211,21 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
     } else if (warp == 1) {
         // ===== MMA issuer =====
         int a_st = 0, a_ph = 0, b_st = 0, b_ph = 0, acc_st = 0, acc_ph = 0;
+#ifdef LG_CNN_TIMING
+        long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const long long t_begin = clock64();
+#endif
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            mbar_wait(smem_u32(&acc_empty[acc_st]), acc_ph ^ 1);
+            { LG_T0(t0); mbar_wait(smem_u32(&acc_empty[acc_st]), acc_ph ^ 1); LG_TACC(0, t0); }
             tc_fence_after();
             for (int kc = 0; kc < A.KC; ++kc) {
-                mbar_wait(smem_u32(&a_full[a_st]), a_ph);
+                { LG_T0(t0); mbar_wait(smem_u32(&a_full[a_st]), a_ph); LG_TACC(1, t0); }
                 const uint32_t a_base = smem_u32(sA + (size_t)a_st * a_stage_bytes);
 #pragma unroll 1
                 for (int tap = 0; tap < 9; ++tap) {
-                    mbar_wait(smem_u32(&b_full[b_st]), b_ph);
+                    { LG_T0(t0); mbar_wait(smem_u32(&b_full[b_st]), b_ph); LG_TACC(2, t0); }
                     tc_fence_after();
+                    LG_T0(t_issue);
                     if (lane == 0) {
                         const int ky = tap / 3, kx = tap - ky * 3;
                         const uint32_t b_base = smem_u32(sB + (size_t)b_st * B_STAGE);
@@ -225,6 +243,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
                         tc_commit(smem_u32(&b_empty[b_st]));
                     }
                     __syncwarp();
+                    LG_TACC(3, t_issue);
                     if (++b_st == NB_STAGES) { b_st = 0; b_ph ^= 1; }
                 }
                 if (lane == 0) tc_commit(smem_u32(&a_empty[a_st]));
@@ -236,19 +255,31 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
             __syncwarp();
             if (++acc_st == ACC_STAGES) { acc_st = 0; acc_ph ^= 1; }
         }
+#ifdef LG_CNN_TIMING
+        if (lane == 0 && blockIdx.x < 148) {
+            for (int k = 0; k < 4; ++k) g_cnn_timing[A.layer][blockIdx.x][k] = (unsigned long long)t_acc[k];
+            g_cnn_timing[A.layer][blockIdx.x][6] = (unsigned long long)(clock64() - t_begin);
+        }
+#endif
     } else {
         // ===== epilogue: TMEM -> registers -> bias + ReLU -> bf16 -> global (plane-major) =====
-        const int wq = warp & 3;     // TMEM lane quarter this warp may read
+        const int wq = warp & 3;                 // TMEM lane quarter this warp may read
+        const int chalf = (warp - 2) >> 2;       // which of the two warps of that quarter: chunks chalf, chalf + 2, ...
+        constexpr int CHUNKS = NC / 64;          // 32-column chunks per warp and tile (1 or 2), loaded together
         if (blockIdx.x == 0) {       // zero rows in front of position 0 of every output plane
             const int et = threadIdx.x - 64;
             const int planes = A.cout / 8;
-            for (int i = et; i < planes * LEAD; i += 128) A.out[(long long)(i / LEAD) * A.R + (i % LEAD)] = make_uint4(0, 0, 0, 0);
+            for (int i = et; i < planes * LEAD; i += 32 * EPI_WARPS) A.out[(long long)(i / LEAD) * A.R + (i % LEAD)] = make_uint4(0, 0, 0, 0);
         }
         int acc_st = 0, acc_ph = 0;
+#ifdef LG_CNN_TIMING
+        long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int tile = item / A.n_split, half = item % A.n_split;
-            mbar_wait(smem_u32(&acc_full[acc_st]), acc_ph);
+            { LG_T0(t0); mbar_wait(smem_u32(&acc_full[acc_st]), acc_ph); LG_TACC(4, t0); }
             tc_fence_after();
+            LG_T0(t_epi);
 #pragma unroll 1
             for (int t = 0; t < UMMA_T; ++t) {
                 const long long q = (long long)tile * TILE_M + t * 128 + wq * 32 + lane;
@@ -258,10 +289,14 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
                     const int r = ql / A.pitch, cc = ql - r * A.pitch;
                     data = (r >= 1) && (cc >= 1);
                 }
-#pragma unroll 1
-                for (int ch = 0; ch < NC / 32; ++ch) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((acc_st * UMMA_T + t) * NC + ch * 32), v);
+                uint32_t v[CHUNKS][32];
+#pragma unroll
+                for (int j = 0; j < CHUNKS; ++j)
+                    tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((acc_st * UMMA_T + t) * NC + (chalf + 2 * j) * 32), v[j]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < CHUNKS; ++j) {
+                    const int ch = chalf + 2 * j;
                     const float* bs = s_bias + half * NC + ch * 32;
                     uint4* o = A.out + (long long)((half * NC + ch * 32) / 8) * A.R + LEAD + q;
 #pragma unroll
@@ -270,7 +305,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
                         if (data) {
                             float f[8];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) f[e] = fmaxf(__uint_as_float(v[g * 8 + e]) + bs[g * 8 + e], 0.f);
+                            for (int e = 0; e < 8; ++e) f[e] = fmaxf(__uint_as_float(v[j][g * 8 + e]) + bs[g * 8 + e], 0.f);
                             w.x = pack_bf16x2(f[0], f[1]); w.y = pack_bf16x2(f[2], f[3]);
                             w.z = pack_bf16x2(f[4], f[5]); w.w = pack_bf16x2(f[6], f[7]);
                         }
@@ -281,8 +316,15 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&acc_empty[acc_st]));
+            LG_TACC(5, t_epi);
             if (++acc_st == ACC_STAGES) { acc_st = 0; acc_ph ^= 1; }
         }
+#ifdef LG_CNN_TIMING
+        if (warp == 2 && lane == 0 && blockIdx.x < 148) {
+            g_cnn_timing[A.layer][blockIdx.x][4] = (unsigned long long)t_acc[4];
+            g_cnn_timing[A.layer][blockIdx.x][5] = (unsigned long long)t_acc[5];
+        }
+#endif
     }
     tc_fence_before();
     __syncthreads();
@@ -523,7 +565,7 @@ static int run_cnn_bf16(lg_context* c, const float* patches, int n, const int32_
             A.in = buf[cur]; A.out = buf[cur ^ 1]; A.wt = wts[l]; A.bias = bias[l];
             A.R = rows_per_plane(L.S, m);
             A.pitch = L.S + 1; A.PP = A.pitch * A.pitch; A.n_dev = n_dev; A.n_host = m;
-            A.KC = L.KC; A.n_split = L.cout / L.NC; A.rows = a_rows(L.S); A.cout = L.cout;
+            A.KC = L.KC; A.n_split = L.cout / L.NC; A.rows = a_rows(L.S); A.cout = L.cout; A.layer = l;
             int rc;
             if (L.KP == 2) rc = launch_conv<2, 64>(A, L.S, sms, st);
             else if (L.NC == 64) rc = launch_conv<8, 64>(A, L.S, sms, st);
@@ -561,3 +603,9 @@ static int run_cnn_bf16(lg_context* c, const float* patches, int n, const int32_
     }
     return LG_OK;
 }
+
+#ifdef LG_CNN_TIMING
+extern "C" int lg_cnn_timing(unsigned long long* out_host) {   // [6][148][8]
+    return cudaMemcpyFromSymbol(out_host, g_cnn_timing, sizeof(g_cnn_timing)) == cudaSuccess ? 0 : -2;
+}
+#endif

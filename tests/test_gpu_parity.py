@@ -350,6 +350,27 @@ def test_cnn_bf16_against_reference_logits(blob, state_dict):
     eng.close()
 
 
+def test_cfg4_cnn_only_65536_patches(blob):
+    """BASELINE config[3]: 65 536 patches through the tensor-core path (13 activation chunks of 5 120) against the
+    fp32 CUDA-core path, logits within the bf16 bar."""
+    eng = _engine(256, 64, 64, 2)
+    eng.set_cnn_weights(blob)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.rand((65536, 9, 32, 32), generator=g, device="cuda")
+    x[:, 1] = (x[:, 1] > 0.5).float()
+    y16 = eng.cnn_forward(x, use_bf16=True)
+    y32 = eng.cnn_forward(x, use_bf16=False)
+    torch.cuda.synchronize()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record(); eng.cnn_forward(x, use_bf16=True); e1.record(); eng.cnn_forward(x, use_bf16=False); e2.record()
+    torch.cuda.synchronize()
+    t16, t32 = e0.elapsed_time(e1), e1.elapsed_time(e2)
+    print(f"cfg4: 65536 patches bf16 tcgen05 {t16:.1f} ms ({65536 * 312.83e6 / t16 / 1e9:.0f} TFLOP/s), fp32 CUDA cores {t32:.1f} ms")
+    np.testing.assert_allclose(y16.cpu().numpy(), y32.cpu().numpy(), atol=1e-2, rtol=1e-2)
+    assert t16 < t32
+    eng.close()
+
+
 # ------------------------------------------------------------------------------------------------------
 # whole path
 # ------------------------------------------------------------------------------------------------------
