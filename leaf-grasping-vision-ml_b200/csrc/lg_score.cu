@@ -42,19 +42,24 @@ __device__ __forceinline__ bool bits_any(const uint32_t* bits, int wpr, int bw, 
 
 __device__ __forceinline__ float exp32(float x) { return (float)exp((double)x); }
 
+// grid = (CTAs per frame, frames): a CTA walks the 32 x 8 tiles of its frame's score rectangle (the rectangle is
+// only known on the device, so the grid cannot be sized to it; a grid over the whole frame would launch ~10x more
+// CTAs than there is work).
 __global__ void __launch_bounds__(SC_TW * SC_TH) score_kernel(lg_context c, LgMaskSrc src, const float* __restrict__ depth,
                                                                lg_camera cam, int full, double* iso_out) {
-    const int b = blockIdx.z;
+    const int b = blockIdx.y;
     const LgRegion r = c.region[b];
     if (!r.ok && !full) return;
     const int W = c.W, H = c.H;
-    const int tx0 = r.sx0 + blockIdx.x * SC_TW, ty0 = r.sy0 + blockIdx.y * SC_TH;
-    if (tx0 >= r.sx1 || ty0 >= r.sy1) return;
+    const int tiles_x = (r.sx1 - r.sx0 + SC_TW - 1) / SC_TW, tiles_y = (r.sy1 - r.sy0 + SC_TH - 1) / SC_TH;
     __shared__ float zt[SC_TH + 6][SC_TW + 6];
     __shared__ float st[SC_TH + 2][SC_TW + 2];
     const int tid = threadIdx.x;
     const size_t fo = (size_t)b * c.P;
     const int id = src.id(b);
+    for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
+    const int tx0 = r.sx0 + (tile % tiles_x) * SC_TW, ty0 = r.sy0 + (tile / tiles_x) * SC_TH;
+    __syncthreads();     // the previous tile's readers of zt / st are done
     // masked depth tile with reflect-101 borders (image_processor.py:60-61)
     for (int i = tid; i < (SC_TH + 6) * (SC_TW + 6); i += SC_TW * SC_TH) {
         const int ly = i / (SC_TW + 6), lx = i - ly * (SC_TW + 6);
@@ -179,6 +184,7 @@ __global__ void __launch_bounds__(SC_TW * SC_TH) score_kernel(lg_context c, LgMa
             c.list_idx[fo + pos] = (unsigned)((size_t)y * W + x);
         }
     }
+    }   // tiles
 }
 
 // fill the per-frame maps with their analytic values outside the score rectangle (full mode only needs
@@ -561,8 +567,10 @@ __global__ void __launch_bounds__(256) normalize_patches_kernel(const float* __r
 
 int lg_run_scores(lg_context* c, LgMaskSrc src, const float* depth, int n, lg_camera cam, int full, double* iso_out,
                   cudaStream_t st) {
-    dim3 grid((c->W + SC_TW - 1) / SC_TW + 1, (c->H + SC_TH - 1) / SC_TH + 1, n);
-    score_kernel<<<grid, SC_TW * SC_TH, 0, st>>>(*c, src, depth, cam, full, iso_out);
+    const int all_tiles = ((c->W + SC_TW - 1) / SC_TW + 1) * ((c->H + SC_TH - 1) / SC_TH + 1);
+    int per_frame = (148 * 8 * 2 + n - 1) / n;          // about two waves of CTAs over the batch, at least 64 per frame
+    per_frame = per_frame < 64 ? 64 : (per_frame > all_tiles ? all_tiles : per_frame);
+    score_kernel<<<dim3(per_frame, n), SC_TW * SC_TH, 0, st>>>(*c, src, depth, cam, full, iso_out);
     LG_LAUNCH_CHECK();
     return LG_OK;
 }
