@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(MED_NT) leaf_median_kernel(lg_context c) {
     const int l = blockIdx.x, b = blockIdx.y, L = c.L;
     const uint32_t* cnt = c.cnt + (size_t)b * L;
     __shared__ unsigned sm[MED_NT / 32 * 3];
-    __shared__ unsigned s_keys[MED_CAP];
+    extern __shared__ unsigned s_keys[];     // [MED_CAP]
     __shared__ unsigned s_n;
     __shared__ int s_bg;
     if (threadIdx.x == 0) { s_bg = background_id(cnt, L); s_n = 0; }
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(MED_NT) leaf_median_kernel(lg_context c) {
             const unsigned i = i0 + threadIdx.x;
             unsigned key = 0;
             bool hit = false;
-            if (i < n) { key = f2key(v[i]); hit = (key & pmask) == prefix; }
+            if (i < n) { key = (f2key(v[i]) - kmin); hit = (key & pmask) == prefix; }
             const unsigned ball = __ballot_sync(0xFFFFFFFFu, hit);
             if (ball) {
                 unsigned base = 0;
@@ -387,14 +387,16 @@ __global__ void __launch_bounds__(MED_NT) leaf_median_kernel(lg_context c) {
         }
         __syncthreads();
     };
+    // keys are ranked relative to the label's smallest key: the search range is [0, kmax - kmin], so the first
+    // digit already splits the values that are present instead of a power-of-two block around them
     if (kmin == kmax) {
-        klo = kmin;
+        klo = 0;
         below = 0; m = n;
     } else {
-        const int top = 31 - __clz(kmin ^ kmax);          // highest differing bit
+        const int top = 31 - __clz(kmax - kmin);          // highest set bit of the largest relative key
         int shift = top & ~1;                              // the digit (shift+1, shift) contains it
         unsigned pmask = shift >= 30 ? 0u : ~((4u << shift) - 1u);
-        unsigned prefix = kmin & pmask;
+        unsigned prefix = 0u;
         if (n <= MED_CAP) { compact(prefix, pmask); in_smem = true; set_below = 0; set_m = n; }
         for (; shift >= 0; shift -= 2) {
             unsigned c0 = 0, c1 = 0, c2 = 0;
@@ -408,7 +410,7 @@ __global__ void __launch_bounds__(MED_NT) leaf_median_kernel(lg_context c) {
                 }
             } else {
                 for (unsigned i = threadIdx.x; i < n; i += MED_NT) {
-                    const unsigned key = f2key(v[i]);
+                    const unsigned key = (f2key(v[i]) - kmin);
                     if ((key & pmask) == prefix) {
                         const unsigned d = (key >> shift) & 3u;
                         c0 += (d == 0); c1 += (d == 1); c2 += (d == 2);
@@ -431,7 +433,7 @@ __global__ void __launch_bounds__(MED_NT) leaf_median_kernel(lg_context c) {
         }
         klo = prefix;
     }
-    float med = key2f(klo);
+    float med = key2f(klo + kmin);
     if (!(n & 1)) {
         // upper middle (rank k_lo + 1): klo again when enough elements are <= klo, else the smallest larger key
         float hi;
@@ -442,7 +444,7 @@ __global__ void __launch_bounds__(MED_NT) leaf_median_kernel(lg_context c) {
             if (in_smem && k_lo + 1 < set_below + set_m) {
                 for (unsigned i = threadIdx.x; i < set_m; i += MED_NT) { const unsigned key = s_keys[i]; if (key > klo) mn = min(mn, key); }
             } else {
-                for (unsigned i = threadIdx.x; i < n; i += MED_NT) { const unsigned key = f2key(v[i]); if (key > klo) mn = min(mn, key); }
+                for (unsigned i = threadIdx.x; i < n; i += MED_NT) { const unsigned key = (f2key(v[i]) - kmin); if (key > klo) mn = min(mn, key); }
             }
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, d));
@@ -451,7 +453,7 @@ __global__ void __launch_bounds__(MED_NT) leaf_median_kernel(lg_context c) {
             __syncthreads();
             mn = 0xFFFFFFFFu;
             for (int w = 0; w < MED_NT / 32; ++w) mn = min(mn, sm[w]);
-            hi = key2f(mn);
+            hi = key2f(mn + kmin);
         }
         med = __fmul_rn(__fadd_rn(med, hi), 0.5f);   // float32 mean of the two middles
     }
@@ -969,7 +971,14 @@ int lg_run_stage1(lg_context* c, const int16_t* labels, const float* depth, int 
     leaf_scatter_kernel<<<dim3(tiles, n), ST_NT, c->L * sizeof(unsigned), st>>>(*c, labels, depth);
     LG_LAUNCH_CHECK();
     lg_mark(c, LG_M_SCATTER, st);
-    leaf_median_kernel<<<dim3(c->L, n), MED_NT, 0, st>>>(*c);
+    {
+        static bool configured = false;
+        if (!configured) {
+            LG_CUDA(cudaFuncSetAttribute(leaf_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MED_CAP * (int)sizeof(unsigned)));
+            configured = true;
+        }
+    }
+    leaf_median_kernel<<<dim3(c->L, n), MED_NT, MED_CAP * sizeof(unsigned), st>>>(*c);
     LG_LAUNCH_CHECK();
     lg_mark(c, LG_M_MEDIAN, st);
     return lg_join(c, 0, aux, st);
