@@ -1,13 +1,16 @@
 // Stage 1 - optimal-leaf selection (reference scripts/utils/leaf_scorer.py:25-203, 277-306).
 //
 // Kernels (all batched over frames, no host synchronisation):
-//   leaf_stats_kernel    one pass over labels+depth: per-label pixel count, coordinate sums, depth sum,
-//                        sum of ray lengths, bounding box, border contact; first leaf pixel of the frame
+//   leaf_stats_kernel    one walk down every column of labels + depth: per-label pixel count, coordinate sums, depth
+//                        sum, sum of ray lengths, bounding box, border contact, depth key range, first leaf pixel of
+//                        the frame; the same walk is the column pass of the union distance transform
 //   leaf_offsets_kernel  exclusive scan of the counts -> where each label's depth values go
 //   leaf_scatter_kernel  groups the depth values by label (order inside a group is irrelevant)
 //   leaf_median_kernel   exact np.median per label by radix selection on the grouped values
-//   edt_col_kernel / edt_row_kernel   exact squared Euclidean distance transform (two passes); used on
-//                        (labels >= 1) to find the background pixel farthest from every leaf
+//   edt_row_kernel / edt_rowmax_kernel   row pass of the exact squared Euclidean distance transform of (labels >= 1),
+//                        as a pruned search for the background pixel farthest from every leaf (the only thing
+//                        leaf_scorer.py:67-71 takes from its distance field)
+//   edt_col_kernel       stand-alone column pass (lg_edt_squared on a caller-supplied mask)
 //   select_leaf_kernel   the per-leaf scores, tall-leaf rule, Pareto front and weighted pick
 //
 // Integer sums are exact and order independent, so results do not depend on scheduling: coordinate
