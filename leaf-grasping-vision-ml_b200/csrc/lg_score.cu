@@ -191,16 +191,30 @@ __global__ void __launch_bounds__(SC_TW * SC_TH) score_kernel(lg_context c, LgMa
 // nothing: the rectangle is the frame).  Not needed in region mode: consumers special-case the outside.
 
 constexpr int NMS_NT = 1024;
+constexpr int NMS_SUB = 6144;      // keys the shared-memory shortlist holds
+constexpr int NMS_TARGET = 5632;   // shortlist = all keys above a histogram threshold, about this many
+constexpr int NMS_BINS = 4096;
+constexpr size_t NMS_SMEM = (size_t)NMS_SUB * (sizeof(double) + sizeof(unsigned)) + NMS_BINS * sizeof(unsigned);
+// _get_candidate_points (grasp_point_selector.py:447-482): 20 rounds of (arg-max of the remaining keys, suppress
+// everything within +-20 px of the pick).  The picks are the first 20 unsuppressed keys in descending order, so they
+// only involve the top few thousand keys: a histogram of the keys (they lie in (0, 1]) gives a threshold, the keys
+// above it go to a shortlist in shared memory and the rounds run there.  If the shortlist runs dry before 20
+// picks the rounds continue on the full list, so the result is that of the full search in every case.
 __global__ void __launch_bounds__(NMS_NT) nms_kernel(lg_context c, const double* ext_score, const uint8_t* ext_valid,
                                                       int32_t* ext_xy, int32_t* ext_count) {
-    const int b = blockIdx.x, tid = threadIdx.x;
+    extern __shared__ __align__(16) unsigned char nms_sm[];
+    double* skey = reinterpret_cast<double*>(nms_sm);
+    unsigned* sidx = reinterpret_cast<unsigned*>(nms_sm + (size_t)NMS_SUB * sizeof(double));
+    unsigned* hist = sidx + NMS_SUB;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const int W = c.W;
     const size_t fo = (size_t)b * c.P;
     lg_frame_result* res = &c.results[b];
     __shared__ int px[LG_TOP_K], py[LG_TOP_K];
     __shared__ double wk[NMS_NT / 32];
     __shared__ unsigned wi[NMS_NT / 32];
-    __shared__ int s_found;
+    __shared__ int s_found, s_tb;
+    __shared__ unsigned s_m, s_total;
     const LgRegion r = c.region[b];
     if (!ext_score && !r.ok) {
         if (tid == 0) { res->n_candidates = 0; res->n_positive = 0; }
@@ -210,39 +224,121 @@ __global__ void __launch_bounds__(NMS_NT) nms_kernel(lg_context c, const double*
     double* key = c.list_key + fo;
     const unsigned* idx = c.list_idx + fo;
     int cnt = 0;
-    for (int it = 0; it < LG_TOP_K; ++it) {
-        double bk = -1.0;
-        unsigned bi = 0;
-        for (unsigned i = tid; i < n; i += NMS_NT) {
-            double k = key[i];
-            if (!(k > 0.0)) continue;
-            const unsigned id = idx[i];
-            if (it > 0) {
-                const int x = (int)(id % W), y = (int)(id / W);
-                if (abs(x - px[it - 1]) <= LG_NMS_REACH && abs(y - py[it - 1]) <= LG_NMS_REACH) { key[i] = -1.0; continue; }
+    // rounds [cnt, 20) over the list (k, id)[0, m); suppressed entries are overwritten with -1
+    auto rounds = [&](double* k_, const unsigned* id_, unsigned m) {
+        for (int it = cnt; it < LG_TOP_K; ++it) {
+            double bk = -1.0;
+            unsigned bi = 0;
+            for (unsigned i = tid; i < m; i += NMS_NT) {
+                const double k = k_[i];
+                if (!(k > 0.0)) continue;
+                const unsigned id = id_[i];
+                if (it > 0) {
+                    const int x = (int)(id % W), y = (int)(id / W);
+                    if (abs(x - px[it - 1]) <= LG_NMS_REACH && abs(y - py[it - 1]) <= LG_NMS_REACH) { k_[i] = -1.0; continue; }
+                }
+                if (k > bk || (k == bk && id > bi)) { bk = k; bi = id; }
             }
-            if (k > bk || (k == bk && id > bi)) { bk = k; bi = id; }
-        }
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            double ok = __shfl_xor_sync(0xFFFFFFFFu, bk, d);
-            unsigned oi = __shfl_xor_sync(0xFFFFFFFFu, bi, d);
-            if (ok > bk || (ok == bk && oi > bi)) { bk = ok; bi = oi; }
-        }
-        if ((tid & 31) == 0) { wk[tid >> 5] = bk; wi[tid >> 5] = bi; }
-        __syncthreads();
-        if (tid == 0) {
-            for (int w = 1; w < NMS_NT / 32; ++w)
-                if (wk[w] > bk || (wk[w] == bk && wi[w] > bi)) { bk = wk[w]; bi = wi[w]; }
-            s_found = bk > 0.0;
-            if (s_found) {
-                px[it] = (int)(bi % W); py[it] = (int)(bi / W);
-                res->cand_x[it] = px[it]; res->cand_y[it] = py[it]; res->trad[it] = bk;
+            for (int d = 16; d > 0; d >>= 1) {
+                const double ok = __shfl_xor_sync(0xFFFFFFFFu, bk, d);
+                const unsigned oi = __shfl_xor_sync(0xFFFFFFFFu, bi, d);
+                if (ok > bk || (ok == bk && oi > bi)) { bk = ok; bi = oi; }
             }
+            if (lane == 0) { wk[tid >> 5] = bk; wi[tid >> 5] = bi; }
+            __syncthreads();
+            if (tid == 0) {
+                for (int w = 1; w < NMS_NT / 32; ++w)
+                    if (wk[w] > bk || (wk[w] == bk && wi[w] > bi)) { bk = wk[w]; bi = wi[w]; }
+                s_found = bk > 0.0;
+                if (s_found) {
+                    px[it] = (int)(bi % W); py[it] = (int)(bi / W);
+                    res->cand_x[it] = px[it]; res->cand_y[it] = py[it]; res->trad[it] = bk;
+                }
+            }
+            __syncthreads();
+            if (!s_found) break;
+            ++cnt;
         }
+    };
+    if (n <= (unsigned)NMS_SUB) {
+        for (unsigned i = tid; i < n; i += NMS_NT) { skey[i] = key[i]; sidx[i] = idx[i]; }
         __syncthreads();
-        if (!s_found) break;
-        ++cnt;
+        rounds(skey, sidx, n);
+    } else {
+        // shortlist, rounds, and - if the shortlist ran dry before 20 picks - a new shortlist from what is left
+        for (int build = 0; cnt < LG_TOP_K; ++build) {
+            if (build > 0) {   // bring the full list up to date: drop everything the picks so far suppress (themselves included)
+                for (unsigned i = tid; i < n; i += NMS_NT) {
+                    if (!(key[i] > 0.0)) continue;
+                    const unsigned id = idx[i];
+                    const int x = (int)(id % W), y = (int)(id / W);
+                    for (int k = 0; k < cnt; ++k)
+                        if (abs(x - px[k]) <= LG_NMS_REACH && abs(y - py[k]) <= LG_NMS_REACH) { key[i] = -1.0; break; }
+                }
+            }
+            for (int i = tid; i < NMS_BINS; i += NMS_NT) hist[i] = 0;
+            if (tid == 0) { s_m = 0; s_tb = -1; s_total = 0; }
+            __syncthreads();
+            for (unsigned i = tid; i < n; i += NMS_NT) {
+                const double k = key[i];
+                if (k > 0.0) atomicAdd(&hist[min(NMS_BINS - 1, (int)(k * (double)NMS_BINS))], 1u);
+            }
+            __syncthreads();
+            if (tid < 32) {   // threshold bin: the highest bin whose suffix count reaches the target without overflowing
+                constexpr int PER = NMS_BINS / 32;
+                unsigned mine = 0;
+                for (int j = 0; j < PER; ++j) mine += hist[lane * PER + j];
+                unsigned suffix = mine;            // inclusive suffix sum over lanes (higher lanes = higher keys)
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const unsigned t = __shfl_down_sync(0xFFFFFFFFu, suffix, d);
+                    if (lane + d < 32) suffix += t;
+                }
+                if (lane == 0) s_total = suffix;
+                const unsigned above = suffix - mine;                       // keys in higher lanes' bins
+                const bool here = above < (unsigned)NMS_TARGET && suffix >= (unsigned)NMS_TARGET;
+                const unsigned who = __ballot_sync(0xFFFFFFFFu, here);
+                if (who == 0u) {                                             // fewer keys left than the target: take all bins
+                    if (lane == 0) s_tb = 0;
+                } else if (lane == (__ffs(who) - 1)) {
+                    unsigned acc = above;
+                    int tb = (lane + 1) * PER;                               // first bin above this lane's range
+                    for (int j = PER - 1; j >= 0; --j) {
+                        const unsigned h = hist[lane * PER + j];
+                        if (acc + h > (unsigned)NMS_SUB) break;
+                        acc += h; tb = lane * PER + j;
+                        if (acc >= (unsigned)NMS_TARGET) break;
+                    }
+                    s_tb = (acc > 0u) ? tb : -1;                             // -1: a single bin overflows the shortlist
+                }
+            }
+            __syncthreads();
+            const int tb = s_tb;
+            const unsigned total = s_total;
+            if (total == 0u) break;                                          // nothing left to pick from
+            if (tb < 0) { rounds(key, idx, n); break; }                      // degenerate key distribution: plain search
+            for (unsigned i0 = 0; i0 < n; i0 += NMS_NT) {
+                const unsigned i = i0 + tid;
+                double k = -1.0;
+                bool take = false;
+                if (i < n) { k = key[i]; take = k > 0.0 && min(NMS_BINS - 1, (int)(k * (double)NMS_BINS)) >= tb; }
+                const unsigned ball = __ballot_sync(0xFFFFFFFFu, take);
+                if (ball) {
+                    unsigned base = 0;
+                    if (lane == 0) base = atomicAdd(&s_m, __popc(ball));
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    const unsigned pos = base + __popc(ball & ((1u << lane) - 1u));
+                    if (take && pos < (unsigned)NMS_SUB) { skey[pos] = k; sidx[pos] = idx[i]; }
+                }
+            }
+            __syncthreads();
+            const unsigned m = s_m;
+            // the first round of this call must not apply the "previous pick" test to stale data: the list is up to date
+            rounds(skey, sidx, m);
+            if (m == total) break;                                           // the shortlist was everything that is left
+            __syncthreads();
+        }
     }
     if (tid == 0) {
         const int n_pos = cnt;
@@ -565,6 +661,15 @@ __global__ void __launch_bounds__(256) normalize_patches_kernel(const float* __r
 
 }  // namespace
 
+#define TRY_SMEM(kernel, bytes)                                                                              \
+    do {                                                                                                     \
+        static bool done__ = false;                                                                          \
+        if (!done__) {                                                                                       \
+            LG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            done__ = true;                                                                                   \
+        }                                                                                                    \
+    } while (0)
+
 int lg_run_scores(lg_context* c, LgMaskSrc src, const float* depth, int n, lg_camera cam, int full, double* iso_out,
                   cudaStream_t st) {
     const int all_tiles = ((c->W + SC_TW - 1) / SC_TW + 1) * ((c->H + SC_TH - 1) / SC_TH + 1);
@@ -576,7 +681,8 @@ int lg_run_scores(lg_context* c, LgMaskSrc src, const float* depth, int n, lg_ca
 }
 
 int lg_run_nms(lg_context* c, int n, cudaStream_t st) {
-    nms_kernel<<<n, NMS_NT, 0, st>>>(*c, nullptr, nullptr, nullptr, nullptr);
+    TRY_SMEM(nms_kernel, NMS_SMEM);
+    nms_kernel<<<n, NMS_NT, NMS_SMEM, st>>>(*c, nullptr, nullptr, nullptr, nullptr);
     LG_LAUNCH_CHECK();
     return LG_OK;
 }
@@ -619,7 +725,8 @@ int lg_run_candidates_from_maps(lg_context* c, const double* score, const uint8_
     LG_LAUNCH_CHECK();
     list_from_maps_kernel<<<dim3((unsigned)((c->P + 255) / 256), n), 256, 0, st>>>(*c, score, valid);
     LG_LAUNCH_CHECK();
-    nms_kernel<<<n, NMS_NT, 0, st>>>(*c, score, valid, xy, count);
+    TRY_SMEM(nms_kernel, NMS_SMEM);
+    nms_kernel<<<n, NMS_NT, NMS_SMEM, st>>>(*c, score, valid, xy, count);
     LG_LAUNCH_CHECK();
     return LG_OK;
 }
