@@ -94,11 +94,15 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// unswizzled K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+// Unswizzled K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
+//   bits [0,14) start address >> 4, [16,30) leading byte offset >> 4 (between the two K chunks of 8 elements),
+//   [32,46) stride byte offset >> 4 (between groups of 8 rows), bit 46 version.
+// the two words of that descriptor: lo = start address >> 4 | LBO >> 4 << 16, hi = SBO >> 4 | version 1 (bit 46)
+__device__ __forceinline__ uint32_t desc_lo(uint32_t addr, uint32_t lbo_bytes) {
+    return ((addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
 }
+constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);      // SBO = 128 B; bit 46 of the descriptor = bit 14 of the high word
+
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n"
@@ -211,6 +215,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
     } else if (warp == 1) {
         // ===== MMA issuer =====
         int a_st = 0, a_ph = 0, b_st = 0, b_ph = 0, acc_st = 0, acc_ph = 0;
+        const uint32_t rows2 = 2u * (uint32_t)A.rows;      // two planes (one K = 16 step) in 16-byte units
 #ifdef LG_CNN_TIMING
         long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         const long long t_begin = clock64();
@@ -227,17 +232,22 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
                     tc_fence_after();
                     LG_T0(t_issue);
                     if (lane == 0) {
+                        // One thread must issue an MMA every 32 (N = 64) / 64 (N = 128) cycles to keep the tensor pipe
+                        // busy, so the descriptors are not rebuilt per MMA: the high words are constant and the low
+                        // word (start address >> 4 | LBO << 16) just advances by the operand's offset in 16-byte
+                        // units (shared-memory addresses stay below 2^18, so the add never carries into the LBO field).
                         const int ky = tap / 3, kx = tap - ky * 3;
-                        const uint32_t b_base = smem_u32(sB + (size_t)b_st * B_STAGE);
-                        const uint32_t a_tap = a_base + (uint32_t)(ky * A.pitch + kx) * 16;
+                        const uint32_t a_lo = desc_lo(a_base + (uint32_t)(ky * A.pitch + kx) * 16, A.rows * 16);
+                        const uint32_t b_lo = desc_lo(smem_u32(sB + (size_t)b_st * B_STAGE), NC * 16);
+                        const uint32_t first_acc = (uint32_t)((kc | tap) != 0);
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(acc_st * UMMA_T * NC);
 #pragma unroll
                         for (int t = 0; t < UMMA_T; ++t) {
 #pragma unroll
                             for (int j = 0; j < KP / 2; ++j) {
-                                const uint64_t ad = umma_desc(a_tap + (uint32_t)(2 * j * A.rows + t * 128) * 16, A.rows * 16, 128);
-                                const uint64_t bd = umma_desc(b_base + (uint32_t)(2 * j * NC) * 16, NC * 16, 128);
-                                umma_bf16(tmem_base + (uint32_t)((acc_st * UMMA_T + t) * NC), ad, bd, IDESC,
-                                          (uint32_t)((kc | tap | j) != 0));
+                                const uint64_t ad = ((uint64_t)DESC_HI << 32) | (uint64_t)(a_lo + (uint32_t)(j * rows2 + t * 128));
+                                const uint64_t bd = ((uint64_t)DESC_HI << 32) | (uint64_t)(b_lo + (uint32_t)(j * 2 * NC));
+                                umma_bf16(d_tmem + (uint32_t)(t * NC), ad, bd, IDESC, j == 0 ? first_acc : 1u);
                             }
                         }
                         tc_commit(smem_u32(&b_empty[b_st]));
