@@ -79,6 +79,7 @@ __global__ void ray_table_kernel(unsigned long long* __restrict__ tab, int H, in
 // fixed point, exact and order independent) and its key range tracked.  Loads run ST_U rows ahead.
 constexpr int ST_U = 8;
 constexpr int STC_NT = 128;   // columns per CTA
+constexpr int STC_BND = 40;   // leaf-run boundaries (20 runs) a column can record for the distance transform
 
 // the vertical run [ya, yb] of label `cur` in column x ends: add its sums to the CTA's table (rare: ~10 per column)
 __device__ __noinline__ void stats_flush_run(SmemLeaf* tab, int cur, int x, int ya, int yb, int W, int H, unsigned kmn, unsigned kmx,
@@ -107,6 +108,10 @@ __global__ void __launch_bounds__(STC_NT, 8) leaf_stats_kernel(lg_context c, con
     const int L = c.L, W = c.W, H = c.H;
     const size_t P = c.P;
     const int b = blockIdx.y;
+    // rows where this column enters (even entries) / leaves (odd entries) the union of all leaves: [STC_BND][STC_NT]
+    uint16_t* bnd = reinterpret_cast<uint16_t*>(tab + L) + threadIdx.x;
+    int nb = 0;
+    bool in_src = false;
     for (int l = threadIdx.x; l < L; l += STC_NT) {
         SmemLeaf z;
         z.cnt = 0; z.sx = 0; z.sy = 0; z.bx0 = 0xFFFFFFFFu; z.by0 = 0xFFFFFFFFu; z.bx1 = 0; z.by1 = 0;
@@ -122,13 +127,14 @@ __global__ void __launch_bounds__(STC_NT, 8) leaf_stats_kernel(lg_context c, con
         const unsigned long long* rt = c.ray_tab + x;
         int cur = -1, ya = 0;
         bool seen_leaf = false;
-        unsigned dcol = 0xFFFFu;                   // rows since the last leaf pixel of this column (EDT)
-        uint16_t* gcol = c.edt_g + (size_t)b * P + x;
         long long sdep = 0;
         unsigned kmn = 0xFFFFFFFFu, kmx = 0;
-        auto step = [&](int y, int l, float dv, uint16_t* gdst) {     // one pixel of the downward walk
-            dcol = l >= 1 ? 0u : min(dcol + 1u, 0xFFFFu);
-            *gdst = (uint16_t)dcol;
+        auto step = [&](int y, int l, float dv) {     // one pixel of the downward walk
+            if ((l >= 1) != in_src) {                 // the column enters / leaves the union of the leaves
+                if (nb < STC_BND) bnd[nb * STC_NT] = (uint16_t)y;
+                ++nb;
+                in_src = !in_src;
+            }
             if (l < 0 || l >= L) { s_bad = 1; l = -1; }
             if (l != cur) {
                 if (cur >= 0) stats_flush_run(tab, cur, x, ya, y - 1, W, H, kmn, kmx, sdep, rt);
@@ -152,7 +158,6 @@ __global__ void __launch_bounds__(STC_NT, 8) leaf_stats_kernel(lg_context c, con
         }
         const int16_t* lrow = lp;        // row y0 of this column
         const float* drow = dp;
-        uint16_t* grow = gcol;
         const size_t bump = (size_t)ST_U * W;
         int y0 = 0;
         for (; y0 + ST_U <= H; y0 += ST_U) {     // full batches: no bounds checks, running row pointers
@@ -172,13 +177,17 @@ __global__ void __launch_bounds__(STC_NT, 8) leaf_stats_kernel(lg_context c, con
                 }
             }
 #pragma unroll
-            for (int k = 0; k < ST_U; ++k) step(y0 + k, cl[k], cd[k], grow + (size_t)k * W);
-            lrow += bump; drow += bump; grow += bump;
+            for (int k = 0; k < ST_U; ++k) step(y0 + k, cl[k], cd[k]);
+            lrow += bump; drow += bump;
         }
 #pragma unroll
         for (int k = 0; k < ST_U; ++k)           // the last H % ST_U rows (already fetched)
-            if (y0 + k < H) step(y0 + k, nl[k], nd[k], grow + (size_t)k * W);
+            if (y0 + k < H) step(y0 + k, nl[k], nd[k]);
         if (cur >= 0) stats_flush_run(tab, cur, x, ya, H - 1, W, H, kmn, kmx, sdep, rt);
+        if (in_src) {                             // close the last run at the bottom edge
+            if (nb < STC_BND) bnd[nb * STC_NT] = (uint16_t)H;
+            ++nb;
+        }
     }
     __syncthreads();
     for (int l = threadIdx.x; l < L; l += STC_NT) {
@@ -202,36 +211,51 @@ __global__ void __launch_bounds__(STC_NT, 8) leaf_stats_kernel(lg_context c, con
         if (s_first != 0xFFFFFFFFu) atomicMin(&c.first_leaf[b], s_first);
         if (s_bad) atomicOr(&c.status[b], LG_ST_LABEL_RANGE);
     }
-    {   // backward sweep of the column distances + chunk minima (whole warps: the reduction needs every lane)
+    {   // Column pass of the union distance transform, from the recorded run boundaries (no second look at the labels):
+        // g(y) = 0 inside a run, else the distance to the nearest run end above / run start below; plus the minimum of
+        // g over every chunk of 32 columns.  Whole warps take part: the reduction needs every lane.
         const bool in = x < W;
-        const int xc = in ? x : W - 1;
-        uint16_t* gp = c.edt_g + (size_t)b * P;
+        uint16_t* gp = c.edt_g + (size_t)b * P + (in ? x : 0);
         uint16_t* gm = c.edt_gmin + (size_t)b * H * c.edt_nchunks;
         const int chunk = x >> 5, lane = threadIdx.x & 31, nchunks = c.edt_nchunks;
-        unsigned d = 0xFFFFu;
-        uint16_t* grow = gp + (size_t)(H - 1) * W + xc;      // row y0 of this column, walking up
-        uint16_t* mrow = gm + (size_t)(H - 1) * nchunks + chunk;
         const bool wr_min = lane == 0 && chunk < nchunks;
-        int y0 = H - 1;
-        for (; y0 - (ST_U - 1) >= 0; y0 -= ST_U) {           // full batches
-            unsigned curv[ST_U];
-#pragma unroll
-            for (int k = 0; k < ST_U; ++k) curv[k] = *(grow - (size_t)k * W);
-#pragma unroll
-            for (int k = 0; k < ST_U; ++k) {
-                d = min(curv[k], min(d + 1u, 0xFFFFu));
-                if (in) *(grow - (size_t)k * W) = (uint16_t)d;
-                const unsigned m = __reduce_min_sync(0xFFFFFFFFu, in ? d : 0xFFFFu);
-                if (wr_min) *(mrow - (size_t)k * nchunks) = (uint16_t)m;
-            }
-            grow -= (size_t)ST_U * W; mrow -= (size_t)ST_U * nchunks;
+        const bool overflow = nb > STC_BND;
+        if (in && overflow) {      // more runs than the table holds (never on real frames): plain two sweeps for this column
+            const int16_t* lp = labels + (size_t)b * P + x;
+            unsigned d = 0xFFFFu;
+            for (int y = 0; y < H; ++y) { d = lp[(size_t)y * W] >= 1 ? 0u : min(d + 1u, 0xFFFFu); gp[(size_t)y * W] = (uint16_t)d; }
+            d = 0xFFFFu;
+            for (int y = H - 1; y >= 0; --y) { d = min((unsigned)gp[(size_t)y * W], min(d + 1u, 0xFFFFu)); gp[(size_t)y * W] = (uint16_t)d; }
         }
-        for (; y0 >= 0; --y0) {                              // the first H % ST_U rows
-            d = min((unsigned)*grow, min(d + 1u, 0xFFFFu));
-            if (in) *grow = (uint16_t)d;
-            const unsigned m = __reduce_min_sync(0xFFFFFFFFu, in ? d : 0xFFFFu);
+        int ri = 0;
+        int next_start = (in && !overflow && nb > 0) ? (int)bnd[0] : 0x7FFFFFF;
+        int cur_last = -1;           // last row of the run the walk is in, -1 when in a gap
+        int last_src = -0x7FFFFFF;   // last leaf row above
+        uint16_t* grow = gp;
+        uint16_t* mrow = gm + chunk;
+        for (int y = 0; y < H; ++y) {
+            unsigned gv = 0xFFFFu;
+            if (in) {
+                if (overflow) {
+                    gv = *grow;
+                } else {
+                    if (y == next_start) {
+                        cur_last = (int)bnd[(ri + 1) * STC_NT] - 1;
+                        ri += 2;
+                        next_start = ri < nb ? (int)bnd[ri * STC_NT] : 0x7FFFFFF;
+                    }
+                    if (cur_last >= 0) {
+                        gv = 0u;
+                        if (y == cur_last) { last_src = y; cur_last = -1; }
+                    } else {
+                        gv = (unsigned)min(min(y - last_src, next_start - y), 0xFFFF);
+                    }
+                    *grow = (uint16_t)gv;
+                }
+            }
+            const unsigned m = __reduce_min_sync(0xFFFFFFFFu, gv);
             if (wr_min) *mrow = (uint16_t)m;
-            grow -= W; mrow -= nchunks;
+            grow += W; mrow += nchunks;
         }
     }
 }
@@ -954,13 +978,14 @@ int lg_run_stage1(lg_context* c, const int16_t* labels, const float* depth, int 
     // per-leaf statistics + column pass of the union distance transform in one walk over the columns
     {
         static size_t configured = 48 * 1024;      // the per-label table grows past the default limit for L > ~850
-        const size_t need = c->L * sizeof(SmemLeaf);
+        const size_t need = c->L * sizeof(SmemLeaf) + (size_t)STC_BND * STC_NT * sizeof(uint16_t);
         if (need > configured) {
             LG_CUDA(cudaFuncSetAttribute(leaf_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
             configured = need;
         }
     }
-    leaf_stats_kernel<<<dim3((c->W + STC_NT - 1) / STC_NT, n), STC_NT, c->L * sizeof(SmemLeaf), st>>>(*c, labels, depth);
+    leaf_stats_kernel<<<dim3((c->W + STC_NT - 1) / STC_NT, n), STC_NT,
+                        c->L * sizeof(SmemLeaf) + (size_t)STC_BND * STC_NT * sizeof(uint16_t), st>>>(*c, labels, depth);
     LG_LAUNCH_CHECK();
     lg_mark(c, LG_M_STATS, st);
     // the row pass (arg-max only) is independent of the medians: it runs beside scatter + median
