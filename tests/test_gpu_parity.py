@@ -544,6 +544,30 @@ def test_label_table_limits(state_dict, blob):
     eng.close()
 
 
+def test_striped_leaf_overflows_the_column_run_table(state_dict, blob):
+    """A leaf made of 60 thin horizontal stripes: every column crosses more leaf runs than leaf_stats_kernel records
+    (STC_BND), so the distance-transform column pass takes its fallback.  Same records and pick as the oracle."""
+    spec = synth.SMALL
+    H, W = spec.height, spec.width
+    P = synth.projection_matrix(spec)
+    lab, dep = synth.make_frame(spec, SEED, 1)
+    lab = lab.copy()
+    stripes = (np.arange(H) // 3) % 2 == 0
+    lab[np.ix_(stripes, np.arange(40, 200))] = 7
+    eng = _engine(1, H, W, 16)
+    eng.set_cnn_weights(blob)
+    ids, rec = eng.select_leaf(torch.from_numpy(lab)[None], torch.from_numpy(dep)[None], _cam(spec))
+    o = O.select_optimal_leaf(lab, dep, P[0, 0], P[0, 2], P[1, 2])
+    assert ids[0] == (o["leaf_id"] if o["leaf_id"] is not None else -1)
+    by_id = {c["leaf_id"]: c for c in o["candidates"]}
+    for r in rec[0][rec[0]["is_candidate"] > 0]:
+        c = by_id[int(r["leaf_id"])]
+        np.testing.assert_allclose([r["clutter"], r["distance"], r["visibility"]], c["scores"], rtol=1e-6, atol=1e-12)
+    res = eng.process_batch(torch.from_numpy(lab)[None].cuda(), torch.from_numpy(dep)[None].cuda(), _cam(spec))
+    _check_frame(res[0], lab, dep, P, state_dict)
+    eng.close()
+
+
 def test_empty_and_degenerate_frames(blob):
     spec = synth.SMALL
     H, W = spec.height, spec.width
