@@ -78,7 +78,13 @@ __global__ void ray_table_kernel(unsigned long long* __restrict__ tab, int H, in
 // box, border contact) or is a difference of two ray_tab entries; per pixel only the depth is accumulated (2^-28
 // fixed point, exact and order independent) and its key range tracked.  Loads run ST_U rows ahead.
 constexpr int ST_U = 8;
-constexpr int STC_NT = 128;   // columns per CTA
+#ifndef LG_STATS_NT
+#define LG_STATS_NT 128
+#endif
+#ifndef LG_STATS_MINB
+#define LG_STATS_MINB 8
+#endif
+constexpr int STC_NT = LG_STATS_NT;   // columns per CTA
 constexpr int STC_BND = 40;   // leaf-run boundaries (20 runs) a column can record for the distance transform
 
 // the vertical run [ya, yb] of label `cur` in column x ends: add its sums to the CTA's table (rare: ~10 per column)
@@ -101,7 +107,7 @@ __device__ __noinline__ void stats_flush_run(SmemLeaf* tab, int cur, int x, int 
 }
 // The same walk is the column pass of the union distance transform (edt_col_kernel with source = label >= 1): the
 // kernel also writes the column distances c.edt_g and, on the way back up, their chunk minima c.edt_gmin.
-__global__ void __launch_bounds__(STC_NT, 8) leaf_stats_kernel(lg_context c, const int16_t* __restrict__ labels,
+__global__ void __launch_bounds__(STC_NT, LG_STATS_MINB) leaf_stats_kernel(lg_context c, const int16_t* __restrict__ labels,
                                                             const float* __restrict__ depth) {
     extern __shared__ SmemLeaf tab[];
     __shared__ unsigned s_first, s_bad;
