@@ -98,6 +98,40 @@ def test_ellipse_rows_restated_equals_opencv():
             np.testing.assert_array_equal(row, se[i])
 
 
+def test_wire_format_round_trip():
+    """msg/masks.msg uint16[] / msg/depth.msg float32[] -> tensors as mask_callback / depth_callback build them
+    (leaf_grasp_node_v3.py:185-205), and the published result string (:168-173)."""
+    from leafgrasp_b200 import wire, _native as N
+    H, W = 6, 9
+    rng = np.random.default_rng(0)
+    ids = rng.integers(0, 40, H * W).astype(np.uint16)
+    dep = rng.random(H * W).astype(np.float32)
+
+    class Msg:            # what rospy hands to the callbacks: a tuple of Python numbers
+        def __init__(self, data):
+            self.imageData = tuple(data.tolist())
+
+    ref_mask = torch.tensor(np.array(Msg(ids).imageData, dtype=np.int16)).reshape(H, W)          # the reference's lines
+    ref_depth = torch.tensor(np.array(Msg(dep).imageData, dtype=np.float32)).reshape(H, W)
+    assert np.array_equal(wire.mask_from_wire(Msg(ids), H, W), ref_mask.numpy())
+    assert np.array_equal(wire.depth_from_wire(Msg(dep), H, W), ref_depth.numpy())
+    lab, d = wire.stage_frames([Msg(ids), ids], [Msg(dep), dep], H, W, pin=False)
+    assert lab.dtype == torch.int16 and d.dtype == torch.float32 and lab.shape == (2, H, W)
+    assert torch.equal(lab[0], ref_mask) and torch.equal(lab[1], ref_mask) and torch.equal(d[1], ref_depth)
+    with pytest.raises(ValueError):
+        wire.mask_from_wire(ids[:-1], H, W)
+    g2, g3, pre = (734, 608), (0.01, -0.02, 0.45), (0.011, -0.021, 0.45)
+    assert wire.format_result(g2, g3, pre) == f"{g2[0]},{g2[1]},{g3[0]},{g3[1]},{g3[2]},{pre[0]},{pre[1]},{pre[2]}"
+    assert wire.format_result(g2, g3, None) == "734,608,0.01,-0.02,0.45"
+    rec = np.zeros(1, dtype=N.FRAME_RESULT)[0]
+    rec["leaf_id"] = -1
+    assert wire.format_frame_result(rec) is None
+    rec["leaf_id"], rec["n_candidates"], rec["grasp_x"], rec["grasp_y"] = 3, 20, 734, 608
+    rec["grasp_3d"] = g3
+    rec["pre_grasp"] = pre
+    assert wire.format_frame_result(rec) == wire.format_result(g2, g3, pre)
+
+
 def test_records_from_result_buffer_matches_numpy_view():
     """The on-device record builder reads the same bytes as the NumPy structured view of lg_frame_result."""
     from leafgrasp_b200 import _native as N, dist as lgd
