@@ -99,6 +99,18 @@ uint64_t lg_context_bytes(const lg_context* ctx);
  * grasp_point_selector.py:52-57). */
 int lg_set_cnn_weights(lg_context* ctx, const float* blob_host, uint64_t n_floats);
 
+/* Any architecture the reference's constructor accepts (model.py:6-86; the hyper-parameter sweep of
+ * train_model_mlflow.py:173-182 produces them): n_blocks encoder blocks with filters[] channels, attention
+ * 0 = none, 1 = spatial, 2 = channel, 3 = hybrid.  Blob layout: cnn.py:pack_weights.  The default architecture
+ * (3 blocks 64/128/256, spatial) runs on the tensor cores (use_bf16) or the fp32 path; the others on the fp32 path. */
+typedef struct lg_cnn_config {
+    int32_t n_blocks;
+    int32_t filters[4];
+    int32_t attention;
+} lg_cnn_config;
+int lg_set_cnn_model(lg_context* ctx, const lg_cnn_config* cfg, const float* blob_host, uint64_t n_floats);
+uint64_t lg_cnn_model_floats(const lg_cnn_config* cfg);   /* 0 for an unsupported architecture */
+
 /* ---- whole path ----------------------------------------------------------------------------- */
 
 /* The per-frame path of leaf_grasp_node_v3.py:110-119 for `frames` independent frames:

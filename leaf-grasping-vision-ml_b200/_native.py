@@ -17,6 +17,21 @@ TOP_K, PATCH, CHANNELS = 20, 32, 9
 ST_NO_LEAF, ST_LABEL_RANGE, ST_RUNS_OVERFLOW, ST_NO_CANDIDATE = 1, 2, 4, 8
 
 
+class CnnConfig(C.Structure):
+    """lg_cnn_config: n_blocks, filters[4], attention (0 none, 1 spatial, 2 channel, 3 hybrid)."""
+    _fields_ = [("n_blocks", C.c_int32), ("filters", C.c_int32 * 4), ("attention", C.c_int32)]
+
+
+ATTENTION_CODES = {"none": 0, "spatial": 1, "channel": 2, "hybrid": 3}
+
+
+def cnn_config(attention_type="spatial", encoder_filters=(64, 128, 256)) -> CnnConfig:
+    f = list(encoder_filters)
+    if attention_type not in ATTENTION_CODES or not 1 <= len(f) <= 4:
+        raise ValueError(f"unsupported GraspPointCNN architecture: {attention_type}, {f}")
+    return CnnConfig(len(f), (C.c_int32 * 4)(*(f + [0] * (4 - len(f)))), ATTENTION_CODES[attention_type])
+
+
 class Camera(C.Structure):
     _fields_ = [("f", C.c_double), ("cx", C.c_double), ("cy", C.c_double)]
 
@@ -44,6 +59,8 @@ SYMBOLS = {
     "lg_last_error": (C.c_char_p, []),
     "lg_context_bytes": (C.c_uint64, [_P]),
     "lg_set_cnn_weights": (C.c_int, [_P, _P, C.c_uint64]),
+    "lg_set_cnn_model": (C.c_int, [_P, C.POINTER(CnnConfig), _P, C.c_uint64]),
+    "lg_cnn_model_floats": (C.c_uint64, [C.POINTER(CnnConfig)]),
     "lg_process_batch": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(Camera), _P, C.c_int, _P]),
     "lg_process_batch_host": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(Camera), _P, C.c_int, _P]),
     "lg_select_leaf": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(Camera), _P, _P, _P]),

@@ -1,14 +1,14 @@
 """GraspPointCNN drop-in (reference scripts/utils/ml_grasp_optimizer/model.py:5-128).
 
-The module keeps the reference's parameter names, so ``load_state_dict`` of a reference checkpoint
-(``checkpoint['model_state_dict']``, grasp_point_selector.py:48-49) works unchanged.  ``forward`` in eval
-mode runs the hand-written CUDA kernels (csrc/lg_cnn*.cu) on BatchNorm-folded weights; there is no
-torch / cuDNN forward behind it.  Training is out of scope: calling it in
-training mode raises.
+The module keeps the reference's constructor, sub-module layout and parameter names, so ``load_state_dict`` of a
+reference checkpoint (``checkpoint['model_state_dict']``, grasp_point_selector.py:48-49) works unchanged for every
+architecture the reference can build (attention 'spatial' / 'channel' / 'hybrid' / 'none', any encoder filter list of
+the sweep in train_model_mlflow.py:173-182).  ``forward`` in eval mode runs the hand-written CUDA kernels
+(csrc/lg_cnn*.cu) on BatchNorm-folded weights; there is no torch / cuDNN forward behind it.  The default architecture
+(the one the live node builds) can run on the tensor cores (``use_bf16``); the variants use the fp32 kernels.
+Training is out of scope: calling it in training mode raises.
 """
 from __future__ import annotations
-
-import ctypes as C
 
 import numpy as np
 import torch
@@ -16,7 +16,6 @@ import torch.nn as nn
 
 from . import _native as N
 
-_FILTERS = (64, 128, 256)
 _BN_EPS = 1e-5
 
 
@@ -28,12 +27,31 @@ def _block(cin, cout):
         nn.MaxPool2d(2), nn.Dropout2d(0.3))
 
 
-def fold_batchnorm(sd: dict) -> list:
-    """Fold eval-mode BatchNorm into the preceding conv / linear.  Returns, in network order, a list of
-    (weight float64 ndarray, bias float64 ndarray): 6 convs [Cout,Cin,3,3], attention [1,256,1,1],
-    4 linears [out,in]."""
+def _channel_attention(c):
+    return nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Conv2d(c, c // 16, 1), nn.ReLU(inplace=True), nn.Conv2d(c // 16, c, 1),
+                         nn.Sigmoid())
+
+
+def architecture_of(sd: dict):
+    """(attention_type, encoder_filters) recovered from a state_dict's keys and shapes."""
+    n_blocks = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("encoder."))
+    filters = [int(sd[f"encoder.{b}.0.weight"].shape[0]) for b in range(n_blocks)]
+    if "spatial_attention.0.weight" in sd:
+        att = "hybrid"
+    elif "attention.0.weight" in sd:
+        att = "spatial"
+    elif "attention.1.weight" in sd:
+        att = "channel"
+    else:
+        att = "none"
+    return att, filters
+
+
+def fold_batchnorm(sd: dict) -> dict:
+    """Fold eval-mode BatchNorm into the preceding conv / linear.  Returns {'convs': [(w [Cout,Cin,3,3], b)] (two per
+    block), 'spatial': (w [1,C,1,1], b) | None, 'channel': ((w1 [C/16,C,1,1], b1), (w2 [C,C/16,1,1], b2)) | None,
+    'fcs': [(w [out,in], b)] x 4}, all float64."""
     g = lambda k: sd[k].detach().double().cpu().numpy()
-    out = []
 
     def fold(wk, bk, bn):
         w, b = g(wk), g(bk)
@@ -41,50 +59,68 @@ def fold_batchnorm(sd: dict) -> list:
             s = g(bn + ".weight") / np.sqrt(g(bn + ".running_var") + _BN_EPS)
             w = w * s.reshape((-1,) + (1,) * (w.ndim - 1))
             b = (b - g(bn + ".running_mean")) * s + g(bn + ".bias")
-        out.append((w, b))
+        return w, b
 
-    for blk in range(3):
-        fold(f"encoder.{blk}.0.weight", f"encoder.{blk}.0.bias", f"encoder.{blk}.1")
-        fold(f"encoder.{blk}.3.weight", f"encoder.{blk}.3.bias", f"encoder.{blk}.4")
-    fold("attention.0.weight", "attention.0.bias", None)
+    att, filters = architecture_of(sd)
+    out = {"convs": [], "spatial": None, "channel": None, "fcs": [], "attention_type": att, "encoder_filters": filters}
+    for blk in range(len(filters)):
+        out["convs"].append(fold(f"encoder.{blk}.0.weight", f"encoder.{blk}.0.bias", f"encoder.{blk}.1"))
+        out["convs"].append(fold(f"encoder.{blk}.3.weight", f"encoder.{blk}.3.bias", f"encoder.{blk}.4"))
+    if att == "spatial":
+        out["spatial"] = fold("attention.0.weight", "attention.0.bias", None)
+    elif att == "channel":
+        out["channel"] = (fold("attention.1.weight", "attention.1.bias", None), fold("attention.3.weight", "attention.3.bias", None))
+    elif att == "hybrid":
+        out["spatial"] = fold("spatial_attention.0.weight", "spatial_attention.0.bias", None)
+        out["channel"] = (fold("channel_attention.1.weight", "channel_attention.1.bias", None),
+                          fold("channel_attention.3.weight", "channel_attention.3.bias", None))
     for lin, bn in ((0, "classifier.1"), (4, "classifier.5"), (8, "classifier.9"), (12, None)):
-        fold(f"classifier.{lin}.weight", f"classifier.{lin}.bias", bn)
+        out["fcs"].append(fold(f"classifier.{lin}.weight", f"classifier.{lin}.bias", bn))
     return out
 
 
 def pack_weights(sd: dict) -> np.ndarray:
     """Folded weights as the float32 blob csrc/lg_cnn.cu reads:
-    conv l: w[ky][kx][Cin][Cout], b[Cout];  attention w[256], b[1];  fc k: w[in][out], b[out]."""
-    folded = fold_batchnorm(sd)
+    conv l: w[ky][kx][Cin][Cout], b[Cout];  spatial attention w[C], b[1];  channel attention w1[C][C/16], b1, w2[C/16][C], b2;
+    fc k: w[in][out], b[out]."""
+    f = fold_batchnorm(sd)
     parts = []
-    for w, b in folded[:6]:
+    for w, b in f["convs"]:
         parts += [np.transpose(w, (2, 3, 1, 0)).ravel(), b.ravel()]
-    aw, ab = folded[6]
-    parts += [aw.ravel(), ab.ravel()]
-    for w, b in folded[7:]:
+    if f["spatial"] is not None:
+        parts += [f["spatial"][0].ravel(), f["spatial"][1].ravel()]
+    if f["channel"] is not None:
+        (w1, b1), (w2, b2) = f["channel"]
+        parts += [np.transpose(w1[:, :, 0, 0], (1, 0)).ravel(), b1.ravel(), np.transpose(w2[:, :, 0, 0], (1, 0)).ravel(), b2.ravel()]
+    for w, b in f["fcs"]:
         parts += [np.transpose(w, (1, 0)).ravel(), b.ravel()]
     return np.ascontiguousarray(np.concatenate(parts).astype(np.float32))
 
 
 class GraspPointCNN(nn.Module):
-    """Same constructor as the reference.  The CUDA path implements the configuration the reference's
-    live code builds (``GraspPointCNN(in_channels=9)``: spatial attention, filters [64,128,256]); the
-    sweep variants of model.py:30-60 are a SURVEY 8f "next" row and raise NotImplementedError."""
+    """Same constructor and sub-modules as the reference (model.py:6-86)."""
 
     def __init__(self, in_channels=9, attention_type="spatial", encoder_filters=(64, 128, 256)):
         super().__init__()
-        if in_channels != 9 or attention_type != "spatial" or tuple(encoder_filters) != _FILTERS:
-            raise NotImplementedError(
-                "CUDA path covers GraspPointCNN(in_channels=9, attention_type='spatial', "
-                "encoder_filters=[64,128,256]) only")
+        if in_channels != 9:
+            raise NotImplementedError("the CUDA path consumes the 9-channel patch tensor of grasp_point_selector.py:127")
         self.attention_type = attention_type
         self.encoder_filters = list(encoder_filters)
+        self._config = N.cnn_config(attention_type if attention_type in N.ATTENTION_CODES else "none", self.encoder_filters)
         self.encoder = nn.ModuleList()
         cin = in_channels
-        for f in encoder_filters:
+        for f in self.encoder_filters:
             self.encoder.append(_block(cin, f))
             cin = f
-        self.attention = nn.Sequential(nn.Conv2d(cin, 1, 1), nn.Sigmoid())
+        if attention_type == "spatial":
+            self.attention = nn.Sequential(nn.Conv2d(cin, 1, 1), nn.Sigmoid())
+        elif attention_type == "channel":
+            self.attention = _channel_attention(cin)
+        elif attention_type == "hybrid":
+            self.spatial_attention = nn.Sequential(nn.Conv2d(cin, 1, 1), nn.Sigmoid())
+            self.channel_attention = _channel_attention(cin)
+        else:   # 'none' (the reference treats every other string like this, model.py:58-59)
+            self.attention = None
         self.gap = nn.AdaptiveAvgPool2d(1)
         self.classifier = nn.Sequential(
             nn.Linear(cin, cin), nn.BatchNorm1d(cin), nn.ReLU(inplace=True), nn.Dropout(0.5),
@@ -105,6 +141,10 @@ class GraspPointCNN(nn.Module):
         self._packed_version = None
         self.use_bf16 = False
 
+    @property
+    def is_default_architecture(self) -> bool:
+        return self.attention_type == "spatial" and self.encoder_filters == [64, 128, 256]
+
     def _version(self):
         return tuple(int(t._version) for t in self.state_dict().values())
 
@@ -122,7 +162,7 @@ class GraspPointCNN(nn.Module):
             self._engine = GraspEngine(1, 64, 64, 2, device=dev)
         ver = self._version()
         if ver != self._packed_version:
-            self._engine.set_cnn_weights(self.packed())
+            self._engine.set_cnn_weights(self.packed(), None if self.is_default_architecture else self._config)
             self._packed_version = ver
         xin = x.detach().to(dev, torch.float32).contiguous()
-        return self._engine.cnn_forward(xin, self.use_bf16).reshape(-1, 1).to(x.device)
+        return self._engine.cnn_forward(xin, self.use_bf16 and self.is_default_architecture).reshape(-1, 1).to(x.device)

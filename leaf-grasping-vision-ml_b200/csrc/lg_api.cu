@@ -162,20 +162,32 @@ extern "C" void lg_destroy(lg_context* c) {
 
 extern "C" uint64_t lg_context_bytes(const lg_context* c) { return c ? c->bytes : 0; }
 
-extern "C" int lg_set_cnn_weights(lg_context* c, const float* blob_host, uint64_t n_floats) {
+extern "C" int lg_set_cnn_model(lg_context* c, const lg_cnn_config* cfg, const float* blob_host, uint64_t n_floats) {
     if (!c) return LG_E_ARG;
     if (!blob_host) { c->cnn.loaded = 0; return LG_OK; }
-    if (n_floats != lg_cnn_blob_floats()) {
-        lg_set_error("lg_set_cnn_weights: blob has %llu floats, expected %llu", (unsigned long long)n_floats,
-                     (unsigned long long)lg_cnn_blob_floats());
+    if (!lg_cnn_config_ok(cfg)) { lg_set_error("lg_set_cnn_model: unsupported architecture"); return LG_E_ARG; }
+    const uint64_t want = lg_cnn_config_floats(cfg);
+    if (n_floats != want) {
+        lg_set_error("lg_set_cnn_model: blob has %llu floats, expected %llu", (unsigned long long)n_floats, (unsigned long long)want);
         return LG_E_ARG;
     }
+    if (c->cnn.blob && c->cnn.n_floats != n_floats) { cudaFree(c->cnn.blob); c->cnn.blob = nullptr; }
     if (!c->cnn.blob) LG_CUDA(cudaMalloc((void**)&c->cnn.blob, n_floats * sizeof(float)));
     LG_CUDA(cudaMemcpy(c->cnn.blob, blob_host, n_floats * sizeof(float), cudaMemcpyHostToDevice));
     c->cnn.n_floats = n_floats;
+    c->cnn.cfg = *cfg;
+    c->cnn.is_default = lg_cnn_config_is_default(cfg) ? 1 : 0;
     c->cnn.loaded = 1;
-    return lg_cnn_prepare_bf16(c);
+    return c->cnn.is_default ? lg_cnn_prepare_bf16(c) : LG_OK;
 }
+
+extern "C" int lg_set_cnn_weights(lg_context* c, const float* blob_host, uint64_t n_floats) {
+    lg_cnn_config def;
+    def.n_blocks = 3; def.filters[0] = 64; def.filters[1] = 128; def.filters[2] = 256; def.filters[3] = 0; def.attention = 1;
+    return lg_set_cnn_model(c, &def, blob_host, n_floats);
+}
+
+extern "C" uint64_t lg_cnn_model_floats(const lg_cnn_config* cfg) { return lg_cnn_config_ok(cfg) ? lg_cnn_config_floats(cfg) : 0; }
 
 cudaStream_t lg_fork(lg_context* c, int k, cudaStream_t st) {
     if (!c->overlap) return st;

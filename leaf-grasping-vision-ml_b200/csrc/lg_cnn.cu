@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(CV_NT) conv3x3_relu_kernel(ConvArgs A) {
     __shared__ float s_in[CV_KC][10][12];            // 8x8 tile + halo, row padded to 12
     __shared__ __align__(16) float s_w[9][CV_KC][CV_CO];
     const int tid = threadIdx.x;
-    const int tiles_x = A.W / 8;
+    const int tiles_x = (A.W + 7) / 8;
     const int ty0 = (blockIdx.x / tiles_x) * 8, tx0 = (blockIdx.x % tiles_x) * 8;
     const int co0 = blockIdx.y * CV_CO;
     const int n = blockIdx.z;
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(CV_NT) conv3x3_relu_kernel(ConvArgs A) {
         for (int i = tid; i < 9 * CV_KC * CV_CO; i += CV_NT) {
             const int t = i / (CV_KC * CV_CO), rem = i - t * (CV_KC * CV_CO), ci = rem / CV_CO, co = rem - ci * CV_CO;
             float v = 0.f;
-            if (ci < kc) v = A.wt[((long long)t * A.Cin + (c0 + ci)) * A.Cout + co0 + co];
+            if (ci < kc && co0 + co < A.Cout) v = A.wt[((long long)t * A.Cin + (c0 + ci)) * A.Cout + co0 + co];
             s_w[t][ci][co] = v;
         }
         __syncthreads();
@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(CV_NT) conv3x3_relu_kernel(ConvArgs A) {
         }
     }
     const int co = co0 + cg * 8;
+    if (co >= A.Cout || ty0 + qy >= A.H || tx0 + qx >= A.W) return;     // partial channel tile / tile beyond a small image
     if (POOL) {
         const int Ho = A.H / 2, Wo = A.W / 2;
         const int oy = (ty0 + qy) / 2, ox = (tx0 + qx) / 2;
@@ -199,6 +200,90 @@ __global__ void __launch_bounds__(TL_NT) cnn_tail_kernel(const float* __restrict
     }
 }
 
+// Attention + global average + classifier for any architecture GraspPointCNN can take (model.py:30-86): C final
+// channels on S2 = s x s positions, attention none / spatial / channel / hybrid.  One CTA per patch, features in
+// shared memory.  Blob: [spatial: w[C], b] [channel: w1[C][C/16], b1[C/16], w2[C/16][C], b2[C]] fc0 w[C][C], b; fc1
+// w[C][C/2], b; fc2 w[C/2][C/4], b; fc3 w[C/4], b (BatchNorm1d folded, weights in-major).
+__global__ void __launch_bounds__(256) cnn_tail_generic_kernel(const float* __restrict__ feat, const float* __restrict__ blob,
+                                                                float* __restrict__ logits, int C, int S2, int attention) {
+    extern __shared__ float sm[];
+    float* f = sm;                    // [S2][C]
+    float* att_s = f + S2 * C;        // [S2]
+    float* att_c = att_s + S2;        // [C]
+    float* va = att_c + C;            // [C]
+    float* vb = va + C;               // [C]
+    const int n = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
+    const float* src = feat + (size_t)n * S2 * C;
+    for (int i = tid; i < S2 * C; i += NT) f[i] = src[i];
+    for (int i = tid; i < S2; i += NT) att_s[i] = 1.f;
+    for (int i = tid; i < C; i += NT) att_c[i] = 1.f;
+    __syncthreads();
+    const float* w = blob;
+    const bool spatial = attention == 1 || attention == 3, channel = attention == 2 || attention == 3;
+    if (spatial) {
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int p = warp; p < S2; p += NT / 32) {
+            float a = 0.f;
+            for (int ch = lane; ch < C; ch += 32) a = fmaf(f[p * C + ch], w[ch], a);
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xFFFFFFFFu, a, d);
+            if (lane == 0) att_s[p] = 1.f / (1.f + expf(-(a + w[C])));
+        }
+        w += C + 1;
+    }
+    if (channel) {
+        const int R = C / 16;
+        const float *w1 = w, *b1 = w1 + C * R, *w2 = b1 + R, *b2 = w2 + R * C;
+        for (int ch = tid; ch < C; ch += NT) {
+            float a = 0.f;
+            for (int p = 0; p < S2; ++p) a += f[p * C + ch];
+            va[ch] = a / (float)S2;                 // AdaptiveAvgPool2d(1) of the un-attended features
+        }
+        __syncthreads();
+        for (int j = tid; j < R; j += NT) {
+            float a = b1[j];
+            for (int ch = 0; ch < C; ++ch) a = fmaf(va[ch], w1[ch * R + j], a);
+            vb[j] = fmaxf(a, 0.f);
+        }
+        __syncthreads();
+        for (int ch = tid; ch < C; ch += NT) {
+            float a = b2[ch];
+            for (int j = 0; j < R; ++j) a = fmaf(vb[j], w2[j * C + ch], a);
+            att_c[ch] = 1.f / (1.f + expf(-a));
+        }
+        w = b2 + C;
+    }
+    __syncthreads();
+    for (int ch = tid; ch < C; ch += NT) {          // x * attention, then global average
+        float a = 0.f;
+        for (int p = 0; p < S2; ++p) a = fmaf(f[p * C + ch] * att_c[ch], att_s[p], a);
+        va[ch] = a / (float)S2;
+    }
+    __syncthreads();
+    int din = C;
+    float *cur = va, *nxt = vb;
+    for (int layer = 0; layer < 3; ++layer) {
+        const int dout = layer == 0 ? C : (layer == 1 ? C / 2 : C / 4);
+        const float* bias = w + (size_t)din * dout;
+        for (int o = tid; o < dout; o += NT) {
+            float a = bias[o];
+            for (int i = 0; i < din; ++i) a = fmaf(cur[i], w[(size_t)i * dout + o], a);
+            nxt[o] = fmaxf(a, 0.f);
+        }
+        __syncthreads();
+        w = bias + dout;
+        din = dout;
+        float* t = cur; cur = nxt; nxt = t;
+    }
+    if (tid < 32) {
+        float a = 0.f;
+        for (int i = tid; i < din; i += 32) a = fmaf(cur[i], w[i], a);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xFFFFFFFFu, a, d);
+        if (tid == 0) logits[n] = a + w[din];
+    }
+}
+
 const int kCin[6] = {9, 64, 64, 128, 128, 256};
 const int kCout[6] = {64, 64, 128, 128, 256, 256};
 const int kHW[6] = {32, 32, 16, 16, 8, 8};
@@ -210,6 +295,75 @@ uint64_t lg_cnn_blob_floats() {
     for (int l = 0; l < 6; ++l) n += 9ull * kCin[l] * kCout[l] + kCout[l];
     n += 256 + 1 + 256 * 256 + 256 + 256 * 128 + 128 + 128 * 64 + 64 + 64 + 1;
     return n;
+}
+
+bool lg_cnn_config_ok(const lg_cnn_config* g) {
+    if (!g || g->n_blocks < 1 || g->n_blocks > 4 || g->attention < 0 || g->attention > 3) return false;
+    for (int b = 0; b < g->n_blocks; ++b)
+        if (g->filters[b] < 8 || g->filters[b] > 1024 || g->filters[b] % 8) return false;
+    const int C = g->filters[g->n_blocks - 1];
+    return C % 16 == 0 && (LG_PATCH >> g->n_blocks) >= 1;
+}
+
+bool lg_cnn_config_is_default(const lg_cnn_config* g) {
+    return g->n_blocks == 3 && g->filters[0] == 64 && g->filters[1] == 128 && g->filters[2] == 256 && g->attention == 1;
+}
+
+uint64_t lg_cnn_config_floats(const lg_cnn_config* g) {
+    uint64_t n = 0;
+    int cin = LG_CHANNELS;
+    for (int b = 0; b < g->n_blocks; ++b) {
+        const uint64_t f = g->filters[b];
+        n += 9ull * cin * f + f + 9ull * f * f + f;
+        cin = (int)f;
+    }
+    const uint64_t C = cin;
+    if (g->attention == 1 || g->attention == 3) n += C + 1;
+    if (g->attention == 2 || g->attention == 3) n += C * (C / 16) + C / 16 + (C / 16) * C + C;
+    n += C * C + C + C * (C / 2) + C / 2 + (C / 2) * (C / 4) + C / 4 + C / 4 + 1;
+    return n;
+}
+
+// fp32 forward of a non-default architecture: the same direct-convolution kernel on every layer, generic tail
+static int run_cnn_generic(lg_context* c, const float* patches, int n, float* logits, cudaStream_t st) {
+    const lg_cnn_config& g = c->cnn.cfg;
+    size_t per_patch = 0;                                  // floats of the largest activation of one patch
+    for (int b = 0, s = LG_PATCH; b < g.n_blocks; ++b, s >>= 1) per_patch = max(per_patch, (size_t)s * s * g.filters[b]);
+    const int chunk = (int)min((size_t)n, c->cnn_act_bytes / (per_patch * sizeof(float)));
+    if (chunk < 1) { lg_set_error("CNN activation scratch too small for this architecture"); return LG_E_CAPACITY; }
+    const int C = g.filters[g.n_blocks - 1], s_final = LG_PATCH >> g.n_blocks, S2 = s_final * s_final;
+    const size_t tail_smem = ((size_t)S2 * C + S2 + 3 * (size_t)C) * sizeof(float);
+    static size_t configured = 48 * 1024;
+    if (tail_smem > configured) {
+        LG_CUDA(cudaFuncSetAttribute(cnn_tail_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
+        configured = tail_smem;
+    }
+    for (int done = 0; done < n; done += chunk) {
+        const int m = min(chunk, n - done);
+        float* buf[2] = {(float*)c->cnn_act0, (float*)c->cnn_act1};
+        int cur = -1;                                       // -1: the input is the patch tensor (NCHW)
+        const float* w = c->cnn.blob;
+        int cin = LG_CHANNELS, hw = LG_PATCH;
+        for (int l = 0; l < 2 * g.n_blocks; ++l) {
+            const int cout = g.filters[l / 2];
+            ConvArgs A;
+            if (cur < 0) { A.in = patches + (size_t)done * LG_CHANNELS * LG_PATCH * LG_PATCH; A.sn = 9 * 32 * 32; A.sc = 32 * 32; A.sy = 32; A.sx = 1; }
+            else { A.in = buf[cur]; A.sn = (long long)hw * hw * cin; A.sy = (long long)hw * cin; A.sx = cin; A.sc = 1; }
+            const int dst = cur < 0 ? 0 : cur ^ 1;
+            A.H = hw; A.W = hw; A.Cin = cin; A.Cout = cout; A.wt = w; A.bias = w + 9ull * cin * cout; A.out = buf[dst];
+            dim3 grid(((hw + 7) / 8) * ((hw + 7) / 8), (cout + CV_CO - 1) / CV_CO, m);
+            if (l & 1) conv3x3_relu_kernel<true><<<grid, CV_NT, 0, st>>>(A);
+            else conv3x3_relu_kernel<false><<<grid, CV_NT, 0, st>>>(A);
+            LG_LAUNCH_CHECK();
+            w += 9ull * cin * cout + cout;
+            cin = cout;
+            if (l & 1) hw >>= 1;
+            cur = dst;
+        }
+        cnn_tail_generic_kernel<<<m, 256, tail_smem, st>>>(buf[cur], w, logits + done, C, S2, g.attention);
+        LG_LAUNCH_CHECK();
+    }
+    return LG_OK;
 }
 
 int lg_run_cnn_bf16(lg_context* c, const float* patches, int n, const int32_t* n_dev, float* logits, cudaStream_t st);
@@ -225,6 +379,13 @@ int lg_run_cnn(lg_context* c, const float* patches, int n, const int32_t* n_dev,
     if (!c->cnn.loaded) {
         lg_set_error("lg_cnn_forward: no weights loaded (lg_set_cnn_weights)");
         return LG_E_ARG;
+    }
+    if (!c->cnn.is_default) {
+        if (use_bf16) {
+            lg_set_error("the bf16 tensor-core path covers the default GraspPointCNN architecture only; use the fp32 path");
+            return LG_E_ARG;
+        }
+        return run_cnn_generic(c, patches, n, logits, st);
     }
     if (use_bf16) return lg_run_cnn_bf16(c, patches, n, n_dev, logits, st);
     // the fp32 anchor path sizes its grids on the host: with a device-side count it simply runs all n slots

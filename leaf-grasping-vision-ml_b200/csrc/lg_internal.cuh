@@ -60,8 +60,10 @@ struct LgOrient {
 struct LgCnn {
     float* blob;        // fp32 blob
     uint64_t n_floats;
-    void* bf16_blob;    // bf16 copy of conv weights, tensor-core layout
+    void* bf16_blob;    // bf16 copy of conv weights, tensor-core layout (default architecture only)
     int loaded;
+    lg_cnn_config cfg;  // architecture the blob belongs to
+    int is_default;     // 3 blocks [64,128,256], spatial attention: the one the live node builds
 };
 
 struct lg_context {
@@ -180,6 +182,9 @@ int lg_run_gather(lg_context* c, LgMaskSrc src, const float* depth, int n, lg_ca
 // n patches; n_dev (device int, may be null) = the number actually present (<= n): the kernels read it on the device
 int lg_run_cnn(lg_context* c, const float* patches, int n, const int32_t* n_dev, float* logits, int use_bf16, cudaStream_t st);
 int lg_run_export_patches(lg_context* c, float* out, int n, cudaStream_t st);
+bool lg_cnn_config_ok(const lg_cnn_config* g);
+bool lg_cnn_config_is_default(const lg_cnn_config* g);
+uint64_t lg_cnn_config_floats(const lg_cnn_config* g);
 int lg_run_fuse(lg_context* c, LgMaskSrc src, const float* depth, int n, lg_camera cam, int have_ml,
                 lg_frame_result* out, cudaStream_t st);
 int lg_run_mask_regions(lg_context* c, const uint8_t* mask, int n, int full, cudaStream_t st);

@@ -64,6 +64,9 @@ class GraspPointSelector:
             raise ValueError("camera parameters not set (f_norm is None)")
         return N.Camera(float(self.f_norm), float(self.camera_cx), float(self.camera_cy))
 
+    def _bf16(self) -> bool:
+        return bool(self.use_bf16_cnn and self.ml_predictor is not None and self.ml_predictor.is_default_architecture)
+
     def _get_engine(self, h, w):
         e = self._engine
         if e is None or (e.H, e.W) != (h, w):
@@ -72,7 +75,11 @@ class GraspPointSelector:
             self._engine_model_version = None
         ver = None if self.ml_predictor is None else self.ml_predictor._version()
         if ver != self._engine_model_version:
-            e.set_cnn_weights(None if self.ml_predictor is None else self.ml_predictor.packed())
+            m = self.ml_predictor
+            if m is None:
+                e.set_cnn_weights(None)
+            else:       # any architecture the reference's constructor accepts; only the default one has a bf16 path
+                e.set_cnn_weights(m.packed(), None if m.is_default_architecture else m._config)
             self._engine_model_version = ver
         return e
 
@@ -82,7 +89,7 @@ class GraspPointSelector:
             h, w = leaf_mask.shape[-2:]
             eng = self._get_engine(h, w)
             r = eng.select_grasp_point(torch.as_tensor(leaf_mask).to(torch.uint8), torch.as_tensor(depth_tensor),
-                                       self._cam(), self.use_bf16_cnn)[0]
+                                       self._cam(), self._bf16())[0]
             self.last_result = r
             if r["n_candidates"] == 0:
                 _log.logwarn("No valid candidate points found")
@@ -144,7 +151,7 @@ class GraspPointSelector:
             ch = [take(depth_tensor), take(mask_t)] + [take(scores[k]) for k in SCORE_KEYS]
             eng = self._get_engine(h, w)
             feats = eng.normalize_patches(torch.stack(ch)[None])
-            logit = eng.cnn_forward(feats, self.use_bf16_cnn)
+            logit = eng.cnn_forward(feats, self._bf16())
             s = torch.sigmoid(logit).item()
             return float(np.tanh(s * 3.0) * 0.5 + 0.5)
         except N.NativeError:

@@ -76,14 +76,19 @@ class GraspEngine:
         return np.frombuffer(buf.cpu().numpy().tobytes(), dtype=dtype)
 
     # ---- CNN ----------------------------------------------------------------------------------------
-    def set_cnn_weights(self, blob):
+    def set_cnn_weights(self, blob, config: "N.CnnConfig | None" = None):
+        """Folded weights (cnn.pack_weights) of the default architecture, or of the one `config` (N.cnn_config) names."""
         with torch.cuda.device(self.device):
             if blob is None:
                 N.check(self.lib.lg_set_cnn_weights(self._ctx, None, 0), "lg_set_cnn_weights")
                 self.has_cnn = False
                 return
             blob = np.ascontiguousarray(blob, dtype=np.float32)
-            N.check(self.lib.lg_set_cnn_weights(self._ctx, blob.ctypes.data_as(C.c_void_p), blob.size), "lg_set_cnn_weights")
+            if config is None:
+                N.check(self.lib.lg_set_cnn_weights(self._ctx, blob.ctypes.data_as(C.c_void_p), blob.size), "lg_set_cnn_weights")
+            else:
+                N.check(self.lib.lg_set_cnn_model(self._ctx, C.byref(config), blob.ctypes.data_as(C.c_void_p), blob.size),
+                        "lg_set_cnn_model")
             self.has_cnn = True
 
     def cnn_forward(self, patches: torch.Tensor, use_bf16: bool = False) -> torch.Tensor:

@@ -829,3 +829,27 @@ def seeded_state_dict(seed: int = 1234) -> dict:
             sd[f"classifier.{bn}.running_var"] = 0.5 + torch.rand(o, generator=g)
             sd[f"classifier.{bn}.num_batches_tracked"] = torch.tensor(100)
     return sd
+
+
+def seeded_state_dict_from_shapes(shapes: dict, seed: int) -> dict:
+    """Deterministic weights for ANY GraspPointCNN architecture, from its state_dict key -> shape table (keys are
+    visited in sorted order).  Used for the architecture-variant golden vectors (tests/golden/make_cnn_variants.py):
+    the reference ships no checkpoints, so generator and tests rebuild the same tensors from the same table."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k in sorted(shapes):
+        shp = tuple(shapes[k])
+        if k.endswith("num_batches_tracked"):
+            sd[k] = torch.tensor(100)
+        elif k.endswith("running_var"):
+            sd[k] = 0.5 + torch.rand(shp, generator=g)
+        elif k.endswith("running_mean"):
+            sd[k] = 0.1 * torch.randn(shp, generator=g)
+        elif k.endswith("bias"):
+            sd[k] = 0.05 * torch.randn(shp, generator=g)
+        elif len(shp) == 1:                      # BatchNorm weight
+            sd[k] = 1.0 + 0.1 * torch.randn(shp, generator=g)
+        else:                                    # conv / linear weight
+            fan_in = int(np.prod(shp[1:]))
+            sd[k] = torch.randn(shp, generator=g) * math.sqrt(2.0 / fan_in)
+    return sd

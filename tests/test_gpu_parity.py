@@ -350,6 +350,27 @@ def test_cnn_bf16_against_reference_logits(blob, state_dict):
     eng.close()
 
 
+def test_cnn_architecture_variants_against_reference_logits():
+    """every architecture of the reference's sweep through the drop-in class on the GPU (fp32
+    kernels), against the logits the reference's own GraspPointCNN produced for the same weights (golden)."""
+    from leafgrasp_b200 import GraspPointCNN
+    meta = json.load(open(os.path.join(GOLD, "cnn_variants.json")))
+    gold = np.load(os.path.join(GOLD, "cnn_variants.npz"))
+    x = torch.from_numpy(gold["x"]).cuda()
+    for i, v in enumerate(meta["variants"]):
+        net = GraspPointCNN(in_channels=9, attention_type=v["attention_type"], encoder_filters=v["encoder_filters"])
+        net.load_state_dict(O.seeded_state_dict_from_shapes(v["shapes"], v["seed"]))
+        net.eval()
+        net.use_bf16 = True          # ignored for non-default architectures: they run the fp32 kernels
+        with torch.no_grad():
+            y = net(x).reshape(-1).cpu().numpy()
+        np.testing.assert_allclose(y, gold[f"logits_{i}"], atol=2e-4, rtol=2e-4, err_msg=str((v["attention_type"], v["encoder_filters"])))
+        # a batch that does not fit one activation chunk gives the same rows
+        with torch.no_grad():
+            yb = net(x.repeat(500, 1, 1, 1)).reshape(500, -1).cpu().numpy()
+        np.testing.assert_allclose(yb, np.tile(y, (500, 1)), atol=1e-6)
+
+
 def test_cfg4_cnn_only_65536_patches(blob):
     """BASELINE config[3]: 65 536 patches through the tensor-core path (13 activation chunks of 5 120) against the
     fp32 CUDA-core path, logits within the bf16 bar."""

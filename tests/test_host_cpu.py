@@ -55,32 +55,72 @@ def test_state_dict_keys_match_reference_layout():
     net.load_state_dict(sd)
     assert pack_weights(net.state_dict()).size == N.lib().lg_cnn_weight_floats()
     with pytest.raises(NotImplementedError):
-        GraspPointCNN(attention_type="channel")
+        GraspPointCNN(in_channels=3)
 
 
-def test_batchnorm_folding_is_exact_enough():
-    """Run the folded weights through plain torch ops and compare with the unfolded oracle forward."""
-    from leafgrasp_b200 import fold_batchnorm
-    sd = O.seeded_state_dict(5)
-    folded = fold_batchnorm(sd)
-    g = torch.Generator().manual_seed(3)
-    x = torch.rand(4, 9, 32, 32, generator=g)
+def _variants():
+    import json
+    meta = json.load(open(os.path.join(ROOT, "tests", "golden", "cnn_variants.json")))
+    return meta["variants"]
+
+
+def test_variant_architectures_keep_the_reference_state_dict_layout():
+    """Every architecture of the reference's sweep: same keys and shapes as the reference's own class produced
+    (tests/golden/cnn_variants.json), and the packed blob has the size the library expects for that architecture."""
+    from leafgrasp_b200 import GraspPointCNN, pack_weights, _native as N
+    from leafgrasp_b200.cnn import architecture_of
+    lib = N.lib()
+    for v in _variants():
+        net = GraspPointCNN(in_channels=9, attention_type=v["attention_type"], encoder_filters=v["encoder_filters"])
+        mine = {k: list(t.shape) for k, t in net.state_dict().items()}
+        assert mine == v["shapes"], (v["attention_type"], v["encoder_filters"])
+        sd = O.seeded_state_dict_from_shapes(v["shapes"], v["seed"])
+        net.load_state_dict(sd)
+        assert architecture_of(sd) == (v["attention_type"], v["encoder_filters"])
+        cfg = N.cnn_config(v["attention_type"], v["encoder_filters"])
+        assert pack_weights(sd).size == lib.lg_cnn_model_floats(cfg)
+    bad = N.cnn_config("spatial", [64, 100])          # 100 channels: not a multiple of 16
+    assert lib.lg_cnn_model_floats(bad) == 0
+
+
+def _folded_forward(folded, x):
+    """The folded weights through plain torch ops (float64): what the CUDA kernels compute."""
     y = x.double()
-    for l in range(6):
-        w, b = folded[l]
+    for l, (w, b) in enumerate(folded["convs"]):
         y = F.relu(F.conv2d(y, torch.from_numpy(w), torch.from_numpy(b), padding=1))
         if l % 2 == 1:
             y = F.max_pool2d(y, 2)
-    aw, ab = folded[6]
-    att = torch.sigmoid(F.conv2d(y, torch.from_numpy(aw), torch.from_numpy(ab)))
-    y = (y * att).mean(dim=(2, 3))
-    for k in range(7, 11):
-        w, b = folded[k]
+    att = torch.ones_like(y[:, :1])
+    if folded["spatial"] is not None:
+        aw, ab = folded["spatial"]
+        att = torch.sigmoid(F.conv2d(y, torch.from_numpy(aw), torch.from_numpy(ab)))
+    catt = torch.ones_like(y[:, :, :1, :1])
+    if folded["channel"] is not None:
+        (w1, b1), (w2, b2) = folded["channel"]
+        h = F.relu(F.conv2d(y.mean(dim=(2, 3), keepdim=True), torch.from_numpy(w1), torch.from_numpy(b1)))
+        catt = torch.sigmoid(F.conv2d(h, torch.from_numpy(w2), torch.from_numpy(b2)))
+    y = (y * att * catt).mean(dim=(2, 3))
+    for k, (w, b) in enumerate(folded["fcs"]):
         y = F.linear(y, torch.from_numpy(w), torch.from_numpy(b))
-        if k != 10:
+        if k != 3:
             y = F.relu(y)
-    ref = O.cnn_forward(sd, x)
-    np.testing.assert_allclose(y.float().numpy(), ref.numpy(), atol=2e-5, rtol=1e-5)
+    return y.float()
+
+
+def test_batchnorm_folding_is_exact_enough():
+    """Run the folded weights through plain torch ops and compare with the unfolded forward: the default architecture
+    against the oracle, the variants against the logits the reference's own class produced (golden)."""
+    from leafgrasp_b200 import fold_batchnorm
+    sd = O.seeded_state_dict(5)
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(4, 9, 32, 32, generator=g)
+    np.testing.assert_allclose(_folded_forward(fold_batchnorm(sd), x).numpy(), O.cnn_forward(sd, x).numpy(), atol=2e-5, rtol=1e-5)
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "cnn_variants.npz"))
+    xv = torch.from_numpy(gold["x"])
+    for i, v in enumerate(_variants()):
+        sdv = O.seeded_state_dict_from_shapes(v["shapes"], v["seed"])
+        y = _folded_forward(fold_batchnorm(sdv), xv).reshape(-1).numpy()
+        np.testing.assert_allclose(y, gold[f"logits_{i}"], atol=5e-5, rtol=1e-4, err_msg=str((v["attention_type"], v["encoder_filters"])))
 
 
 def test_ellipse_rows_restated_equals_opencv():
