@@ -28,23 +28,41 @@ def camera_from_projection(P) -> N.Camera:
 
 
 class GraspEngine:
-    def __init__(self, max_frames: int, height: int, width: int, max_labels: int = 128, device=None):
+    """lanes > 1: process_batch splits a batch into `lanes` contiguous parts, part 0 on the caller's stream and the main
+    context, the others on their own stream and context.  Frames are independent, so the parts only meet in the result
+    buffer; running them side by side lets one part's latency-bound stages (per-frame sweeps, the 20 arg-max rounds)
+    fill the gaps of the other's.  Every other call uses the main context."""
+
+    def __init__(self, max_frames: int, height: int, width: int, max_labels: int = 128, device=None, lanes: int = 1):
         if not torch.cuda.is_available():
             raise N.NativeError("GraspEngine needs a CUDA device; this package has no CPU fallback")
         self.lib = N.lib()
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.B, self.H, self.W, self.L = int(max_frames), int(height), int(width), int(max_labels)
         self._ctx = C.c_void_p(0)
+        self._lane_ctx, self._lane_streams = [], []
+        self.lanes_active = True
         with torch.cuda.device(self.device):
             N.check(self.lib.lg_create(C.byref(self._ctx), self.B, self.H, self.W, self.L), "lg_create")
+            per = -(-self.B // max(1, int(lanes)))
+            for _ in range(1, max(1, int(lanes))):
+                ctx = C.c_void_p(0)
+                N.check(self.lib.lg_create(C.byref(ctx), per, self.H, self.W, self.L), "lg_create")
+                self._lane_ctx.append(ctx)
+                self._lane_streams.append(torch.cuda.Stream(device=self.device))
         self.has_cnn = False
+
+    def _all_ctx(self):
+        return [self._ctx] + self._lane_ctx
 
     def close(self):
         if getattr(self, "_ctx", None) and self._ctx.value:
             with torch.cuda.device(self.device):
                 torch.cuda.synchronize()
-                self.lib.lg_destroy(self._ctx)
+                for ctx in self._all_ctx():
+                    self.lib.lg_destroy(ctx)
             self._ctx = C.c_void_p(0)
+            self._lane_ctx = []
 
     def __del__(self):
         try:
@@ -54,11 +72,12 @@ class GraspEngine:
 
     def set_overlap(self, on: bool):
         """Run independent stages side by side on the library's internal stream (default) or serialised."""
-        N.check(self.lib.lg_set_overlap(self._ctx, int(bool(on))), "lg_set_overlap")
+        for ctx in self._all_ctx():
+            N.check(self.lib.lg_set_overlap(ctx, int(bool(on))), "lg_set_overlap")
 
     @property
     def context_bytes(self) -> int:
-        return int(self.lib.lg_context_bytes(self._ctx))
+        return sum(int(self.lib.lg_context_bytes(ctx)) for ctx in self._all_ctx())
 
     # ---- helpers ---------------------------------------------------------------------------------
     def _frames(self, t, dtype, name):
@@ -80,15 +99,17 @@ class GraspEngine:
         """Folded weights (cnn.pack_weights) of the default architecture, or of the one `config` (N.cnn_config) names."""
         with torch.cuda.device(self.device):
             if blob is None:
-                N.check(self.lib.lg_set_cnn_weights(self._ctx, None, 0), "lg_set_cnn_weights")
+                for ctx in self._all_ctx():
+                    N.check(self.lib.lg_set_cnn_weights(ctx, None, 0), "lg_set_cnn_weights")
                 self.has_cnn = False
                 return
             blob = np.ascontiguousarray(blob, dtype=np.float32)
-            if config is None:
-                N.check(self.lib.lg_set_cnn_weights(self._ctx, blob.ctypes.data_as(C.c_void_p), blob.size), "lg_set_cnn_weights")
-            else:
-                N.check(self.lib.lg_set_cnn_model(self._ctx, C.byref(config), blob.ctypes.data_as(C.c_void_p), blob.size),
-                        "lg_set_cnn_model")
+            for ctx in self._all_ctx():
+                if config is None:
+                    N.check(self.lib.lg_set_cnn_weights(ctx, blob.ctypes.data_as(C.c_void_p), blob.size), "lg_set_cnn_weights")
+                else:
+                    N.check(self.lib.lg_set_cnn_model(ctx, C.byref(config), blob.ctypes.data_as(C.c_void_p), blob.size),
+                            "lg_set_cnn_model")
             self.has_cnn = True
 
     def cnn_forward(self, patches: torch.Tensor, use_bf16: bool = False) -> torch.Tensor:
@@ -125,10 +146,28 @@ class GraspEngine:
         depth = self._frames(depth, torch.float32, "depth")
         n = labels.shape[0]
         res = self._new_results(n)
+        parts = self.lane_split(n)
         with torch.cuda.device(self.device):
-            N.check(self.lib.lg_process_batch(self._ctx, _ptr(labels), _ptr(depth), n, C.byref(cam), _ptr(res),
-                                              int(use_bf16), _stream()), "lg_process_batch")
+            cur = torch.cuda.current_stream()
+            for k in range(1, len(parts)):           # before anything of this call is queued on the caller's stream:
+                self._lane_streams[k - 1].wait_stream(cur)   # the lanes only wait for what precedes the call (the inputs)
+            for k, (lo, hi) in enumerate(parts):
+                ctx = self._ctx if k == 0 else self._lane_ctx[k - 1]
+                stream = cur if k == 0 else self._lane_streams[k - 1]
+                rp = C.c_void_p(res.data_ptr() + lo * N.FRAME_RESULT.itemsize)
+                N.check(self.lib.lg_process_batch(ctx, _ptr(labels[lo:hi]), _ptr(depth[lo:hi]), hi - lo, C.byref(cam), rp,
+                                                  int(use_bf16), C.c_void_p(stream.cuda_stream)), "lg_process_batch")
+            for k in range(1, len(parts)):
+                cur.wait_stream(self._lane_streams[k - 1])
         return self._records(res, N.FRAME_RESULT) if sync else res
+
+    def lane_split(self, n: int):
+        """[(lo, hi)] frame ranges of the parts a batch of n frames is processed in (one range without lanes)."""
+        lanes = 1 + len(self._lane_ctx) if self.lanes_active else 1
+        if lanes == 1 or n < 2 * lanes:
+            return [(0, n)]
+        per = -(-n // lanes)
+        return [(lo, min(n, lo + per)) for lo in range(0, n, per)]
 
     def process_batch_host(self, labels_host, depth_host, cam: N.Camera, use_bf16: bool = False):
         """Pinned (or plain) HOST tensors in, structured ndarray out; copies are inside the call."""

@@ -495,9 +495,16 @@ def test_batch_invariance_and_scheduling_independence(blob):
     c = eng.process_batch(labs, deps, _cam(spec))                     # serialised stages
     eng.set_overlap(True)
     single = eng.process_batch(labs[:1], deps[:1], _cam(spec))        # batch of one
+    from leafgrasp_b200 import GraspEngine
+    eng3 = GraspEngine(n, spec.height, spec.width, 128, lanes=3)      # three parts side by side on their own streams
+    eng3.set_cnn_weights(blob)
+    assert eng3.lane_split(n) == [(0, 8), (8, 16), (16, 24)] and eng3.lane_split(5) == [(0, 5)]
+    d = eng3.process_batch(labs, deps, _cam(spec))
+    eng3.close()
     for name in _EXACT_FIELDS + ("logit",):
         np.testing.assert_array_equal(a[name], b[name], err_msg=name)
         np.testing.assert_array_equal(a[name], c[name], err_msg=name)
+        np.testing.assert_array_equal(a[name], d[name], err_msg=name)
         np.testing.assert_array_equal(a[name][:1], single[name], err_msg=name)
         for k in range(6, n):                                          # same frame, other slot
             np.testing.assert_array_equal(a[name][k], a[name][k % 6], err_msg=name)
