@@ -853,3 +853,241 @@ def seeded_state_dict_from_shapes(shapes: dict, seed: int) -> dict:
             fan_in = int(np.prod(shp[1:]))
             sd[k] = torch.randn(shp, generator=g) * math.sqrt(2.0 / fan_in)
     return sd
+
+
+# ----------------------------------------------------------------------------------------------
+# training-sample collector      (ml_grasp_optimizer/data_collector.py:83-348, 420-487)
+# ----------------------------------------------------------------------------------------------
+# The reference draws its negatives, its depth noise and its score jitter from the unseeded global
+# generators of `random` and `torch`.  Those streams cannot be pinned, so the restatement takes the
+# generator as an argument: `CollectorRng` below is the counter-based one the CUDA path uses, and
+# tests/golden/make_collector.py injects the very same object into the unmodified reference module
+# (as its `random` / `torch.randn_like`), so every other step of the reference is held bit for bit.
+COLLECTOR_NEG_MAX = 3          # data_collector.py:306
+COLLECTOR_ATTEMPTS = 10        # data_collector.py:303
+KIND_POSITIVE, KIND_ROT90, KIND_ROT180, KIND_ROT270, KIND_TIP, KIND_STEM, KIND_EDGE = range(7)
+_M64 = (1 << 64) - 1
+# streams of the counter-based generator
+RNG_NOISE_FACTOR, RNG_SCORE_JITTER, RNG_PICK, RNG_NORMAL = 1, 2, 3, 4
+
+
+def mix64(z: int) -> int:
+    """splitmix64 finaliser."""
+    z &= _M64
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+    return z ^ (z >> 31)
+
+
+def _mix64_np(z: np.ndarray) -> np.ndarray:
+    z = z.astype(np.uint64)
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+class CollectorRng:
+    """draw(stream, a, b) = mix64(mix64(seed + 0x9E3779B97F4A7C15 * (frame + 1)) ^ (stream << 56 | a << 32 | b))."""
+
+    def __init__(self, seed: int, frame: int):
+        self.base = mix64(seed + 0x9E3779B97F4A7C15 * (frame + 1))
+
+    def draw(self, stream: int, a: int, b: int) -> int:
+        return mix64(self.base ^ ((stream << 56) | (a << 32) | b))
+
+    def uniform01(self, stream: int, a: int, b: int = 0) -> float:
+        return (self.draw(stream, a, b) >> 11) * 2.0 ** -53
+
+    def noise_factor(self, k: int) -> float:          # random.uniform(0.01, 0.02), data_collector.py:271
+        return 0.01 + (0.02 - 0.01) * self.uniform01(RNG_NOISE_FACTOR, k)
+
+    def score_jitter(self, k: int) -> float:          # random.uniform(0.95, 1.0), data_collector.py:281
+        return 0.95 + (1.0 - 0.95) * self.uniform01(RNG_SCORE_JITTER, k)
+
+    def pick(self, attempt: int, kind: int, n: int) -> int:      # random.sample(points, 1), :319-327
+        return self.draw(RNG_PICK, attempt, kind) % n
+
+    def normal_patch(self, k: int) -> np.ndarray:
+        """float32 [32,32] standard normals for rotation k (Box-Muller in float64, one pair per pixel)."""
+        i = np.arange(PATCH * PATCH, dtype=np.uint64)
+        with np.errstate(over="ignore"):
+            key = np.uint64(self.base) ^ ((np.uint64(RNG_NORMAL) << np.uint64(56)) | (np.uint64(k) << np.uint64(32)))
+            a = _mix64_np(key ^ (i * np.uint64(2)))
+            b = _mix64_np(key ^ (i * np.uint64(2) + np.uint64(1)))
+        u1 = ((a >> np.uint64(11)).astype(np.float64) + 1.0) * 2.0 ** -53
+        u2 = (b >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
+        z = np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+        return z.astype(np.float32).reshape(PATCH, PATCH)
+
+
+def collector_tip_points(mask_u8: np.ndarray, use_cv2: bool = True):
+    """data_collector.py:420-440: local maxima (5x5) of the chamfer field on the leaf, largest quarter.
+    list.sort is stable, so ties keep np.where's raster order."""
+    mask_u8 = np.ascontiguousarray(mask_u8, dtype=np.uint8)
+    dist = chamfer5(mask_u8, use_cv2)
+    if use_cv2:
+        dil = cv2.dilate(dist, np.ones((5, 5), np.uint8))
+    else:
+        dil = ndi.maximum_filter(dist, size=5, mode="constant", cval=-np.inf)
+    ys, xs = np.where((dil == dist) & (mask_u8 > 0))
+    pts = list(zip(xs.tolist(), ys.tolist()))
+    pts.sort(key=lambda p: dist[p[1], p[0]], reverse=True)
+    return pts[:max(1, len(pts) // 4)]
+
+
+def erode5_twice(mask_u8: np.ndarray, use_cv2: bool = True) -> np.ndarray:
+    """cv2.erode(m, ellipse 5x5, iterations=2): two literal passes, out-of-image pixels never constrain."""
+    se = ellipse_se(5)
+    if use_cv2:
+        return cv2.erode(np.ascontiguousarray(mask_u8, dtype=np.uint8), se, iterations=2)
+    m = np.asarray(mask_u8) != 0
+    H, W = m.shape
+    for _ in range(2):
+        pad = np.ones((H + 4, W + 4), dtype=bool)
+        pad[2:2 + H, 2:2 + W] = m
+        out = np.ones((H, W), dtype=bool)
+        for j in range(5):
+            for i in range(5):
+                if se[j, i]:
+                    out &= pad[j:j + H, i:i + W]
+        m = out
+    return m.astype(np.uint8)
+
+
+def collector_stem_points(mask_u8: np.ndarray, use_cv2: bool = True):
+    """data_collector.py:442-459: leaf pixels of the bottom quarter of the image that survive two erosions."""
+    H = mask_u8.shape[0]
+    stem = np.array(mask_u8, dtype=np.uint8, copy=True)
+    stem[:int(0.75 * H)] = 0
+    ys, xs = np.where(erode5_twice(stem, use_cv2) > 0)
+    return list(zip(xs.tolist(), ys.tolist()))
+
+
+def outer_border(mask_u8: np.ndarray, sx: int, sy: int):
+    """Pixels of the outer border of the component whose raster-first pixel is (sx, sy), in the order
+    cv2.findContours(RETR_EXTERNAL, CHAIN_APPROX_NONE) lists them: the Moore trace of
+    moore_contour_area runs the other way round, so it is the start followed by that trace reversed."""
+    DX = (1, 1, 0, -1, -1, -1, 0, 1)
+    DY = (0, 1, 1, 1, 0, -1, -1, -1)
+    H, W = mask_u8.shape
+    bit = lambda x, y: 0 <= x < W and 0 <= y < H and mask_u8[y, x] != 0
+    cx, cy, db, first, pts = sx, sy, 4, -1, []
+    while True:
+        d = -1
+        for k in range(1, 9):
+            dd = (db + k) % 8
+            if bit(cx + DX[dd], cy + DY[dd]):
+                d = dd
+                break
+        if d < 0:
+            pts.append((cx, cy))
+            break
+        if cx == sx and cy == sy and first >= 0 and d == first:
+            break
+        if first < 0:
+            first = d
+        pts.append((cx, cy))
+        cx, cy = cx + DX[d], cy + DY[d]
+        db = (d + (5 if d % 2 else 6)) % 8
+    return [pts[0]] + pts[:0:-1]
+
+
+def collector_edge_points(mask_u8: np.ndarray, use_cv2: bool = True):
+    """data_collector.py:461-487: points of the largest outer contour where the turn angle
+    |atan2(v1 x v2, v1 . v2)| is below pi/4.  Border steps are the eight unit moves, whose mutual angles
+    are multiples of pi/4, and arctan2(1, 1) is not below np.pi / 4: the test holds exactly where the
+    border doubles back (previous point == next point), or the contour is a single pixel."""
+    mask_u8 = np.ascontiguousarray(mask_u8, dtype=np.uint8)
+    contours, _ = cv2.findContours(mask_u8, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_NONE)
+    if not contours:
+        return []
+    contour = max(contours, key=cv2.contourArea)
+    if use_cv2:
+        pts = [tuple(p) for p in contour.reshape(-1, 2).tolist()]
+    else:
+        pts = outer_border(mask_u8, int(contour[0, 0, 0]), int(contour[0, 0, 1]))
+    n = len(pts)
+    return [pts[i] for i in range(n) if pts[i - 1] == pts[(i + 1) % n]]
+
+
+def collector_extract(x, y, mask_u8, depth, scores):
+    """data_collector.py:91-173 (_extract_patches): raw 32x32 windows by plain slicing, or None.
+    Python slicing decides what "out of bounds" means: a negative start wraps and gives an empty or
+    short window, an end beyond the image a short one; both fail the shape test."""
+    h = PATCH // 2
+    depth = np.asarray(depth, dtype=np.float32)
+    dp = depth[y - h:y + h, x - h:x + h]
+    mp = np.asarray(mask_u8)[y - h:y + h, x - h:x + h] != 0
+    if dp.size == 0 or dp.shape != (PATCH, PATCH) or mp.shape != (PATCH, PATCH):
+        return None
+    if not np.isfinite(dp).all() or not mp.any():
+        return None
+    sp = []
+    for name in SCORE_CHANNELS:
+        p = np.asarray(scores[name])[y - h:y + h, x - h:x + h]
+        if not np.isfinite(p).all():
+            return None
+        sp.append(p.astype(np.float32))
+    return dp.copy(), mp.astype(np.float32), np.stack(sp)
+
+
+def collector_rotate_point(point, angle, size=PATCH):
+    """data_collector.py:402-418 (the point is rotated about (16,16) in whatever frame it is given in)."""
+    x, y = point
+    c = size // 2
+    a = np.radians(angle)
+    x -= c
+    y -= c
+    nx = x * np.cos(a) - y * np.sin(a)
+    ny = x * np.sin(a) + y * np.cos(a)
+    return (int(nx + c), int(ny + c))
+
+
+def collect_sample(mask_u8, depth, scores, grasp_point, total_score, rng: CollectorRng, use_cv2=True):
+    """data_collector.py:175-348 without the bookkeeping: the samples one call appends, in order.
+    Each sample is a dict(kind, label, is_augmented, grasp_point, total_score, patch float32 [9,32,32])
+    with channels depth, mask, then SCORE_CHANNELS - the layout dataset.py stacks for training.
+    Returns None where the reference returns False before adding anything."""
+    mask_u8 = np.ascontiguousarray(mask_u8, dtype=np.uint8)
+    H, W = mask_u8.shape
+    x, y = int(grasp_point[0]), int(grasp_point[1])
+    h = PATCH // 2
+    if x < 0 or y < 0 or x >= W or y >= H:
+        return None
+    if y < h or y >= H - h or x < h or x >= W - h:               # _check_boundaries, :83-89
+        return None
+    got = collector_extract(x, y, mask_u8, depth, scores)
+    if got is None:
+        return None
+    dp, mp, sp = got
+    out = [dict(kind=KIND_POSITIVE, label=1, is_augmented=False, grasp_point=(x, y),
+                total_score=float(total_score), patch=np.concatenate([dp[None], mp[None], sp]))]
+    for k in (1, 2, 3):                                          # :250-299
+        rd = np.rot90(dp, k)
+        rm = (np.rot90(mp, k) > 0.5).astype(np.float32)
+        rs = np.rot90(sp, k, axes=(-2, -1))
+        factor = np.float32(rng.noise_factor(k))
+        mean = torch.from_numpy(np.ascontiguousarray(rd)).mean().numpy()          # torch's float32 mean
+        noisy = np.maximum(rd + rng.normal_patch(k) * np.float32(factor * mean), np.float32(0))
+        out.append(dict(kind=KIND_POSITIVE + k, label=1, is_augmented=True,
+                        grasp_point=collector_rotate_point((x, y), 90 * k),
+                        total_score=float(total_score * rng.score_jitter(k)),
+                        patch=np.concatenate([noisy[None], rm[None], rs]).astype(np.float32)))
+    sets = (collector_tip_points(mask_u8, use_cv2), collector_stem_points(mask_u8, use_cv2),
+            collector_edge_points(mask_u8, use_cv2))
+    collected = 0
+    for attempt in range(COLLECTOR_ATTEMPTS):                    # :309-341
+        if collected >= COLLECTOR_NEG_MAX:
+            break
+        for kind, pts in enumerate(sets):
+            if not pts or collected >= COLLECTOR_NEG_MAX:
+                continue
+            px, py = pts[rng.pick(attempt, kind, len(pts))]
+            got = collector_extract(px, py, mask_u8, depth, scores)
+            if got is None:
+                continue
+            dpn, mpn, spn = got
+            out.append(dict(kind=KIND_TIP + kind, label=0, is_augmented=False, grasp_point=(int(px), int(py)),
+                            total_score=0.0, patch=np.concatenate([dpn[None], mpn[None], spn])))
+            collected += 1
+    return out

@@ -224,3 +224,63 @@ def test_chamfer_two_sweeps_equal_norm_minimum():
         yy, xx = np.mgrid[0:H, 0:W]
         brute = N(xx[..., None] - qx, yy[..., None] - qy).min(-1)
         np.testing.assert_array_equal(two_sweeps, brute)
+
+
+# ---------------------------------------------------------------------------------------------------
+# training-sample collector: oracle vs the reference's own collector
+# ---------------------------------------------------------------------------------------------------
+import collector_util as CU  # noqa: E402
+
+
+@pytest.mark.parametrize("name", CU.CASES)
+@pytest.mark.parametrize("use_cv2", [True, False])
+def test_collector_against_reference(name, use_cv2):
+    mask, dep, P, g, _, _ = CU.case_inputs(name)
+    f, cx, cy = P[0, 0], P[0, 2], P[1, 2]
+    assert O.collector_tip_points(mask, use_cv2) == [tuple(p) for p in g["set_tip"].tolist()]
+    assert O.collector_stem_points(mask, use_cv2) == [tuple(p) for p in g["set_stem"].tolist()]
+    assert O.collector_edge_points(mask, use_cv2) == [tuple(p) for p in g["set_edge"].tolist()]
+    s = O.score_maps(mask, dep, f, cx, cy, "reference", use_cv2)
+    total = float(np.max(s["traditional_score"]))
+    np.testing.assert_allclose(total, float(g["total_score"]), rtol=1e-6)
+    rng = O.CollectorRng(int(g["rng_seed"]), int(g["frame_index"]))
+    out = O.collect_sample(mask, dep, s, tuple(g["grasp"].tolist()), float(g["total_score"]), rng, use_cv2)
+    assert [o["label"] for o in out] == g["labels"].tolist()
+    assert [int(o["is_augmented"]) for o in out] == g["is_augmented"].tolist()
+    assert [list(o["grasp_point"]) for o in out] == g["points"].tolist()
+    np.testing.assert_allclose([o["total_score"] for o in out], g["total_scores"], rtol=1e-15)
+    for i, o in enumerate(out):
+        # channels come from float maps that may differ in the last ulp between hosts (see RTOL above);
+        # the depth of the augmented samples carries torch's float32 mean and the float64 Box-Muller normals
+        np.testing.assert_allclose(o["patch"], g["patches"][i], rtol=RTOL, atol=1e-6, err_msg=f"sample {i}")
+        if not o["is_augmented"]:
+            assert np.array_equal(o["patch"][:2], g["patches"][i][:2])
+
+
+def test_collector_primitives_random_masks():
+    """Restated erosion / border order / turn test against cv2 and the reference's literal angle formula."""
+    rng = np.random.default_rng(5)
+    for _ in range(60):
+        H, W = rng.integers(6, 40, 2)
+        m = (rng.random((H, W)) < rng.uniform(0.4, 0.95)).astype(np.uint8)
+        assert np.array_equal(O.erode5_twice(m, True) > 0, O.erode5_twice(m, False) > 0)
+        contours, _ = cv2.findContours(m, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_NONE)
+        for c in contours:
+            pts = [tuple(p) for p in c.reshape(-1, 2).tolist()]
+            assert O.outer_border(m, *pts[0]) == pts
+            lit = []
+            for i in range(len(c)):                      # data_collector.py:472-483, literally
+                prev, curr, nxt = c[i - 1][0], c[i][0], c[(i + 1) % len(c)][0]
+                v1, v2 = prev - curr, nxt - curr
+                ang = np.abs(np.arctan2(v1[0] * v2[1] - v1[1] * v2[0], np.dot(v1, v2)))
+                if ang < np.pi / 4:
+                    lit.append((curr[0], curr[1]))
+            n = len(pts)
+            assert lit == [pts[i] for i in range(n) if pts[i - 1] == pts[(i + 1) % n]]
+        assert O.collector_edge_points(m, True) == O.collector_edge_points(m, False)
+        assert O.collector_tip_points(m, True) == O.collector_tip_points(m, False)
+    for a in (90, 180, 270):
+        for p in ((0, 0), (16, 16), (239, 301), (479, 359), (17, 3)):
+            x, y = p[0] - 16, p[1] - 16
+            c, s = np.cos(np.radians(a)), np.sin(np.radians(a))
+            assert O.collector_rotate_point(p, a) == (int(x * c - y * s + 16), int(x * s + y * c + 16))
