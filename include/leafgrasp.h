@@ -179,6 +179,42 @@ int lg_cnn_forward(lg_context* ctx, const float* patches, int n, float* logits, 
  * (>= 2048 patches).  Used by the per-layer parity tests. */
 int lg_cnn_bf16_features(lg_context* ctx, const float* patches, int n, int layer, float* features, void* stream);
 
+/* ---- training samples ---------------------------------------------------- */
+
+/* EnhancedGraspDataCollector.collect_sample (ml_grasp_optimizer/data_collector.py:175-348) for every frame of the
+ * batch the context has just processed: call it right after lg_process_batch (pass the same `labels`, mask NULL) or
+ * lg_select_grasp_point (pass the same `mask`, labels NULL) with the same depth, on the same stream.
+ * Per frame LG_SAMPLES_PER_FRAME slots: 0 = the positive sample at the grasp point, 1..3 = its rot90 copies with
+ * depth noise and score jitter (:250-299), 4..6 = up to three negatives from the tip / stem / edge candidate sets
+ * (:301-348, 420-487).  patches float32 [frames][7][9][32][32]: RAW (un-normalised) windows, channels depth, mask,
+ * sdf_score, approach_score, flatness_map, isolation_map, distance_map, accessibility_map, stem_penalty (:139-143);
+ * meta [frames][7]; set_sizes int32 [frames][3] = sizes of the tip (largest quarter), stem and edge sets.
+ * A slot with valid == 0 holds no sample (the reference added none: window leaves the image, non-finite depth, ...).
+ * grasp_xy int32 [frames][2] (device) overrides the grasp points, NULL = the ones just selected; total_score double
+ * [frames] (device) is the `total_score` argument, NULL = max of traditional_score over the frame (the reference's
+ * call site, grasp_point_selector_bkp.py:146-152).
+ * Randomness: the reference uses the global generators of `random` and `torch`; here every draw is a pure function
+ * of (seed, first_frame_index + frame, purpose, counter) - see oracle CollectorRng for the definition.
+ * The call reuses scratch of the candidate search (NMS lists) and of the chamfer transform; lg_frame_result is kept. */
+#define LG_SAMPLES_PER_FRAME 7
+typedef struct lg_sample_meta {
+    int32_t valid;          /* 1: the slot holds a sample */
+    int32_t label;          /* 1 positive, 0 negative */
+    int32_t is_augmented;
+    int32_t kind;           /* 0 positive, 1..3 rot90 x k, 4 tip, 5 stem, 6 edge */
+    int32_t x, y;           /* 'grasp_point' as the reference stores it (rotated copies: _rotate_point, :402-418) */
+    double total_score;
+} lg_sample_meta;
+int lg_collect_samples(lg_context* ctx, const int16_t* labels, const uint8_t* mask, const float* depth, int frames,
+                       uint64_t seed, uint64_t first_frame_index, const int32_t* grasp_xy, const double* total_score,
+                       float* patches, lg_sample_meta* meta, int32_t* set_sizes, void* stream);
+/* Points of a candidate set in the reference's list order (_get_tip_points / _get_stem_points / _get_edge_points,
+ * :420-487), after lg_collect_samples on the same batch: kind 0 tip, 1 stem, 2 edge; ranks uint32 [frames][nq]
+ * (device) are taken modulo the set size; xy int32 [frames][nq][2], (-1, -1) for an empty set. */
+int lg_collector_points(lg_context* ctx, const int16_t* labels, const uint8_t* mask, int frames, int kind,
+                        const uint32_t* ranks, int nq, int32_t* xy, void* stream);
+uint64_t lg_sizeof_sample_meta(void);
+
 /* ---- stage 2 on a caller-supplied leaf mask --------------------------------------------------- */
 
 /* GraspPointSelector.select_grasp_point (grasp_point_selector.py:184-253) for one binary leaf mask per

@@ -51,6 +51,13 @@ FRAME_RESULT = np.dtype([
     ("angle", np.float64), ("sdf_max", np.float32), ("region", np.int32, (4,)),
 ], align=True)
 
+SAMPLES_PER_FRAME = 7
+SAMPLE_KINDS = ("positive", "rot90", "rot180", "rot270", "tip", "stem", "edge")
+SAMPLE_META = np.dtype([
+    ("valid", np.int32), ("label", np.int32), ("is_augmented", np.int32), ("kind", np.int32),
+    ("x", np.int32), ("y", np.int32), ("total_score", np.float64),
+], align=True)
+
 # every symbol include/leafgrasp.h declares: (name, restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -72,6 +79,9 @@ SYMBOLS = {
     "lg_cnn_bf16_features": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
     "lg_select_grasp_point": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(Camera), _P, C.c_int, _P]),
     "lg_leaf_orientation": (C.c_int, [_P, _P, C.c_int, _P, _P]),
+    "lg_collect_samples": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_uint64, C.c_uint64, _P, _P, _P, _P, _P, _P]),
+    "lg_collector_points": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, C.c_int, _P, _P]),
+    "lg_sizeof_sample_meta": (C.c_uint64, []),
     "lg_patches": (C.c_int, [_P, _P, C.c_int, _P]),
     "lg_normalize_patches": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "lg_set_profiling": (C.c_int, [_P, C.c_int]),
@@ -104,7 +114,8 @@ def lib():
         fn = getattr(h, name)      # AttributeError here = header and library disagree
         fn.restype = res
         fn.argtypes = args
-    if h.lg_sizeof_frame_result() != FRAME_RESULT.itemsize or h.lg_sizeof_leaf_record() != LEAF_RECORD.itemsize:
+    if (h.lg_sizeof_frame_result() != FRAME_RESULT.itemsize or h.lg_sizeof_leaf_record() != LEAF_RECORD.itemsize or
+            h.lg_sizeof_sample_meta() != SAMPLE_META.itemsize):
         raise NativeError("struct layout mismatch between _native.py and include/leafgrasp.h")
     _lib = h
     return h

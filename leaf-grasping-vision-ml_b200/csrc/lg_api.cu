@@ -358,6 +358,31 @@ extern "C" int lg_normalize_patches(lg_context* c, const float* raw, int n, floa
     return lg_run_normalize_patches(raw, n, out, (cudaStream_t)stream);
 }
 
+extern "C" int lg_collect_samples(lg_context* c, const int16_t* labels, const uint8_t* mask, const float* depth, int frames,
+                                  uint64_t seed, uint64_t first_frame_index, const int32_t* grasp_xy, const double* total_score,
+                                  float* patches, lg_sample_meta* meta, int32_t* set_sizes, void* stream) {
+    if (!c || !depth || !patches || !meta || !set_sizes || frames < 1 || (labels == nullptr) == (mask == nullptr)) {
+        lg_set_error("lg_collect_samples: bad arguments (exactly one of labels / mask)");
+        return LG_E_ARG;
+    }
+    if (frames > c->B) return LG_E_CAPACITY;
+    LgMaskSrc src{labels, mask, labels ? c->leaf_id : nullptr};
+    return lg_run_collect(c, src, depth, frames, seed, first_frame_index, grasp_xy, total_score, patches, meta, set_sizes,
+                          (cudaStream_t)stream);
+}
+
+extern "C" int lg_collector_points(lg_context* c, const int16_t* labels, const uint8_t* mask, int frames, int kind,
+                                   const uint32_t* ranks, int nq, int32_t* xy, void* stream) {
+    if (!c || !ranks || !xy || frames < 1 || nq < 1 || kind < 0 || kind > 2 || (labels == nullptr) == (mask == nullptr)) {
+        lg_set_error("lg_collector_points: bad arguments");
+        return LG_E_ARG;
+    }
+    if (frames > c->B) return LG_E_CAPACITY;
+    LgMaskSrc src{labels, mask, labels ? c->leaf_id : nullptr};
+    return lg_run_collector_points(c, src, frames, kind, ranks, nq, xy, (cudaStream_t)stream);
+}
+
+extern "C" uint64_t lg_sizeof_sample_meta(void) { return sizeof(lg_sample_meta); }
 extern "C" uint64_t lg_sizeof_frame_result(void) { return sizeof(lg_frame_result); }
 extern "C" uint64_t lg_sizeof_leaf_record(void) { return sizeof(lg_leaf_record); }
 extern "C" uint64_t lg_cnn_weight_floats(void) { return lg_cnn_blob_floats(); }

@@ -54,6 +54,7 @@ struct LgOrient {
     int n_hull;
     unsigned status;
     unsigned pad;
+    int win_lx, win_ly;  // raster-first pixel of the winning contour's component, bitmask coordinates; -1 = none
 };
 
 // Folded CNN weights on the device (see cnn.py:pack_weights for the blob layout)
@@ -187,4 +188,9 @@ bool lg_cnn_config_is_default(const lg_cnn_config* g);
 uint64_t lg_cnn_config_floats(const lg_cnn_config* g);
 int lg_run_fuse(lg_context* c, LgMaskSrc src, const float* depth, int n, lg_camera cam, int have_ml,
                 lg_frame_result* out, cudaStream_t st);
+int lg_run_collect(lg_context* c, LgMaskSrc src, const float* depth, int n, unsigned long long seed, unsigned long long first_index,
+                   const int32_t* grasp_xy, const double* total, float* patches, lg_sample_meta* meta, int32_t* set_sizes,
+                   cudaStream_t st);
+int lg_run_collector_points(lg_context* c, LgMaskSrc src, int n, int kind, const uint32_t* ranks, int nq, int32_t* xy,
+                            cudaStream_t st);
 int lg_run_mask_regions(lg_context* c, const uint8_t* mask, int n, int full, cudaStream_t st);

@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(OR_NT) orient_kernel(lg_context c, LgMaskSrc s
         if (tid == 0) {
             LgOrient o;
             o.angle = CUDART_NAN; o.cos_a = 1; o.sin_a = 0; o.major = o.minor = o.cx = o.cy = 0;
-            o.has_angle = 0; o.n_hull = 0; o.status = 0; o.pad = 0;
+            o.has_angle = 0; o.n_hull = 0; o.win_lx = o.win_ly = -1; o.status = 0; o.pad = 0;
             *out = o;
         }
         return;
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(OR_NT) orient_kernel(lg_context c, LgMaskSrc s
         if (tid == 0) {
             LgOrient o;
             o.angle = CUDART_NAN; o.cos_a = 1; o.sin_a = 0; o.major = o.minor = o.cx = o.cy = 0;
-            o.has_angle = 0; o.n_hull = 0; o.status = s_fail ? LG_ST_RUNS_OVERFLOW : 0; o.pad = 0;
+            o.has_angle = 0; o.n_hull = 0; o.win_lx = o.win_ly = -1; o.status = s_fail ? LG_ST_RUNS_OVERFLOW : 0; o.pad = 0;
             *out = o;
             if (s_fail) atomicOr(&c.status[b], LG_ST_RUNS_OVERFLOW);
         }
@@ -345,6 +345,7 @@ __global__ void __launch_bounds__(OR_NT) orient_kernel(lg_context c, LgMaskSrc s
         o.cos_a = cos(o.angle); o.sin_a = sin(o.angle);
         o.major = fmaxf(R.w, R.h); o.minor = fminf(R.w, R.h); o.cx = R.cx; o.cy = R.cy;
         o.has_angle = 1; o.n_hull = nh; o.status = 0; o.pad = 0;
+        o.win_lx = rx0[win]; o.win_ly = ry[win];
         *out = o;
     }
 }

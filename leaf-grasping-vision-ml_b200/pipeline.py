@@ -200,6 +200,51 @@ class GraspEngine:
                                                    int(use_bf16), _stream()), "lg_select_grasp_point")
         return self._records(res, N.FRAME_RESULT)
 
+    # ---- training samples (data_collector.py:175-348) ---------------------------------------------------
+    def collect_samples(self, depth, labels=None, mask=None, seed: int = 0, first_frame_index: int = 0, grasp_xy=None,
+                        total_score=None):
+        """Samples of the batch this engine has just processed: call right after process_batch (pass the same labels)
+        or select_grasp_point (pass the same mask).  Returns (patches float32 device [n,7,9,32,32], meta structured
+        ndarray [n,7] (SAMPLE_META), set_sizes int32 ndarray [n,3])."""
+        if (labels is None) == (mask is None):
+            raise ValueError("pass exactly one of labels / mask")
+        if self._lane_ctx and self.lanes_active:
+            raise N.NativeError("collect_samples needs the whole batch in one context: build the engine with lanes=1")
+        depth = self._frames(depth, torch.float32, "depth")
+        src = self._frames(labels, torch.int16, "labels") if labels is not None else self._frames(mask, torch.uint8, "mask")
+        n = depth.shape[0]
+        if grasp_xy is not None:
+            grasp_xy = torch.as_tensor(np.asarray(grasp_xy, dtype=np.int32).reshape(n, 2)).to(self.device).contiguous()
+        if total_score is not None:
+            total_score = torch.as_tensor(np.asarray(total_score, dtype=np.float64).reshape(n)).to(self.device).contiguous()
+        patches = torch.zeros(n, N.SAMPLES_PER_FRAME, N.CHANNELS, N.PATCH, N.PATCH, dtype=torch.float32, device=self.device)
+        meta = torch.zeros(n * N.SAMPLES_PER_FRAME * N.SAMPLE_META.itemsize, dtype=torch.uint8, device=self.device)
+        sizes = torch.zeros(n, 3, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.lg_collect_samples(self._ctx, _ptr(src if labels is not None else None),
+                                                _ptr(src if mask is not None else None), _ptr(depth), n,
+                                                C.c_uint64(int(seed) & (2 ** 64 - 1)), C.c_uint64(int(first_frame_index)),
+                                                _ptr(grasp_xy), _ptr(total_score), _ptr(patches), _ptr(meta), _ptr(sizes),
+                                                _stream()), "lg_collect_samples")
+        return patches, self._records(meta, N.SAMPLE_META).reshape(n, N.SAMPLES_PER_FRAME), sizes.cpu().numpy()
+
+    def collector_points(self, kind: int, ranks, labels=None, mask=None) -> np.ndarray:
+        """Points (x, y) of a candidate set by rank in the reference's list order, after collect_samples on the same
+        batch: kind 0 tip, 1 stem, 2 edge; ranks [n, nq] are taken modulo the set size."""
+        if (labels is None) == (mask is None):
+            raise ValueError("pass exactly one of labels / mask")
+        src = self._frames(labels, torch.int16, "labels") if labels is not None else self._frames(mask, torch.uint8, "mask")
+        n = src.shape[0]
+        ranks = torch.as_tensor(np.asarray(ranks, dtype=np.uint32).reshape(n, -1).astype(np.int64)).to(torch.int32)
+        ranks = ranks.to(self.device).contiguous()
+        nq = ranks.shape[1]
+        xy = torch.empty(n, nq, 2, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.lg_collector_points(self._ctx, _ptr(src if labels is not None else None),
+                                                 _ptr(src if mask is not None else None), n, int(kind), _ptr(ranks), nq,
+                                                 _ptr(xy), _stream()), "lg_collector_points")
+        return xy.cpu().numpy()
+
     def last_patches(self, n: int) -> torch.Tensor:
         out = torch.empty(n, N.TOP_K, N.CHANNELS, N.PATCH, N.PATCH, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):

@@ -1043,11 +1043,12 @@ def collector_rotate_point(point, angle, size=PATCH):
     return (int(nx + c), int(ny + c))
 
 
-def collect_sample(mask_u8, depth, scores, grasp_point, total_score, rng: CollectorRng, use_cv2=True):
+def collect_sample(mask_u8, depth, scores, grasp_point, total_score, rng: CollectorRng, use_cv2=True, trace=None):
     """data_collector.py:175-348 without the bookkeeping: the samples one call appends, in order.
     Each sample is a dict(kind, label, is_augmented, grasp_point, total_score, patch float32 [9,32,32])
     with channels depth, mask, then SCORE_CHANNELS - the layout dataset.py stacks for training.
-    Returns None where the reference returns False before adding anything."""
+    Returns None where the reference returns False before adding anything.  `trace` (a list) receives one
+    (attempt, kind, point, accepted) per negative pick."""
     mask_u8 = np.ascontiguousarray(mask_u8, dtype=np.uint8)
     H, W = mask_u8.shape
     x, y = int(grasp_point[0]), int(grasp_point[1])
@@ -1084,6 +1085,8 @@ def collect_sample(mask_u8, depth, scores, grasp_point, total_score, rng: Collec
                 continue
             px, py = pts[rng.pick(attempt, kind, len(pts))]
             got = collector_extract(px, py, mask_u8, depth, scores)
+            if trace is not None:
+                trace.append((attempt, kind, (int(px), int(py)), got is not None))
             if got is None:
                 continue
             dpn, mpn, spn = got

@@ -220,3 +220,58 @@ def test_frame_sharding_and_gather_two_ranks():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert got == [float(i) for i in range(10)]
+
+
+# ---------------------------------------------------------------------------------------------------
+# training-sample collector: host side (data_collector.py), no device needed
+# ---------------------------------------------------------------------------------------------------
+def _fake_collect(n, rng):
+    from leafgrasp_b200 import _native as N
+    patches = rng.random((n, N.SAMPLES_PER_FRAME, 9, 32, 32)).astype(np.float32)
+    meta = np.zeros((n, N.SAMPLES_PER_FRAME), dtype=N.SAMPLE_META)
+    for b in range(n):
+        pos_ok = b != 1                                     # frame 1: collect_sample returned False
+        for k in range(N.SAMPLES_PER_FRAME):
+            m = meta[b, k]
+            m["kind"] = k
+            if not pos_ok or (k == 6 and b % 2 == 0):       # some frames find only two negatives
+                continue
+            m["valid"], m["label"], m["is_augmented"] = 1, int(k < 4), int(1 <= k <= 3)
+            m["x"], m["y"], m["total_score"] = 100 + b, 50 + k, 0.5 if k < 4 else 0.0
+    return patches, meta
+
+
+def test_collector_host_bookkeeping_and_file_format(tmp_path):
+    from leafgrasp_b200 import EnhancedGraspDataCollector, _native as N
+    assert N.SAMPLE_META.itemsize == 32
+    rng = np.random.default_rng(0)
+    col = EnhancedGraspDataCollector(resume=False, data_dir=str(tmp_path / "d"))
+    patches, meta = _fake_collect(5, rng)
+    assert col.collect_batch(patches, meta) == 4
+    assert col.frames_seen == 5
+    assert col.stats == {"positive_samples": 4, "augmented_samples": 12, "negative_samples": 4 * 3 - 3}
+    assert len(col.samples) == 4 * 7 - 3
+    s0 = col.samples[0]
+    assert set(s0) == {"depth_patch", "mask_patch", "score_patches", "total_score", "grasp_point", "label", "is_augmented"}
+    assert s0["score_patches"].shape == (7, 32, 32) and s0["grasp_point"] == (100, 50) and s0["label"] == 1
+    np.testing.assert_array_equal(s0["depth_patch"].numpy(), patches[0, 0, 0])
+    np.testing.assert_array_equal(col.samples[1]["score_patches"].numpy(), patches[0, 1, 2:])
+    col.save_samples()
+    data = torch.load(str(tmp_path / "d" / "training_data.pt"))
+    # the layout ml_grasp_optimizer/dataset.py reads (data_collector.py:515-523)
+    assert set(data) == {"depth_patches", "mask_patches", "score_patches", "labels", "total_scores", "grasp_points",
+                         "is_augmented"}
+    assert data["depth_patches"].shape == (25, 32, 32) and data["score_patches"].shape == (25, 7, 32, 32)
+    assert data["grasp_points"].shape == (25, 2) and data["is_augmented"].dtype == torch.bool
+    text = open(tmp_path / "d" / "collection_metadata.txt").read()
+    assert "Original positive samples: 4" in text and "Total samples: 25" in text
+    assert open(tmp_path / "d" / "collection_progress.txt").read() == "last_frame: 4\n"
+    # resume picks the samples and the counters up again (data_collector.py:42-81)
+    col2 = EnhancedGraspDataCollector(resume=True, data_dir=str(tmp_path / "d"))
+    assert col2.stats == col.stats and len(col2.samples) == 25 and col2.frames_seen == 4
+    assert col2.samples[3]["grasp_point"] == col.samples[3]["grasp_point"]
+    # resume=False clears the directory (:19-21)
+    col3 = EnhancedGraspDataCollector(resume=False, data_dir=str(tmp_path / "d"))
+    assert col3.samples == [] and not os.path.exists(tmp_path / "d" / "training_data.pt")
+    with pytest.raises(Exception):
+        col3.collect_sample(torch.zeros(4, 4, dtype=torch.bool), torch.zeros(4, 4), None, {}, (1, 1), 0.5)   # no engine
