@@ -31,7 +31,8 @@ constexpr int LEAD = 64;        // zero rows in front of every plane (>= pitch +
 constexpr int TILE_M = 512;     // positions per work item: 4 UMMA tiles of 128 rows
 constexpr int UMMA_T = 4;
 __host__ __device__ constexpr int nb_stages(int nc) { return nc == 64 ? 8 : 5; }   // weight stages in flight (what shared memory allows)
-constexpr int CONV_THREADS = 320;   // warp 0 producer, warp 1 MMA issuer + TMEM owner, warps 2-9 epilogue
+constexpr int CONV_THREADS = 416;   // warp 0 producer, warp 1 MMA issuer + TMEM owner, warps 2-9 epilogue, warps 10-12 further MMA issuers
+constexpr int ISSUER2_WARP = 10;
 constexpr int EPI_WARPS = 8;        // two warps per TMEM lane quarter, each taking every other 32-column chunk
 
 // Optional pipeline timers (build with -DLG_CNN_TIMING): per CTA, cycles the MMA warp spent waiting for the
@@ -59,6 +60,7 @@ struct UmmaConvArgs {
     int rows;             // shared-memory rows per plane of the A stage: TILE_M + 2 * pitch + 2, rounded up to 8
     int cout;
     int layer;            // 0..5 (timers only)
+    int issuers;          // MMA-issuing warps (1, 2 or 4): warp 1 and warps 10.., each owning UMMA_T / issuers accumulator tiles
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -124,6 +126,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
         : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Same wait, but naming the 32 destination registers of a load issued earlier as read-write operands: the compiler
+// must then treat their values as produced here, not at the (asynchronous) load, whatever it schedules in between.
+__device__ __forceinline__ void tmem_ld_wait_regs(uint32_t* v) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+                   "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+                   "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :
+                 : "memory");
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
@@ -149,8 +162,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
     uint64_t* b_full = bars + 4;        // [NB]
     uint64_t* b_empty = bars + 4 + NB_STAGES;
     uint64_t* acc_full = bars + 4 + 2 * NB_STAGES;   // [2]
-    uint64_t* acc_empty = acc_full + 2;              // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* acc_empty = acc_full + 2;              // [2][UMMA_T]: one per accumulator tile, so that the next item's MMAs
+                                                     // on tile t start as soon as the epilogue has read tile t
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2 * UMMA_T);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_patches = A.n_dev ? min(*A.n_dev, A.n_host) : A.n_host;
@@ -160,9 +174,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
 
     for (int i = threadIdx.x; i < A.cout; i += CONV_THREADS) s_bias[i] = A.bias[i];
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&a_full[i]), 1); mbar_init(smem_u32(&a_empty[i]), 1); }
-        for (int i = 0; i < NB_STAGES; ++i) { mbar_init(smem_u32(&b_full[i]), 1); mbar_init(smem_u32(&b_empty[i]), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), EPI_WARPS); }
+        // every issuing warp commits once to the "operand consumed" / "accumulators complete" barriers
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&a_full[i]), 1); mbar_init(smem_u32(&a_empty[i]), A.issuers); }
+        for (int i = 0; i < NB_STAGES; ++i) { mbar_init(smem_u32(&b_full[i]), 1); mbar_init(smem_u32(&b_empty[i]), A.issuers); }
+        for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&acc_full[i]), A.issuers);
+        for (int i = 0; i < 2 * UMMA_T; ++i) mbar_init(smem_u32(&acc_empty[i]), EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -198,7 +214,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
                 for (int kc = 0; kc < A.KC; ++kc) {
 #pragma unroll 1
                     for (int tap = 0; tap < 9; ++tap) {
-                        if (tap == 1) {   // prefetch the next input stage behind the first weight stage
+                        // Prefetch the next input stage.  The weight loads run NB_STAGES taps ahead of the MMAs, so at this
+                        // tap the MMAs have just left the previous chunk and its input stage is free: asking earlier would
+                        // park this thread on a_empty while the weight pipeline behind it drains.
+                        if (tap == (NB_STAGES < 8 ? NB_STAGES : 8)) {
                             if (kc + 1 < A.KC) issue_a(item, kc + 1);
                             else if (item + (int)gridDim.x < n_items) issue_a(item + gridDim.x, 0);
                         }
@@ -212,8 +231,14 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
+    } else if (warp == 1 || warp >= ISSUER2_WARP) {
+        // ===== MMA issuer(s) =====
+        // One thread needs ~60 cycles per tcgen05.mma, an MMA keeps the tensor pipe busy for 32 (N = 64) or 64 (N = 128)
+        // cycles: with two issuing warps (on different schedulers), each owning half of the item's accumulator tiles, the
+        // issue cost is no longer the limiter.
+        const int issuer = (warp == 1) ? 0 : warp - ISSUER2_WARP + 1;
+        if (issuer >= A.issuers) goto done;
+        const int t_count = UMMA_T / A.issuers, t_base = issuer * t_count;
         int a_st = 0, a_ph = 0, b_st = 0, b_ph = 0, acc_st = 0, acc_ph = 0;
         const uint32_t rows2 = 2u * (uint32_t)A.rows;      // two planes (one K = 16 step) in 16-byte units
 #ifdef LG_CNN_TIMING
@@ -221,7 +246,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
         const long long t_begin = clock64();
 #endif
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            { LG_T0(t0); mbar_wait(smem_u32(&acc_empty[acc_st]), acc_ph ^ 1); LG_TACC(0, t0); }
+            {
+                LG_T0(t0);
+                for (int tt = 0; tt < t_count; ++tt) mbar_wait(smem_u32(&acc_empty[acc_st * UMMA_T + t_base + tt]), acc_ph ^ 1);
+                LG_TACC(0, t0);
+            }
             tc_fence_after();
             for (int kc = 0; kc < A.KC; ++kc) {
                 { LG_T0(t0); mbar_wait(smem_u32(&a_full[a_st]), a_ph); LG_TACC(1, t0); }
@@ -242,7 +271,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
                         const uint32_t first_acc = (uint32_t)((kc | tap) != 0);
                         const uint32_t d_tmem = tmem_base + (uint32_t)(acc_st * UMMA_T * NC);
 #pragma unroll
-                        for (int t = 0; t < UMMA_T; ++t) {
+                        for (int tt = 0; tt < UMMA_T; ++tt) {
+                            if (tt >= t_count) break;
+                            const int t = t_base + tt;
 #pragma unroll
                             for (int j = 0; j < KP / 2; ++j) {
                                 const uint64_t ad = ((uint64_t)DESC_HI << 32) | (uint64_t)(a_lo + (uint32_t)(j * rows2 + t * 128));
@@ -266,12 +297,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
             if (++acc_st == ACC_STAGES) { acc_st = 0; acc_ph ^= 1; }
         }
 #ifdef LG_CNN_TIMING
-        if (lane == 0 && blockIdx.x < 148) {
+        if (warp == 1 && lane == 0 && blockIdx.x < 148) {
             for (int k = 0; k < 4; ++k) g_cnn_timing[A.layer][blockIdx.x][k] = (unsigned long long)t_acc[k];
             g_cnn_timing[A.layer][blockIdx.x][6] = (unsigned long long)(clock64() - t_begin);
         }
 #endif
-    } else {
+    } else if (warp < ISSUER2_WARP) {
         // ===== epilogue: TMEM -> registers -> bias + ReLU -> bf16 -> global (plane-major) =====
         const int wq = warp & 3;                 // TMEM lane quarter this warp may read
         const int chalf = (warp - 2) >> 2;       // which of the two warps of that quarter: chunks chalf, chalf + 2, ...
@@ -290,8 +321,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
             { LG_T0(t0); mbar_wait(smem_u32(&acc_full[acc_st]), acc_ph); LG_TACC(4, t0); }
             tc_fence_after();
             LG_T0(t_epi);
-#pragma unroll 1
-            for (int t = 0; t < UMMA_T; ++t) {
+            // bias + ReLU + bf16 pack + store of one 128-row tile held in registers
+            auto store_tile = [&](int t, uint32_t (&v)[CHUNKS][32]) {
                 const long long q = (long long)tile * TILE_M + t * 128 + wq * 32 + lane;
                 bool data = q < Q;
                 if (data) {
@@ -299,11 +330,6 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
                     const int r = ql / A.pitch, cc = ql - r * A.pitch;
                     data = (r >= 1) && (cc >= 1);
                 }
-                uint32_t v[CHUNKS][32];
-#pragma unroll
-                for (int j = 0; j < CHUNKS; ++j)
-                    tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((acc_st * UMMA_T + t) * NC + (chalf + 2 * j) * 32), v[j]);
-                tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < CHUNKS; ++j) {
                     const int ch = chalf + 2 * j;
@@ -322,10 +348,39 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
                         o[(long long)g * A.R] = w;
                     }
                 }
+            };
+            auto tile_addr = [&](int t, int j) {
+                return tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((acc_st * UMMA_T + t) * NC + (chalf + 2 * j) * 32);
+            };
+            // a tile that has reached the registers is handed back to the MMA issuers before it is converted and stored
+            auto release_tile = [&](int t) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&acc_empty[acc_st * UMMA_T + t]));
+            };
+            if constexpr (CHUNKS == 1) {
+                // N = 64: the epilogue is what bounds these layers, so the TMEM read of tile t + 1 is in flight while
+                // tile t is converted and stored (two register buffers)
+                uint32_t va[1][32], vb[1][32];
+                tmem_ld32(tile_addr(0, 0), va[0]);
+#pragma unroll
+                for (int t = 0; t < UMMA_T; ++t) {
+                    tmem_ld_wait_regs((t & 1) ? vb[0] : va[0]);
+                    release_tile(t);
+                    if (t + 1 < UMMA_T) tmem_ld32(tile_addr(t + 1, 0), (t & 1) ? va[0] : vb[0]);
+                    store_tile(t, (t & 1) ? vb : va);
+                }
+            } else {
+#pragma unroll 1
+                for (int t = 0; t < UMMA_T; ++t) {
+                    uint32_t v[CHUNKS][32];
+#pragma unroll
+                    for (int j = 0; j < CHUNKS; ++j) tmem_ld32(tile_addr(t, j), v[j]);
+                    tmem_ld_wait();
+                    release_tile(t);
+                    store_tile(t, v);
+                }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&acc_empty[acc_st]));
             LG_TACC(5, t_epi);
             if (++acc_st == ACC_STAGES) { acc_st = 0; acc_ph ^= 1; }
         }
@@ -336,6 +391,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
         }
 #endif
     }
+done:
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -538,11 +594,13 @@ extern "C" int lg_cnn_bf16_features(lg_context* c, const float* patches, int n, 
 static int run_cnn_bf16(lg_context* c, const float* patches, int n, const int32_t* n_dev, float* logits, int stop_layer,
                         float* feat_out, cudaStream_t st) {
     if (!c->cnn.bf16_blob) { lg_set_error("bf16 CNN weights are not prepared"); return LG_E_ARG; }
-    static int sms = 0;
+    static int sms = 0, issuers = 4;
     if (!sms) {
         int dev = 0;
         LG_CUDA(cudaGetDevice(&dev));
         LG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const char* e = getenv("LG_CNN_ISSUERS");     // measurement switch: 1 = single issuing warp
+        if (e && (e[0] == '1' || e[0] == '2' || e[0] == '4')) issuers = e[0] - '0';
     }
     // bias pointers inside the fp32 blob; bf16 weights inside bf16_blob
     const float* bias[6];
@@ -575,7 +633,7 @@ static int run_cnn_bf16(lg_context* c, const float* patches, int n, const int32_
             A.in = buf[cur]; A.out = buf[cur ^ 1]; A.wt = wts[l]; A.bias = bias[l];
             A.R = rows_per_plane(L.S, m);
             A.pitch = L.S + 1; A.PP = A.pitch * A.pitch; A.n_dev = n_dev; A.n_host = m;
-            A.KC = L.KC; A.n_split = L.cout / L.NC; A.rows = a_rows(L.S); A.cout = L.cout; A.layer = l;
+            A.KC = L.KC; A.n_split = L.cout / L.NC; A.rows = a_rows(L.S); A.cout = L.cout; A.layer = l; A.issuers = issuers;
             int rc;
             if (L.KP == 2) rc = launch_conv<2, 64>(A, L.S, sms, st);
             else if (L.NC == 64) rc = launch_conv<8, 64>(A, L.S, sms, st);
