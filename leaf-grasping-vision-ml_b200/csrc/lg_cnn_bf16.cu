@@ -17,6 +17,12 @@
 // Outputs at halo positions are computed and discarded (6 % / 11 % / 21 % of the rows at 32 / 16 / 8 px) and
 // written as zeros, which makes the output directly the next layer's input.  LEAD zero rows precede position 0.
 //
+// Layers followed by a 2x2 max-pool (the second conv of a block at 32 and 16 px) use BLOCKED tiles instead: with the
+// stride between groups of 8 rows (SBO) set to one image row (pitch * 16 B) instead of 128 B, the 128 rows of an MMA
+// tile are an 8-column x 16-row block of pixels.  A warp of the epilogue then holds 8 columns x 4 rows, the four pixels
+// of every pooling window sit in lanes l, l^1, l^8, l^9, and the pool is two shuffles on the packed bf16 values: the
+// un-pooled activation (the largest tensor of the network) is never written, and no halo row is computed.
+//
 // Weights: bf16, BatchNorm folded, packed [n_split][Cin/64][tap][8 planes][NC][8] so that the B operand of one
 // (channel chunk, tap) stage is one contiguous bulk copy, again unswizzled K-major (LBO = NC * 16 B).
 #include <cuda_bf16.h>
@@ -30,7 +36,8 @@ namespace {
 constexpr int LEAD = 64;        // zero rows in front of every plane (>= pitch + 1)
 constexpr int TILE_M = 512;     // positions per work item: 4 UMMA tiles of 128 rows
 constexpr int UMMA_T = 4;
-__host__ __device__ constexpr int nb_stages(int nc) { return nc == 64 ? 8 : 5; }   // weight stages in flight (what shared memory allows)
+// weight stages in flight (what shared memory allows; the blocked input stage of the pooled layers is a little larger)
+__host__ __device__ constexpr int nb_stages(int nc, bool pool) { return nc == 64 ? 8 : (pool ? 4 : 5); }
 constexpr int CONV_THREADS = 416;   // warp 0 producer, warp 1 MMA issuer + TMEM owner, warps 2-9 epilogue, warps 10-12 further MMA issuers
 constexpr int ISSUER2_WARP = 10;
 constexpr int EPI_WARPS = 8;        // two warps per TMEM lane quarter, each taking every other 32-column chunk
@@ -60,6 +67,7 @@ struct UmmaConvArgs {
     int rows;             // shared-memory rows per plane of the A stage: TILE_M + 2 * pitch + 2, rounded up to 8
     int cout;
     int layer;            // 0..5 (timers only)
+    long long Rout;       // POOL kernels (2x2 max-pool fused into the epilogue, S = 32 or 16): rows per plane of the pooled output
     int issuers;          // MMA-issuing warps (1, 2 or 4): warp 1 and warps 10.., each owning UMMA_T / issuers accumulator tiles
 };
 
@@ -144,12 +152,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 
 // One work item = TILE_M consecutive output positions x NC output channels.  KP = planes (8 channels each) per
 // input-channel chunk: 8 for the 64-channel chunks of layers 1-5, 2 for the 9 (padded to 16) channels of layer 0.
-template <int KP, int NC>
+template <int KP, int NC, bool POOL>
 __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int ACC_STAGES = 512 / (UMMA_T * NC);          // 2 (NC = 64) or 1 (NC = 128) accumulator sets in TMEM
     constexpr uint32_t B_STAGE = KP * NC * 16;
-    constexpr int NB_STAGES = nb_stages(NC);
+    constexpr int NB_STAGES = nb_stages(NC, POOL);
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NC >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t a_stage_bytes = (uint32_t)KP * A.rows * 16;
     unsigned char* sA = smem;
@@ -170,7 +178,14 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
     const int n_patches = A.n_dev ? min(*A.n_dev, A.n_host) : A.n_host;
     const long long Q = (long long)n_patches * A.PP;                       // positions that carry data
     const int n_tiles = (int)((Q + A.pitch + 1 + TILE_M - 1) / TILE_M);      // + the zero row behind the last patch
-    const int n_items = n_tiles * A.n_split;
+    // blocked items: half a 32x32 patch (4 column blocks x 16 rows) or two 16x16 patches (2 column blocks each)
+    const bool pool32 = POOL && A.pitch == 33;
+    const int n_items = POOL ? (pool32 ? 2 * n_patches : (n_patches + 1) / 2) : n_tiles * A.n_split;
+    // first position (pixel (y0, 0) of the item's first patch) of a blocked item
+    auto pool_base = [&](int item) -> long long {
+        return pool32 ? (long long)(item >> 1) * A.PP + (long long)(1 + 16 * (item & 1)) * A.pitch + 1
+                      : (long long)(2 * item) * A.PP + A.pitch + 1;
+    };
 
     for (int i = threadIdx.x; i < A.cout; i += CONV_THREADS) s_bias[i] = A.bias[i];
     if (threadIdx.x == 0) {
@@ -199,7 +214,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
                 mbar_wait(smem_u32(&a_empty[a_st]), a_ph ^ 1);
                 const uint32_t bar = smem_u32(&a_full[a_st]);
                 mbar_expect_tx(bar, a_stage_bytes);
-                const long long rho0 = LEAD + (long long)tile * TILE_M - A.pitch - 1;
+                const long long rho0 = LEAD + (POOL ? pool_base(item) : (long long)tile * TILE_M) - A.pitch - 1;
                 const uint32_t dst = smem_u32(sA + (size_t)a_st * a_stage_bytes);
 #pragma unroll 1
                 for (int p = 0; p < KP; ++p)
@@ -269,6 +284,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
                         const uint32_t a_lo = desc_lo(a_base + (uint32_t)(ky * A.pitch + kx) * 16, A.rows * 16);
                         const uint32_t b_lo = desc_lo(smem_u32(sB + (size_t)b_st * B_STAGE), NC * 16);
                         const uint32_t first_acc = (uint32_t)((kc | tap) != 0);
+                        const uint32_t desc_hi = POOL ? ((uint32_t)A.pitch | (1u << 14)) : DESC_HI;   // SBO: one image row / 128 B
                         const uint32_t d_tmem = tmem_base + (uint32_t)(acc_st * UMMA_T * NC);
 #pragma unroll
                         for (int tt = 0; tt < UMMA_T; ++tt) {
@@ -276,7 +292,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
                             const int t = t_base + tt;
 #pragma unroll
                             for (int j = 0; j < KP / 2; ++j) {
-                                const uint64_t ad = ((uint64_t)DESC_HI << 32) | (uint64_t)(a_lo + (uint32_t)(j * rows2 + t * 128));
+                                // first row of tile t inside the stage, in 16-byte units
+                            const uint32_t t_off = !POOL ? (uint32_t)(t * 128)
+                                                   : pool32 ? (uint32_t)(t * 8) : (uint32_t)((t >> 1) * A.PP + (t & 1) * 8);
+                            const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + (uint32_t)(j * rows2) + t_off);
                                 const uint64_t bd = ((uint64_t)DESC_HI << 32) | (uint64_t)(b_lo + (uint32_t)(j * 2 * NC));
                                 umma_bf16(d_tmem + (uint32_t)(t * NC), ad, bd, IDESC, j == 0 ? first_acc : 1u);
                             }
@@ -310,7 +329,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
         if (blockIdx.x == 0) {       // zero rows in front of position 0 of every output plane
             const int et = threadIdx.x - 64;
             const int planes = A.cout / 8;
-            for (int i = et; i < planes * LEAD; i += 32 * EPI_WARPS) A.out[(long long)(i / LEAD) * A.R + (i % LEAD)] = make_uint4(0, 0, 0, 0);
+            const long long Ro = POOL ? A.Rout : A.R;
+            for (int i = et; i < planes * LEAD; i += 32 * EPI_WARPS) A.out[(long long)(i / LEAD) * Ro + (i % LEAD)] = make_uint4(0, 0, 0, 0);
         }
         int acc_st = 0, acc_ph = 0;
 #ifdef LG_CNN_TIMING
@@ -349,6 +369,38 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
                     }
                 }
             };
+            // blocked tile: bias + ReLU + bf16 pack, 2x2 max over lanes (l, l^1, l^8, l^9), store by the window's first lane
+            auto store_tile_pool = [&](int t, uint32_t (&v)[CHUNKS][32]) {
+                const int S = A.pitch - 1, po = (S >> 1) + 1, PPo = po * po;
+                const int patch = pool32 ? (item >> 1) : 2 * item + (t >> 1);
+                const int y = (pool32 ? 16 * (item & 1) : 0) + wq * 4 + (lane >> 3);
+                const int x = (pool32 ? 8 * t : 8 * (t & 1)) + (lane & 7);
+                const bool writer = ((lane & 9) == 0) && patch < n_patches;
+                const long long qo = (long long)patch * PPo + (long long)((y >> 1) + 1) * po + (x >> 1) + 1;
+#pragma unroll
+                for (int j = 0; j < CHUNKS; ++j) {
+                    const int ch = chalf + 2 * j;
+                    const float* bs = s_bias + half * NC + ch * 32;
+                    uint4* o = A.out + (long long)((half * NC + ch * 32) / 8) * A.Rout + LEAD + qo;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float f0 = fmaxf(__uint_as_float(v[j][g * 8 + 2 * e]) + bs[g * 8 + 2 * e], 0.f);
+                            const float f1 = fmaxf(__uint_as_float(v[j][g * 8 + 2 * e + 1]) + bs[g * 8 + 2 * e + 1], 0.f);
+                            uint32_t m = pack_bf16x2(f0, f1);
+                            uint32_t o1 = __shfl_xor_sync(0xFFFFFFFFu, m, 1);
+                            __nv_bfloat162 a = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&m), *reinterpret_cast<__nv_bfloat162*>(&o1));
+                            m = *reinterpret_cast<uint32_t*>(&a);
+                            uint32_t o8 = __shfl_xor_sync(0xFFFFFFFFu, m, 8);
+                            a = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&m), *reinterpret_cast<__nv_bfloat162*>(&o8));
+                            w[e] = *reinterpret_cast<uint32_t*>(&a);
+                        }
+                        if (writer) o[(long long)g * A.Rout] = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            };
             auto tile_addr = [&](int t, int j) {
                 return tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)((acc_st * UMMA_T + t) * NC + (chalf + 2 * j) * 32);
             };
@@ -368,7 +420,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
                     tmem_ld_wait_regs((t & 1) ? vb[0] : va[0]);
                     release_tile(t);
                     if (t + 1 < UMMA_T) tmem_ld32(tile_addr(t + 1, 0), (t & 1) ? va[0] : vb[0]);
-                    store_tile(t, (t & 1) ? vb : va);
+                    if (POOL) store_tile_pool(t, (t & 1) ? vb : va); else store_tile(t, (t & 1) ? vb : va);
                 }
             } else {
 #pragma unroll 1
@@ -378,7 +430,30 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
                     for (int j = 0; j < CHUNKS; ++j) tmem_ld32(tile_addr(t, j), v[j]);
                     tmem_ld_wait();
                     release_tile(t);
-                    store_tile(t, v);
+                    if (POOL) store_tile_pool(t, v); else store_tile(t, v);
+                }
+            }
+            if (POOL) {
+                // zero halo of the pooled layout (row 0 and column 0 of every patch, and the row behind the last patch)
+                const int S = A.pitch - 1, So = S >> 1, po = So + 1, PPo = po * po, planes = A.cout / 8;
+                const int et = threadIdx.x - 64;
+                const int np = pool32 ? 1 : 2;
+                for (int k = 0; k < np; ++k) {
+                    const int patch = pool32 ? (item >> 1) : 2 * item + k;
+                    if (patch >= n_patches) break;
+                    const bool top = !pool32 || (item & 1) == 0, bottom = !pool32 || (item & 1) == 1;
+                    const int r_lo = pool32 ? 8 * (item & 1) + 1 : 1, r_n = pool32 ? 8 : So;
+                    const int n_top = top ? po : 0;
+                    const int n_tail = (bottom && patch == n_patches - 1) ? po + 1 : 0;
+                    const int cnt = n_top + r_n + n_tail;
+                    for (int i = et; i < cnt * planes; i += 32 * EPI_WARPS) {
+                        const int pl = i / cnt, z = i - pl * cnt;
+                        long long qo;
+                        if (z < n_top) qo = (long long)patch * PPo + z;
+                        else if (z < n_top + r_n) qo = (long long)patch * PPo + (long long)(r_lo + z - n_top) * po;
+                        else qo = (long long)(patch + 1) * PPo + (z - n_top - r_n);
+                        A.out[(long long)pl * A.Rout + LEAD + qo] = make_uint4(0, 0, 0, 0);
+                    }
                 }
             }
             LG_TACC(5, t_epi);
@@ -506,13 +581,18 @@ const LayerCfg kLayers[6] = {{9, 64, 32, 2, 1, 64},   {64, 64, 32, 8, 1, 64},   
 inline long long rows_per_plane(int S, long long n) {
     const long long pitch = S + 1, Q = n * pitch * pitch;
     const long long tiles = (Q + pitch + 1 + TILE_M - 1) / TILE_M;
-    return LEAD + tiles * TILE_M + 64;
+    return LEAD + tiles * TILE_M + 640;      // slack: the blocked input stage of the last pooled item reads ~600 rows from its base
 }
-inline int a_rows(int S) { return (TILE_M + 2 * (S + 1) + 2 + 7) / 8 * 8; }
+// rows of one input stage: the item's positions plus one image row and one pixel on either side
+inline int a_rows(int S, bool pool) {
+    const int span = !pool ? TILE_M : (S == 32 ? 15 * 33 + 32 : 17 * 17 + 15 * 17 + 16);
+    return (span + 2 * (S + 1) + 2 + 7) / 8 * 8;
+}
 
-template <int KP, int NC>
+template <int KP, int NC, bool POOL>
 size_t conv_smem(int S) {
-    return 2 * (size_t)KP * a_rows(S) * 16 + (size_t)nb_stages(NC) * KP * NC * 16 + 256 * sizeof(float) + 32 * sizeof(uint64_t) + 16;
+    return 2 * (size_t)KP * a_rows(S, POOL) * 16 + (size_t)nb_stages(NC, POOL) * KP * NC * 16 + 256 * sizeof(float) +
+           32 * sizeof(uint64_t) + 16;
 }
 
 uint16_t f2bf(float f) {
@@ -526,18 +606,19 @@ uint16_t f2bf(float f) {
 // packed bf16 weight offsets (in uint4 units) of every layer inside cnn.bf16_blob
 size_t layer_w_units(const LayerCfg& l) { return (size_t)(l.cout / l.NC) * l.KC * 9 * l.KP * l.NC; }
 
-template <int KP, int NC>
+template <int KP, int NC, bool POOL>
 int launch_conv(const UmmaConvArgs& A, int S, int sms, cudaStream_t st) {
     static size_t configured = 0;
-    const size_t smem = conv_smem<KP, NC>(S);
+    const size_t smem = conv_smem<KP, NC, POOL>(S);
     if (smem > configured) {
-        LG_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<KP, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LG_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<KP, NC, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     const long long Qmax = (long long)A.n_host * A.PP;
-    const int items = (int)((Qmax + A.pitch + 1 + TILE_M - 1) / TILE_M) * A.n_split;
+    const int items = POOL ? (S == 32 ? 2 * A.n_host : (A.n_host + 1) / 2)
+                           : (int)((Qmax + A.pitch + 1 + TILE_M - 1) / TILE_M) * A.n_split;
     const int grid = items < sms ? items : sms;
-    conv3x3_umma_kernel<KP, NC><<<grid, CONV_THREADS, smem, st>>>(A);
+    conv3x3_umma_kernel<KP, NC, POOL><<<grid, CONV_THREADS, smem, st>>>(A);
     LG_LAUNCH_CHECK();
     return LG_OK;
 }
@@ -594,13 +675,15 @@ extern "C" int lg_cnn_bf16_features(lg_context* c, const float* patches, int n, 
 static int run_cnn_bf16(lg_context* c, const float* patches, int n, const int32_t* n_dev, float* logits, int stop_layer,
                         float* feat_out, cudaStream_t st) {
     if (!c->cnn.bf16_blob) { lg_set_error("bf16 CNN weights are not prepared"); return LG_E_ARG; }
-    static int sms = 0, issuers = 4;
+    static int sms = 0, issuers = 4, fuse_pool = 1;
     if (!sms) {
         int dev = 0;
         LG_CUDA(cudaGetDevice(&dev));
         LG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         const char* e = getenv("LG_CNN_ISSUERS");     // measurement switch: 1 = single issuing warp
         if (e && (e[0] == '1' || e[0] == '2' || e[0] == '4')) issuers = e[0] - '0';
+        const char* fp = getenv("LG_CNN_FUSE_POOL");  // measurement switch: 0 = separate pool kernels after layers 1 and 3
+        if (fp && fp[0] == '0') fuse_pool = 0;
     }
     // bias pointers inside the fp32 blob; bf16 weights inside bf16_blob
     const float* bias[6];
@@ -633,14 +716,16 @@ static int run_cnn_bf16(lg_context* c, const float* patches, int n, const int32_
             A.in = buf[cur]; A.out = buf[cur ^ 1]; A.wt = wts[l]; A.bias = bias[l];
             A.R = rows_per_plane(L.S, m);
             A.pitch = L.S + 1; A.PP = A.pitch * A.pitch; A.n_dev = n_dev; A.n_host = m;
-            A.KC = L.KC; A.n_split = L.cout / L.NC; A.rows = a_rows(L.S); A.cout = L.cout; A.layer = l; A.issuers = issuers;
+            const bool fused_pool = fuse_pool && (l == 1 || l == 3);   // second conv of the 32 px and 16 px blocks
+            A.KC = L.KC; A.n_split = L.cout / L.NC; A.rows = a_rows(L.S, fused_pool); A.cout = L.cout; A.layer = l; A.issuers = issuers;
+            A.Rout = rows_per_plane(L.S / 2, m);
             int rc;
-            if (L.KP == 2) rc = launch_conv<2, 64>(A, L.S, sms, st);
-            else if (L.NC == 64) rc = launch_conv<8, 64>(A, L.S, sms, st);
-            else rc = launch_conv<8, 128>(A, L.S, sms, st);
+            if (L.KP == 2) rc = launch_conv<2, 64, false>(A, L.S, sms, st);
+            else if (L.NC == 64) rc = fused_pool ? launch_conv<8, 64, true>(A, L.S, sms, st) : launch_conv<8, 64, false>(A, L.S, sms, st);
+            else rc = fused_pool ? launch_conv<8, 128, true>(A, L.S, sms, st) : launch_conv<8, 128, false>(A, L.S, sms, st);
             if (rc) return rc;
             cur ^= 1;
-            if (l & 1) {   // max-pool after the second conv of each block
+            if ((l & 1) && !fused_pool) {   // max-pool after the second conv of each block
                 const int planes = L.cout / 8;
                 if (l == 5) {
                     const long long total = (long long)m * 16 * planes;
