@@ -17,6 +17,17 @@
 namespace {
 
 constexpr int OR_NT = 128;
+// The serial sections (union-find over runs, border trace, hull, calipers) are chains of dependent loads; on global
+// scratch every link costs an L2 round trip (the data was written by other threads of the CTA, so L1 does not hold it).
+// Working sets that fit are therefore staged in shared memory: the bitmask, the run tables, and - aliased on the run
+// tables, which are dead by then - the row extents, hull points and caliper work arrays.  Larger leaves use the global
+// scratch as before.
+constexpr int OR_S_BITS = 8192;     // bitmask words (32 KB)
+constexpr int OR_S_RUNS = 1536;     // runs: 3 x u16 + 6 x i32 per run (45 KB)
+constexpr int OR_S_ROWS = 960;      // rows of the winning component: 12 ints per row (45 KB), aliases the run tables
+constexpr int OR_S_ROWF = 1104;     // row -> first run table (rows of the bounding box + 2)
+constexpr size_t OR_SMEM = (size_t)OR_S_BITS * 4 + (size_t)OR_S_ROWF * 4 + (size_t)OR_S_ROWS * 8 + (size_t)OR_S_RUNS * 30;
+static_assert((size_t)OR_S_ROWS * 40 <= (size_t)OR_S_RUNS * 30, "hull points and caliper arrays alias the run tables");
 
 struct Bits {
     const uint32_t* w;
@@ -157,7 +168,7 @@ __global__ void __launch_bounds__(OR_NT) orient_kernel(lg_context c, LgMaskSrc s
     const int b = blockIdx.x, tid = threadIdx.x;
     const LgRegion r = c.region[b];
     LgOrient* out = &c.orient[b];
-    __shared__ int s_total, s_win, s_ytop, s_ybot, s_fail;
+    __shared__ int s_total, s_win, s_ytop, s_ybot, s_fail, s_wlx, s_wly;
     if (!r.ok) {
         if (tid == 0) {
             LgOrient o;
@@ -172,9 +183,15 @@ __global__ void __launch_bounds__(OR_NT) orient_kernel(lg_context c, LgMaskSrc s
     const int bw = r.x1 - r.x0 + 2, bh = r.y1 - r.y0 + 2;
     const int wpr = (bw + 31) >> 5;
     uint32_t* bits = c.bits + (size_t)b * c.bits_stride;
+    extern __shared__ __align__(16) unsigned char or_smem[];
+    uint32_t* s_bits = reinterpret_cast<uint32_t*>(or_smem);
+    int32_t* s_rowf = reinterpret_cast<int32_t*>(or_smem + (size_t)OR_S_BITS * 4);
+    int32_t* s_ext = s_rowf + OR_S_ROWF;
+    unsigned char* s_work = reinterpret_cast<unsigned char*>(s_ext + 2 * OR_S_ROWS);
+    const bool bits_in_smem = bh * wpr <= OR_S_BITS;
     const size_t fo = (size_t)b * c.P;
     const int id = src.id(b);
-    // 1. bitmask
+    // 1. bitmask (global copy: the stem-penalty and pre-grasp dilations and the sample collector read it later)
     for (int i = tid; i < bh * wpr; i += OR_NT) {
         const int ly = i / wpr, wi = i - ly * wpr;
         const int y = oy + ly;
@@ -186,10 +203,12 @@ __global__ void __launch_bounds__(OR_NT) orient_kernel(lg_context c, LgMaskSrc s
             }
         }
         bits[i] = word;
+        if (bits_in_smem) s_bits[i] = word;
     }
     __syncthreads();
+    if (bits_in_smem) bits = s_bits;
     Bits B{bits, wpr, bw, bh};
-    int32_t* row_first = c.row_first + (size_t)b * (H + 3);
+    int32_t* row_first = (bh + 1 <= OR_S_ROWF) ? s_rowf : c.row_first + (size_t)b * (H + 3);
     // 2. runs per row
     for (int ly = tid; ly < bh; ly += OR_NT) {
         int cnt = 0;
@@ -221,15 +240,17 @@ __global__ void __launch_bounds__(OR_NT) orient_kernel(lg_context c, LgMaskSrc s
         }
         return;
     }
-    uint16_t* rx0 = c.run_x0 + (size_t)b * c.run_cap;
-    uint16_t* rx1 = c.run_x1 + (size_t)b * c.run_cap;
-    uint16_t* ry = c.run_y + (size_t)b * c.run_cap;
-    int32_t* parent = c.run_parent + (size_t)b * c.run_cap * 6;
-    int32_t* cpix = parent + c.run_cap;
-    int32_t* cx0 = cpix + c.run_cap;
-    int32_t* cx1 = cx0 + c.run_cap;
-    int32_t* cy0 = cx1 + c.run_cap;
-    int32_t* cy1 = cy0 + c.run_cap;
+    const bool runs_in_smem = total <= OR_S_RUNS;
+    const int rcap = runs_in_smem ? OR_S_RUNS : c.run_cap;
+    int32_t* parent = runs_in_smem ? reinterpret_cast<int32_t*>(s_work) : c.run_parent + (size_t)b * c.run_cap * 6;
+    int32_t* cpix = parent + rcap;
+    int32_t* cx0 = cpix + rcap;
+    int32_t* cx1 = cx0 + rcap;
+    int32_t* cy0 = cx1 + rcap;
+    int32_t* cy1 = cy0 + rcap;
+    uint16_t* rx0 = runs_in_smem ? reinterpret_cast<uint16_t*>(cy1 + rcap) : c.run_x0 + (size_t)b * c.run_cap;
+    uint16_t* rx1 = runs_in_smem ? rx0 + rcap : c.run_x1 + (size_t)b * c.run_cap;
+    uint16_t* ry = runs_in_smem ? rx1 + rcap : c.run_y + (size_t)b * c.run_cap;
     // 3. extract runs
     for (int ly = tid; ly < bh; ly += OR_NT) {
         int o = row_first[ly];
@@ -297,13 +318,16 @@ __global__ void __launch_bounds__(OR_NT) orient_kernel(lg_context c, LgMaskSrc s
             // cv2 lists contours last-found first and max() keeps the first maximum: ties go to the later start
             if (a > best_a || (a == best_a && i > win)) { best_a = a; win = i; }
         }
-        s_win = win; s_ytop = cy0[win]; s_ybot = cy1[win];
+        s_win = win; s_ytop = cy0[win]; s_ybot = cy1[win]; s_wlx = rx0[win]; s_wly = ry[win];
     }
     __syncthreads();
     const int win = s_win, ytop = s_ytop, ybot = s_ybot;
     // per-frame scratch of 12*(H+2) ints: hull points | per-row (minx, maxx) | float work arrays
-    int32_t* hull = c.hull + (size_t)b * (12 * (H + 2));
-    int32_t* ext = hull + 4 * (H + 2);
+    const int nrows = ybot - ytop + 1;
+    const bool hull_in_smem = runs_in_smem && nrows <= OR_S_ROWS;   // (the global run tables do not alias the hull scratch)
+    int32_t* hull = hull_in_smem ? reinterpret_cast<int32_t*>(s_work) : c.hull + (size_t)b * (12 * (H + 2));
+    int32_t* ext = hull_in_smem ? s_ext : hull + 4 * (H + 2);
+    const int wlx = s_wlx, wly = s_wly;
     // 7. winner's row extents
     for (int ly = ytop + tid; ly <= ybot; ly += OR_NT) {
         int mn = 1 << 30, mx = -1;
@@ -336,7 +360,7 @@ __global__ void __launch_bounds__(OR_NT) orient_kernel(lg_context c, LgMaskSrc s
         if (nh > 1 && hull[2 * (nh - 1)] == hull[0] && hull[2 * (nh - 1) + 1] == hull[1]) --nh;
         // the closing turn at the start vertex can still be flat: drop a last point collinear with it
         while (nh >= 3 && crossz(hull[2 * (nh - 2)], hull[2 * (nh - 2) + 1], hull[2 * (nh - 1)], hull[2 * (nh - 1) + 1], hull[0], hull[1]) >= 0) --nh;
-        float* fs = reinterpret_cast<float*>(hull + 6 * (H + 2));
+        float* fs = hull_in_smem ? reinterpret_cast<float*>(hull + 4 * OR_S_ROWS) : reinterpret_cast<float*>(hull + 6 * (H + 2));
         RectOut R = min_area_rect(hull, nh, fs, fs + nh, fs + 2 * nh);
         double ang = (double)R.angle_deg;
         if (R.w < R.h) ang = ang + 90.0;
@@ -345,7 +369,7 @@ __global__ void __launch_bounds__(OR_NT) orient_kernel(lg_context c, LgMaskSrc s
         o.cos_a = cos(o.angle); o.sin_a = sin(o.angle);
         o.major = fmaxf(R.w, R.h); o.minor = fminf(R.w, R.h); o.cx = R.cx; o.cy = R.cy;
         o.has_angle = 1; o.n_hull = nh; o.status = 0; o.pad = 0;
-        o.win_lx = rx0[win]; o.win_ly = ry[win];
+        o.win_lx = wlx; o.win_ly = wly;
         *out = o;
     }
 }
@@ -404,7 +428,12 @@ __global__ void mask_clear_kernel(lg_context c, int n) {
 }  // namespace
 
 int lg_run_orientation(lg_context* c, LgMaskSrc src, int n, cudaStream_t st) {
-    orient_kernel<<<n, OR_NT, 0, st>>>(*c, src, n);
+    static bool configured = false;
+    if (!configured) {
+        LG_CUDA(cudaFuncSetAttribute(orient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OR_SMEM));
+        configured = true;
+    }
+    orient_kernel<<<n, OR_NT, OR_SMEM, st>>>(*c, src, n);
     LG_LAUNCH_CHECK();
     return LG_OK;
 }
