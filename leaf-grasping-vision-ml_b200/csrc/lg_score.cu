@@ -531,81 +531,101 @@ __global__ void export_patches_kernel(lg_context c, float* __restrict__ out) {
 // ---------------------------------------------------------------------------------------------------
 // fusion + 3-D points
 // ---------------------------------------------------------------------------------------------------
-__global__ void fuse_kernel(lg_context c, LgMaskSrc src, const float* __restrict__ depth, lg_camera cam, int have_ml, int n) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per frame: lane k owns candidate k (rescale + fusion term), the pick is a warp arg-max with the serial
+// loop's rule (a later candidate replaces the current best only if strictly larger), and the 31 rows of the pre-grasp
+// dilation element are tested by 31 lanes at once.
+__global__ void __launch_bounds__(32) fuse_kernel(lg_context c, LgMaskSrc src, const float* __restrict__ depth, lg_camera cam, int have_ml, int n) {
+    const int b = blockIdx.x, lane = threadIdx.x;
     if (b >= n) return;
     lg_frame_result* res = &c.results[b];
     const LgRegion r = c.region[b];
     const int W = c.W, H = c.H;
     const size_t fo = (size_t)b * c.P;
-    res->status = c.status[b];
-    res->leaf_id = c.leaf_id[b];
-    res->region[0] = r.x0; res->region[1] = r.y0; res->region[2] = r.x1; res->region[3] = r.y1;
-    const LgOrient o = c.orient[b];
-    res->angle = o.angle;
-    const uint32_t* mxq = c.dt_max + (size_t)b * 2;
-    res->sdf_max = __fmul_rn((float)max(mxq[0], mxq[1]), 1.0f / 65536.0f);
-    res->best_index = -1; res->ml_used = 0; res->best_score = 0.0;
-    res->grasp_x = -1; res->grasp_y = -1;
-    for (int k = 0; k < 3; ++k) { res->grasp_3d[k] = CUDART_NAN; res->pre_grasp[k] = CUDART_NAN; }
     const int nc = r.ok ? res->n_candidates : 0;
-    if (!r.ok) { res->n_candidates = 0; res->n_positive = 0; }
-    for (int k = 0; k < LG_TOP_K; ++k) {
+    if (lane == 0) {
+        res->status = c.status[b];
+        res->leaf_id = c.leaf_id[b];
+        res->region[0] = r.x0; res->region[1] = r.y0; res->region[2] = r.x1; res->region[3] = r.y1;
+        res->angle = c.orient[b].angle;
+        const uint32_t* mxq = c.dt_max + (size_t)b * 2;
+        res->sdf_max = __fmul_rn((float)max(mxq[0], mxq[1]), 1.0f / 65536.0f);
+        if (!r.ok) { res->n_candidates = 0; res->n_positive = 0; }
+    }
+    // per candidate: ML score and the fused score (:205-237)
+    double comb = -CUDART_INF, trad_k = 0.0;
+    bool has_comb = false;
+    if (lane < LG_TOP_K) {
+        const int k = lane;
         const bool mlk = have_ml && nc > 1 && k < nc && res->ml_valid[k];
+        if (k < nc) trad_k = res->trad[k];
         if (mlk) {
             const float lg = c.logits[c.slot_map[b * LG_TOP_K + k]];
             res->logit[k] = lg;
             const float s = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-lg)));
-            res->ml[k] = tanh((double)s * 3.0) * 0.5 + 0.5;
+            const double ml = tanh((double)s * 3.0) * 0.5 + 0.5;
+            res->ml[k] = ml;
+            const double conf = 1.0 - fabs(ml - 0.5) * 2.0;
+            const double w = fmin(0.3, conf * 0.6);
+            comb = (1.0 - w) * trad_k + w * ml;
+            has_comb = true;
         } else {
             res->logit[k] = CUDART_NAN_F; res->ml[k] = CUDART_NAN; res->ml_valid[k] = 0;
         }
     }
-    if (nc == 0) return;
-    int best = 0;
-    double best_score = res->trad[0];
-    int ml_used = 0;
-    if (have_ml && nc > 1) {
-        for (int k = 0; k < nc; ++k) {
-            if (!res->ml_valid[k]) continue;
-            const double ml = res->ml[k];
-            const double conf = 1.0 - fabs(ml - 0.5) * 2.0;
-            const double w = fmin(0.3, conf * 0.6);
-            const double comb = (1.0 - w) * res->trad[k] + w * ml;
-            if (comb > best_score) { best_score = comb; best = k; ml_used = 1; }
+    if (nc == 0) {
+        if (lane == 0) {
+            res->best_index = -1; res->ml_used = 0; res->best_score = 0.0;
+            res->grasp_x = -1; res->grasp_y = -1;
+            for (int k = 0; k < 3; ++k) { res->grasp_3d[k] = CUDART_NAN; res->pre_grasp[k] = CUDART_NAN; }
         }
+        return;
     }
-    res->best_index = best; res->best_score = best_score; res->ml_used = ml_used;
+    // the serial loop starts from (trad[0], candidate 0) and takes candidate k when its fused score is strictly larger:
+    // the winner is the largest fused score (first one among equals) if that beats trad[0], else candidate 0
+    double best_score = has_comb ? comb : -CUDART_INF;
+    int best = has_comb ? lane : 0x7FFFFFFF;
+    if (!(best_score == best_score)) { best_score = -CUDART_INF; best = 0x7FFFFFFF; }     // NaN never wins a '>' test
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const double os = __shfl_xor_sync(0xFFFFFFFFu, best_score, d);
+        const int ok = __shfl_xor_sync(0xFFFFFFFFu, best, d);
+        if (os > best_score || (os == best_score && ok < best)) { best_score = os; best = ok; }
+    }
+    const double trad0 = __shfl_sync(0xFFFFFFFFu, trad_k, 0);
+    int ml_used = 0;
+    if (best != 0x7FFFFFFF && best_score > trad0) ml_used = 1;
+    else { best = 0; best_score = trad0; }
     const int u = res->cand_x[best], v = res->cand_y[best];
-    res->grasp_x = u; res->grasp_y = v;
     const double z = (double)depth[fo + (size_t)v * W + u];
     const double X = (z * ((double)u - cam.cx)) / cam.f, Y = (z * ((double)v - cam.cy)) / cam.f;
-    res->grasp_3d[0] = X; res->grasp_3d[1] = Y; res->grasp_3d[2] = z;
     // pre-grasp (:754-819)
     const double nrm = sqrt(X * X + Y * Y + z * z);
     const double d0 = X / nrm, d1 = Y / nrm;
     const uint32_t* bits = c.bits + (size_t)b * c.bits_stride;
     const int ox = r.x0 - 1, oy = r.y0 - 1, bw = r.x1 - r.x0 + 2, bh = r.y1 - r.y0 + 2, wpr = (bw + 31) >> 5;
     bool found = false;
+    double p0 = 0.0, p1 = 0.0;
     for (int i = 0; i < 5 && !found; ++i) {
         const double dist = 0.05 + (double)i * 0.01;
         const double t0 = X - d0 * dist, t1 = Y - d1 * dist;
         const int pu = (int)((t0 * cam.f / z) + cam.cx), pv = (int)((t1 * cam.f / z) + cam.cy);
         if (!(pu >= 0 && pu < W && pv >= 0 && pv < H)) continue;
-        bool blocked = false;
-        for (int j = 0; j < LG_SE_PRE && !blocked; ++j)
-            blocked = bits_any(bits, wpr, bw, bh, pv + j - LG_SE_PRE / 2 - oy, pu + c.se31_a[j] - LG_SE_PRE / 2 - ox,
-                               pu + c.se31_b[j] - LG_SE_PRE / 2 - ox);
+        bool hit = false;
+        if (lane < LG_SE_PRE)
+            hit = bits_any(bits, wpr, bw, bh, pv + lane - LG_SE_PRE / 2 - oy, pu + c.se31_a[lane] - LG_SE_PRE / 2 - ox,
+                           pu + c.se31_b[lane] - LG_SE_PRE / 2 - ox);
+        const bool blocked = __any_sync(0xFFFFFFFFu, hit);
         if (!blocked) {
             const double e0 = t0 - X, e1 = t1 - Y;
-            if (sqrt(e0 * e0 + e1 * e1 + 0.0) >= 0.05) {
-                res->pre_grasp[0] = t0; res->pre_grasp[1] = t1; res->pre_grasp[2] = z;
-                found = true;
-            }
+            if (sqrt(e0 * e0 + e1 * e1 + 0.0) >= 0.05) { p0 = t0; p1 = t1; found = true; }
         }
     }
-    if (!found) {
-        res->pre_grasp[0] = X - d0 * 0.10; res->pre_grasp[1] = Y - d1 * 0.10; res->pre_grasp[2] = z;
+    if (!found) { p0 = X - d0 * 0.10; p1 = Y - d1 * 0.10; }
+    if (lane == 0) {
+        res->best_index = best; res->best_score = best_score; res->ml_used = ml_used;
+        res->grasp_x = u; res->grasp_y = v;
+        res->grasp_3d[0] = X; res->grasp_3d[1] = Y; res->grasp_3d[2] = z;
+        res->pre_grasp[0] = p0; res->pre_grasp[1] = p1; res->pre_grasp[2] = z;
     }
 }
 
@@ -705,7 +725,7 @@ int lg_run_export_patches(lg_context* c, float* out, int n, cudaStream_t st) {
 
 int lg_run_fuse(lg_context* c, LgMaskSrc src, const float* depth, int n, lg_camera cam, int have_ml, lg_frame_result* out,
                 cudaStream_t st) {
-    fuse_kernel<<<(n + 63) / 64, 64, 0, st>>>(*c, src, depth, cam, have_ml, n);
+    fuse_kernel<<<n, 32, 0, st>>>(*c, src, depth, cam, have_ml, n);
     LG_LAUNCH_CHECK();
     if (out && out != c->results)
         LG_CUDA(cudaMemcpyAsync(out, c->results, sizeof(lg_frame_result) * n, cudaMemcpyDeviceToDevice, st));

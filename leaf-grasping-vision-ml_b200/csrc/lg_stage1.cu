@@ -836,10 +836,12 @@ struct SelScratch {   // per label, in shared memory
     int cand;
 };
 
-__global__ void select_leaf_kernel(lg_context c, lg_camera cam, int32_t* leaf_out, lg_leaf_record* rec_out) {
+// One warp per frame: lanes take the labels (record reset, id list), then the leaves (scores, Pareto test); the two
+// order-sensitive steps keep the reference's order - numpy's pairwise sum of the medians on one lane, and "first maximum
+// wins" for the weighted pick (smallest list position among equal scores).
+__global__ void __launch_bounds__(32) select_leaf_kernel(lg_context c, lg_camera cam, int32_t* leaf_out, lg_leaf_record* rec_out) {
     extern __shared__ unsigned char sraw[];
-    const int b = blockIdx.x, L = c.L, W = c.W, H = c.H;
-    if (threadIdx.x != 0) return;
+    const int b = blockIdx.x, L = c.L, W = c.W, H = c.H, lane = threadIdx.x;
     SelScratch* s = reinterpret_cast<SelScratch*>(sraw);
     float* meds = reinterpret_cast<float*>(sraw + sizeof(SelScratch) * L);
     const size_t o = (size_t)b * L;
@@ -847,30 +849,39 @@ __global__ void select_leaf_kernel(lg_context c, lg_camera cam, int32_t* leaf_ou
     LgRegion reg;
     reg.x0 = reg.y0 = reg.x1 = reg.y1 = 0; reg.ok = 0; reg.sx0 = reg.sy0 = reg.sx1 = reg.sy1 = 0;
     int best_id = -1;
-    const int bg = background_id(cnt, L);
-    int n_ids = 0;
-    for (int l = 0; l < L; ++l) {
-        if (rec_out) {
+    // background = the smallest id present; the other ids present, in ascending order
+    int bg = -1, n_ids = 0;
+    for (int l0 = 0; l0 < L; l0 += 32) {
+        const int l = l0 + lane;
+        const bool present = l < L && cnt[l] != 0;
+        unsigned m = __ballot_sync(0xFFFFFFFFu, present);
+        if (bg < 0 && m) { bg = l0 + __ffs(m) - 1; m &= m - 1; }      // the background is not listed
+        const bool listed = present && l != bg;
+        if (rec_out && l < L) {                                        // listed leaves are overwritten below
             lg_leaf_record r;
             memset(&r, 0, sizeof(r));
             r.leaf_id = l;
             rec_out[o + l] = r;
         }
-        if (cnt[l] && l != bg) {
-            s[n_ids].id = l;
-            s[n_ids].med = c.median[o + l];
-            meds[n_ids] = s[n_ids].med;
-            ++n_ids;
+        if (listed) {
+            const int k = n_ids + __popc(m & ((1u << lane) - 1u));
+            s[k].id = l;
+            s[k].med = c.median[o + l];
+            meds[k] = s[k].med;
         }
+        n_ids += __popc(m);
     }
+    __syncwarp();
     if (n_ids > 0 && !(c.status[b] & LG_ST_LABEL_RANGE)) {
-        const float mean_med = __fdiv_rn(np_pairwise_sum_f32(meds, n_ids), (float)n_ids);
+        float mean_med = 0.f;
+        if (lane == 0) mean_med = __fdiv_rn(np_pairwise_sum_f32(meds, n_ids), (float)n_ids);
+        mean_med = __shfl_sync(0xFFFFFFFFu, mean_med, 0);
         const unsigned fl = c.first_leaf[b];
         const double pmin_x = (double)(fl % W), pmin_y = (double)(fl / W);
         const unsigned far = 0xFFFFFFFFu - (unsigned)(c.edt_best[b] & 0xFFFFFFFFull);
         const double pmax_x = (double)(far % W), pmax_y = (double)(far / W);
         int n_tall_c = 0, n_c = 0;
-        for (int k = 0; k < n_ids; ++k) {
+        for (int k = lane; k < n_ids; k += 32) {
             const int l = s[k].id;
             s[k].tall = s[k].med < mean_med;
             s[k].cand = 0;
@@ -903,11 +914,18 @@ __global__ void select_leaf_kernel(lg_context c, lg_camera cam, int32_t* leaf_ou
             }
             if (rec_out) rec_out[o + l] = r;
         }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            n_c += __shfl_xor_sync(0xFFFFFFFFu, n_c, d);
+            n_tall_c += __shfl_xor_sync(0xFFFFFFFFu, n_tall_c, d);
+        }
+        __syncwarp();
         if (n_c > 0) {
             const int want_tall = n_tall_c > 0;
             const double scale = want_tall ? 1.1 : 1.0;
             double best_score = -CUDART_INF;
-            for (int i = 0; i < n_ids; ++i) {
+            int best_k = 0x7FFFFFFF;
+            for (int i = lane; i < n_ids; i += 32) {          // ascending i per lane: a later equal score never replaces
                 if (!s[i].cand || (want_tall && !s[i].tall)) continue;
                 const double a0 = s[i].s0 * scale, a1 = s[i].s1 * scale, a2 = s[i].s2 * scale;
                 bool dominated = false;
@@ -920,10 +938,18 @@ __global__ void select_leaf_kernel(lg_context c, lg_camera cam, int32_t* leaf_ou
                 }
                 if (dominated) continue;
                 const double w = ((0.0 + 0.35 * s[i].s0) + 0.35 * s[i].s1) + 0.3 * s[i].s2;
-                if (w > best_score) { best_score = w; best_id = s[i].id; }
+                if (w > best_score) { best_score = w; best_k = i; }
             }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {                // maximum score, smallest list position among equals
+                const double os = __shfl_xor_sync(0xFFFFFFFFu, best_score, d);
+                const int ok = __shfl_xor_sync(0xFFFFFFFFu, best_k, d);
+                if (os > best_score || (os == best_score && ok < best_k)) { best_score = os; best_k = ok; }
+            }
+            if (best_k != 0x7FFFFFFF) best_id = s[best_k].id;
         }
     }
+    if (lane != 0) return;
     if (best_id >= 0) {
         reg.x0 = (int)c.bx0[o + best_id]; reg.x1 = (int)c.bx1[o + best_id] + 1;
         reg.y0 = (int)c.by0[o + best_id]; reg.y1 = (int)c.by1[o + best_id] + 1;
