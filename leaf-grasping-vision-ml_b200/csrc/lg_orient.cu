@@ -32,36 +32,57 @@ static_assert((size_t)OR_S_ROWS * 40 <= (size_t)OR_S_RUNS * 30, "hull points and
 struct Bits {
     const uint32_t* w;
     int wpr, bw, bh;
-    __device__ __forceinline__ int get(int lx, int ly) const {
-        if (lx < 0 || ly < 0 || lx >= bw || ly >= bh) return 0;
-        return (w[ly * wpr + (lx >> 5)] >> (lx & 31)) & 1u;
-    }
 };
 
-__device__ int uf_find(int32_t* parent, int i) {
-    while (parent[i] != i) {
-        parent[i] = parent[parent[i]];
-        i = parent[i];
-    }
+// Lock-free union-find on run indices (shared or global memory).  Roots only ever decrease.
+__device__ __forceinline__ int uf_root(const int32_t* parent, int i) {
+    int p = ((const volatile int32_t*)parent)[i];
+    while (p != i) { i = p; p = ((const volatile int32_t*)parent)[i]; }
     return i;
 }
+__device__ void uf_union(int32_t* parent, int a, int b) {
+    while (true) {
+        a = uf_root(parent, a);
+        b = uf_root(parent, b);
+        if (a == b) return;
+        if (a < b) { const int t = a; a = b; b = t; }     // a > b: hang a under b
+        const int old = atomicMin(&parent[a], b);
+        if (old == a) return;                              // a was still a root
+        a = old;                                           // somebody re-parented a meanwhile: join that tree with b's
+    }
+}
 
-// |shoelace| * 2 of the outer border that starts at the raster-first pixel (sx, sy) of a component
+// bits (lx-1, lx, lx+1) of row ly as bits 0..2; pixels outside the bitmask read as 0
+__device__ __forceinline__ unsigned bits3(const Bits& B, int lx, int ly) {
+    if (ly < 0 || ly >= B.bh) return 0u;
+    const uint32_t* row = B.w + ly * B.wpr;
+    const int x0 = lx - 1, wi = x0 >> 5, o = x0 & 31;                 // x0 = -1 -> wi = -1, o = 31
+    const uint32_t lo = (wi >= 0 && wi < B.wpr) ? row[wi] : 0u;
+    const uint32_t hi = (o > 29 && wi + 1 >= 0 && wi + 1 < B.wpr) ? row[wi + 1] : 0u;
+    return __funnelshift_r(lo, hi, o) & 7u;
+}
+
+// |shoelace| * 2 of the outer border that starts at the raster-first pixel (sx, sy) of a component.
+// Moore tracing: from the current pixel the eight neighbours are examined clockwise, starting behind the direction
+// the trace arrived from.  The three rows around the pixel are fetched at once and folded into an 8-bit neighbour
+// mask (bit d = neighbour in direction d, 0 = east, clockwise in image coordinates), so that a step costs one round
+// of loads instead of up to eight dependent probes.
 __device__ long long trace_twice_area(const Bits& B, int sx, int sy) {
     const int DX[8] = {1, 1, 0, -1, -1, -1, 0, 1};
     const int DY[8] = {0, 1, 1, 1, 0, -1, -1, -1};
     int cx = sx, cy = sy, db = 4, first = -1;
     long long a00 = 0;
     for (long long guard = 0; guard < (1ll << 26); ++guard) {
-        int d = -1;
-        for (int k = 1; k <= 8; ++k) {
-            int dd = (db + k) & 7;
-            if (B.get(cx + DX[dd], cy + DY[dd])) { d = dd; break; }
-        }
-        if (d < 0) break;
+        const unsigned wm = bits3(B, cx, cy - 1), w0 = bits3(B, cx, cy), wp = bits3(B, cx, cy + 1);
+        const unsigned nb = ((w0 >> 2) & 1u) | (((wp >> 2) & 1u) << 1) | (((wp >> 1) & 1u) << 2) | ((wp & 1u) << 3) |
+                            ((w0 & 1u) << 4) | ((wm & 1u) << 5) | (((wm >> 1) & 1u) << 6) | (((wm >> 2) & 1u) << 7);
+        if (nb == 0) break;                                   // isolated pixel
+        const int r = (db + 1) & 7;
+        const unsigned rot = ((nb >> r) | (nb << (8 - r))) & 0xFFu;
+        const int d = (r + __ffs(rot) - 1) & 7;               // first set neighbour in the order db+1, db+2, ...
         if (cx == sx && cy == sy && first >= 0 && d == first) break;
         if (first < 0) first = d;
-        int nx = cx + DX[d], ny = cy + DY[d];
+        const int nx = cx + DX[d], ny = cy + DY[d];
         a00 += (long long)cx * ny - (long long)nx * cy;
         cx = nx; cy = ny;
         db = (d + ((d & 1) ? 5 : 6)) & 7;
@@ -74,7 +95,18 @@ struct RectOut {
 };
 
 // OpenCV rotatingCalipers(CALIPERS_MINAREARECT) + the tail of cv::minAreaRect, float32, no FMA.
-__device__ RectOut min_area_rect(const int32_t* hull, int n, float* vx, float* vy, float* inv) {
+// edge i = hull[i] -> hull[i + 1] (the whole CTA takes part)
+__device__ void rect_edges(const int32_t* hull, int n, float* vx, float* vy, float* inv) {
+    for (int i = threadIdx.x; i < n; i += OR_NT) {
+        const int j = (i + 1 < n) ? i + 1 : 0;
+        const double dx = (double)(float)hull[2 * j] - (double)(float)hull[2 * i];
+        const double dy = (double)(float)hull[2 * j + 1] - (double)(float)hull[2 * i + 1];
+        vx[i] = (float)dx; vy[i] = (float)dy;
+        inv[i] = (float)(1.0 / sqrt(dx * dx + dy * dy));
+    }
+}
+
+__device__ RectOut min_area_rect(const int32_t* hull, int n, const float* vx, const float* vy, const float* inv) {
     RectOut R;
     R.cx = R.cy = R.w = R.h = R.angle_deg = 0.f;
     if (n == 1) { R.cx = (float)hull[0]; R.cy = (float)hull[1]; return R; }
@@ -91,17 +123,12 @@ __device__ RectOut min_area_rect(const int32_t* hull, int n, float* vx, float* v
     int left = 0, bottom = 0, right = 0, top = 0;
     float px0 = (float)hull[0], py0 = (float)hull[1];
     float left_x = px0, right_x = px0, top_y = py0, bottom_y = py0;
-    for (int i = 0; i < n; ++i) {
+    for (int i = 0; i < n; ++i) {          // vx, vy, inv: edge vectors and inverse lengths, filled by rect_edges
+        px0 = (float)hull[2 * i]; py0 = (float)hull[2 * i + 1];
         if (px0 < left_x) { left_x = px0; left = i; }
         if (px0 > right_x) { right_x = px0; right = i; }
         if (py0 > top_y) { top_y = py0; top = i; }
         if (py0 < bottom_y) { bottom_y = py0; bottom = i; }
-        int j = (i + 1 < n) ? i + 1 : 0;
-        float qx = (float)hull[2 * j], qy = (float)hull[2 * j + 1];
-        double dx = (double)qx - (double)px0, dy = (double)qy - (double)py0;
-        vx[i] = (float)dx; vy[i] = (float)dy;
-        inv[i] = (float)(1.0 / sqrt(dx * dx + dy * dy));
-        px0 = qx; py0 = qy;
     }
     float orientation = 0.f;
     {
@@ -169,6 +196,7 @@ __global__ void __launch_bounds__(OR_NT) orient_kernel(lg_context c, LgMaskSrc s
     const LgRegion r = c.region[b];
     LgOrient* out = &c.orient[b];
     __shared__ int s_total, s_win, s_ytop, s_ybot, s_fail, s_wlx, s_wly;
+    __shared__ int s_redp[OR_NT / 32], s_redi[OR_NT / 32], s_nborder, s_big;
     if (!r.ok) {
         if (tid == 0) {
             LgOrient o;
@@ -208,6 +236,37 @@ __global__ void __launch_bounds__(OR_NT) orient_kernel(lg_context c, LgMaskSrc s
     __syncthreads();
     if (bits_in_smem) bits = s_bits;
     Bits B{bits, wpr, bw, bh};
+    // Number of leaf pixels with a background pixel among their 8 neighbours (all components together).  Every pixel of
+    // a component that is not such a border pixel lies strictly inside the component's outer contour, so
+    // 2 * (pixels of the component - border pixels) bounds twice the contour area from below (Pick's theorem), which
+    // usually decides the largest-contour question without tracing anything (step 6).
+    {
+        int nbp = 0;
+        for (int i = tid; i < bh * wpr; i += OR_NT) {
+            const int ly = i / wpr, wi = i - ly * wpr;
+            const uint32_t m = bits[i];
+            if (!m) continue;
+            uint32_t inner = 0xFFFFFFFFu;
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy) {
+                const int yy = ly + dy;
+                uint32_t c0 = 0, l0 = 0, r0 = 0;
+                if (yy >= 0 && yy < bh) {
+                    const uint32_t* row = bits + yy * wpr;
+                    c0 = row[wi];
+                    l0 = wi > 0 ? row[wi - 1] : 0u;
+                    r0 = wi + 1 < wpr ? row[wi + 1] : 0u;
+                }
+                inner &= c0 & ((c0 << 1) | (l0 >> 31)) & ((c0 >> 1) | (r0 << 31));
+            }
+            nbp += __popc(m & ~inner);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) nbp += __shfl_xor_sync(0xFFFFFFFFu, nbp, d);
+        if ((tid & 31) == 0) s_redp[tid >> 5] = nbp;
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int w = 0; w < OR_NT / 32; ++w) t += s_redp[w]; s_nborder = t; }
+    }
     int32_t* row_first = (bh + 1 <= OR_S_ROWF) ? s_rowf : c.row_first + (size_t)b * (H + 3);
     // 2. runs per row
     for (int ly = tid; ly < bh; ly += OR_NT) {
@@ -277,46 +336,75 @@ __global__ void __launch_bounds__(OR_NT) orient_kernel(lg_context c, LgMaskSrc s
         }
         if (open) { rx0[o] = (uint16_t)start; rx1[o] = (uint16_t)(bw - 1); ry[o] = (uint16_t)ly; ++o; }
     }
-    for (int i = tid; i < total; i += OR_NT) { parent[i] = i; cpix[i] = 0; }
+    for (int i = tid; i < total; i += OR_NT) {
+        parent[i] = i; cpix[i] = 0; cx0[i] = 0x7FFFFFFF; cx1[i] = -1; cy0[i] = 0x7FFFFFFF; cy1[i] = -1;
+    }
     __syncthreads();
-    // 4..6 serial: components, contour areas, winner
-    if (tid == 0) {
-        for (int ly = 1; ly < bh; ++ly) {
-            int i = row_first[ly], iend = row_first[ly + 1];
-            int j = row_first[ly - 1], jend = row_first[ly];
-            while (i < iend && j < jend) {
-                if ((int)rx1[j] + 1 < (int)rx0[i]) ++j;
-                else if ((int)rx1[i] + 1 < (int)rx0[j]) ++i;
-                else {
-                    int ra = uf_find(parent, i), rb = uf_find(parent, j);
-                    if (ra < rb) parent[rb] = ra; else if (rb < ra) parent[ra] = rb;
-                    if (rx1[j] < rx1[i]) ++j; else ++i;
-                }
-            }
-        }
-        int big = -1;
-        for (int i = 0; i < total; ++i) {
-            int root = uf_find(parent, i);
-            parent[i] = root;
-            int len = (int)rx1[i] - (int)rx0[i] + 1;
-            if (cpix[root] == 0) { cx0[root] = rx0[i]; cx1[root] = rx1[i]; cy0[root] = ry[i]; cy1[root] = ry[i]; }
+    // 4. components: one thread per row links the runs of its row with the touching runs of the row above (lock-free
+    //    union-find, the smaller run index becomes the root: a component's root is its raster-first run)
+    for (int ly = 1 + tid; ly < bh; ly += OR_NT) {
+        int i = row_first[ly], iend = row_first[ly + 1];
+        int j = row_first[ly - 1], jend = row_first[ly];
+        while (i < iend && j < jend) {
+            if ((int)rx1[j] + 1 < (int)rx0[i]) ++j;
+            else if ((int)rx1[i] + 1 < (int)rx0[j]) ++i;
             else {
-                cx0[root] = min(cx0[root], (int)rx0[i]); cx1[root] = max(cx1[root], (int)rx1[i]);
-                cy1[root] = ry[i];
+                uf_union(parent, i, j);
+                if (rx1[j] < rx1[i]) ++j; else ++i;
             }
-            cpix[root] += len;
         }
-        for (int i = 0; i < total; ++i)
-            if (parent[i] == i && (big < 0 || cpix[i] > cpix[big])) big = i;
-        long long best_a = trace_twice_area(B, rx0[big], ry[big]);
+    }
+    __syncthreads();
+    for (int i = tid; i < total; i += OR_NT) parent[i] = uf_root(parent, i);     // a write only ever shortens a path
+    __syncthreads();
+    // 5. per-component pixel count and bounding box (integer atomics: order independent)
+    for (int i = tid; i < total; i += OR_NT) {
+        const int root = parent[i];
+        atomicAdd(&cpix[root], (int)rx1[i] - (int)rx0[i] + 1);
+        atomicMin(&cx0[root], (int)rx0[i]); atomicMax(&cx1[root], (int)rx1[i]);
+        atomicMin(&cy0[root], (int)ry[i]); atomicMax(&cy1[root], (int)ry[i]);
+    }
+    __syncthreads();
+    // the component with most pixels, the first one among equals
+    {
+        int bp = -1, bi = 0x7FFFFFFF;
+        for (int i = tid; i < total; i += OR_NT)
+            if (parent[i] == i && cpix[i] > bp) { bp = cpix[i]; bi = i; }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const int op = __shfl_xor_sync(0xFFFFFFFFu, bp, d), oi = __shfl_xor_sync(0xFFFFFFFFu, bi, d);
+            if (op > bp || (op == bp && oi < bi)) { bp = op; bi = oi; }
+        }
+        if ((tid & 31) == 0) { s_redp[tid >> 5] = bp; s_redi[tid >> 5] = bi; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int bp = s_redp[0], big = s_redi[0];
+        for (int w = 1; w < OR_NT / 32; ++w)
+            if (s_redp[w] > bp || (s_redp[w] == bp && s_redi[w] < big)) { bp = s_redp[w]; big = s_redi[w]; }
+        s_big = big;
+    }
+    __syncthreads();
+    // 6. winner = outer contour of largest polygon area.  A component whose bounding box cannot hold the lower bound
+    //    of the biggest component's area is out; only if some component survives that test are contours traced (serial).
+    const int big = s_big;
+    const long long area_lb = 2ll * ((long long)cpix[big] - (long long)s_nborder);
+    int contender = 0;
+    for (int i = tid; i < total; i += OR_NT)
+        if (parent[i] == i && i != big && 2ll * (cx1[i] - cx0[i]) * (cy1[i] - cy0[i]) >= area_lb) contender = 1;
+    contender = __syncthreads_or(contender);
+    if (tid == 0) {
         int win = big;
-        for (int i = 0; i < total; ++i) {
-            if (parent[i] != i || i == big) continue;
-            long long bound = 2ll * (cx1[i] - cx0[i]) * (cy1[i] - cy0[i]);   // twice the bbox polygon area
-            if (bound < best_a) continue;
-            long long a = trace_twice_area(B, rx0[i], ry[i]);
-            // cv2 lists contours last-found first and max() keeps the first maximum: ties go to the later start
-            if (a > best_a || (a == best_a && i > win)) { best_a = a; win = i; }
+        if (contender) {
+            long long best_a = trace_twice_area(B, rx0[big], ry[big]);
+            for (int i = 0; i < total; ++i) {
+                if (parent[i] != i || i == big) continue;
+                long long bound = 2ll * (cx1[i] - cx0[i]) * (cy1[i] - cy0[i]);   // twice the bbox polygon area
+                if (bound < best_a) continue;
+                long long a = trace_twice_area(B, rx0[i], ry[i]);
+                // cv2 lists contours last-found first and max() keeps the first maximum: ties go to the later start
+                if (a > best_a || (a == best_a && i > win)) { best_a = a; win = i; }
+            }
         }
         s_win = win; s_ytop = cy0[win]; s_ybot = cy1[win]; s_wlx = rx0[win]; s_wly = ry[win];
     }
@@ -360,7 +448,14 @@ __global__ void __launch_bounds__(OR_NT) orient_kernel(lg_context c, LgMaskSrc s
         if (nh > 1 && hull[2 * (nh - 1)] == hull[0] && hull[2 * (nh - 1) + 1] == hull[1]) --nh;
         // the closing turn at the start vertex can still be flat: drop a last point collinear with it
         while (nh >= 3 && crossz(hull[2 * (nh - 2)], hull[2 * (nh - 2) + 1], hull[2 * (nh - 1)], hull[2 * (nh - 1) + 1], hull[0], hull[1]) >= 0) --nh;
-        float* fs = hull_in_smem ? reinterpret_cast<float*>(hull + 4 * OR_S_ROWS) : reinterpret_cast<float*>(hull + 6 * (H + 2));
+        s_total = nh;
+    }
+    __syncthreads();
+    const int nh = s_total;
+    float* fs = hull_in_smem ? reinterpret_cast<float*>(hull + 4 * OR_S_ROWS) : reinterpret_cast<float*>(hull + 6 * (H + 2));
+    if (nh >= 3) rect_edges(hull, nh, fs, fs + nh, fs + 2 * nh);
+    __syncthreads();
+    if (tid == 0) {
         RectOut R = min_area_rect(hull, nh, fs, fs + nh, fs + 2 * nh);
         double ang = (double)R.angle_deg;
         if (R.w < R.h) ang = ang + 90.0;
