@@ -268,6 +268,44 @@ def test_orientation_against_opencv():
     eng.close()
 
 
+def test_orientation_largest_contour_rules():
+    """Which component wins (cv2: max contourArea over the external contours, first maximum in cv2's list order), on
+    masks where pixel count and contour area disagree: the kernel skips the border trace when a lower bound of the
+    biggest component's contour area already exceeds every other component's bounding box, and traces otherwise."""
+    H, W = 240, 320
+    masks = []
+    m = np.zeros((H, W), np.uint8)                       # ring (few pixels, large contour) vs solid disc (more pixels)
+    cv2.circle(m, (90, 120), 70, 1, 6); cv2.circle(m, (240, 120), 40, 1, -1); masks.append(m)
+    m = np.zeros((H, W), np.uint8)                       # two identical rectangles: equal areas, the later start wins
+    m[30:90, 40:140] = 1; m[130:190, 170:270] = 1; masks.append(m)
+    m = np.zeros((H, W), np.uint8)                       # the same with the first one a pixel larger
+    m[30:91, 40:140] = 1; m[130:190, 170:270] = 1; masks.append(m)
+    m = np.zeros((H, W), np.uint8)                       # one big leaf and specks: no trace needed
+    cv2.ellipse(m, (160, 120), (120, 60), 25.0, 0, 360, 1, -1)
+    for (x, y) in ((5, 5), (300, 20), (20, 220), (310, 230), (160, 5)):
+        m[y:y + 2, x:x + 3] = 1
+    masks.append(m)
+    m = np.zeros((H, W), np.uint8)                       # thin diagonal line (area 0) and a small blob
+    for t in range(150):
+        m[20 + t, 30 + t] = 1
+    m[200:206, 250:258] = 1; masks.append(m)
+    m = np.zeros((H, W), np.uint8); m[100, 100] = 1; masks.append(m)            # a single pixel
+    m = np.zeros((H, W), np.uint8); m[0:H, 0:50] = 1; m[0:40, 0:W] = 1; masks.append(m)   # L-shape along the image border
+    m = np.zeros((H, W), np.uint8)                       # comb: many pixels on the border, tiny interior
+    m[60:180:2, 40:280] = 1; m[60:180, 40:42] = 1; cv2.circle(m, (160, 215), 18, 1, -1); masks.append(m)
+    m = np.zeros((H, W), np.uint8)                       # two rings, nested bounding boxes
+    cv2.circle(m, (160, 120), 100, 1, 3); cv2.circle(m, (160, 120), 60, 1, 3); masks.append(m)
+    masks = np.stack(masks)
+    eng = _engine(len(masks), H, W, 2)
+    out = eng.leaf_orientation(torch.from_numpy(masks)).cpu().numpy()
+    for k, m in enumerate(masks):
+        ang_re = O.leaf_orientation_restated(m)
+        assert out[k, 0] == ang_re[0], (k, out[k, 0], ang_re[0])
+        np.testing.assert_allclose(out[k, 1:3], [ang_re[1], ang_re[2]], rtol=1e-6, err_msg=f"mask {k}")
+        np.testing.assert_allclose(out[k, 3:5], ang_re[3], rtol=1e-6, atol=1e-4, err_msg=f"mask {k}")
+    eng.close()
+
+
 # ------------------------------------------------------------------------------------------------------
 # CNN
 # ------------------------------------------------------------------------------------------------------
