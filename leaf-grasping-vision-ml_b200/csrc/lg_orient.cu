@@ -225,9 +225,12 @@ __global__ void __launch_bounds__(OR_NT) orient_kernel(lg_context c, LgMaskSrc s
         const int y = oy + ly;
         uint32_t word = 0;
         if (y >= r.y0 && y < r.y1) {
-            for (int k = 0; k < 32; ++k) {
+            const size_t rowo = (size_t)y * W;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {     // loads from clamped addresses, so that all 32 are in flight together
                 const int x = ox + wi * 32 + k;
-                if (x >= r.x0 && x < r.x1 && src.at(fo, (size_t)y * W + x, id)) word |= 1u << k;
+                const bool ok = x >= r.x0 && x < r.x1;
+                word |= (uint32_t)(src.at(fo, rowo + (ok ? x : r.x0), id) && ok) << k;
             }
         }
         bits[i] = word;
