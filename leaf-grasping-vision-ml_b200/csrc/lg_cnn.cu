@@ -110,7 +110,11 @@ __global__ void __launch_bounds__(CV_NT) conv3x3_relu_kernel(ConvArgs A) {
 // then the four linear layers run for all of them together.
 constexpr int TL_NT = 256;
 constexpr int TL_PB = 8;
-__global__ void __launch_bounds__(TL_NT) cnn_tail_kernel(const float* __restrict__ feat, const float* __restrict__ blob_tail,
+// act != nullptr: the features come straight from the last tensor-core convolution instead - bf16, plane-major with
+// halo (8x8 pixels per patch on a 9x9 grid, `lead` zero rows in front, act_rows rows per plane of 8 channels) - and the
+// final 2x2 max-pool is taken while they are loaded.
+__global__ void __launch_bounds__(TL_NT) cnn_tail_kernel(const float* __restrict__ feat, const uint4* __restrict__ act,
+                                                          long long act_rows, int lead, const float* __restrict__ blob_tail,
                                                           float* __restrict__ logits, int n_host, const int32_t* __restrict__ n_dev) {
     const int n = n_dev ? min(*n_dev, n_host) : n_host;
     if ((int)blockIdx.x * TL_PB >= n) return;
@@ -131,9 +135,31 @@ __global__ void __launch_bounds__(TL_NT) cnn_tail_kernel(const float* __restrict
     const float* b3 = w3 + 64;
     for (int p = 0; p < TL_PB; ++p) {
         if (p >= np) { s_a[p][tid] = 0.f; continue; }
-        const float* f = feat + (size_t)(n0 + p) * 16 * 256;
         __syncthreads();
-        for (int i = tid; i < 16 * 256; i += TL_NT) s_f[i >> 8][i & 255] = f[i];
+        if (act) {
+            for (int i = tid; i < 16 * 32; i += TL_NT) {            // (pooled pixel, plane of 8 channels)
+                const int px = i >> 5, pl = i & 31;
+                const uint4* src = act + (long long)pl * act_rows + lead + (long long)(n0 + p) * 81 + (2 * (px >> 2) + 1) * 9 + 2 * (px & 3) + 1;
+                const uint4 q[4] = {src[0], src[1], src[9], src[10]};
+                float m[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) m[e] = 0.f;              // post-ReLU values: 0 is the identity of max
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t w[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        m[2 * e] = fmaxf(m[2 * e], __uint_as_float(w[e] << 16));
+                        m[2 * e + 1] = fmaxf(m[2 * e + 1], __uint_as_float(w[e] & 0xFFFF0000u));
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) s_f[px][pl * 8 + e] = m[e];
+            }
+        } else {
+            const float* f = feat + (size_t)(n0 + p) * 16 * 256;
+            for (int i = tid; i < 16 * 256; i += TL_NT) s_f[i >> 8][i & 255] = f[i];
+        }
         __syncthreads();
         {   // attention logit per pixel: 16 pixels x 256 channels, 16 threads per pixel
             const int px = tid >> 4, l = tid & 15;
@@ -370,7 +396,16 @@ int lg_run_cnn_bf16(lg_context* c, const float* patches, int n, const int32_t* n
 
 // attention + average + MLP on fp32 NHWC [n][4][4][256] features (shared by the fp32 and the bf16 conv paths)
 int lg_launch_cnn_tail(const float* feat, const float* blob_tail, float* logits, int n, const int32_t* n_dev, cudaStream_t st) {
-    cnn_tail_kernel<<<(n + TL_PB - 1) / TL_PB, TL_NT, 0, st>>>(feat, blob_tail, logits, n, n_dev);
+    cnn_tail_kernel<<<(n + TL_PB - 1) / TL_PB, TL_NT, 0, st>>>(feat, nullptr, 0, 0, blob_tail, logits, n, n_dev);
+    LG_LAUNCH_CHECK();
+    return LG_OK;
+}
+
+// the same on the bf16 output of the last tensor-core convolution (plane-major, 9x9 halo layout): pools while loading
+int lg_launch_cnn_tail_bf16(const void* act, long long act_rows, int lead, const float* blob_tail, float* logits, int n,
+                            const int32_t* n_dev, cudaStream_t st) {
+    cnn_tail_kernel<<<(n + TL_PB - 1) / TL_PB, TL_NT, 0, st>>>(nullptr, reinterpret_cast<const uint4*>(act), act_rows, lead,
+                                                                blob_tail, logits, n, n_dev);
     LG_LAUNCH_CHECK();
     return LG_OK;
 }

@@ -627,6 +627,8 @@ int launch_conv(const UmmaConvArgs& A, int S, int sms, cudaStream_t st) {
 
 uint64_t lg_cnn_blob_floats();
 int lg_launch_cnn_tail(const float* feat, const float* blob_tail, float* logits, int n, const int32_t* n_dev, cudaStream_t st);
+int lg_launch_cnn_tail_bf16(const void* act, long long act_rows, int lead, const float* blob_tail, float* logits, int n,
+                            const int32_t* n_dev, cudaStream_t st);
 
 // Pack the folded fp32 weights (cnn.py:pack_weights layout) into the bf16 operand layout; synchronous.
 int lg_cnn_prepare_bf16(lg_context* c) {
@@ -725,6 +727,7 @@ static int run_cnn_bf16(lg_context* c, const float* patches, int n, const int32_
             else rc = fused_pool ? launch_conv<8, 128, true>(A, L.S, sms, st) : launch_conv<8, 128, false>(A, L.S, sms, st);
             if (rc) return rc;
             cur ^= 1;
+            if (l == 5 && stop_layer != 5) break;   // the tail kernel pools the last layer's output while it loads it
             if ((l & 1) && !fused_pool) {   // max-pool after the second conv of each block
                 const int planes = L.cout / 8;
                 if (l == 5) {
@@ -751,7 +754,7 @@ static int run_cnn_bf16(lg_context* c, const float* patches, int n, const int32_
                 return LG_OK;
             }
         }
-        int rc = lg_launch_cnn_tail(reinterpret_cast<const float*>(buf[cur]), tail, logits + done, m, n_dev, st);
+        int rc = lg_launch_cnn_tail_bf16(buf[cur], rows_per_plane(8, m), LEAD, tail, logits + done, m, n_dev, st);
         if (rc) return rc;
     }
     return LG_OK;
