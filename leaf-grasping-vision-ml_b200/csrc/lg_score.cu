@@ -225,17 +225,20 @@ __global__ void __launch_bounds__(NMS_NT) nms_kernel(lg_context c, const double*
     const unsigned* idx = c.list_idx + fo;
     int cnt = 0;
     // rounds [cnt, 20) over the list (k, id)[0, m); suppressed entries are overwritten with -1
-    auto rounds = [&](double* k_, const unsigned* id_, unsigned m) {
+    // ids: flat pixel indices (the global list) or, PACKED, y << 16 | x (the shared-memory shortlist: no division per key
+    // and round); both order like the flat index, which breaks ties between equal keys
+    auto rounds = [&](double* k_, const unsigned* id_, unsigned m, const bool packed) {
         for (int it = cnt; it < LG_TOP_K; ++it) {
             double bk = -1.0;
             unsigned bi = 0;
+            const int qx = it > 0 ? px[it - 1] : 0, qy = it > 0 ? py[it - 1] : 0;
             for (unsigned i = tid; i < m; i += NMS_NT) {
                 const double k = k_[i];
                 if (!(k > 0.0)) continue;
                 const unsigned id = id_[i];
                 if (it > 0) {
-                    const int x = (int)(id % W), y = (int)(id / W);
-                    if (abs(x - px[it - 1]) <= LG_NMS_REACH && abs(y - py[it - 1]) <= LG_NMS_REACH) { k_[i] = -1.0; continue; }
+                    const int x = packed ? (int)(id & 0xFFFFu) : (int)(id % W), y = packed ? (int)(id >> 16) : (int)(id / W);
+                    if (abs(x - qx) <= LG_NMS_REACH && abs(y - qy) <= LG_NMS_REACH) { k_[i] = -1.0; continue; }
                 }
                 if (k > bk || (k == bk && id > bi)) { bk = k; bi = id; }
             }
@@ -247,13 +250,20 @@ __global__ void __launch_bounds__(NMS_NT) nms_kernel(lg_context c, const double*
             }
             if (lane == 0) { wk[tid >> 5] = bk; wi[tid >> 5] = bi; }
             __syncthreads();
-            if (tid == 0) {
-                for (int w = 1; w < NMS_NT / 32; ++w)
-                    if (wk[w] > bk || (wk[w] == bk && wi[w] > bi)) { bk = wk[w]; bi = wi[w]; }
-                s_found = bk > 0.0;
-                if (s_found) {
-                    px[it] = (int)(bi % W); py[it] = (int)(bi / W);
-                    res->cand_x[it] = px[it]; res->cand_y[it] = py[it]; res->trad[it] = bk;
+            if (tid < 32) {      // second level: one warp over the per-warp winners
+                bk = wk[lane]; bi = wi[lane];
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    const double ok = __shfl_xor_sync(0xFFFFFFFFu, bk, d);
+                    const unsigned oi = __shfl_xor_sync(0xFFFFFFFFu, bi, d);
+                    if (ok > bk || (ok == bk && oi > bi)) { bk = ok; bi = oi; }
+                }
+                if (tid == 0) {
+                    s_found = bk > 0.0;
+                    if (s_found) {
+                        px[it] = packed ? (int)(bi & 0xFFFFu) : (int)(bi % W); py[it] = packed ? (int)(bi >> 16) : (int)(bi / W);
+                        res->cand_x[it] = px[it]; res->cand_y[it] = py[it]; res->trad[it] = bk;
+                    }
                 }
             }
             __syncthreads();
@@ -261,10 +271,11 @@ __global__ void __launch_bounds__(NMS_NT) nms_kernel(lg_context c, const double*
             ++cnt;
         }
     };
+    auto pack_id = [&](unsigned id) { return ((id / (unsigned)W) << 16) | (id % (unsigned)W); };
     if (n <= (unsigned)NMS_SUB) {
-        for (unsigned i = tid; i < n; i += NMS_NT) { skey[i] = key[i]; sidx[i] = idx[i]; }
+        for (unsigned i = tid; i < n; i += NMS_NT) { skey[i] = key[i]; sidx[i] = pack_id(idx[i]); }
         __syncthreads();
-        rounds(skey, sidx, n);
+        rounds(skey, sidx, n, true);
     } else {
         // shortlist, rounds, and - if the shortlist ran dry before 20 picks - a new shortlist from what is left
         for (int build = 0; cnt < LG_TOP_K; ++build) {
@@ -317,7 +328,7 @@ __global__ void __launch_bounds__(NMS_NT) nms_kernel(lg_context c, const double*
             const int tb = s_tb;
             const unsigned total = s_total;
             if (total == 0u) break;                                          // nothing left to pick from
-            if (tb < 0) { rounds(key, idx, n); break; }                      // degenerate key distribution: plain search
+            if (tb < 0) { rounds(key, idx, n, false); break; }                      // degenerate key distribution: plain search
             for (unsigned i0 = 0; i0 < n; i0 += NMS_NT) {
                 const unsigned i = i0 + tid;
                 double k = -1.0;
@@ -329,13 +340,13 @@ __global__ void __launch_bounds__(NMS_NT) nms_kernel(lg_context c, const double*
                     if (lane == 0) base = atomicAdd(&s_m, __popc(ball));
                     base = __shfl_sync(0xFFFFFFFFu, base, 0);
                     const unsigned pos = base + __popc(ball & ((1u << lane) - 1u));
-                    if (take && pos < (unsigned)NMS_SUB) { skey[pos] = k; sidx[pos] = idx[i]; }
+                    if (take && pos < (unsigned)NMS_SUB) { skey[pos] = k; sidx[pos] = pack_id(idx[i]); }
                 }
             }
             __syncthreads();
             const unsigned m = s_m;
             // the first round of this call must not apply the "previous pick" test to stale data: the list is up to date
-            rounds(skey, sidx, m);
+            rounds(skey, sidx, m, true);
             if (m == total) break;                                           // the shortlist was everything that is left
             __syncthreads();
         }
