@@ -387,6 +387,7 @@ __global__ void __launch_bounds__(MED_NT) leaf_median_kernel(lg_context c) {
     __shared__ unsigned sm[MED_NT / 32 * 3];
     extern __shared__ unsigned s_keys[];     // [MED_CAP]
     __shared__ unsigned s_n;
+    __shared__ unsigned s_hist[256], s_sel[3];
     __shared__ int s_bg;
     if (threadIdx.x == 0) { s_bg = background_id(cnt, L); s_n = 0; }
     __syncthreads();
@@ -431,6 +432,47 @@ __global__ void __launch_bounds__(MED_NT) leaf_median_kernel(lg_context c) {
         unsigned pmask = shift >= 30 ? 0u : ~((4u << shift) - 1u);
         unsigned prefix = 0u;
         if (n <= MED_CAP) { compact(prefix, pmask); in_smem = true; set_below = 0; set_m = n; }
+        else {
+            // Segments that do not fit: the first pass over the segment resolves the top 7-8 bits of the range at once
+            // (a 256-bin histogram in shared memory), which normally leaves few enough candidates to compact them in
+            // the second pass; two-bit digits would stream the segment once per factor of four.
+            int s0 = max(top - 7, 0);
+            s0 += s0 & 1;                                      // even, so that the two-bit rounds end at bit 0
+            for (int i = threadIdx.x; i < 256; i += MED_NT) s_hist[i] = 0;
+            __syncthreads();
+            for (unsigned i = threadIdx.x; i < n; i += MED_NT) atomicAdd(&s_hist[(f2key(v[i]) - kmin) >> s0], 1u);
+            __syncthreads();
+            if (threadIdx.x < 32) {                            // the bin that holds rank k_lo
+                unsigned mine = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) mine += s_hist[8 * lane + j];
+                unsigned incl = mine;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const unsigned t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                const unsigned excl = incl - mine;
+                if (k_lo >= excl && k_lo < incl) {
+                    unsigned acc = excl;
+                    for (int j = 0; j < 8; ++j) {
+                        const unsigned h = s_hist[8 * lane + j];
+                        if (k_lo < acc + h) { s_sel[0] = 8u * lane + j; s_sel[1] = acc; s_sel[2] = h; break; }
+                        acc += h;
+                    }
+                }
+            }
+            __syncthreads();
+            prefix = s_sel[0] << s0;
+            below = s_sel[1];
+            m = s_sel[2];
+            pmask = s0 == 0 ? 0xFFFFFFFFu : ~((1u << s0) - 1u);
+            shift = s0 - 2;
+            if (m <= MED_CAP && s0 > 0) {
+                compact(prefix, pmask);
+                in_smem = true; set_below = below; set_m = m;
+            }
+        }
         for (; shift >= 0; shift -= 2) {
             unsigned c0 = 0, c1 = 0, c2 = 0;
             if (in_smem) {
