@@ -233,3 +233,29 @@ def test_collector_host_class_end_to_end(tmp_path):
     # a grasp point too close to the border gives nothing (data_collector.py:83-89)
     assert not col.collect_sample(torch.from_numpy(mask.astype(bool)).cuda(), torch.from_numpy(dep).cuda(), None, {},
                                   (5, 100), 0.5)
+
+
+def test_collector_full_size_frames():
+    """The metric's frame size (1440x1080, 30 leaves): samples of two frames of a batch against the oracle."""
+    spec, n = synth.CFG2, 2
+    lab, dep = synth.make_batch(spec, CU.CC.CONFIG_SEED, 0, n)
+    P = synth.projection_matrix(spec)
+    f, cx, cy = P[0, 0], P[0, 2], P[1, 2]
+    eng = _engine(n, spec.height, spec.width)
+    lt, dt = torch.from_numpy(lab).cuda(), torch.from_numpy(dep).cuda()
+    res = eng.process_batch(lt, dt, _cam(P))
+    patches, meta, sizes = eng.collect_samples(dt, labels=lt, seed=9, first_frame_index=7)
+    patches = patches.cpu().numpy()
+    for b in range(n):
+        assert res["leaf_id"][b] >= 0 and res["n_candidates"][b] > 0
+        mask = (lab[b] == res["leaf_id"][b]).astype(np.uint8)
+        s = O.score_maps(mask, dep[b], f, cx, cy, "strict")
+        g = (int(res["grasp_x"][b]), int(res["grasp_y"][b]))
+        want = O.collect_sample(mask, dep[b], s, g, float(np.max(s["traditional_score"])), O.CollectorRng(9, 7 + b))
+        assert sizes[b].tolist() == [len(O.collector_tip_points(mask)), len(O.collector_stem_points(mask)),
+                                     len(O.collector_edge_points(mask))]
+        valid = [k for k in range(N.SAMPLES_PER_FRAME) if meta[b, k]["valid"]]
+        assert want is not None and len(valid) == len(want)
+        for k, w in zip(valid, want):
+            assert (int(meta[b, k]["x"]), int(meta[b, k]["y"])) == tuple(w["grasp_point"])
+            _check_patch(patches[b, k], w["patch"], bool(w["is_augmented"]), f"frame {b} slot {k}")

@@ -219,10 +219,15 @@ def test_score_maps_against_strict_oracle(spec_name, idx):
     assert ulp.max() <= 1 and (ulp > 0).mean() < 1e-3
     for k in F64_MAPS:
         np.testing.assert_allclose(got[k][0].cpu().numpy(), ref[k], rtol=1e-9, atol=1e-12, err_msg=k)
-    # and within the north-star tolerance of the reference-arithmetic maps
-    rr = O.score_maps(mask, dep, P[0, 0], P[0, 2], P[1, 2], "reference")
+    # and within the north-star tolerance of what the reference itself produced (golden samples of its maps; the
+    # oracle's "reference" arithmetic is not used here: torch's CPU convolution picks its algorithm per host CPU)
+    fn = [f["file"] for f in META["frames"] if f["spec"] == spec_name and f["index"] == idx][0]
+    g = np.load(os.path.join(GOLD, fn))
+    assert int(g["leaf_id"]) == leaf
+    yx = g["sample_yx"]
     for k in F64_MAPS + ("flatness_map",):
-        np.testing.assert_allclose(got[k][0].cpu().numpy(), rr[k], rtol=1e-5, atol=1e-6, err_msg=k)
+        np.testing.assert_allclose(got[k][0].cpu().numpy()[yx[:, 0], yx[:, 1]].astype(np.float64), g["sample_" + k],
+                                   rtol=1e-5, atol=1e-6, err_msg=k)
     eng.close()
 
 
