@@ -1,8 +1,10 @@
 // GraspPointCNN forward on the 5th-generation tensor cores (reference scripts/utils/ml_grasp_optimizer/model.py:102-128).
 //
-// The six 3x3 convolutions run as bf16 implicit GEMMs: tcgen05.mma (cta_group::1, kind::f16, M=128) issued by
-// one thread, fp32 accumulators in TMEM, operands brought to shared memory by cp.async.bulk + mbarrier, epilogue
-// (bias + ReLU + bf16 pack) from TMEM with tcgen05.ld.  Attention / average / MLP tail: cnn_tail_kernel (fp32).
+// The six 3x3 convolutions run as bf16 implicit GEMMs: tcgen05.mma (cta_group::1, kind::f16, M=128), fp32 accumulators
+// in TMEM, operands brought to shared memory by cp.async.bulk + mbarrier, epilogue (bias + ReLU [+ 2x2 max-pool] + bf16
+// pack) from TMEM with tcgen05.ld.  Warp roles: one producer, four MMA-issuing warps (one elected thread each, each owning
+// one of the item's four accumulator tiles), eight epilogue warps.  Attention / average / MLP tail: cnn_tail_kernel (fp32),
+// which also takes the last max-pool.
 //
 // Activation layout ("plane-major, shared-halo flat"): a feature map of C channels on S x S pixels for n patches is
 // C/8 planes; plane p holds, for every flat position, the 8 channels 8p..8p+7 as one 16-byte unit.  Positions are
