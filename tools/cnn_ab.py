@@ -1,6 +1,6 @@
 """A/B timing of the tensor-core CNN (LG_CNN_ISSUERS=1|2|4 selects the number of MMA-issuing warps): python tools/cnn_ab.py [patches]"""
 import os, sys
-ROOT = "/root/repo"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
 import numpy as np, torch
 import leafgrasp_oracle as O
