@@ -128,6 +128,13 @@ int lg_process_batch_host(lg_context* ctx, const int16_t* labels_host, const flo
                           const lg_camera* cam_host, lg_frame_result* results_host, int use_bf16_cnn,
                           void* stream);
 
+/* Candidate records for the multi-GPU aggregation (the only exchange between ranks is one all-gather of
+ * fixed-size records): when `records` (DEVICE float32 [frames][LG_TOP_K][4], caller-owned, NULL = off) is set, every
+ * following lg_process_batch / lg_process_batch_host call also writes, per frame and candidate slot, (x, y, traditional
+ * score, ML score or 0) - (-1, -1, 0, 0) in unused slots - straight from the fusion kernel; frame i of a call goes to
+ * records + i * 80 floats.  The buffer is the send buffer of the NCCL all-gather; nothing is reshuffled on the host. */
+int lg_set_record_output(lg_context* ctx, float* records);
+
 /* ---- stage 1: OptimalLeafSelector.select_optimal_leaf (leaf_scorer.py:25-203) ---------------- */
 
 /* leaf_id int32 [frames] (-1 = None); records lg_leaf_record [frames][max_labels] (entry i describes
@@ -231,6 +238,10 @@ int lg_leaf_orientation(lg_context* ctx, const uint8_t* mask, int frames, double
  * call fed to the CNN (rows of candidates without an ML score are zero). */
 int lg_patches(lg_context* ctx, float* patches_out, int frames, void* stream);
 
+/* ImageProcessor.smooth_depth (image_processor.py:56-64): reflect padding by 2 + the 5x5 Gaussian (sigma = 5/6, float32
+ * taps) on n float32 images of height x width (>= 3 x 3), any size, no context needed.  out float32 [n][height][width]. */
+int lg_smooth_depth(const float* depth, int n, int height, int width, float* out, void* stream);
+
 /* Per-patch min-max normalisation of get_ml_score (grasp_point_selector.py:83-123) on caller-built raw
  * patches float32 [n][9][32][32] (channel 1, the mask, is passed through). */
 int lg_normalize_patches(lg_context* ctx, const float* raw, int n, float* out, void* stream);
@@ -245,6 +256,10 @@ int lg_set_profiling(lg_context* ctx, int on);
  *  transform is fused into leaf_stats).  A stage's time runs from the previous mark on the stream it ran on; stages on the
  * internal stream overlap the others, so the sum can exceed the step time.  Synchronises on the recorded events. */
 int lg_stage_times(lg_context* ctx, float* ms, int n);
+/* The same, averaged over the lg_process_batch calls made since lg_set_profiling(ctx, 1) (the last 32 at most; the
+ * host-buffer entry point makes one call per chunk): a benchmark can time every stage of its whole timed region
+ * without synchronising between steps.  calls_out (may be NULL) = number of calls averaged. */
+int lg_stage_times_mean(lg_context* ctx, float* ms, int n, int* calls_out);
 /* Independent stages (union distance transform | per-leaf statistics, orientation | chamfer transforms) run side by
  * side on an internal stream that forks from and joins `stream`; on = 0 serialises them on `stream` (clean per-stage
  * times).  Default: on, unless the environment has LG_NO_OVERLAP=1.  Results are identical either way. */

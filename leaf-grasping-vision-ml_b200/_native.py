@@ -84,8 +84,11 @@ SYMBOLS = {
     "lg_sizeof_sample_meta": (C.c_uint64, []),
     "lg_patches": (C.c_int, [_P, _P, C.c_int, _P]),
     "lg_normalize_patches": (C.c_int, [_P, _P, C.c_int, _P, _P]),
+    "lg_smooth_depth": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "lg_set_record_output": (C.c_int, [_P, _P]),
     "lg_set_profiling": (C.c_int, [_P, C.c_int]),
     "lg_stage_times": (C.c_int, [_P, _P, C.c_int]),
+    "lg_stage_times_mean": (C.c_int, [_P, _P, C.c_int, _P]),
     "lg_set_overlap": (C.c_int, [_P, C.c_int]),
     "lg_launch_count": (C.c_uint64, []),
     "lg_sizeof_frame_result": (C.c_uint64, []),

@@ -5,7 +5,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
 #include <new>
+#include <utility>
 
 #include "lg_internal.cuh"
 
@@ -29,6 +32,21 @@ void lg_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* lg_last_error(void) { return g_err; }
+
+int lg_ensure_smem_impl(const void* kernel, size_t bytes) {
+    if (bytes <= 48 * 1024) return LG_OK;                 // within the default limit: nothing to opt in to
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> granted;
+    int dev = 0;
+    LG_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& have = granted[std::make_pair(dev, kernel)];
+    if (bytes > have) {
+        LG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        have = bytes;
+    }
+    return LG_OK;
+}
 
 namespace {
 
@@ -106,10 +124,10 @@ extern "C" int lg_create(lg_context** out, int max_frames, int height, int width
     A(&c->patches, B * LG_TOP_K * (size_t)(LG_CHANNELS * LG_PATCH * LG_PATCH)); A(&c->logits, B * LG_TOP_K);
     A(&c->slot_map, B * LG_TOP_K); A(&c->cnn_count, 1);
     A(&c->results, B);
+    // the two CNN activation buffers are allocated when a model is loaded (ensure_cnn_scratch): a context that never
+    // runs the CNN (OptimalLeafSelector's) does not pay for them
     c->cnn_cap = (int)(B * LG_TOP_K < 2048 ? 2048 : B * LG_TOP_K);
     c->cnn_act_bytes = (size_t)c->cnn_cap * 32 * 32 * 64 * sizeof(float);
-    if (!rc) { rc = dev_alloc(c, (unsigned char**)&c->cnn_act0, c->cnn_act_bytes); }
-    if (!rc) { rc = dev_alloc(c, (unsigned char**)&c->cnn_act1, c->cnn_act_bytes); }
     A(&c->in_labels, B * P); A(&c->in_depth, B * P); A(&c->results_all, B);
     if (rc) { lg_destroy(c); return rc; }
     {
@@ -155,12 +173,19 @@ extern "C" void lg_destroy(lg_context* c) {
         if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
     }
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
-    for (int i = 0; i < LG_PROF_MARKS; ++i)
-        if (c->prof_ev[i]) cudaEventDestroy(c->prof_ev[i]);
+    for (int r = 0; r < LG_PROF_RING; ++r)
+        for (int i = 0; i < LG_PROF_MARKS; ++i)
+            if (c->prof_ev[r][i]) cudaEventDestroy(c->prof_ev[r][i]);
     delete c;
 }
 
 extern "C" uint64_t lg_context_bytes(const lg_context* c) { return c ? c->bytes : 0; }
+
+static int ensure_cnn_scratch(lg_context* c) {
+    if (!c->cnn_act0) TRY(dev_alloc(c, (unsigned char**)&c->cnn_act0, c->cnn_act_bytes));
+    if (!c->cnn_act1) TRY(dev_alloc(c, (unsigned char**)&c->cnn_act1, c->cnn_act_bytes));
+    return LG_OK;
+}
 
 extern "C" int lg_set_cnn_model(lg_context* c, const lg_cnn_config* cfg, const float* blob_host, uint64_t n_floats) {
     if (!c) return LG_E_ARG;
@@ -178,6 +203,7 @@ extern "C" int lg_set_cnn_model(lg_context* c, const lg_cnn_config* cfg, const f
     c->cnn.cfg = *cfg;
     c->cnn.is_default = lg_cnn_config_is_default(cfg) ? 1 : 0;
     c->cnn.loaded = 1;
+    TRY(ensure_cnn_scratch(c));
     return c->cnn.is_default ? lg_cnn_prepare_bf16(c) : LG_OK;
 }
 
@@ -226,24 +252,30 @@ static int run_stage2(lg_context* c, LgMaskSrc src, const float* depth, int n, l
                       cudaStream_t st) {
     // inside transform on the leaf rectangle (+ its distance map), outside transform on the whole frame (max only)
     cudaStream_t aux = lg_fork(c, 1, st);          // orientation runs beside the two chamfer transforms
-    TRY(lg_run_orientation(c, src, n, aux));
+    int rc = lg_run_orientation(c, src, n, aux);
     lg_mark(c, LG_M_ORIENT, aux);
     // outside transform: only its maximum is used (sdf normalisation) -> branch and bound, sweeps only as fallback
-    TRY(lg_run_outside_max(c, src, n, st));
-    TRY(lg_run_chamfer(c, src, n, full ? 0 : 1, 0, 2, c->di, nullptr, c->dt_max, c->need_full, st));
+    if (!rc) rc = lg_run_outside_max(c, src, n, st);
+    if (!rc) rc = lg_run_chamfer(c, src, n, full ? 0 : 1, 0, 2, c->di, nullptr, c->dt_max, c->need_full, st);
     lg_mark(c, LG_M_CHAMFER, st);
-    TRY(lg_join(c, 1, aux, st));
+    const int rcj = lg_join(c, 1, aux, st);        // also on an error path: the side stream must not stay unordered
+    if (rc) return rc;
+    TRY(rcj);
     TRY(lg_run_scores(c, src, depth, n, cam, full, iso_out, st));
     lg_mark(c, LG_M_SCORE, st);
     return LG_OK;
 }
 
-extern "C" int lg_process_batch(lg_context* c, const int16_t* labels, const float* depth, int frames, const lg_camera* cam,
-                                lg_frame_result* results, int use_bf16_cnn, void* stream) {
+static int process_batch_impl(lg_context* c, const int16_t* labels, const float* depth, int frames, const lg_camera* cam,
+                              lg_frame_result* results, float* rec_out, int use_bf16_cnn, void* stream) {
     TRY(check_batch(c, labels, depth, frames));
     if (!cam) return LG_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    if (c->prof_on) memset(c->prof_seen, 0, sizeof(c->prof_seen));
+    if (c->prof_on) {
+        c->prof_slot = c->prof_calls % LG_PROF_RING;
+        ++c->prof_calls;
+        memset(c->prof_seen[c->prof_slot], 0, sizeof(c->prof_seen[0]));
+    }
     lg_mark(c, LG_M_START, st);
     TRY(lg_run_stage1(c, labels, depth, frames, *cam, st));
     TRY(lg_run_select(c, frames, *cam, nullptr, c->records, st));
@@ -258,8 +290,19 @@ extern "C" int lg_process_batch(lg_context* c, const int16_t* labels, const floa
         TRY(lg_run_cnn(c, c->patches, frames * LG_TOP_K, c->cnn_count, c->logits, use_bf16_cnn, st));
         lg_mark(c, LG_M_CNN, st);
     }
-    TRY(lg_run_fuse(c, src, depth, frames, *cam, have_ml, results, st));
+    TRY(lg_run_fuse(c, src, depth, frames, *cam, have_ml, results, rec_out, st));
     lg_mark(c, LG_M_FUSE, st);
+    return LG_OK;
+}
+
+extern "C" int lg_process_batch(lg_context* c, const int16_t* labels, const float* depth, int frames, const lg_camera* cam,
+                                lg_frame_result* results, int use_bf16_cnn, void* stream) {
+    return process_batch_impl(c, labels, depth, frames, cam, results, c ? c->rec_out : nullptr, use_bf16_cnn, stream);
+}
+
+extern "C" int lg_set_record_output(lg_context* c, float* records) {
+    if (!c) return LG_E_ARG;
+    c->rec_out = records;
     return LG_OK;
 }
 
@@ -286,7 +329,8 @@ extern "C" int lg_process_batch_host(lg_context* c, const int16_t* labels_host, 
         const size_t off = (size_t)k * chunk * c->P;
         const int m = frames - k * chunk < chunk ? frames - k * chunk : chunk;
         LG_CUDA(cudaStreamWaitEvent(st, c->copy_ev[k], 0));
-        TRY(lg_process_batch(c, c->in_labels + off, c->in_depth + off, m, cam, c->results_all + (size_t)k * chunk, use_bf16_cnn, stream));
+        TRY(process_batch_impl(c, c->in_labels + off, c->in_depth + off, m, cam, c->results_all + (size_t)k * chunk,
+                               c->rec_out ? c->rec_out + (size_t)k * chunk * LG_TOP_K * 4 : nullptr, use_bf16_cnn, stream));
     }
     LG_CUDA(cudaMemcpyAsync(results_host, c->results_all, sizeof(lg_frame_result) * frames, cudaMemcpyDeviceToHost, st));
     LG_CUDA(cudaStreamSynchronize(st));
@@ -334,7 +378,7 @@ extern "C" int lg_select_grasp_point(lg_context* c, const uint8_t* mask, const f
         TRY(lg_run_gather(c, src, depth, frames, *cam, st));
         TRY(lg_run_cnn(c, c->patches, frames * LG_TOP_K, c->cnn_count, c->logits, use_bf16_cnn, st));
     }
-    TRY(lg_run_fuse(c, src, depth, frames, *cam, have_ml, results, st));
+    TRY(lg_run_fuse(c, src, depth, frames, *cam, have_ml, results, nullptr, st));
     return LG_OK;
 }
 
@@ -351,6 +395,16 @@ extern "C" int lg_leaf_orientation(lg_context* c, const uint8_t* mask, int frame
 extern "C" int lg_patches(lg_context* c, float* patches_out, int frames, void* stream) {
     if (!c || !patches_out || frames < 1 || frames > c->B) return LG_E_ARG;
     return lg_run_export_patches(c, patches_out, frames, (cudaStream_t)stream);
+}
+
+extern "C" int lg_smooth_depth(const float* depth, int n, int height, int width, float* out, void* stream) {
+    if (!depth || !out || n < 1 || height < 3 || width < 3) {
+        lg_set_error("lg_smooth_depth: bad arguments (reflect padding by 2 needs an image of at least 3 x 3)");
+        return LG_E_ARG;
+    }
+    float g[25];
+    memcpy(g, kGaussBits, sizeof(g));
+    return lg_run_smooth_depth(depth, n, height, width, g, out, (cudaStream_t)stream);
 }
 
 extern "C" int lg_normalize_patches(lg_context* c, const float* raw, int n, float* out, void* stream) {
@@ -389,22 +443,26 @@ extern "C" uint64_t lg_cnn_weight_floats(void) { return lg_cnn_blob_floats(); }
 
 extern "C" int lg_set_profiling(lg_context* c, int on) {
     if (!c) return LG_E_ARG;
-    if (on && !c->prof_ev[0]) {
-        for (int i = 0; i < LG_PROF_MARKS; ++i) LG_CUDA(cudaEventCreate(&c->prof_ev[i]));
+    if (on && !c->prof_ev[0][0]) {
+        for (int r = 0; r < LG_PROF_RING; ++r)
+            for (int i = 0; i < LG_PROF_MARKS; ++i) LG_CUDA(cudaEventCreate(&c->prof_ev[r][i]));
     }
     c->prof_on = on ? 1 : 0;
+    c->prof_slot = 0;
+    c->prof_calls = 0;
     memset(c->prof_seen, 0, sizeof(c->prof_seen));
     return LG_OK;
 }
 
-/* ms[i] = device time of stage i of the last lg_process_batch call = time between the mark recorded after it and the
- * mark that precedes it on the stream it ran on (stages on the auxiliary stream start at their fork mark, stages that
- * follow a join start at the join mark); 0 for stages that did not run.  Stages on different streams overlap, so the
- * sum can exceed the step time.  Synchronises on the recorded events. */
-extern "C" int lg_stage_times(lg_context* c, float* ms, int n) {
-    if (!c || !ms || n < LG_M_COUNT) return LG_E_ARG;
-    for (int i = 0; i < n; ++i) ms[i] = 0.f;
-    if (!c->prof_on || !c->prof_seen[LG_M_START]) return LG_OK;
+/* ms[i] = device time of stage i of one recorded lg_process_batch call = time between the mark recorded after it and
+ * the mark that precedes it on the stream it ran on (stages on the auxiliary stream start at their fork mark, stages
+ * that follow a join start at the join mark); 0 for stages that did not run.  Stages on different streams overlap, so
+ * the sum can exceed the step time.  Synchronises on the recorded events. */
+static int stage_times_of_slot(lg_context* c, int slot, float* ms) {
+    const int* seen = c->prof_seen[slot];
+    cudaEvent_t* ev = c->prof_ev[slot];
+    for (int i = 0; i < LG_M_COUNT; ++i) ms[i] = 0.f;
+    if (!seen[LG_M_START]) return LG_OK;
     int pred[LG_PROF_MARKS];
     for (int i = 0; i < LG_PROF_MARKS; ++i) pred[i] = i - 1;
     pred[LG_M_START] = -1;
@@ -412,19 +470,41 @@ extern "C" int lg_stage_times(lg_context* c, float* ms, int n) {
     pred[LG_M_JOIN1] = LG_M_EDT_ROW; pred[LG_M_SELECT] = LG_M_JOIN1;
     pred[LG_M_FORK2] = LG_M_SELECT;  pred[LG_M_ORIENT] = LG_M_FORK2; pred[LG_M_CHAMFER] = LG_M_SELECT;
     pred[LG_M_JOIN2] = LG_M_ORIENT;  pred[LG_M_SCORE] = LG_M_JOIN2;
-    if (!c->prof_seen[LG_M_FORK1]) {   // overlap off: stats (+ column pass), row pass, scatter, median on the caller's stream
+    if (!seen[LG_M_FORK1]) {   // overlap off: stats (+ column pass), row pass, scatter, median on the caller's stream
         pred[LG_M_EDT_COL] = LG_M_STATS; pred[LG_M_SCATTER] = LG_M_EDT_ROW; pred[LG_M_JOIN1] = LG_M_MEDIAN;
     }
-    if (!c->prof_seen[LG_M_FORK2]) { pred[LG_M_ORIENT] = LG_M_SELECT; pred[LG_M_CHAMFER] = LG_M_ORIENT; pred[LG_M_JOIN2] = LG_M_CHAMFER; }
+    if (!seen[LG_M_FORK2]) { pred[LG_M_ORIENT] = LG_M_SELECT; pred[LG_M_CHAMFER] = LG_M_ORIENT; pred[LG_M_JOIN2] = LG_M_CHAMFER; }
     for (int i = 1; i < LG_M_COUNT; ++i) {
-        if (!c->prof_seen[i]) continue;
+        if (!seen[i]) continue;
         int p = pred[i];
-        while (p >= 0 && !c->prof_seen[p]) p = pred[p];
+        while (p >= 0 && !seen[p]) p = pred[p];
         if (p < 0) continue;
-        LG_CUDA(cudaEventSynchronize(c->prof_ev[i]));
-        LG_CUDA(cudaEventSynchronize(c->prof_ev[p]));
-        LG_CUDA(cudaEventElapsedTime(&ms[i], c->prof_ev[p], c->prof_ev[i]));
+        LG_CUDA(cudaEventSynchronize(ev[i]));
+        LG_CUDA(cudaEventSynchronize(ev[p]));
+        LG_CUDA(cudaEventElapsedTime(&ms[i], ev[p], ev[i]));
     }
+    return LG_OK;
+}
+
+extern "C" int lg_stage_times(lg_context* c, float* ms, int n) {
+    if (!c || !ms || n < LG_M_COUNT) return LG_E_ARG;
+    for (int i = 0; i < n; ++i) ms[i] = 0.f;
+    if (!c->prof_on || c->prof_calls == 0) return LG_OK;
+    return stage_times_of_slot(c, c->prof_slot, ms);
+}
+
+extern "C" int lg_stage_times_mean(lg_context* c, float* ms, int n, int* calls_out) {
+    if (!c || !ms || n < LG_M_COUNT) return LG_E_ARG;
+    for (int i = 0; i < n; ++i) ms[i] = 0.f;
+    const int calls = c->prof_calls < LG_PROF_RING ? c->prof_calls : LG_PROF_RING;
+    if (calls_out) *calls_out = c->prof_on ? calls : 0;
+    if (!c->prof_on || calls == 0) return LG_OK;
+    for (int r = 0; r < calls; ++r) {
+        float one[LG_PROF_MARKS];
+        TRY(stage_times_of_slot(c, r, one));
+        for (int i = 0; i < LG_M_COUNT; ++i) ms[i] += one[i];
+    }
+    for (int i = 0; i < LG_M_COUNT; ++i) ms[i] /= (float)calls;
     return LG_OK;
 }
 

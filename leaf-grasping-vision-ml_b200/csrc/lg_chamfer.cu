@@ -592,24 +592,16 @@ int lg_run_chamfer(lg_context* c, LgMaskSrc src, int n, int rect_mode, int inver
     if (aligned && !force_generic) {
         const int threads = ((c->W / 8 + 31) / 32) * 32;
         const size_t sm8 = (size_t)3 * (c->W + 8) * sizeof(int);
-        static size_t configured8 = 0;
-        if (sm8 > configured8) {
-            LG_CUDA(cudaFuncSetAttribute(chamfer8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm8));
-            LG_CUDA(cudaFuncSetAttribute(chamfer8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm8));
-            configured8 = sm8;
-        }
+        LG_ENSURE_SMEM(chamfer8_kernel<true>, sm8);
+        LG_ENSURE_SMEM(chamfer8_kernel<false>, sm8);
         if (src.labels) chamfer8_kernel<true><<<dim3(n, nvar), threads, sm8, st>>>(A);
         else chamfer8_kernel<false><<<dim3(n, nvar), threads, sm8, st>>>(A);
         LG_LAUNCH_CHECK();
         return LG_OK;
     }
     size_t sm = (size_t)(3 * (c->W + 4) + 2 * c->W) * sizeof(int);
-    static size_t configured = 0;
-    if (sm > configured) {
-        LG_CUDA(cudaFuncSetAttribute(chamfer_kernel<3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        LG_CUDA(cudaFuncSetAttribute(chamfer_kernel<CH_MAXI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        configured = sm;
-    }
+    LG_ENSURE_SMEM((chamfer_kernel<3, 4>), sm);
+    LG_ENSURE_SMEM((chamfer_kernel<CH_MAXI, 2>), sm);
     if (c->W <= 3 * CH_NT) chamfer_kernel<3, 4><<<dim3(n, nvar), CH_NT, sm, st>>>(A);
     else chamfer_kernel<CH_MAXI, 2><<<dim3(n, nvar), CH_NT, sm, st>>>(A);
     LG_LAUNCH_CHECK();

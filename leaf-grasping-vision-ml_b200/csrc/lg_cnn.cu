@@ -359,11 +359,7 @@ static int run_cnn_generic(lg_context* c, const float* patches, int n, float* lo
     if (chunk < 1) { lg_set_error("CNN activation scratch too small for this architecture"); return LG_E_CAPACITY; }
     const int C = g.filters[g.n_blocks - 1], s_final = LG_PATCH >> g.n_blocks, S2 = s_final * s_final;
     const size_t tail_smem = ((size_t)S2 * C + S2 + 3 * (size_t)C) * sizeof(float);
-    static size_t configured = 48 * 1024;
-    if (tail_smem > configured) {
-        LG_CUDA(cudaFuncSetAttribute(cnn_tail_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
-        configured = tail_smem;
-    }
+    LG_ENSURE_SMEM(cnn_tail_generic_kernel, tail_smem);
     for (int done = 0; done < n; done += chunk) {
         const int m = min(chunk, n - done);
         float* buf[2] = {(float*)c->cnn_act0, (float*)c->cnn_act1};

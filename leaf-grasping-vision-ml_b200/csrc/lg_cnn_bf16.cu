@@ -610,12 +610,8 @@ size_t layer_w_units(const LayerCfg& l) { return (size_t)(l.cout / l.NC) * l.KC 
 
 template <int KP, int NC, bool POOL>
 int launch_conv(const UmmaConvArgs& A, int S, int sms, cudaStream_t st) {
-    static size_t configured = 0;
     const size_t smem = conv_smem<KP, NC, POOL>(S);
-    if (smem > configured) {
-        LG_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<KP, NC, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    LG_ENSURE_SMEM((conv3x3_umma_kernel<KP, NC, POOL>), smem);
     const long long Qmax = (long long)A.n_host * A.PP;
     const int items = POOL ? (S == 32 ? 2 * A.n_host : (A.n_host + 1) / 2)
                            : (int)((Qmax + A.pitch + 1 + TILE_M - 1) / TILE_M) * A.n_split;

@@ -21,6 +21,7 @@
 #define LG_SE_STEM 30
 #define LG_SE_PRE 31
 #define LG_PROF_MARKS 20
+#define LG_PROF_RING 32
 #define LG_BND_CAP 16384
 #define LG_MAX_HOST_CHUNKS 64
 #define LG_HOST_CHUNK_FRAMES 32
@@ -118,6 +119,7 @@ struct lg_context {
     int32_t* slot_map;                       // [B*20] compact patch index of every (frame, candidate), -1 = no ML score
     int32_t* cnn_count;                      // [1] number of valid slots of the current batch
     lg_frame_result* results;                // [B]
+    float* rec_out;                          // caller-owned [frames][20][4] candidate records (lg_set_record_output), or null
     // CNN scratch
     void* cnn_act0;
     void* cnn_act1;
@@ -138,9 +140,13 @@ struct lg_context {
     cudaEvent_t ev_fork[2], ev_join[2];
     int overlap;
     // optional per-stage timing (lg_set_profiling): events recorded on the stream the stage runs on
+    // (a ring of event sets: the per-stage times of up to LG_PROF_RING consecutive calls can be read back afterwards,
+    // so a benchmark does not have to synchronise after every step to time the stages of its timed region)
     int prof_on;
-    cudaEvent_t prof_ev[LG_PROF_MARKS];
-    int prof_seen[LG_PROF_MARKS];
+    int prof_slot;                           // ring slot of the call in progress / last call
+    int prof_calls;                          // lg_process_batch calls since lg_set_profiling(ctx, 1)
+    cudaEvent_t prof_ev[LG_PROF_RING][LG_PROF_MARKS];
+    int prof_seen[LG_PROF_RING][LG_PROF_MARKS];
     // constants
     float gauss[25];
     int se30_a[LG_SE_STEM], se30_b[LG_SE_STEM];   // per structuring-element row: first / last+1 column
@@ -156,6 +162,14 @@ void lg_set_error(const char* fmt, ...);
             return LG_E_CUDA;                                                               \
         }                                                                                   \
     } while (0)
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device, per-kernel setting: the sizes already granted are kept
+// per (device, kernel) behind a mutex, so that several devices or host threads in one process each get theirs.
+int lg_ensure_smem_impl(const void* kernel, size_t bytes);
+#define LG_ENSURE_SMEM(kernel, bytes)                                        \
+    do {                                                                     \
+        int rc__ = lg_ensure_smem_impl((const void*)(kernel), (size_t)(bytes)); \
+        if (rc__) return rc__;                                               \
+    } while (0)
 extern unsigned long long g_lg_launches;
 #define LG_LAUNCH_CHECK()            \
     do {                             \
@@ -163,7 +177,7 @@ extern unsigned long long g_lg_launches;
         LG_CUDA(cudaGetLastError()); \
     } while (0)
 static inline void lg_mark(lg_context* c, int id, cudaStream_t st) {
-    if (c->prof_on) { cudaEventRecord(c->prof_ev[id], st); c->prof_seen[id] = 1; }
+    if (c->prof_on) { cudaEventRecord(c->prof_ev[c->prof_slot][id], st); c->prof_seen[c->prof_slot][id] = 1; }
 }
 
 // stage launchers (defined across the .cu files); all asynchronous on `st`
@@ -187,7 +201,8 @@ bool lg_cnn_config_ok(const lg_cnn_config* g);
 bool lg_cnn_config_is_default(const lg_cnn_config* g);
 uint64_t lg_cnn_config_floats(const lg_cnn_config* g);
 int lg_run_fuse(lg_context* c, LgMaskSrc src, const float* depth, int n, lg_camera cam, int have_ml,
-                lg_frame_result* out, cudaStream_t st);
+                lg_frame_result* out, float* rec_out, cudaStream_t st);
+int lg_run_smooth_depth(const float* in, int n, int h, int w, const float* gauss25, float* out, cudaStream_t st);
 int lg_run_collect(lg_context* c, LgMaskSrc src, const float* depth, int n, unsigned long long seed, unsigned long long first_index,
                    const int32_t* grasp_xy, const double* total, float* patches, lg_sample_meta* meta, int32_t* set_sizes,
                    cudaStream_t st);

@@ -526,11 +526,7 @@ __global__ void mask_clear_kernel(lg_context c, int n) {
 }  // namespace
 
 int lg_run_orientation(lg_context* c, LgMaskSrc src, int n, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        LG_CUDA(cudaFuncSetAttribute(orient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OR_SMEM));
-        configured = true;
-    }
+    LG_ENSURE_SMEM(orient_kernel, OR_SMEM);
     orient_kernel<<<n, OR_NT, OR_SMEM, st>>>(*c, src, n);
     LG_LAUNCH_CHECK();
     return LG_OK;

@@ -545,7 +545,10 @@ __global__ void export_patches_kernel(lg_context c, float* __restrict__ out) {
 // One warp per frame: lane k owns candidate k (rescale + fusion term), the pick is a warp arg-max with the serial
 // loop's rule (a later candidate replaces the current best only if strictly larger), and the 31 rows of the pre-grasp
 // dilation element are tested by 31 lanes at once.
-__global__ void __launch_bounds__(32) fuse_kernel(lg_context c, LgMaskSrc src, const float* __restrict__ depth, lg_camera cam, int have_ml, int n) {
+// rec (optional): the frame's candidate records for the multi-GPU aggregation, float32 [20][4] = (x, y, traditional score,
+// ML score or 0), (-1, -1, 0, 0) in unused slots - written here so that no host or framework code reshuffles results.
+__global__ void __launch_bounds__(32) fuse_kernel(lg_context c, LgMaskSrc src, const float* __restrict__ depth, lg_camera cam, int have_ml, int n,
+                                                  float4* __restrict__ rec) {
     const int b = blockIdx.x, lane = threadIdx.x;
     if (b >= n) return;
     lg_frame_result* res = &c.results[b];
@@ -581,6 +584,11 @@ __global__ void __launch_bounds__(32) fuse_kernel(lg_context c, LgMaskSrc src, c
             has_comb = true;
         } else {
             res->logit[k] = CUDART_NAN_F; res->ml[k] = CUDART_NAN; res->ml_valid[k] = 0;
+        }
+        if (rec) {
+            float4 r4 = make_float4(-1.f, -1.f, 0.f, 0.f);
+            if (k < nc) r4 = make_float4((float)res->cand_x[k], (float)res->cand_y[k], (float)trad_k, mlk ? (float)res->ml[k] : 0.f);
+            rec[(size_t)b * LG_TOP_K + k] = r4;
         }
     }
     if (nc == 0) {
@@ -690,16 +698,40 @@ __global__ void __launch_bounds__(256) normalize_patches_kernel(const float* __r
     for (int q = 0; q < 4; ++q) dst[tid + q * 256] = norm ? __fdiv_rn(__fsub_rn(v[q], mn), den) : v[q];
 }
 
+// ImageProcessor.smooth_depth (image_processor.py:56-64): reflect padding by 2 and the 5x5 Gaussian, taps added in
+// row-major order like the fused flatness path above; any image size >= 3 x 3
+struct GaussTaps { float g[25]; };
+__global__ void __launch_bounds__(256) smooth_depth_kernel(const float* __restrict__ in, float* __restrict__ out, int h, int w,
+                                                            GaussTaps taps) {
+    __shared__ float t[8 + 4][32 + 4];
+    const size_t fo = (size_t)blockIdx.z * h * w;
+    const int tx0 = blockIdx.x * 32, ty0 = blockIdx.y * 8;
+    for (int i = threadIdx.x; i < 12 * 36; i += 256) {
+        const int ly = i / 36, lx = i - ly * 36;
+        const int y = reflect101(ty0 - 2 + ly, h), x = reflect101(tx0 - 2 + lx, w);
+        t[ly][lx] = in[fo + (size_t)min(max(y, 0), h - 1) * w + min(max(x, 0), w - 1)];
+    }
+    __syncthreads();
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    const int x = tx0 + lx, y = ty0 + ly;
+    if (x >= w || y >= h) return;
+    float acc = __fmul_rn(taps.g[0], t[ly][lx]);
+#pragma unroll
+    for (int k = 1; k < 25; ++k) acc = __fadd_rn(acc, __fmul_rn(taps.g[k], t[ly + k / 5][lx + k % 5]));
+    out[fo + (size_t)y * w + x] = acc;
+}
+
 }  // namespace
 
-#define TRY_SMEM(kernel, bytes)                                                                              \
-    do {                                                                                                     \
-        static bool done__ = false;                                                                          \
-        if (!done__) {                                                                                       \
-            LG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
-            done__ = true;                                                                                   \
-        }                                                                                                    \
-    } while (0)
+int lg_run_smooth_depth(const float* in, int n, int h, int w, const float* gauss25, float* out, cudaStream_t st) {
+    GaussTaps taps;
+    for (int k = 0; k < 25; ++k) taps.g[k] = gauss25[k];
+    smooth_depth_kernel<<<dim3((w + 31) / 32, (h + 7) / 8, n), 256, 0, st>>>(in, out, h, w, taps);
+    LG_LAUNCH_CHECK();
+    return LG_OK;
+}
+
+#define TRY_SMEM(kernel, bytes) LG_ENSURE_SMEM(kernel, bytes)
 
 int lg_run_scores(lg_context* c, LgMaskSrc src, const float* depth, int n, lg_camera cam, int full, double* iso_out,
                   cudaStream_t st) {
@@ -735,8 +767,8 @@ int lg_run_export_patches(lg_context* c, float* out, int n, cudaStream_t st) {
 }
 
 int lg_run_fuse(lg_context* c, LgMaskSrc src, const float* depth, int n, lg_camera cam, int have_ml, lg_frame_result* out,
-                cudaStream_t st) {
-    fuse_kernel<<<n, 32, 0, st>>>(*c, src, depth, cam, have_ml, n);
+                float* rec_out, cudaStream_t st) {
+    fuse_kernel<<<n, 32, 0, st>>>(*c, src, depth, cam, have_ml, n, reinterpret_cast<float4*>(rec_out));
     LG_LAUNCH_CHECK();
     if (out && out != c->results)
         LG_CUDA(cudaMemcpyAsync(out, c->results, sizeof(lg_frame_result) * n, cudaMemcpyDeviceToDevice, st));

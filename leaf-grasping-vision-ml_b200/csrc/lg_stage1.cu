@@ -1025,11 +1025,7 @@ static int run_edt_rows(lg_context* c, int n, uint32_t* d2, cudaStream_t st) {
     edt_row_kernel<<<dim3(n, seed_ctas), EDT_NT, sm, st>>>(c->edt_g, nullptr, c->edt_best, c->H, c->W, c->P, stride, 0, seed);
     LG_LAUNCH_CHECK();
     const size_t smw = (size_t)(EDTW_NT / 32) * (c->W + 128) * sizeof(unsigned);
-    static size_t configured = 0;
-    if (smw > configured) {
-        LG_CUDA(cudaFuncSetAttribute(edt_rowmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw));
-        configured = smw;
-    }
+    LG_ENSURE_SMEM(edt_rowmax_kernel, smw);
     int per_frame = (148 * 4 * 2 + n - 1) / n;       // about two waves of CTAs over the batch
     const int max_ctas = (c->H - seed + EDTW_NT / 32 - 1) / (EDTW_NT / 32);
     per_frame = per_frame < 1 ? 1 : (per_frame > max_ctas ? max_ctas : per_frame);
@@ -1050,14 +1046,7 @@ int lg_run_stage1(lg_context* c, const int16_t* labels, const float* depth, int 
         c->ray_valid = 1;
     }
     // per-leaf statistics + column pass of the union distance transform in one walk over the columns
-    {
-        static size_t configured = 48 * 1024;      // the per-label table grows past the default limit for L > ~850
-        const size_t need = c->L * sizeof(SmemLeaf) + (size_t)STC_BND * STC_NT * sizeof(uint16_t);
-        if (need > configured) {
-            LG_CUDA(cudaFuncSetAttribute(leaf_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-            configured = need;
-        }
-    }
+    LG_ENSURE_SMEM(leaf_stats_kernel, c->L * sizeof(SmemLeaf) + (size_t)STC_BND * STC_NT * sizeof(uint16_t));
     leaf_stats_kernel<<<dim3((c->W + STC_NT - 1) / STC_NT, n), STC_NT,
                         c->L * sizeof(SmemLeaf) + (size_t)STC_BND * STC_NT * sizeof(uint16_t), st>>>(*c, labels, depth);
     LG_LAUNCH_CHECK();
@@ -1073,13 +1062,7 @@ int lg_run_stage1(lg_context* c, const int16_t* labels, const float* depth, int 
     leaf_scatter_kernel<<<dim3(tiles, n), ST_NT, c->L * sizeof(unsigned), st>>>(*c, labels, depth);
     LG_LAUNCH_CHECK();
     lg_mark(c, LG_M_SCATTER, st);
-    {
-        static bool configured = false;
-        if (!configured) {
-            LG_CUDA(cudaFuncSetAttribute(leaf_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MED_CAP * (int)sizeof(unsigned)));
-            configured = true;
-        }
-    }
+    LG_ENSURE_SMEM(leaf_median_kernel, MED_CAP * sizeof(unsigned));
     leaf_median_kernel<<<dim3(c->L, n), MED_NT, MED_CAP * sizeof(unsigned), st>>>(*c);
     LG_LAUNCH_CHECK();
     lg_mark(c, LG_M_MEDIAN, st);

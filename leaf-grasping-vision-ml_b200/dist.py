@@ -22,6 +22,8 @@ def records_from_results(res, device) -> torch.Tensor:
     import numpy as np
     rec = np.stack([res["cand_x"].astype(np.float32), res["cand_y"].astype(np.float32),
                     res["trad"].astype(np.float32), np.nan_to_num(res["ml"]).astype(np.float32)], axis=-1)
+    unused = np.arange(rec.shape[1])[None, :] >= res["n_candidates"][:, None]
+    rec[unused] = (-1.0, -1.0, 0.0, 0.0)        # same convention as the records the fusion kernel writes
     return torch.from_numpy(rec).to(device)
 
 
@@ -41,11 +43,31 @@ def records_from_result_buffer(buf: torch.Tensor, n_frames: int) -> torch.Tensor
     y = field("cand_y", torch.int32).to(torch.float32)
     trad = field("trad", torch.float64).to(torch.float32)
     ml = torch.nan_to_num(field("ml", torch.float64)).to(torch.float32)
-    return torch.stack([x, y, trad, ml], dim=-1)
+    rec = torch.stack([x, y, trad, ml], dim=-1)
+    ncand = field("n_candidates", torch.int32)
+    unused = torch.arange(rec.shape[1], device=rec.device)[None, :] >= ncand
+    rec[unused] = torch.tensor([-1.0, -1.0, 0.0, 0.0], device=rec.device)
+    return rec
+
+
+def gather_records_async(local: torch.Tensor, out: "torch.Tensor | None" = None):
+    """ONE all-gather of equally sized per-rank record blocks [frames_per_rank, 20, 4] (the buffer the fusion kernel
+    filled through GraspEngine.set_record_output) into out [world * frames_per_rank, 20, 4], issued asynchronously:
+    NCCL runs it on its own stream after the work already queued on the current stream, so it overlaps whatever the
+    caller launches next.  Returns (out, work); work.wait() orders the current stream after the gather (work is None
+    without a process group)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return local, None
+    world = dist.get_world_size()
+    if out is None:
+        out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    work = dist.all_gather_into_tensor(out, local, async_op=True)
+    return out, work
 
 
 def gather_candidate_records(local: torch.Tensor, n_frames: int) -> torch.Tensor:
-    """All-gather of the per-rank record blocks into [n_frames, 20, 4] on every rank."""
+    """All-gather of the per-rank record blocks into [n_frames, 20, 4] on every rank (blocks may differ in size by one
+    frame: shard_range)."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return local
     world, rank = dist.get_world_size(), dist.get_rank()

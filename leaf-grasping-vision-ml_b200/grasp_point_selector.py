@@ -95,7 +95,11 @@ class GraspPointSelector:
                 _log.logwarn("No valid candidate points found")
                 return None, None, None
             g2 = (int(r["grasp_x"]), int(r["grasp_y"]))
-            return g2, tuple(float(v) for v in r["grasp_3d"]), tuple(float(v) for v in r["pre_grasp"])
+            g3 = tuple(float(v) for v in r["grasp_3d"])
+            pre = tuple(float(v) for v in r["pre_grasp"])
+            if any(np.isnan(v) for v in pre):     # depth 0 / NaN at the pick: the reference's projection raises inside
+                pre = None                        # calculate_pre_grasp_point, which then returns None (:754-819)
+            return g2, g3, pre
         except N.NativeError:
             raise
         except Exception as e:  # noqa: BLE001

@@ -1,16 +1,20 @@
 """ImageProcessor drop-in (reference scripts/utils/image_processor.py:8-64).
 
 On the B200 path the Gaussian / Sobel stencils live inside the fused score kernel (csrc/lg_score.cu), so
-this class only carries the constructor arguments and the kernel tensors the reference exposes through
-``get_kernel``; ``smooth_depth`` is kept for callers that use it on its own and runs the same fused kernel
-on an all-ones mask... it is not needed by ``GraspPointSelector`` here.
+``GraspPointSelector`` here does not call this class; it carries the constructor arguments, the kernel
+tensors the reference exposes through ``get_kernel``, and ``smooth_depth`` (image_processor.py:56-64) as a
+stand-alone device kernel (``lg_smooth_depth``) for callers that use it on its own.
 """
 from __future__ import annotations
 
 import colorsys
 
+import ctypes as C
+
 import numpy as np
 import torch
+
+from . import _native as N
 
 
 class ImageProcessor:
@@ -44,3 +48,21 @@ class ImageProcessor:
     def calculate_centroid(self, leaf_mask):
         ys, xs = torch.where(leaf_mask)
         return float(xs.float().mean()), float(ys.float().mean())
+
+    def smooth_depth(self, depth_patch, device):
+        """Reflect-pad by 2 + 5x5 Gaussian of a 2-D float image (image_processor.py:56-64) on the CUDA device; returns a
+        float32 tensor [h, w] on that device.  No CPU fallback: raises without a GPU."""
+        if not torch.cuda.is_available():
+            raise N.NativeError("ImageProcessor.smooth_depth needs a CUDA device; there is no CPU fallback")
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            dev = torch.device("cuda", torch.cuda.current_device())
+        x = torch.as_tensor(depth_patch).to(dev, torch.float32).contiguous()
+        if x.dim() != 2:
+            raise ValueError(f"smooth_depth expects a 2-D image, got {tuple(x.shape)}")
+        h, w = x.shape
+        out = torch.empty_like(x)
+        with torch.cuda.device(dev):
+            N.check(N.lib().lg_smooth_depth(C.c_void_p(x.data_ptr()), 1, h, w, C.c_void_p(out.data_ptr()),
+                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)), "lg_smooth_depth")
+        return out

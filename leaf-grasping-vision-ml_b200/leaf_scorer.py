@@ -44,6 +44,18 @@ class OptimalLeafSelector:
             eng = self._get_engine(h, w)
             cam = N.Camera(float(self.f_norm), float(self.camera_cx), float(self.camera_cy))
             ids, rec = eng.select_leaf(mask_tensor, depth_tensor, cam)
+            if ids[0] < 0:
+                # "no leaf" is also what a label id outside the engine's tables produces (LG_ST_LABEL_RANGE); the
+                # reference accepts any int16 id, so check (on this rare path only) and grow the tables
+                mt = torch.as_tensor(mask_tensor)
+                lo, top = (int(mt.min()), int(mt.max())) if mt.numel() else (0, 0)
+                if lo < 0 or top >= 1024:
+                    raise ValueError(f"label ids must lie in [0, 1024) (found {lo}..{top})")
+                if top >= self.max_labels:
+                    self.max_labels = min(1024, max(2 * self.max_labels, top + 1))
+                    self._engine = None
+                    eng = self._get_engine(h, w)
+                    ids, rec = eng.select_leaf(mask_tensor, depth_tensor, cam)
             rec = rec[0]
             self.last_records = rec[rec["area"] > 0]
             self._tall_leaves = [int(r["leaf_id"]) for r in self.last_records if r["is_tall"]]

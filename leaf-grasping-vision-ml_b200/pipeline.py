@@ -51,6 +51,7 @@ class GraspEngine:
                 self._lane_ctx.append(ctx)
                 self._lane_streams.append(torch.cuda.Stream(device=self.device))
         self.has_cnn = False
+        self._records = None
 
     def _all_ctx(self):
         return [self._ctx] + self._lane_ctx
@@ -155,6 +156,11 @@ class GraspEngine:
                 ctx = self._ctx if k == 0 else self._lane_ctx[k - 1]
                 stream = cur if k == 0 else self._lane_streams[k - 1]
                 rp = C.c_void_p(res.data_ptr() + lo * N.FRAME_RESULT.itemsize)
+                if self._lane_ctx and self._records is not None:      # every part writes at its own frame offset
+                    if self._records.shape[0] < n:
+                        raise ValueError("record buffer holds fewer frames than the batch")
+                    N.check(self.lib.lg_set_record_output(ctx, C.c_void_p(self._records.data_ptr() + lo * N.TOP_K * 16)),
+                            "lg_set_record_output")
                 N.check(self.lib.lg_process_batch(ctx, _ptr(labels[lo:hi]), _ptr(depth[lo:hi]), hi - lo, C.byref(cam), rp,
                                                   int(use_bf16), C.c_void_p(stream.cuda_stream)), "lg_process_batch")
             for k in range(1, len(parts)):
@@ -169,9 +175,45 @@ class GraspEngine:
         per = -(-n // lanes)
         return [(lo, min(n, lo + per)) for lo in range(0, n, per)]
 
+    def _host_frames(self, t, dtype, name):
+        t = torch.as_tensor(t)
+        if t.dim() == 2:
+            t = t.unsqueeze(0)
+        if t.device.type != "cpu":
+            raise ValueError(f"{name}: process_batch_host takes HOST tensors (got {t.device}); use process_batch")
+        if t.dtype != dtype:
+            raise ValueError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+        if t.dim() != 3 or tuple(t.shape[1:]) != (self.H, self.W):
+            raise ValueError(f"{name}: expected [n, {self.H}, {self.W}], got {tuple(t.shape)}")
+        if not t.is_contiguous():
+            raise ValueError(f"{name}: must be contiguous")
+        if t.shape[0] < 1 or t.shape[0] > self.B:
+            raise ValueError(f"{name}: {t.shape[0]} frames, the engine was built for 1..{self.B}")
+        return t
+
+    def set_record_output(self, records: "torch.Tensor | None"):
+        """Device float32 tensor [>= frames, 20, 4] that every following process_batch / process_batch_host call fills
+        with the frames' candidate records (x, y, traditional score, ML score), written by the fusion kernel; None = off.
+        With lanes, part k writes at its frame offset.  This is the send buffer of dist.gather_candidate_records."""
+        if records is not None:
+            if (not records.is_cuda or records.dtype != torch.float32 or not records.is_contiguous()
+                    or records.dim() != 3 or tuple(records.shape[1:]) != (N.TOP_K, 4)):
+                raise ValueError("records: expected a contiguous CUDA float32 tensor [frames, 20, 4]")
+        self._records = records
+        if records is None or not self._lane_ctx:
+            N.check(self.lib.lg_set_record_output(self._ctx, _ptr(records)), "lg_set_record_output")
+            for ctx in self._lane_ctx:
+                N.check(self.lib.lg_set_record_output(ctx, None), "lg_set_record_output")
+
     def process_batch_host(self, labels_host, depth_host, cam: N.Camera, use_bf16: bool = False):
-        """Pinned (or plain) HOST tensors in, structured ndarray out; copies are inside the call."""
+        """Pinned (or plain) HOST tensors int16 / float32 [n, H, W] in, structured ndarray out; copies are inside the call."""
+        labels_host = self._host_frames(labels_host, torch.int16, "labels")
+        depth_host = self._host_frames(depth_host, torch.float32, "depth")
         n = labels_host.shape[0]
+        if depth_host.shape[0] != n:
+            raise ValueError("labels and depth hold different numbers of frames")
+        if self._lane_ctx and getattr(self, "_records", None) is not None:
+            N.check(self.lib.lg_set_record_output(self._ctx, _ptr(self._records)), "lg_set_record_output")
         out = np.empty(n, dtype=N.FRAME_RESULT)
         with torch.cuda.device(self.device):
             N.check(self.lib.lg_process_batch_host(self._ctx, _ptr(labels_host), _ptr(depth_host), n, C.byref(cam),

@@ -115,3 +115,41 @@ def make_batch(spec: FrameSpec, config_seed: int, first_index: int, count: int):
     for i in range(count):
         lab[i], dep[i] = make_frame(spec, config_seed, first_index + i)
     return lab, dep
+
+
+def seeded_state_dict(seed: int = 1234) -> dict:
+    """Deterministic random-init GraspPointCNN weights for benchmarks and smoke runs (the reference ships no
+    checkpoint): He-scaled conv / linear weights like model.py:89-100 and non-trivial BatchNorm statistics, keys as
+    in SURVEY.md appendix A.9.  Draw for draw the tensors the test oracle builds for the same seed
+    (tests/test_host_cpu.py checks the two stay equal), so benchmarked batches and golden vectors share one model."""
+    import math
+
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    randn = lambda *shape: torch.randn(*shape, generator=g)
+    sd = {}
+
+    def batchnorm(prefix, n):
+        sd[prefix + ".weight"] = 1.0 + 0.1 * randn(n)
+        sd[prefix + ".bias"] = 0.1 * randn(n)
+        sd[prefix + ".running_mean"] = 0.1 * randn(n)
+        sd[prefix + ".running_var"] = 0.5 + torch.rand(n, generator=g)
+        sd[prefix + ".num_batches_tracked"] = torch.tensor(100)
+
+    cin = 9
+    for blk, cout in enumerate((64, 128, 256)):
+        for conv, ci in ((0, cin), (3, cout)):
+            sd[f"encoder.{blk}.{conv}.weight"] = randn(cout, ci, 3, 3) * math.sqrt(2.0 / (cout * 9))
+            sd[f"encoder.{blk}.{conv}.bias"] = randn(cout) * 0.05
+            batchnorm(f"encoder.{blk}.{conv + 1}", cout)
+        cin = cout
+    sd["attention.0.weight"] = randn(1, 256, 1, 1) * math.sqrt(2.0) * 0.1
+    sd["attention.0.bias"] = torch.zeros(1)
+    widths = (256, 256, 128, 64, 1)
+    for k, lin in enumerate((0, 4, 8, 12)):
+        fan_in, fan_out = widths[k], widths[k + 1]
+        sd[f"classifier.{lin}.weight"] = randn(fan_out, fan_in) * math.sqrt(2.0 / fan_in)
+        sd[f"classifier.{lin}.bias"] = randn(fan_out) * 0.05
+        if lin != 12:
+            batchnorm(f"classifier.{lin + 1}", fan_out)
+    return sd

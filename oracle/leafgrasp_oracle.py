@@ -503,6 +503,17 @@ def _corr_taps(padded: np.ndarray, k: np.ndarray, H: int, W: int) -> np.ndarray:
     return acc
 
 
+def smooth_depth(depth_patch: np.ndarray, arith: str = "reference") -> np.ndarray:
+    """ImageProcessor.smooth_depth (image_processor.py:56-64): reflect padding by 2, then the 5x5 Gaussian; float32 [h,w].
+    "reference" makes the reference's torch calls, "strict" accumulates the 25 taps one by one (what the CUDA kernel does)."""
+    z = np.ascontiguousarray(depth_patch, dtype=np.float32)
+    g = gaussian_kernel(5)
+    if arith == "reference":
+        pz = F.pad(torch.from_numpy(z)[None, None], (2, 2, 2, 2), mode="reflect")
+        return F.conv2d(pz, torch.from_numpy(g)[None, None]).squeeze().numpy()
+    return _corr_taps(np.pad(z, 2, mode="reflect"), g, z.shape[0], z.shape[1])
+
+
 def flatness_map(depth: np.ndarray, mask_u8: np.ndarray, arith: str = "reference") -> np.ndarray:
     """grasp_point_selector.py:262,635-657 + image_processor.py:56-64.  float32 [H,W], NOT masked."""
     H, W = mask_u8.shape

@@ -1,0 +1,256 @@
+"""GPU parity tests added in round 2 (run with ``-m gpu``): the second golden set produced by the unmodified reference
+(eight more 1440x1080 frames, one 4K frame, ImageProcessor.smooth_depth), the candidate records the fusion kernel writes
+for the multi-GPU aggregation, the bf16 / fp32 pick rule, two host threads driving two contexts, and a wide sweep of the
+benchmark's workloads against the strict oracle.  Everything goes through the C-ABI; nothing reads /root/reference."""
+import json
+import os
+import threading
+
+import numpy as np
+import pytest
+import torch
+
+import leafgrasp_oracle as O
+from leafgrasp_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+META = json.load(open(os.path.join(GOLD, "golden_meta_r2.json")))
+SEED = META["config_seed"]
+
+
+def _engine(frames, H, W, labels=128, **kw):
+    from leafgrasp_b200 import GraspEngine
+    return GraspEngine(frames, H, W, labels, **kw)
+
+
+def _cam(spec):
+    from leafgrasp_b200 import camera_from_projection
+    return camera_from_projection(synth.projection_matrix(spec))
+
+
+@pytest.fixture(scope="module")
+def blob():
+    from leafgrasp_b200 import pack_weights
+    return pack_weights(synth.seeded_state_dict(META["cnn_seed"]))
+
+
+def _against_golden(r, g):
+    assert r["leaf_id"] == int(g["leaf_id"])
+    n_pos = int(g["n_positive"])
+    assert r["n_positive"] == n_pos
+    got = np.stack([r["cand_x"][:n_pos], r["cand_y"][:n_pos]], axis=1)
+    np.testing.assert_array_equal(got, g["candidates"][:n_pos])
+    np.testing.assert_allclose(r["trad"][:n_pos], g["trad_at"][:n_pos], rtol=1e-5)
+    assert abs(r["angle"] - float(g["angle"])) < 1e-6
+    assert (int(r["grasp_x"]), int(r["grasp_y"])) == tuple(g["grasp_2d"].tolist())
+    np.testing.assert_allclose(r["grasp_3d"], g["grasp_3d"], rtol=1e-12)
+    np.testing.assert_allclose(r["pre_grasp"], g["pre_grasp"], rtol=1e-9)
+    n_ml = int(g["n_ml"])
+    assert int(r["ml_valid"].sum()) == n_ml
+    if n_ml:
+        np.testing.assert_allclose(r["logit"][r["ml_valid"] > 0], g["logits"], atol=2e-4)
+
+
+@pytest.mark.parametrize("spec_name", ["CFG2", "CFG3"])
+def test_reference_golden_second_set(spec_name, blob):
+    """Frames answered by the unmodified reference (tests/golden/make_golden_r2.py), processed as ONE batch: the benchmark's
+    workload (eight 1440x1080 / 30-leaf frames, one of them with an empty valid region) and BASELINE config 3 (4K, 100 leaves)."""
+    frames = [f for f in META["frames"] if f["spec"] == spec_name]
+    spec = getattr(synth, spec_name)
+    lab = np.stack([synth.make_frame(spec, SEED, f["index"])[0] for f in frames])
+    dep = np.stack([synth.make_frame(spec, SEED, f["index"])[1] for f in frames])
+    eng = _engine(len(frames), spec.height, spec.width, 128)
+    eng.set_cnn_weights(blob)
+    res = eng.process_batch(torch.from_numpy(lab).cuda(), torch.from_numpy(dep).cuda(), _cam(spec))
+    for f, r in zip(frames, res):
+        _against_golden(r, np.load(os.path.join(GOLD, f["file"])))
+    eng.close()
+
+
+def test_smooth_depth_against_reference_golden():
+    """ImageProcessor.smooth_depth (image_processor.py:56-64) through the drop-in class against the reference's output
+    (torch CPU conv2d): float32 within a few ulp of the 25-term sum (1e-6 relative)."""
+    import sys
+    sys.path.insert(0, GOLD)
+    from make_golden_r2_inputs import smooth_input
+    from leafgrasp_b200 import ImageProcessor
+    gold = np.load(os.path.join(GOLD, "smooth_depth.npz"))
+    for case in META["smooth_depth"]:
+        h, w = case["height"], case["width"]
+        x = smooth_input(case["name"], h, w)
+        ip = ImageProcessor(h, w, 21, 5)
+        y = ip.smooth_depth(torch.from_numpy(x), torch.device("cuda"))
+        assert y.is_cuda and y.dtype == torch.float32 and tuple(y.shape) == (h, w)
+        np.testing.assert_allclose(y.cpu().numpy(), gold[case["name"]], rtol=1e-6, atol=1e-7, err_msg=case["name"])
+        # also from a device tensor and from float64 input, like the reference's GPUManager.to_device path
+        y2 = ip.smooth_depth(torch.from_numpy(x.astype(np.float64)).cuda(), "cuda")
+        assert torch.equal(y, y2)
+    with pytest.raises(Exception):
+        ImageProcessor(2, 2, 21, 5).smooth_depth(torch.zeros(2, 2), "cuda")      # reflect padding by 2 needs >= 3 px
+
+
+def test_candidate_records_written_by_fusion_kernel(blob):
+    """lg_set_record_output: the [frames, 20, 4] float32 block the all-gather sends is written by fuse_kernel and equals
+    the records derived from the result structs - for the device entry point, the chunked host entry point (40 frames =
+    two chunks) and with two lanes."""
+    from leafgrasp_b200 import dist as lgd
+    spec = synth.SMALL
+    n = 40
+    lab, dep = synth.make_batch(spec, SEED, 0, 8)
+    lab, dep = np.tile(lab, (5, 1, 1)), np.tile(dep, (5, 1, 1))
+    lab[3] = 0                                     # a frame without leaves: all slots unused
+    for lanes in (1, 2):
+        eng = _engine(n, spec.height, spec.width, 16, lanes=lanes)
+        eng.set_cnn_weights(blob)
+        rec = torch.full((n, 20, 4), 7.0, device="cuda")
+        eng.set_record_output(rec)
+        res = eng.process_batch(torch.from_numpy(lab).cuda(), torch.from_numpy(dep).cuda(), _cam(spec))
+        exp = lgd.records_from_results(res, "cpu")
+        assert torch.equal(rec.cpu(), exp), f"lanes {lanes}"
+        assert torch.equal(rec[3].cpu(), torch.tensor([-1.0, -1.0, 0.0, 0.0]).expand(20, 4))
+        rec.fill_(7.0)
+        res_h = eng.process_batch_host(torch.from_numpy(lab).pin_memory(), torch.from_numpy(dep).pin_memory(), _cam(spec))
+        assert torch.equal(rec.cpu(), lgd.records_from_results(res_h, "cpu")), f"host call, lanes {lanes}"
+        eng.set_record_output(None)
+        rec.fill_(7.0)
+        eng.process_batch(torch.from_numpy(lab).cuda(), torch.from_numpy(dep).cuda(), _cam(spec))
+        assert bool((rec == 7.0).all())            # switched off: the buffer is left alone
+        eng.close()
+
+
+def test_process_batch_host_rejects_wrong_buffers(blob):
+    spec = synth.SMALL
+    eng = _engine(2, spec.height, spec.width, 16)
+    lab, dep = synth.make_batch(spec, SEED, 0, 2)
+    with pytest.raises(ValueError):
+        eng.process_batch_host(torch.from_numpy(lab.astype(np.int32)), torch.from_numpy(dep), _cam(spec))
+    with pytest.raises(ValueError):
+        eng.process_batch_host(torch.from_numpy(lab), torch.from_numpy(dep.astype(np.float64)), _cam(spec))
+    with pytest.raises(ValueError):
+        eng.process_batch_host(torch.from_numpy(lab).cuda(), torch.from_numpy(dep), _cam(spec))
+    with pytest.raises(ValueError):
+        eng.process_batch_host(torch.from_numpy(lab[:, :-1]), torch.from_numpy(dep), _cam(spec))
+    res = eng.process_batch_host(lab, dep, _cam(spec))          # NumPy arrays (pageable) are accepted
+    assert res.shape == (2,) and (res["leaf_id"] > 0).all()
+    eng.close()
+
+
+def _fused_scores(r):
+    """The fusion rule (grasp_point_selector.py:205-237) recomputed on the host from a result record: fused score per
+    candidate (NaN where no ML score), and the pick the serial loop makes."""
+    n = int(r["n_candidates"])
+    trad, ml, ok = r["trad"][:n], r["ml"][:n], r["ml_valid"][:n] > 0
+    conf = 1.0 - np.abs(ml - 0.5) * 2.0
+    w = np.minimum(0.3, conf * 0.6)
+    comb = np.where(ok, (1.0 - w) * trad + w * ml, np.nan)
+    best, best_score = 0, trad[0]
+    if n > 1:
+        for k in range(n):
+            if ok[k] and comb[k] > best_score:
+                best, best_score = k, comb[k]
+    return comb, best, best_score
+
+
+def test_bf16_pick_rule_against_fp32(blob):
+    """Tensor-core CNN inside the whole path on 32 benchmark frames: candidates identical, logits within the bf16 bar, the
+    kernel's pick equals the fusion rule applied to its own ML scores (exact), and it equals the fp32 pick on every frame
+    whose fp32 decision margin exceeds twice the largest change bf16 makes to any fused score of that frame."""
+    spec = synth.CFG2
+    n = 32
+    lab, dep = synth.make_batch(spec, SEED, 300, n)
+    eng = _engine(n, spec.height, spec.width, 128)
+    eng.set_cnn_weights(blob)
+    labs, deps = torch.from_numpy(lab).cuda(), torch.from_numpy(dep).cuda()
+    r32 = eng.process_batch(labs, deps, _cam(spec), use_bf16=False)
+    r16 = eng.process_batch(labs, deps, _cam(spec), use_bf16=True)
+    for name in ("leaf_id", "n_candidates", "cand_x", "cand_y", "trad", "ml_valid"):
+        np.testing.assert_array_equal(r32[name], r16[name], err_msg=name)
+    ok = r32["ml_valid"] > 0
+    np.testing.assert_allclose(r16["logit"][ok], r32["logit"][ok], atol=1e-2, rtol=1e-2)
+    decided, agree = 0, 0
+    for a, b in zip(r32, r16):
+        if a["n_candidates"] == 0:
+            continue
+        c32, best32, s32 = _fused_scores(a)
+        c16, best16, _ = _fused_scores(b)
+        assert int(b["best_index"]) == best16 and int(a["best_index"]) == best32
+        others = np.concatenate([np.delete(np.nan_to_num(c32, nan=-np.inf), best32), [a["trad"][0] if best32 != 0 else -np.inf]])
+        margin = s32 - others.max() if others.size else np.inf
+        shift = np.nanmax(np.abs(c16 - c32)) if np.isfinite(c32).any() else 0.0
+        if margin > 2.0 * shift:
+            decided += 1
+            assert best16 == best32, f"margin {margin} shift {shift}"
+        agree += int(best16 == best32)
+    assert decided >= n // 2                      # the rule is not vacuous on this workload
+    assert agree >= 0.9 * n, f"fused pick agreement {agree}/{n}"
+    eng.close()
+
+
+def test_two_host_threads_two_contexts(blob):
+    """two host threads, each with its own context and stream, at the same time (launch attributes
+    are kept per device behind a mutex, not in unsynchronised statics)."""
+    spec = synth.SMALL
+    lab, dep = synth.make_batch(spec, SEED, 0, 4)
+    ref_eng = _engine(4, spec.height, spec.width, 16)
+    ref_eng.set_cnn_weights(blob)
+    ref = ref_eng.process_batch(torch.from_numpy(lab).cuda(), torch.from_numpy(dep).cuda(), _cam(spec))
+    ref_eng.close()
+    out, err = {}, []
+
+    def worker(k):
+        try:
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                eng = _engine(4, spec.height, spec.width, 16)
+                eng.set_cnn_weights(blob)
+                for _ in range(5):
+                    out[k] = eng.process_batch(torch.from_numpy(lab).cuda(), torch.from_numpy(dep).cuda(), _cam(spec))
+                eng.close()
+        except Exception as e:  # noqa: BLE001
+            err.append(e)
+
+    ts = [threading.Thread(target=worker, args=(k,)) for k in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not err, err
+    for k in range(2):
+        for name in ("leaf_id", "cand_x", "cand_y", "grasp_x", "grasp_y", "best_index"):
+            np.testing.assert_array_equal(out[k][name], ref[name])
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("spec_name,first,count", [("CFG2", 1000, 64), ("CFG3", 1000, 4)])
+def test_wide_sweep_against_strict_oracle(spec_name, first, count, blob):
+    """64 frames of the benchmark's workload and 4 frames of the 4K / 100-leaf workload, one batch each, against the strict
+    oracle (evaluated on the host cores in parallel): leaf id, every candidate pixel in order, traditional scores, logits,
+    the fused pick and both 3-D points."""
+    from oracle_pool import strict_answers
+    spec = getattr(synth, spec_name)
+    idx = list(range(first, first + count))
+    ans = strict_answers(spec_name, SEED, idx, META["cnn_seed"])
+    lab, dep = synth.make_batch(spec, SEED, first, count)
+    eng = _engine(count, spec.height, spec.width, 128)
+    eng.set_cnn_weights(blob)
+    res = eng.process_batch(torch.from_numpy(lab).cuda(), torch.from_numpy(dep).cuda(), _cam(spec))
+    eng.close()
+    n_checked = 0
+    for r, o in zip(res, ans):
+        assert int(r["leaf_id"]) == o["leaf_id"]
+        if o["leaf_id"] < 0:
+            continue
+        n = len(o["picks"])
+        assert int(r["n_candidates"]) == n
+        assert list(zip(r["cand_x"][:n].tolist(), r["cand_y"][:n].tolist())) == o["picks"]
+        np.testing.assert_allclose(r["trad"][:n], o["trad_at"], rtol=1e-9)
+        for k in range(n):
+            assert bool(r["ml_valid"][k]) == (o["logits"][k] is not None)
+            if o["logits"][k] is not None:
+                assert abs(r["logit"][k] - o["logits"][k]) < 2e-4
+        assert (int(r["grasp_x"]), int(r["grasp_y"])) == o["grasp"]
+        np.testing.assert_allclose(r["grasp_3d"], o["grasp_3d"], rtol=1e-12)
+        np.testing.assert_allclose(r["pre_grasp"], o["pre_grasp"], rtol=1e-9)
+        n_checked += 1
+    assert n_checked >= count * 3 // 4

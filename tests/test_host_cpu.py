@@ -179,10 +179,13 @@ def test_records_from_result_buffer_matches_numpy_view():
     rec = np.zeros(5, dtype=N.FRAME_RESULT)
     rec["cand_x"] = rng.integers(0, 1440, (5, 20)); rec["cand_y"] = rng.integers(0, 1080, (5, 20))
     rec["trad"] = rng.random((5, 20)); rec["ml"] = rng.random((5, 20)); rec["ml"][2, 7:] = np.nan
+    rec["n_candidates"] = [20, 0, 20, 13, 1]
     buf = torch.from_numpy(np.frombuffer(rec.tobytes(), dtype=np.uint8).copy())
     a = lgd.records_from_result_buffer(buf, 5)
     b = lgd.records_from_results(rec, "cpu")
     assert a.shape == (5, 20, 4) and torch.equal(a, b)
+    assert torch.equal(a[3, 13:], torch.tensor([-1.0, -1.0, 0.0, 0.0]).expand(7, 4))     # unused slots
+    assert a[3, 12, 0] == float(rec["cand_x"][3, 12]) and a[2, 9, 3] == 0.0               # NaN ML score -> 0
 
 
 def _dist_worker(rank, world, port, out):
@@ -194,8 +197,13 @@ def _dist_worker(rank, world, port, out):
     rec = torch.zeros(hi - lo, 20, 4)
     rec[:, :, 0] = torch.arange(lo, hi).float()[:, None]
     allrec = lgd.gather_candidate_records(rec, 10)
+    # the benchmark's aggregation: equal blocks, one asynchronous all-gather after the last step
+    mine = torch.full((3, 20, 4), float(rank))
+    agg, work = lgd.gather_records_async(mine)
+    if work is not None:
+        work.wait()
     if rank == 0:
-        out.put(allrec[:, 0, 0].tolist())
+        out.put((allrec[:, 0, 0].tolist(), agg[:, 0, 0].tolist()))
     dist.destroy_process_group()
 
 
@@ -219,7 +227,34 @@ def test_frame_sharding_and_gather_two_ranks():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    assert got == [float(i) for i in range(10)]
+    assert got[0] == [float(i) for i in range(10)]
+    assert got[1] == [0.0] * 3 + [1.0] * 3
+
+
+def test_benchmark_weights_equal_the_oracle_weights():
+    """bench.py / smoke() take their random-init model from the product package (synth.seeded_state_dict); the golden
+    vectors were made with the oracle's: the two generators must produce the same tensors."""
+    import leafgrasp_oracle as O
+    from leafgrasp_b200 import synth
+    a, b = synth.seeded_state_dict(1234), O.seeded_state_dict(1234)
+    assert list(a) == list(b)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_process_batch_host_validates_its_buffers():
+    """The throughput entry point hands raw host pointers to the library: dtype, shape, device and contiguity are
+    checked first (a wrong buffer would otherwise be read out of bounds)."""
+    from leafgrasp_b200.pipeline import GraspEngine
+    eng = GraspEngine.__new__(GraspEngine)          # no device needed for the checks
+    eng.B, eng.H, eng.W = 4, 6, 8
+    ok = torch.zeros(2, 6, 8, dtype=torch.int16)
+    assert eng._host_frames(ok, torch.int16, "labels") is ok
+    assert eng._host_frames(np.zeros((6, 8), np.float32), torch.float32, "depth").shape == (1, 6, 8)
+    for bad in (torch.zeros(2, 6, 8, dtype=torch.int32), torch.zeros(2, 6, 9, dtype=torch.int16),
+                torch.zeros(5, 6, 8, dtype=torch.int16), torch.zeros(2, 6, 16, dtype=torch.int16)[:, :, ::2]):
+        with pytest.raises(ValueError):
+            eng._host_frames(bad, torch.int16, "labels")
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -20,8 +20,11 @@ MAP_KEYS = ("sdf_score", "approach_score", "flatness_map", "isolation_map", "dis
 RTOL, ATOL = 1e-6, 1e-7
 
 
+META2 = json.load(open(os.path.join(GOLD, "golden_meta_r2.json")))     # second set (make_golden_r2.py)
+
+
 def _frames():
-    return [(f["spec"], f["index"], f["file"]) for f in META["frames"]]
+    return [(f["spec"], f["index"], f["file"]) for f in META["frames"] + META2["frames"]]
 
 
 @pytest.fixture(scope="module")
@@ -98,6 +101,18 @@ def test_full_maps_small_frame(state_dict):
         pt = O.patch_tensor(mask, dep, s, int(x), int(y))
         np.testing.assert_allclose(pt, g["patches"][i], rtol=1e-6, atol=1e-7)
     assert picks[:n_pos] == [tuple(p) for p in ref_picks[:n_pos].tolist()]
+
+
+def test_smooth_depth_against_reference():
+    """ImageProcessor.smooth_depth: the restatement in both arithmetic modes against the reference's own output."""
+    import sys
+    sys.path.insert(0, GOLD)
+    from make_golden_r2_inputs import smooth_input
+    gold = np.load(os.path.join(GOLD, "smooth_depth.npz"))
+    for case in META2["smooth_depth"]:
+        x = smooth_input(case["name"], case["height"], case["width"])
+        np.testing.assert_allclose(O.smooth_depth(x, "reference"), gold[case["name"]], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(O.smooth_depth(x, "strict"), gold[case["name"]], rtol=RTOL, atol=ATOL)
 
 
 def test_cnn_against_reference_module(state_dict):
