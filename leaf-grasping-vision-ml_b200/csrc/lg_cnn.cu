@@ -355,7 +355,7 @@ static int run_cnn_generic(lg_context* c, const float* patches, int n, float* lo
     const lg_cnn_config& g = c->cnn.cfg;
     size_t per_patch = 0;                                  // floats of the largest activation of one patch
     for (int b = 0, s = LG_PATCH; b < g.n_blocks; ++b, s >>= 1) per_patch = max(per_patch, (size_t)s * s * g.filters[b]);
-    const int chunk = (int)min((size_t)n, c->cnn_act_bytes / (per_patch * sizeof(float)));
+    const int chunk = (int)min(min((size_t)n, (size_t)32768), c->cnn_act_bytes / (per_patch * sizeof(float)));   // gridDim.z <= 65535
     if (chunk < 1) { lg_set_error("CNN activation scratch too small for this architecture"); return LG_E_CAPACITY; }
     const int C = g.filters[g.n_blocks - 1], s_final = LG_PATCH >> g.n_blocks, S2 = s_final * s_final;
     const size_t tail_smem = ((size_t)S2 * C + S2 + 3 * (size_t)C) * sizeof(float);
@@ -421,8 +421,9 @@ int lg_run_cnn(lg_context* c, const float* patches, int n, const int32_t* n_dev,
     if (use_bf16) return lg_run_cnn_bf16(c, patches, n, n_dev, logits, st);
     // the fp32 anchor path sizes its grids on the host: with a device-side count it simply runs all n slots
     const float* blob = c->cnn.blob;
-    for (int done = 0; done < n; done += c->cnn_cap) {
-        const int m = min(c->cnn_cap, n - done);
+    const int cap = min(c->cnn_cap, 32768);               // patches ride on gridDim.z (<= 65535)
+    for (int done = 0; done < n; done += cap) {
+        const int m = min(cap, n - done);
         const float* in = patches + (size_t)done * LG_CHANNELS * LG_PATCH * LG_PATCH;
         float* a0 = (float*)c->cnn_act0;
         float* a1 = (float*)c->cnn_act1;

@@ -51,7 +51,7 @@ class GraspEngine:
                 self._lane_ctx.append(ctx)
                 self._lane_streams.append(torch.cuda.Stream(device=self.device))
         self.has_cnn = False
-        self._records = None
+        self._rec_out = None
 
     def _all_ctx(self):
         return [self._ctx] + self._lane_ctx
@@ -156,10 +156,10 @@ class GraspEngine:
                 ctx = self._ctx if k == 0 else self._lane_ctx[k - 1]
                 stream = cur if k == 0 else self._lane_streams[k - 1]
                 rp = C.c_void_p(res.data_ptr() + lo * N.FRAME_RESULT.itemsize)
-                if self._lane_ctx and self._records is not None:      # every part writes at its own frame offset
-                    if self._records.shape[0] < n:
+                if self._lane_ctx and self._rec_out is not None:      # every part writes at its own frame offset
+                    if self._rec_out.shape[0] < n:
                         raise ValueError("record buffer holds fewer frames than the batch")
-                    N.check(self.lib.lg_set_record_output(ctx, C.c_void_p(self._records.data_ptr() + lo * N.TOP_K * 16)),
+                    N.check(self.lib.lg_set_record_output(ctx, C.c_void_p(self._rec_out.data_ptr() + lo * N.TOP_K * 16)),
                             "lg_set_record_output")
                 N.check(self.lib.lg_process_batch(ctx, _ptr(labels[lo:hi]), _ptr(depth[lo:hi]), hi - lo, C.byref(cam), rp,
                                                   int(use_bf16), C.c_void_p(stream.cuda_stream)), "lg_process_batch")
@@ -199,7 +199,7 @@ class GraspEngine:
             if (not records.is_cuda or records.dtype != torch.float32 or not records.is_contiguous()
                     or records.dim() != 3 or tuple(records.shape[1:]) != (N.TOP_K, 4)):
                 raise ValueError("records: expected a contiguous CUDA float32 tensor [frames, 20, 4]")
-        self._records = records
+        self._rec_out = records
         if records is None or not self._lane_ctx:
             N.check(self.lib.lg_set_record_output(self._ctx, _ptr(records)), "lg_set_record_output")
             for ctx in self._lane_ctx:
@@ -212,8 +212,8 @@ class GraspEngine:
         n = labels_host.shape[0]
         if depth_host.shape[0] != n:
             raise ValueError("labels and depth hold different numbers of frames")
-        if self._lane_ctx and getattr(self, "_records", None) is not None:
-            N.check(self.lib.lg_set_record_output(self._ctx, _ptr(self._records)), "lg_set_record_output")
+        if self._lane_ctx and self._rec_out is not None:
+            N.check(self.lib.lg_set_record_output(self._ctx, _ptr(self._rec_out)), "lg_set_record_output")
         out = np.empty(n, dtype=N.FRAME_RESULT)
         with torch.cuda.device(self.device):
             N.check(self.lib.lg_process_batch_host(self._ctx, _ptr(labels_host), _ptr(depth_host), n, C.byref(cam),
