@@ -9,6 +9,7 @@
 #include <mutex>
 #include <new>
 #include <utility>
+#include <vector>
 
 #include "lg_internal.cuh"
 
@@ -79,6 +80,7 @@ int dev_alloc(lg_context* c, T** p, size_t count) {
     if (bytes == 0) bytes = sizeof(T);
     LG_CUDA(cudaMalloc((void**)p, bytes));
     c->bytes += bytes;
+    static_cast<std::vector<void*>*>(c->allocs)->push_back((void*)*p);
     return LG_OK;
 }
 
@@ -101,15 +103,23 @@ extern "C" int lg_create(lg_context** out, int max_frames, int height, int width
     memset(c, 0, sizeof(*c));
     c->B = max_frames; c->H = height; c->W = width; c->L = max_labels;
     c->P = (size_t)height * width;
+    c->allocs = new (std::nothrow) std::vector<void*>();
+    if (!c->allocs) { delete c; return LG_E_ARG; }
     const size_t B = max_frames, L = max_labels, P = c->P;
     int rc = LG_OK;
     auto A = [&](auto pp, size_t count) { if (!rc) rc = dev_alloc(c, pp, count); };
     A(&c->cnt, B * L); A(&c->sx, B * L); A(&c->sy, B * L); A(&c->sdep, B * L); A(&c->sdist, B * L);
     A(&c->bx0, B * L); A(&c->bx1, B * L); A(&c->by0, B * L); A(&c->by1, B * L); A(&c->border, B * L);
     A(&c->kmin, B * L); A(&c->kmax, B * L); A(&c->ray_tab, P);
-    A(&c->first_leaf, B); A(&c->seg_off, B * (L + 1)); A(&c->seg_cur, B * L); A(&c->seg, B * P); A(&c->median, B * L);
+    A(&c->first_leaf, B); A(&c->seg, B * P); A(&c->median, B * L);
+    c->lstride = (int)((L + 1 + 7) & ~(size_t)7);
+    A(&c->tile_off, B * (size_t)height * c->lstride);
+    c->ub_stride = ((size_t)height * ((width + 7) / 8) + 15) & ~(size_t)15;
+    A(&c->ubits, B * c->ub_stride);
     c->edt_nchunks = (width + 31) / 32;
-    A(&c->edt_g, B * P); A(&c->edt_gmin, B * (size_t)height * c->edt_nchunks); A(&c->edt_best, B); A(&c->leaf_id, B); A(&c->records, B * L); A(&c->status, B); A(&c->region, B);
+    c->Hw = (height + 31) / 32; c->H8 = (height + 7) / 8;
+    A(&c->vbits, B * (size_t)c->Hw * width); A(&c->vup, B * (size_t)c->Hw * width); A(&c->vdn, B * (size_t)c->Hw * width);
+    A(&c->edt_gmin, B * (size_t)height * c->edt_nchunks); A(&c->edt_g8, B * (size_t)c->H8 * c->edt_nchunks); A(&c->edt_best, B); A(&c->leaf_id, B); A(&c->records, B * L); A(&c->status, B); A(&c->region, B);
     A(&c->dt_fwd, 2 * B * P); A(&c->di, B * P); A(&c->dt_max, B * 2);
     A(&c->bnd_list, B * (size_t)LG_BND_CAP); A(&c->bnd_count, B); A(&c->need_full, B);
     c->bits_stride = (size_t)((width + 2 + 31) / 32) * (height + 2);
@@ -156,14 +166,14 @@ extern "C" int lg_create(lg_context** out, int max_frames, int height, int width
 
 extern "C" void lg_destroy(lg_context* c) {
     if (!c) return;
-    void* ptrs[] = {c->slot_map, c->cnn_count, c->bnd_list, c->bnd_count, c->need_full, c->edt_gmin, c->kmin, c->kmax, c->ray_tab, c->cnt, c->sx, c->sy, c->sdep, c->sdist, c->bx0, c->bx1, c->by0, c->by1, c->border, c->first_leaf,
-                    c->seg_off, c->seg_cur, c->seg, c->median, c->edt_g, c->edt_best, c->leaf_id, c->records, c->status,
-                    c->region, c->dt_fwd, c->di, c->dt_max, c->bits, c->run_x0, c->run_x1, c->run_y, c->run_parent,
-                    c->row_first, c->hull, c->orient, c->m_sdf, c->m_app, c->m_acc, c->m_trad, c->m_flat, c->m_stem,
-                    c->m_valid, c->list_key, c->list_idx, c->list_n, c->patches, c->logits, c->results, c->cnn_act0,
-                    c->cnn_act1, c->in_labels, c->in_depth, c->results_all, c->cnn.blob, c->cnn.bf16_blob};
-    for (void* p : ptrs)
-        if (p) cudaFree(p);
+    if (c->allocs) {
+        std::vector<void*>* v = static_cast<std::vector<void*>*>(c->allocs);
+        for (void* p : *v)
+            if (p) cudaFree(p);
+        delete v;
+    }
+    if (c->cnn.blob) cudaFree(c->cnn.blob);
+    if (c->cnn.bf16_blob) cudaFree(c->cnn.bf16_blob);
     for (int i = 0; i < LG_MAX_HOST_CHUNKS; ++i)
         if (c->copy_ev[i]) cudaEventDestroy(c->copy_ev[i]);
     if (c->copy_gate) cudaEventDestroy(c->copy_gate);
@@ -173,9 +183,12 @@ extern "C" void lg_destroy(lg_context* c) {
         if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
     }
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
-    for (int r = 0; r < LG_PROF_RING; ++r)
-        for (int i = 0; i < LG_PROF_MARKS; ++i)
-            if (c->prof_ev[r][i]) cudaEventDestroy(c->prof_ev[r][i]);
+    if (c->prof) {
+        for (int r = 0; r < LG_PROF_RING; ++r)
+            for (int i = 0; i < LG_PROF_MARKS; ++i)
+                if (c->prof->ev[r][i]) cudaEventDestroy(c->prof->ev[r][i]);
+        delete c->prof;
+    }
     delete c;
 }
 
@@ -271,10 +284,11 @@ static int process_batch_impl(lg_context* c, const int16_t* labels, const float*
     TRY(check_batch(c, labels, depth, frames));
     if (!cam) return LG_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    if (c->prof_on) {
-        c->prof_slot = c->prof_calls % LG_PROF_RING;
-        ++c->prof_calls;
-        memset(c->prof_seen[c->prof_slot], 0, sizeof(c->prof_seen[0]));
+    if (c->prof && c->prof->on) {
+        LgProf* p = c->prof;
+        p->slot = p->calls % LG_PROF_RING;
+        ++p->calls;
+        memset(p->seen[p->slot], 0, sizeof(p->seen[0]));
     }
     lg_mark(c, LG_M_START, st);
     TRY(lg_run_stage1(c, labels, depth, frames, *cam, st));
@@ -443,14 +457,18 @@ extern "C" uint64_t lg_cnn_weight_floats(void) { return lg_cnn_blob_floats(); }
 
 extern "C" int lg_set_profiling(lg_context* c, int on) {
     if (!c) return LG_E_ARG;
-    if (on && !c->prof_ev[0][0]) {
+    if (!c->prof) {
+        if (!on) return LG_OK;
+        c->prof = new (std::nothrow) LgProf();
+        if (!c->prof) return LG_E_ARG;
+        memset(c->prof, 0, sizeof(LgProf));
         for (int r = 0; r < LG_PROF_RING; ++r)
-            for (int i = 0; i < LG_PROF_MARKS; ++i) LG_CUDA(cudaEventCreate(&c->prof_ev[r][i]));
+            for (int i = 0; i < LG_PROF_MARKS; ++i) LG_CUDA(cudaEventCreate(&c->prof->ev[r][i]));
     }
-    c->prof_on = on ? 1 : 0;
-    c->prof_slot = 0;
-    c->prof_calls = 0;
-    memset(c->prof_seen, 0, sizeof(c->prof_seen));
+    c->prof->on = on ? 1 : 0;
+    c->prof->slot = 0;
+    c->prof->calls = 0;
+    memset(c->prof->seen, 0, sizeof(c->prof->seen));
     return LG_OK;
 }
 
@@ -459,8 +477,8 @@ extern "C" int lg_set_profiling(lg_context* c, int on) {
  * that follow a join start at the join mark); 0 for stages that did not run.  Stages on different streams overlap, so
  * the sum can exceed the step time.  Synchronises on the recorded events. */
 static int stage_times_of_slot(lg_context* c, int slot, float* ms) {
-    const int* seen = c->prof_seen[slot];
-    cudaEvent_t* ev = c->prof_ev[slot];
+    const int* seen = c->prof->seen[slot];
+    cudaEvent_t* ev = c->prof->ev[slot];
     for (int i = 0; i < LG_M_COUNT; ++i) ms[i] = 0.f;
     if (!seen[LG_M_START]) return LG_OK;
     int pred[LG_PROF_MARKS];
@@ -489,16 +507,17 @@ static int stage_times_of_slot(lg_context* c, int slot, float* ms) {
 extern "C" int lg_stage_times(lg_context* c, float* ms, int n) {
     if (!c || !ms || n < LG_M_COUNT) return LG_E_ARG;
     for (int i = 0; i < n; ++i) ms[i] = 0.f;
-    if (!c->prof_on || c->prof_calls == 0) return LG_OK;
-    return stage_times_of_slot(c, c->prof_slot, ms);
+    if (!c->prof || !c->prof->on || c->prof->calls == 0) return LG_OK;
+    return stage_times_of_slot(c, c->prof->slot, ms);
 }
 
 extern "C" int lg_stage_times_mean(lg_context* c, float* ms, int n, int* calls_out) {
     if (!c || !ms || n < LG_M_COUNT) return LG_E_ARG;
     for (int i = 0; i < n; ++i) ms[i] = 0.f;
-    const int calls = c->prof_calls < LG_PROF_RING ? c->prof_calls : LG_PROF_RING;
-    if (calls_out) *calls_out = c->prof_on ? calls : 0;
-    if (!c->prof_on || calls == 0) return LG_OK;
+    const bool on = c->prof && c->prof->on;
+    const int calls = !on ? 0 : (c->prof->calls < LG_PROF_RING ? c->prof->calls : LG_PROF_RING);
+    if (calls_out) *calls_out = calls;
+    if (calls == 0) return LG_OK;
     for (int r = 0; r < calls; ++r) {
         float one[LG_PROF_MARKS];
         TRY(stage_times_of_slot(c, r, one));

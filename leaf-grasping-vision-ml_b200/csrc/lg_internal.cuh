@@ -68,10 +68,21 @@ struct LgCnn {
     int is_default;     // 3 blocks [64,128,256], spatial attention: the one the live node builds
 };
 
+// Per-stage timing (lg_set_profiling): a ring of event sets, so that the stage times of up to LG_PROF_RING consecutive calls
+// can be read back afterwards and a benchmark does not have to synchronise after every step of its timed region.
+struct LgProf {
+    int on;
+    int slot;                                // ring slot of the call in progress / last call
+    int calls;                               // lg_process_batch calls since lg_set_profiling(ctx, 1)
+    cudaEvent_t ev[LG_PROF_RING][LG_PROF_MARKS];
+    int seen[LG_PROF_RING][LG_PROF_MARKS];
+};
+
 struct lg_context {
     int B, H, W, L;
     size_t P;
     uint64_t bytes;
+    void* allocs;                  // std::vector<void*>* of everything dev_alloc handed out (freed by lg_destroy)
     // ---- stage 1 tables, [B][L] unless noted
     uint32_t* cnt;
     unsigned long long *sx, *sy, *sdep, *sdist;
@@ -81,12 +92,19 @@ struct lg_context {
     lg_camera ray_cam;
     int ray_valid;
     uint32_t* first_leaf;          // [B] flat index of the first pixel with label >= 1
-    uint32_t* seg_off;             // [B][L+1]
-    uint32_t* seg_cur;             // [B][L]
-    float* seg;                    // [B][P] depth values grouped by label
+    float* seg;                    // [B][P] depth values of the leaf pixels, grouped by label inside every image row
+    uint16_t* tile_off;            // [B][H][lstride] per row: offset of every label's sub-block, entry L = total
+    int lstride;
+    uint8_t* ubits;                // [B][H][ceil(W/8)] (frame stride ub_stride) bit x%8 of byte x/8: pixel belongs to a leaf
+    size_t ub_stride;
     float* median;                 // [B][L]
-    uint16_t* edt_g;               // [B][P] column distances
-    uint16_t* edt_gmin;            // [B][H][edt_nchunks] minimum of edt_g over each chunk of 32 columns
+    // column pass of the exact distance transform (of the leaf union, or of a caller's mask): per column vertical bit
+    // words of the sources and the distance to the nearest source above / below every word
+    uint32_t* vbits;               // [B][Hw][W]
+    uint16_t *vup, *vdn;           // [B][Hw][W]
+    int Hw, H8;                    // ceil(H / 32), ceil(H / 8)
+    uint16_t* edt_gmin;            // [B][H][edt_nchunks] minimum of the column distance over each chunk of 32 columns
+    uint16_t* edt_g8;              // [B][H8][edt_nchunks] the same over blocks of 8 rows
     int edt_nchunks;
     unsigned long long* edt_best;  // [B] packed (d2 << 32 | ~index)
     int32_t* leaf_id;              // [B]
@@ -140,13 +158,7 @@ struct lg_context {
     cudaEvent_t ev_fork[2], ev_join[2];
     int overlap;
     // optional per-stage timing (lg_set_profiling): events recorded on the stream the stage runs on
-    // (a ring of event sets: the per-stage times of up to LG_PROF_RING consecutive calls can be read back afterwards,
-    // so a benchmark does not have to synchronise after every step to time the stages of its timed region)
-    int prof_on;
-    int prof_slot;                           // ring slot of the call in progress / last call
-    int prof_calls;                          // lg_process_batch calls since lg_set_profiling(ctx, 1)
-    cudaEvent_t prof_ev[LG_PROF_RING][LG_PROF_MARKS];
-    int prof_seen[LG_PROF_RING][LG_PROF_MARKS];
+    LgProf* prof;                            // host-side state, kept out of this struct: kernels take the struct by value
     // constants
     float gauss[25];
     int se30_a[LG_SE_STEM], se30_b[LG_SE_STEM];   // per structuring-element row: first / last+1 column
@@ -177,7 +189,8 @@ extern unsigned long long g_lg_launches;
         LG_CUDA(cudaGetLastError()); \
     } while (0)
 static inline void lg_mark(lg_context* c, int id, cudaStream_t st) {
-    if (c->prof_on) { cudaEventRecord(c->prof_ev[c->prof_slot][id], st); c->prof_seen[c->prof_slot][id] = 1; }
+    LgProf* p = c->prof;
+    if (p && p->on) { cudaEventRecord(p->ev[p->slot][id], st); p->seen[p->slot][id] = 1; }
 }
 
 // stage launchers (defined across the .cu files); all asynchronous on `st`

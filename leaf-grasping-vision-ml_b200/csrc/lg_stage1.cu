@@ -1,16 +1,18 @@
 // Stage 1 - optimal-leaf selection (reference scripts/utils/leaf_scorer.py:25-203, 277-306).
 //
 // Kernels (all batched over frames, no host synchronisation):
-//   leaf_stats_kernel    one walk down every column of labels + depth: per-label pixel count, coordinate sums, depth
-//                        sum, sum of ray lengths, bounding box, border contact, depth key range, first leaf pixel of
-//                        the frame; the same walk is the column pass of the union distance transform
-//   leaf_offsets_kernel  exclusive scan of the counts -> where each label's depth values go
-//   leaf_scatter_kernel  groups the depth values by label (order inside a group is irrelevant)
-//   leaf_median_kernel   exact np.median per label by radix selection on the grouped values
-//   edt_row_kernel / edt_rowmax_kernel   row pass of the exact squared Euclidean distance transform of (labels >= 1),
-//                        as a pruned search for the background pixel farthest from every leaf (the only thing
-//                        leaf_scorer.py:67-71 takes from its distance field)
-//   edt_col_kernel       stand-alone column pass (lg_edt_squared on a caller-supplied mask)
+//   leaf_rows_kernel     ONE pass over labels + depth, 128-bit loads, 8 pixels per thread: per-label pixel count, coordinate
+//                        sums, depth sum, sum of ray lengths, bounding box, border contact, depth key range, first leaf
+//                        pixel of the frame - and, from the same registers, the depth values of the leaf pixels grouped
+//                        by label inside every image row (what the median needs) and the bit mask of the leaf union
+//                        (what the distance transform needs).  Nothing re-reads the inputs.
+//   leaf_median_kernel   exact np.median per label by radix selection over the label's per-row sub-blocks
+//   edt_vcol_kernel      column pass of the exact squared Euclidean distance transform of the leaf union, from the bit
+//                        mask: per column vertical bit words + the distance to the nearest leaf pixel above / below every
+//                        32-row word (column distances are then three loads and a few bit operations, never stored), and
+//                        the minima of the column distance over 32-column chunks per row and per block of 8 rows
+//   edt_seed_kernel / edt_blockmax_kernel / edt_row_kernel   row pass as a pruned search for the background pixel
+//                        farthest from every leaf (the only thing leaf_scorer.py:67-71 takes from its distance field)
 //   select_leaf_kernel   the per-leaf scores, tall-leaf rule, Pareto front and weighted pick
 //
 // Integer sums are exact and order independent, so results do not depend on scheduling: coordinate
@@ -21,19 +23,13 @@
 
 namespace {
 
-constexpr int ST_NT = 256;
-constexpr int ST_PX = 8;
+constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr double DEP_SCALE = 268435456.0;       // 2^28
 constexpr double DIST_SCALE = 68719476736.0;    // 2^36
 
-struct SmemLeaf {
-    unsigned cnt, sx, sy, bx0, bx1, by0, by1, border, kmin, kmax;
-    unsigned long long sdep, sdist;
-};
-
 __device__ __forceinline__ unsigned f2key(float f) {   // order-preserving float -> uint32 key
-    unsigned u = __float_as_uint(f);
-    return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+    const unsigned u = __float_as_uint(f);
+    return u ^ ((unsigned)((int)u >> 31) | 0x80000000u);
 }
 __device__ __forceinline__ float key2f(unsigned k) {
     unsigned u = (k & 0x80000000u) ? (k ^ 0x80000000u) : ~k;
@@ -46,157 +42,330 @@ __global__ void clear_tables_kernel(lg_context c, int n) {
         c.cnt[i] = 0; c.sx[i] = 0; c.sy[i] = 0; c.sdep[i] = 0; c.sdist[i] = 0;
         c.bx0[i] = 0xFFFFFFFFu; c.by0[i] = 0xFFFFFFFFu; c.bx1[i] = 0; c.by1[i] = 0; c.border[i] = 0;
         c.kmin[i] = 0xFFFFFFFFu; c.kmax[i] = 0;
-        c.seg_cur[i] = 0;
     }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         c.first_leaf[i] = 0xFFFFFFFFu; c.edt_best[i] = 0ull; c.status[i] = 0; c.list_n[i] = 0;
     }
 }
 
-// ray_tab[y * W + x] = sum over rows y' <= y of round(2^36 * sqrt(((x - cx)^2 + (y' - cy)^2) / f^2 + 1)): column-wise prefix
+// ray_tab[y * W + x] = sum over columns x' <= x of round(2^36 * sqrt(((x' - cx)^2 + (y - cy)^2) / f^2 + 1)): row-wise prefix
 // sums of the length of the viewing ray through a pixel per unit depth (leaf_scorer.py:104-113 with X = md (x - cx) / f,
-// Y = md (y - cy) / f, Z = md).  The sum over a vertical run of pixels is then a difference of two entries.  The table
-// depends on the camera only: it is built once per camera and read (L2-resident) by every frame.
+// Y = md (y - cy) / f, Z = md).  The sum over a horizontal run of pixels is then a difference of two entries; the per-pixel
+// terms are integers, so any grouping of the pixels gives the same total.  The table depends on the camera only: it is
+// built once per camera and read (L2-resident) by every frame.  One warp per row: 32-pixel segments, warp scan, carry.
 __global__ void ray_table_kernel(unsigned long long* __restrict__ tab, int H, int W, lg_camera cam) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= W) return;
+    const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (y >= H) return;
     const double inv_f2 = 1.0 / (cam.f * cam.f);
-    const double ddx = (double)x - cam.cx;
-    unsigned long long acc = 0;
-    for (int y = 0; y < H; ++y) {
-        const double ddy = (double)y - cam.cy;
-        const double sv = sqrt((ddx * ddx + ddy * ddy) * inv_f2 + 1.0);
-        acc += (unsigned long long)__double2ll_rn(sv * DIST_SCALE);
-        tab[(size_t)y * W + x] = acc;
+    const double ddy = (double)y - cam.cy;
+    unsigned long long carry = 0;
+    for (int x0 = 0; x0 < W; x0 += 32) {
+        const int x = x0 + lane;
+        unsigned long long v = 0;
+        if (x < W) {
+            const double ddx = (double)x - cam.cx;
+            v = (unsigned long long)__double2ll_rn(sqrt((ddx * ddx + ddy * ddy) * inv_f2 + 1.0) * DIST_SCALE);
+        }
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long t = __shfl_up_sync(FULL, v, d);
+            if (lane >= d) v += t;
+        }
+        v += carry;
+        if (x < W) tab[(size_t)y * W + x] = v;
+        carry = __shfl_sync(FULL, v, 31);
     }
 }
 
-// One pass over labels + depth.  A thread walks down one column: labels are piecewise constant along a column
-// (a leaf is ~100 rows tall), so the thread carries the sums of its current run in registers and updates the CTA's
-// shared-memory table only when the label changes - about ten updates per column instead of one per 8 pixels.
-// Everything that depends on the pixel position only has a closed form per run (count, coordinate sums, bounding
-// box, border contact) or is a difference of two ray_tab entries; per pixel only the depth is accumulated (2^-28
-// fixed point, exact and order independent) and its key range tracked.  Loads run ST_U rows ahead.
-constexpr int ST_U = 8;
-#ifndef LG_STATS_NT
-#define LG_STATS_NT 128
-#endif
-#ifndef LG_STATS_MINB
-#define LG_STATS_MINB 8
-#endif
-constexpr int STC_NT = LG_STATS_NT;   // columns per CTA
-constexpr int STC_BND = 40;   // leaf-run boundaries (20 runs) a column can record for the distance transform
+// ---------------------------------------------------------------------------------------------------
+// the one pass over the inputs
+// ---------------------------------------------------------------------------------------------------
+// A CTA owns a range of image rows of one frame; one iteration handles one row ("tile"), a thread 8 consecutive pixels.
+//
+// Statistics.  Labels are piecewise constant (a leaf is 100-350 px wide): a thread's 8 pixels almost always carry one
+// label, and the threads of a warp (256 px) one to three.  Everything that depends on the position only has a closed form
+// (count, coordinate sums, bounding box, border contact) or is a difference of two ray_tab entries; per pixel only the depth
+// is accumulated (2^-28 fixed point, exact and order independent) and its key range tracked.  Threads whose 8 pixels are
+// uniform are reduced per label with full-warp redux operations (a short loop over the distinct labels of the warp), and
+// one lane per label updates the CTA's shared-memory table; the few threads that contain a label boundary (~12 per row)
+// add their runs directly.  What only depends on the row - pixel count, sum of y, vertical extent, top / bottom border -
+// is added once per row and label by the warp that scans the row's counts.  The table goes to the frame's table once,
+// when the CTA is done.
+//
+// Grouped depth values.  np.median needs the depths of every leaf's pixels.  Inside a row the leaf pixels are stored
+// grouped by ascending label: seg[y * W + off[l] ...], with the row's offsets off[0..L] (u16) in tile_off.  The positions
+// inside a row do not depend on any other row, so no frame-wide count or scan is needed before the values can be written,
+// and the median kernel walks the rows of its label's bounding box.  Only labels >= 1 are stored: the reference drops the
+// smallest id present (the background), which is 0 whenever 0 occurs at all.
+//
+// Union mask.  ubits[y][x / 8] bit x % 8 = (label of pixel (x, y) >= 1): one byte per thread and row.
+constexpr int TS_PX = 8;
 
-// the vertical run [ya, yb] of label `cur` in column x ends: add its sums to the CTA's table (rare: ~10 per column)
-__device__ __noinline__ void stats_flush_run(SmemLeaf* tab, int cur, int x, int ya, int yb, int W, int H, unsigned kmn, unsigned kmx,
-                                             long long sdep, const unsigned long long* rt) {
-    SmemLeaf* t = &tab[cur];
-    const unsigned len = (unsigned)(yb - ya + 1);
-    atomicAdd(&t->cnt, len);
-    if (cur > 0) {
-        atomicAdd(&t->sx, (unsigned)x * len);
-        atomicAdd(&t->sy, (unsigned)(ya + yb) * len / 2u);
-        atomicMin(&t->bx0, (unsigned)x); atomicMax(&t->bx1, (unsigned)x);
-        atomicMin(&t->by0, (unsigned)ya); atomicMax(&t->by1, (unsigned)yb);
-        if (x == 0 || x == W - 1 || ya == 0 || yb == H - 1) atomicOr(&t->border, 1u);
-        atomicMin(&t->kmin, kmn); atomicMax(&t->kmax, kmx);
-        atomicAdd(&t->sdep, (unsigned long long)sdep);
-        const unsigned long long hi = rt[(size_t)yb * W], lo = ya > 0 ? rt[(size_t)(ya - 1) * W] : 0ull;
-        atomicAdd(&t->sdist, hi - lo);
-    }
-}
-// The same walk is the column pass of the union distance transform (edt_col_kernel with source = label >= 1): the
-// kernel also writes the column distances c.edt_g and, on the way back up, their chunk minima c.edt_gmin.
-__global__ void __launch_bounds__(STC_NT, LG_STATS_MINB) leaf_stats_kernel(lg_context c, const int16_t* __restrict__ labels,
-                                                            const float* __restrict__ depth) {
-    extern __shared__ SmemLeaf tab[];
+struct SmemLeaf {
+    unsigned cnt, sx, sy, bx0, bx1, by0, by1, border, kmin, kmax;
+    unsigned long long sdep, sdist;
+};
+
+template <bool VEC>
+__global__ void __launch_bounds__(512, 2) leaf_rows_kernel(lg_context c, const int16_t* __restrict__ labels,
+                                                           const float* __restrict__ depth, int rows_per_cta) {
+    extern __shared__ __align__(16) unsigned char ts_smem[];
     __shared__ unsigned s_first, s_bad;
-    const int L = c.L, W = c.W, H = c.H;
+    const int L = c.L, W = c.W, H = c.H, NT = blockDim.x;
     const size_t P = c.P;
-    const int b = blockIdx.y;
-    // rows where this column enters (even entries) / leaves (odd entries) the union of all leaves: [STC_BND][STC_NT]
-    uint16_t* bnd = reinterpret_cast<uint16_t*>(tab + L) + threadIdx.x;
-    int nb = 0;
-    bool in_src = false;
-    for (int l = threadIdx.x; l < L; l += STC_NT) {
+    SmemLeaf* tab = reinterpret_cast<SmemLeaf*>(ts_smem);
+    unsigned* cur2 = reinterpret_cast<unsigned*>(tab + L);        // [2][L]: per-row pixel counts, then write cursors
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int l = tid; l < L; l += NT) {
         SmemLeaf z;
         z.cnt = 0; z.sx = 0; z.sy = 0; z.bx0 = 0xFFFFFFFFu; z.by0 = 0xFFFFFFFFu; z.bx1 = 0; z.by1 = 0;
         z.border = 0; z.kmin = 0xFFFFFFFFu; z.kmax = 0; z.sdep = 0; z.sdist = 0;
         tab[l] = z;
+        cur2[l] = 0; cur2[L + l] = 0;
     }
-    if (threadIdx.x == 0) { s_first = 0xFFFFFFFFu; s_bad = 0; }
+    if (tid == 0) { s_first = 0xFFFFFFFFu; s_bad = 0; }
     __syncthreads();
-    const int x = blockIdx.x * STC_NT + threadIdx.x;
-    if (x < W) {
-        const int16_t* lp = labels + (size_t)b * P + x;
-        const float* dp = depth + (size_t)b * P + x;
-        const unsigned long long* rt = c.ray_tab + x;
-        int cur = -1, ya = 0;
-        bool seen_leaf = false;
+    const int16_t* lp = labels + (size_t)b * P;
+    const float* dp = depth + (size_t)b * P;
+    float* seg = c.seg + (size_t)b * P;
+    uint8_t* ub = c.ubits + (size_t)b * c.ub_stride;
+    const int ubw = (W + 7) >> 3;
+    const int row0 = blockIdx.x * rows_per_cta, row1 = min(row0 + rows_per_cta, H);
+    uint16_t* toff_base = c.tile_off + (size_t)b * H * c.lstride;
+    const int x0 = tid * TS_PX;
+    const int npx = max(0, min(TS_PX, W - x0));
+    const unsigned lanes_lt = (1u << lane) - 1u;
+    const unsigned llim = (unsigned)L * 0x00010001u;      // L in both halfwords (L <= 1024)
+
+    // 2^28 * depth is exact in float32 (power-of-two scale), so the fixed-point term equals the float64 formulation
+    auto fixed28 = [](float v) -> long long { return __float2ll_rn(fminf(fmaxf(v, -2048.f), 2048.f) * 268435456.f); };
+
+    // Items (label il >= 0 or -1 for none, pixels [ix, ix + ilen) of the current row, their depth sum and key range) are
+    // reduced per distinct label of the warp with full-warp redux operations; one lane per label updates the shared-memory
+    // table.  Returns the lanes that hold an item with this lane's label (0 for label <= 0: nothing to place).
+    const unsigned long long* rrow = nullptr;
+    unsigned* tcnt = nullptr;
+    auto reduce_items = [&](int il, unsigned ix, unsigned ilen, long long isdep, unsigned ikmn, unsigned ikmx) -> unsigned {
+        unsigned gmask = 0;
+        unsigned todo = __ballot_sync(FULL, il >= 0);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            const int cl = __shfl_sync(FULL, il, src);
+            const bool mine = il == cl;
+            const unsigned gm = __ballot_sync(FULL, mine);
+            todo &= ~gm;
+            const unsigned gpx = __reduce_add_sync(FULL, mine ? ilen : 0u);
+            if (cl == 0) {
+                if (lane == src) atomicAdd(&tcnt[0], gpx);
+                continue;
+            }
+            if (mine) gmask = gm;
+            const unsigned gsx = __reduce_add_sync(FULL, mine ? ilen * ix + ilen * (ilen - 1u) / 2u : 0u);
+            const unsigned gxa = __reduce_min_sync(FULL, mine ? ix : 0xFFFFFFFFu);
+            const unsigned gxb = __reduce_max_sync(FULL, mine ? ix + ilen - 1u : 0u);
+            const unsigned gkmn = __reduce_min_sync(FULL, mine ? ikmn : 0xFFFFFFFFu);
+            const unsigned gkmx = __reduce_max_sync(FULL, mine ? ikmx : 0u);
+            // 64-bit sums as two redux operations: value = hi * 2^24 + lo, lo in [0, 2^24)
+            const unsigned glo = __reduce_add_sync(FULL, mine ? (unsigned)(isdep & 0xFFFFFFll) : 0u);
+            const int ghi = __reduce_add_sync(FULL, mine ? (int)(isdep >> 24) : 0);
+            unsigned long long gray = 0;
+            if (gxb - gxa + 1u == gpx) {
+                // the group's pixels are one horizontal run: one lane takes the difference of two table entries
+                if (lane == src) gray = rrow[gxb] - (gxa > 0 ? rrow[gxa - 1] : 0ull);
+            } else {
+                unsigned long long d = 0;
+                if (mine) d = rrow[ix + ilen - 1u] - (ix > 0 ? rrow[ix - 1] : 0ull);
+                const unsigned rlo = __reduce_add_sync(FULL, (unsigned)(d & 0xFFFFFFull));
+                const unsigned rhi = __reduce_add_sync(FULL, (unsigned)(d >> 24));
+                gray = ((unsigned long long)rhi << 24) + rlo;
+            }
+            if (lane == src) {
+                SmemLeaf* t = &tab[cl];
+                atomicAdd(&tcnt[cl], gpx);
+                atomicAdd(&t->sx, gsx);
+                atomicMin(&t->bx0, gxa); atomicMax(&t->bx1, gxb);
+                atomicMin(&t->kmin, gkmn); atomicMax(&t->kmax, gkmx);
+                atomicAdd(&t->sdep, (unsigned long long)(((long long)ghi << 24) + (long long)glo));
+                atomicAdd(&t->sdist, gray);
+            }
+        }
+        return gmask;
+    };
+
+    // the next row's pixels are in flight while the current row is reduced
+    uint4 nl = make_uint4(0, 0, 0, 0);
+    float nd[TS_PX];
+#pragma unroll
+    for (int k = 0; k < TS_PX; ++k) nd[k] = 0.f;
+    auto fetch = [&](int y) {
+        const size_t p0 = (size_t)y * W + x0;
+        if (VEC) {
+            if (npx > 0) {
+                nl = *reinterpret_cast<const uint4*>(lp + p0);
+                const float4 d0 = *reinterpret_cast<const float4*>(dp + p0), d1 = *reinterpret_cast<const float4*>(dp + p0 + 4);
+                nd[0] = d0.x; nd[1] = d0.y; nd[2] = d0.z; nd[3] = d0.w; nd[4] = d1.x; nd[5] = d1.y; nd[6] = d1.z; nd[7] = d1.w;
+            }
+        } else {
+            unsigned w[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int k = 0; k < TS_PX; ++k) {
+                const bool ok = k < npx;
+                const unsigned v = ok ? (unsigned)(unsigned short)lp[p0 + k] : 0u;
+                w[k >> 1] |= v << (16 * (k & 1));
+                nd[k] = ok ? dp[p0 + k] : 0.f;
+            }
+            nl = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    };
+    if (row0 < row1) fetch(row0);
+    int buf = 0;
+    for (int y = row0; y < row1; ++y, buf ^= 1) {
+        tcnt = cur2 + buf * L;
+        rrow = c.ray_tab + (size_t)y * W;
+        const int16_t* lrow = lp + (size_t)y * W;
+        const float* drow = dp + (size_t)y * W;
+        const uint4 cl4 = nl;
+        float val[TS_PX];
+#pragma unroll
+        for (int k = 0; k < TS_PX; ++k) val[k] = nd[k];
+        if (y + 1 < row1) fetch(y + 1);
+        // ---- this thread's 8 pixels, branch free: union byte, labels outside the table, uniformity
+        const unsigned cw[4] = {cl4.x, cl4.y, cl4.z, cl4.w};
+        unsigned ubyte = 0, badw = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const unsigned pos = __vcmpgts2(cw[q], 0u);                 // 0xFFFF per halfword that is >= 1
+            ubyte |= ((pos & 1u) | ((pos >> 15) & 2u)) << (2 * q);
+            badw |= __vcmplts2(cw[q], 0u) | __vcmpges2(cw[q], llim);
+        }
+        if (npx < TS_PX) {                                              // ragged end of the row (only without 128-bit loads)
+            ubyte &= (1u << npx) - 1u;
+            if (npx == 0) badw = 0;
+        }
+        const bool uniform = npx == TS_PX && cl4.x == cl4.y && cl4.y == cl4.z && cl4.z == cl4.w && (cl4.x >> 16) == (cl4.x & 0xFFFFu);
+        const bool mixed = npx > 0 && !uniform;
+        if (badw) s_bad = 1;
+        if (npx > 0) ub[(size_t)y * ubw + tid] = (uint8_t)ubyte;
+        {
+            const unsigned first = ubyte ? (unsigned)((size_t)y * W) + (unsigned)x0 + (unsigned)(__ffs(ubyte) - 1) : 0xFFFFFFFFu;
+            const unsigned wm = __reduce_min_sync(FULL, first);
+            if (lane == 0 && wm != 0xFFFFFFFFu) atomicMin(&s_first, wm);
+        }
+        // left / right image border (top / bottom rows are handled per row below)
+        if (x0 == 0 && npx > 0) { const int lb_ = (int)(short)(cl4.x & 0xFFFFu); if (lb_ >= 1 && lb_ < L) atomicOr(&tab[lb_].border, 1u); }
+        if (npx > 0 && x0 + npx == W) { const int le = (int)lrow[W - 1]; if (le >= 1 && le < L) atomicOr(&tab[le].border, 1u); }
+        // ---- uniform threads: one item of 8 pixels each
+        const int l0 = (int)(short)(cl4.x & 0xFFFFu);
+        const int ul = (uniform && !badw) ? l0 : -1;
         long long sdep = 0;
         unsigned kmn = 0xFFFFFFFFu, kmx = 0;
-        auto step = [&](int y, int l, float dv) {     // one pixel of the downward walk
-            if ((l >= 1) != in_src) {                 // the column enters / leaves the union of the leaves
-                if (nb < STC_BND) bnd[nb * STC_NT] = (uint16_t)y;
-                ++nb;
-                in_src = !in_src;
-            }
-            if (l < 0 || l >= L) { s_bad = 1; l = -1; }
-            if (l != cur) {
-                if (cur >= 0) stats_flush_run(tab, cur, x, ya, y - 1, W, H, kmn, kmx, sdep, rt);
-                cur = l; ya = y; sdep = 0; kmn = 0xFFFFFFFFu; kmx = 0;
-                if (l >= 1 && !seen_leaf) { atomicMin(&s_first, (unsigned)((size_t)y * W + x)); seen_leaf = true; }
-            }
-            if (l > 0) {
-                // 2^28 * depth is exact in float32 (power-of-two scale), so this equals the float64 formulation
-                const float dd = fminf(fmaxf(dv, -2048.f), 2048.f);
-                sdep += __float2ll_rn(dd * 268435456.f);
-                const unsigned key = f2key(dv);
+        if (ul >= 1) {
+#pragma unroll
+            for (int k = 0; k < TS_PX; ++k) {
+                sdep += fixed28(val[k]);
+                const unsigned key = f2key(val[k]);
                 kmn = min(kmn, key); kmx = max(kmx, key);
             }
-        };
-        int nl[ST_U];
-        float nd[ST_U];
-#pragma unroll
-        for (int k = 0; k < ST_U; ++k) {
-            nl[k] = k < H ? (int)lp[(size_t)k * W] : 0;
-            nd[k] = k < H ? dp[(size_t)k * W] : 0.f;
         }
-        const int16_t* lrow = lp;        // row y0 of this column
-        const float* drow = dp;
-        const size_t bump = (size_t)ST_U * W;
-        int y0 = 0;
-        for (; y0 + ST_U <= H; y0 += ST_U) {     // full batches: no bounds checks, running row pointers
-            int cl[ST_U];
-            float cd[ST_U];
+        const unsigned gmask = reduce_items(ul, (unsigned)x0, TS_PX, sdep, kmn, kmx);
+        // ---- threads with a label boundary (about a dozen per row): their pixels are dealt out one per lane, four
+        //      threads at a time, and go through the same reduction as items of one pixel (values re-read through L1)
+        const unsigned mixed_lanes = __ballot_sync(FULL, mixed);
+        for (unsigned mm = mixed_lanes; mm; ) {
+            const unsigned srcl = __fns(mm, 0, (lane >> 3) + 1);         // the (lane / 8 + 1)-th remaining mixed lane
+            const int x = srcl != 0xFFFFFFFFu ? ((warp << 5) + (int)srcl) * TS_PX + (lane & 7) : W;
+            int il = -1;
+            long long isdep = 0;
+            unsigned ikey = 0;
+            if (x < W) {
+                il = (int)lrow[x];
+                if (il < 0 || il >= L) il = -1;
+                if (il >= 1) { const float v = drow[x]; isdep = fixed28(v); ikey = f2key(v); }
+            }
+            reduce_items(il, (unsigned)x, 1u, isdep, ikey, ikey);
 #pragma unroll
-            for (int k = 0; k < ST_U; ++k) { cl[k] = nl[k]; cd[k] = nd[k]; }
-            if (y0 + 2 * ST_U <= H) {            // next batch in flight while this one is reduced
-#pragma unroll
-                for (int k = 0; k < ST_U; ++k) { nl[k] = (int)lrow[bump + (size_t)k * W]; nd[k] = drow[bump + (size_t)k * W]; }
-            } else {
-#pragma unroll
-                for (int k = 0; k < ST_U; ++k) {
-                    const bool ok = y0 + ST_U + k < H;
-                    nl[k] = ok ? (int)lrow[bump + (size_t)k * W] : 0;
-                    nd[k] = ok ? drow[bump + (size_t)k * W] : 0.f;
+            for (int q = 0; q < 4; ++q) mm &= mm - 1u;                  // four mixed lanes done
+        }
+        __syncthreads();
+        // ---- per row and label (warp 0; lane owns labels [la, lb)): pixel count, sum of y, vertical extent, top / bottom
+        //      border; then the row's offsets = exclusive scan of the counts of the labels >= 1.  The other warps clear the
+        //      other buffer for the next row meanwhile (everybody left its cursors behind before the barrier above).
+        if (warp == 0) {
+            const int chunk = (L + 31) >> 5;
+            const int la = min(lane * chunk, L), lb = min(la + chunk, L);
+            const bool edge_row = y == 0 || y == H - 1;
+            unsigned mine = 0;
+            for (int l = la; l < lb; ++l) {
+                const unsigned n = tcnt[l];
+                if (n) {
+                    SmemLeaf* t = &tab[l];
+                    t->cnt += n;
+                    if (l >= 1) {
+                        t->sy += (unsigned)y * n;
+                        t->by0 = min(t->by0, (unsigned)y); t->by1 = max(t->by1, (unsigned)y);
+                        if (edge_row) atomicOr(&t->border, 1u);
+                        mine += n;
+                    }
                 }
             }
+            unsigned incl = mine;
 #pragma unroll
-            for (int k = 0; k < ST_U; ++k) step(y0 + k, cl[k], cd[k]);
-            lrow += bump; drow += bump;
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned t = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl += t;
+            }
+            unsigned run = incl - mine;
+            uint16_t* toff = toff_base + (size_t)y * c.lstride;
+            for (int l = la; l < lb; ++l) {
+                const unsigned n = l >= 1 ? tcnt[l] : 0u;
+                toff[l] = (uint16_t)run;
+                tcnt[l] = run;
+                run += n;
+            }
+            if (lane == 31) toff[L] = (uint16_t)incl;
         }
+        if (warp != 0 || NT == 32) {
+            unsigned* other = cur2 + (buf ^ 1) * L;
+            const int first_t = NT == 32 ? 0 : 32, n_t = NT == 32 ? 32 : NT - 32;
+            for (int l = tid - first_t; l < L; l += n_t) other[l] = 0;
+        }
+        __syncthreads();
+        // ---- placement: one cursor bump per label group, the values go out in lane order
+        {
+            float* segr = seg + (size_t)y * W;
+            unsigned base = 0;
+            const int leader = gmask ? __ffs(gmask) - 1 : lane;
+            if (gmask && lane == leader) base = atomicAdd(&tcnt[ul], (unsigned)(TS_PX * __popc(gmask)));
+            base = __shfl_sync(FULL, base, leader);
+            if (gmask) {
+                float* o = segr + base + TS_PX * __popc(gmask & lanes_lt);
 #pragma unroll
-        for (int k = 0; k < ST_U; ++k)           // the last H % ST_U rows (already fetched)
-            if (y0 + k < H) step(y0 + k, nl[k], nd[k]);
-        if (cur >= 0) stats_flush_run(tab, cur, x, ya, H - 1, W, H, kmn, kmx, sdep, rt);
-        if (in_src) {                             // close the last run at the bottom edge
-            if (nb < STC_BND) bnd[nb * STC_NT] = (uint16_t)H;
-            ++nb;
+                for (int k = 0; k < TS_PX; ++k) o[k] = val[k];
+            }
+            for (unsigned mm = mixed_lanes; mm; ) {
+                const unsigned srcl = __fns(mm, 0, (lane >> 3) + 1);
+                const int x = srcl != 0xFFFFFFFFu ? ((warp << 5) + (int)srcl) * TS_PX + (lane & 7) : W;
+                int il = -1;
+                if (x < W) { il = (int)lrow[x]; if (il >= L) il = -1; }
+                unsigned todo = __ballot_sync(FULL, il >= 1);
+                while (todo) {
+                    const int src = __ffs(todo) - 1;
+                    const int cl = __shfl_sync(FULL, il, src);
+                    const bool mine = il == cl;
+                    const unsigned gm = __ballot_sync(FULL, mine);
+                    todo &= ~gm;
+                    unsigned pbase = 0;
+                    if (lane == src) pbase = atomicAdd(&tcnt[cl], (unsigned)__popc(gm));
+                    pbase = __shfl_sync(FULL, pbase, src);
+                    if (mine) segr[pbase + __popc(gm & lanes_lt)] = drow[x];
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) mm &= mm - 1u;
+            }
         }
     }
     __syncthreads();
-    for (int l = threadIdx.x; l < L; l += STC_NT) {
+    for (int l = tid; l < L; l += NT) {
         const SmemLeaf t = tab[l];
         if (t.cnt) {
             const size_t o = (size_t)b * L + l;
@@ -213,56 +382,9 @@ __global__ void __launch_bounds__(STC_NT, LG_STATS_MINB) leaf_stats_kernel(lg_co
             }
         }
     }
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         if (s_first != 0xFFFFFFFFu) atomicMin(&c.first_leaf[b], s_first);
         if (s_bad) atomicOr(&c.status[b], LG_ST_LABEL_RANGE);
-    }
-    {   // Column pass of the union distance transform, from the recorded run boundaries (no second look at the labels):
-        // g(y) = 0 inside a run, else the distance to the nearest run end above / run start below; plus the minimum of
-        // g over every chunk of 32 columns.  Whole warps take part: the reduction needs every lane.
-        const bool in = x < W;
-        uint16_t* gp = c.edt_g + (size_t)b * P + (in ? x : 0);
-        uint16_t* gm = c.edt_gmin + (size_t)b * H * c.edt_nchunks;
-        const int chunk = x >> 5, lane = threadIdx.x & 31, nchunks = c.edt_nchunks;
-        const bool wr_min = lane == 0 && chunk < nchunks;
-        const bool overflow = nb > STC_BND;
-        if (in && overflow) {      // more runs than the table holds (never on real frames): plain two sweeps for this column
-            const int16_t* lp = labels + (size_t)b * P + x;
-            unsigned d = 0xFFFFu;
-            for (int y = 0; y < H; ++y) { d = lp[(size_t)y * W] >= 1 ? 0u : min(d + 1u, 0xFFFFu); gp[(size_t)y * W] = (uint16_t)d; }
-            d = 0xFFFFu;
-            for (int y = H - 1; y >= 0; --y) { d = min((unsigned)gp[(size_t)y * W], min(d + 1u, 0xFFFFu)); gp[(size_t)y * W] = (uint16_t)d; }
-        }
-        int ri = 0;
-        int next_start = (in && !overflow && nb > 0) ? (int)bnd[0] : 0x7FFFFFF;
-        int cur_last = -1;           // last row of the run the walk is in, -1 when in a gap
-        int last_src = -0x7FFFFFF;   // last leaf row above
-        uint16_t* grow = gp;
-        uint16_t* mrow = gm + chunk;
-        for (int y = 0; y < H; ++y) {
-            unsigned gv = 0xFFFFu;
-            if (in) {
-                if (overflow) {
-                    gv = *grow;
-                } else {
-                    if (y == next_start) {
-                        cur_last = (int)bnd[(ri + 1) * STC_NT] - 1;
-                        ri += 2;
-                        next_start = ri < nb ? (int)bnd[ri * STC_NT] : 0x7FFFFFF;
-                    }
-                    if (cur_last >= 0) {
-                        gv = 0u;
-                        if (y == cur_last) { last_src = y; cur_last = -1; }
-                    } else {
-                        gv = (unsigned)min(min(y - last_src, next_start - y), 0xFFFF);
-                    }
-                    *grow = (uint16_t)gv;
-                }
-            }
-            const unsigned m = __reduce_min_sync(0xFFFFFFFFu, gv);
-            if (wr_min) *mrow = (uint16_t)m;
-            grow += W; mrow += nchunks;
-        }
     }
 }
 
@@ -271,91 +393,6 @@ __device__ __forceinline__ int background_id(const uint32_t* cnt, int L) {
     for (int l = 0; l < L; ++l)
         if (cnt[l]) return l;
     return -1;
-}
-
-__global__ void leaf_offsets_kernel(lg_context c, int n) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= n) return;
-    const uint32_t* cnt = c.cnt + (size_t)b * c.L;
-    uint32_t* off = c.seg_off + (size_t)b * (c.L + 1);
-    int bg = background_id(cnt, c.L);
-    uint32_t o = 0;
-    for (int l = 0; l < c.L; ++l) {
-        off[l] = o;
-        if (cnt[l] && l != bg) o += cnt[l];
-    }
-    off[c.L] = o;
-}
-
-// Groups the depth values by label.  Global atomics are taken once per (CTA, label): the CTA counts its
-// pixels per label in shared memory, reserves one contiguous range per label in the frame's segment and
-// hands out positions inside it from shared-memory cursors.
-__global__ void __launch_bounds__(ST_NT) leaf_scatter_kernel(lg_context c, const int16_t* __restrict__ labels,
-                                                              const float* __restrict__ depth) {
-    extern __shared__ unsigned s_cur[];   // [L] count, then absolute write cursor
-    const int L = c.L;
-    const size_t P = c.P;
-    const int b = blockIdx.y;
-    const size_t base = ((size_t)blockIdx.x * ST_NT + threadIdx.x) * ST_PX;
-    const uint32_t* cnt = c.cnt + (size_t)b * L;
-    __shared__ int s_bg;
-    if (threadIdx.x == 0) s_bg = background_id(cnt, L);
-    for (int l = threadIdx.x; l < L; l += ST_NT) s_cur[l] = 0;
-    __syncthreads();
-    const int bg = s_bg;
-    const int16_t* lp = labels + (size_t)b * P;
-    const float* dp = depth + (size_t)b * P;
-    int lab[ST_PX];
-    float val[ST_PX];
-    const int npx = base < P ? (int)min((size_t)ST_PX, P - base) : 0;
-    if (npx == ST_PX && ((reinterpret_cast<uintptr_t>(lp + base) | reinterpret_cast<uintptr_t>(dp + base)) & 15) == 0) {
-        const uint4 lv = *reinterpret_cast<const uint4*>(lp + base);
-        const float4 d0 = *reinterpret_cast<const float4*>(dp + base), d1 = *reinterpret_cast<const float4*>(dp + base + 4);
-        const unsigned w[4] = {lv.x, lv.y, lv.z, lv.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { lab[2 * k] = (int16_t)(w[k] & 0xFFFFu); lab[2 * k + 1] = (int16_t)(w[k] >> 16); }
-        val[0] = d0.x; val[1] = d0.y; val[2] = d0.z; val[3] = d0.w; val[4] = d1.x; val[5] = d1.y; val[6] = d1.z; val[7] = d1.w;
-    } else {
-#pragma unroll
-        for (int k = 0; k < ST_PX; ++k) {
-            lab[k] = k < npx ? (int)lp[base + k] : -1;
-            val[k] = k < npx ? dp[base + k] : 0.f;
-        }
-    }
-    // run starts: bit k set when pixel k opens a run; labels that are not scattered become -1
-    unsigned starts = 0;
-#pragma unroll
-    for (int k = 0; k < ST_PX; ++k) {
-        if (lab[k] < 0 || lab[k] >= L || lab[k] == bg) lab[k] = -1;
-        if (k == 0 || lab[k] != lab[k - 1]) starts |= 1u << k;
-    }
-#pragma unroll
-    for (int k = 0; k < ST_PX; ++k) {
-        if (((starts >> k) & 1u) && lab[k] >= 0) {
-            const unsigned rest = starts >> (k + 1);
-            const int len = rest ? __ffs(rest) : ST_PX - k;
-            atomicAdd(&s_cur[lab[k]], (unsigned)len);
-        }
-    }
-    __syncthreads();
-    for (int l = threadIdx.x; l < L; l += ST_NT) {
-        const unsigned n = s_cur[l];
-        if (n) s_cur[l] = c.seg_off[(size_t)b * (L + 1) + l] + atomicAdd(&c.seg_cur[(size_t)b * L + l], n);
-    }
-    __syncthreads();
-    float* seg = c.seg + (size_t)b * P;
-    unsigned pos = 0;
-#pragma unroll
-    for (int k = 0; k < ST_PX; ++k) {
-        if (lab[k] >= 0) {
-            if ((starts >> k) & 1u) {
-                const unsigned rest = starts >> (k + 1);
-                const int len = rest ? __ffs(rest) : ST_PX - k;
-                pos = atomicAdd(&s_cur[lab[k]], (unsigned)len);
-            }
-            seg[pos++] = val[k];
-        }
-    }
 }
 
 template <int NT>
@@ -377,10 +414,12 @@ __device__ __forceinline__ void block_sum3(unsigned& a, unsigned& b, unsigned& c
 
 constexpr int MED_NT = 256;
 constexpr int MED_CAP = 4096;    // candidate keys kept in shared memory once the search range is this small
-// np.median(depth[labels == l]) for every label of every frame (leaf_scorer.py:41-47): radix selection on the
-// values grouped by leaf_scatter_kernel, two key bits per pass.  The passes start at the first bit in which the
-// label's smallest and largest key differ (leaf_stats_kernel), and as soon as the surviving candidates fit in
-// shared memory they are compacted there, so only the first two or three passes stream the whole segment.
+// np.median(depth[labels == l]) for every label of every frame (leaf_scorer.py:41-47): radix selection on the label's
+// values, which leaf_rows_kernel left grouped by label inside every image row.  A pass over the values walks the rows of
+// the label's bounding box, one warp per row: two entries of the row's offset table give the sub-block.  Keys are
+// ranked relative to the label's smallest key; a label that does not fit shared memory gets one streaming pass with a
+// 256-bin histogram of the top 7-8 bits of its key range, a second pass compacts the <= 4096 candidates of the median's
+// bin into shared memory, and two-bit radix rounds finish there.
 __global__ void __launch_bounds__(MED_NT) leaf_median_kernel(lg_context c) {
     const int l = blockIdx.x, b = blockIdx.y, L = c.L;
     const uint32_t* cnt = c.cnt + (size_t)b * L;
@@ -392,37 +431,59 @@ __global__ void __launch_bounds__(MED_NT) leaf_median_kernel(lg_context c) {
     if (threadIdx.x == 0) { s_bg = background_id(cnt, L); s_n = 0; }
     __syncthreads();
     const unsigned n = cnt[l];
-    if (n == 0 || l == s_bg) {
+    if (n == 0 || l == s_bg || l == 0) {
         if (threadIdx.x == 0) c.median[(size_t)b * L + l] = CUDART_NAN_F;
         return;
     }
-    const float* v = c.seg + (size_t)b * c.P + c.seg_off[(size_t)b * (L + 1) + l];
-    const unsigned kmin = c.kmin[(size_t)b * L + l], kmax = c.kmax[(size_t)b * L + l];
+    const size_t o = (size_t)b * L + l;
+    const unsigned kmin = c.kmin[o], kmax = c.kmax[o];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // rows that hold pixels of this label
+    const unsigned W = (unsigned)c.W;
+    const int t_first = (int)c.by0[o], t_last = (int)c.by1[o];
+    const float* seg = c.seg + (size_t)b * c.P;
+    const uint16_t* toff = c.tile_off + (size_t)b * c.H * c.lstride + l;
+    // f(key, valid) for every value of the label; whole warps call it together (valid = false on the padding lanes)
+    // (warp w takes rows t_first + w, + 8, ...; its lanes fetch the offsets of 32 of those rows at once)
+    auto for_each_key = [&](auto f) {
+        constexpr int NW = MED_NT / 32;
+        for (int base = t_first + warp; base <= t_last; base += NW * 32) {
+            const int tr = base + NW * lane;
+            unsigned a = 0, z = 0;
+            if (tr <= t_last) { const uint16_t* e = toff + (size_t)tr * c.lstride; a = e[0]; z = e[1]; }
+            unsigned live = __ballot_sync(FULL, z > a);
+            while (live) {
+                const int s = __ffs(live) - 1;
+                live &= live - 1;
+                const unsigned aa = __shfl_sync(FULL, a, s), zz = __shfl_sync(FULL, z, s);
+                const float* v = seg + (size_t)(base + NW * s) * W;
+                for (unsigned i0 = aa; i0 < zz; i0 += 32) {
+                    const unsigned i = i0 + lane;
+                    const bool ok = i < zz;
+                    f(ok ? f2key(v[i]) - kmin : 0u, ok);
+                }
+            }
+        }
+    };
     const unsigned k_lo = (n & 1) ? n / 2 : n / 2 - 1;   // rank of the lower middle
     unsigned klo;            // key of rank k_lo
     unsigned below = 0;      // elements whose key is smaller than every current candidate
     unsigned m = n;          // current candidates
     bool in_smem = false;
     unsigned set_below = 0, set_m = 0;   // the compacted set: its size and the number of elements below it
-    const int lane = threadIdx.x & 31;
     auto compact = [&](unsigned prefix, unsigned pmask) {   // candidates (key & pmask) == prefix -> s_keys
-        for (unsigned i0 = 0; i0 < n; i0 += MED_NT) {
-            const unsigned i = i0 + threadIdx.x;
-            unsigned key = 0;
-            bool hit = false;
-            if (i < n) { key = (f2key(v[i]) - kmin); hit = (key & pmask) == prefix; }
-            const unsigned ball = __ballot_sync(0xFFFFFFFFu, hit);
+        for_each_key([&](unsigned key, bool ok) {
+            const bool hit = ok && (key & pmask) == prefix;
+            const unsigned ball = __ballot_sync(FULL, hit);
             if (ball) {
                 unsigned base = 0;
                 if (lane == 0) base = atomicAdd(&s_n, __popc(ball));
-                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                base = __shfl_sync(FULL, base, 0);
                 if (hit) s_keys[base + __popc(ball & ((1u << lane) - 1u))] = key;
             }
-        }
+        });
         __syncthreads();
     };
-    // keys are ranked relative to the label's smallest key: the search range is [0, kmax - kmin], so the first
-    // digit already splits the values that are present instead of a power-of-two block around them
     if (kmin == kmax) {
         klo = 0;
         below = 0; m = n;
@@ -433,14 +494,11 @@ __global__ void __launch_bounds__(MED_NT) leaf_median_kernel(lg_context c) {
         unsigned prefix = 0u;
         if (n <= MED_CAP) { compact(prefix, pmask); in_smem = true; set_below = 0; set_m = n; }
         else {
-            // Segments that do not fit: the first pass over the segment resolves the top 7-8 bits of the range at once
-            // (a 256-bin histogram in shared memory), which normally leaves few enough candidates to compact them in
-            // the second pass; two-bit digits would stream the segment once per factor of four.
             int s0 = max(top - 7, 0);
             s0 += s0 & 1;                                      // even, so that the two-bit rounds end at bit 0
             for (int i = threadIdx.x; i < 256; i += MED_NT) s_hist[i] = 0;
             __syncthreads();
-            for (unsigned i = threadIdx.x; i < n; i += MED_NT) atomicAdd(&s_hist[(f2key(v[i]) - kmin) >> s0], 1u);
+            for_each_key([&](unsigned key, bool ok) { if (ok) atomicAdd(&s_hist[key >> s0], 1u); });
             __syncthreads();
             if (threadIdx.x < 32) {                            // the bin that holds rank k_lo
                 unsigned mine = 0;
@@ -484,13 +542,12 @@ __global__ void __launch_bounds__(MED_NT) leaf_median_kernel(lg_context c) {
                     }
                 }
             } else {
-                for (unsigned i = threadIdx.x; i < n; i += MED_NT) {
-                    const unsigned key = (f2key(v[i]) - kmin);
-                    if ((key & pmask) == prefix) {
+                for_each_key([&](unsigned key, bool ok) {
+                    if (ok && (key & pmask) == prefix) {
                         const unsigned d = (key >> shift) & 3u;
                         c0 += (d == 0); c1 += (d == 1); c2 += (d == 2);
                     }
-                }
+                });
             }
             block_sum3<MED_NT>(c0, c1, c2, sm);
             const unsigned kk = k_lo - below;
@@ -519,7 +576,7 @@ __global__ void __launch_bounds__(MED_NT) leaf_median_kernel(lg_context c) {
             if (in_smem && k_lo + 1 < set_below + set_m) {
                 for (unsigned i = threadIdx.x; i < set_m; i += MED_NT) { const unsigned key = s_keys[i]; if (key > klo) mn = min(mn, key); }
             } else {
-                for (unsigned i = threadIdx.x; i < n; i += MED_NT) { const unsigned key = (f2key(v[i]) - kmin); if (key > klo) mn = min(mn, key); }
+                for_each_key([&](unsigned key, bool ok) { if (ok && key > klo) mn = min(mn, key); });
             }
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, d));
@@ -538,107 +595,164 @@ __global__ void __launch_bounds__(MED_NT) leaf_median_kernel(lg_context c) {
 // ---------------------------------------------------------------------------------------------------
 // exact squared Euclidean distance transform
 // ---------------------------------------------------------------------------------------------------
-struct EdtSrc {
-    const int16_t* labels;   // source (distance 0) where labels >= 1
-    const uint8_t* mask;     // source where mask == 0
-    __device__ __forceinline__ bool is_source(size_t i) const { return labels ? (labels[i] >= 1) : (mask[i] == 0); }
+// Column pass without a distance image.  For every column the kernel keeps the source pixels as vertical bit words
+// (bit r of word yw = row 32 yw + r is a source) plus, per word, the distance from its first row to the nearest source
+// strictly above (vup) and from its last row to the nearest source strictly below (vdn).  The column distance g(x, y) of
+// any pixel is then three coalesced loads and a count-leading / find-first on the word (g_of), so the row pass computes it
+// where it needs it instead of reading a [H][W] image the column pass would have to write (2 B/px, and the row pass reads
+// about 1/32 of it).  What the arg-max search reads everywhere are the minima of g over 32-column chunks: per row (gmin)
+// and per block of 8 rows (g8).
+struct SrcUnionBits {       // source = leaf pixel of the union mask leaf_rows_kernel wrote (rows of ceil(W / 8) bytes)
+    const uint8_t* ub;
+    size_t stride;
+    int ubw;
+    __device__ __forceinline__ bool at(int b, int x, int y) const {
+        return (ub[(size_t)b * stride + (size_t)y * ubw + (x >> 3)] >> (x & 7)) & 1u;
+    }
+};
+struct SrcMaskZero {        // source = zero pixel of a caller-supplied u8 mask (lg_edt_squared)
+    const uint8_t* mask;
+    size_t P;
+    int W;
+    __device__ __forceinline__ bool at(int b, int x, int y) const { return mask[(size_t)b * P + (size_t)y * W + x] == 0; }
 };
 
-// pass 1: per column, distance (in rows) to the nearest source pixel in that column; 0xFFFF = none.
-// gmin (optional): for every row the minimum of g over each chunk of 32 columns (one warp), [H][nchunks] per frame -
-// the arg-max search reads these instead of the rows themselves.
-__global__ void edt_col_kernel(EdtSrc src, uint16_t* __restrict__ g, uint16_t* __restrict__ gmin, int nchunks, int H, int W,
-                               size_t P) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+struct EdtCols {            // one frame's column-pass results
+    const uint32_t* vbits;  // [Hw][W]
+    const uint16_t* vup;    // [Hw][W]
+    const uint16_t* vdn;    // [Hw][W]
+    int W;
+    // column distance of pixel (x, y): 0 on a source, 0xFFFF when the column has none
+    __device__ __forceinline__ unsigned g_of(int x, int y) const {
+        const int r = y & 31;
+        const size_t o = (size_t)(y >> 5) * W + x;
+        const unsigned w = vbits[o];
+        if ((w >> r) & 1u) return 0u;
+        const unsigned mu = w << (31 - r), md = w >> r;
+        const unsigned du = mu ? (unsigned)__clz(mu) : (unsigned)r + vup[o];
+        const unsigned dd = md ? (unsigned)(__ffs(md) - 1) : (unsigned)(31 - r) + vdn[o];
+        return min(min(du, dd), 0xFFFFu);
+    }
+};
+__device__ __forceinline__ EdtCols edt_cols_of(const lg_context& c, int b) {
+    const size_t o = (size_t)b * c.Hw * c.W;
+    return EdtCols{c.vbits + o, c.vup + o, c.vdn + o, c.W};
+}
+
+constexpr int VC_NT = 128;
+template <class SRC>
+__global__ void __launch_bounds__(VC_NT) edt_vcol_kernel(lg_context c, SRC src, int want_min) {
+    const int W = c.W, H = c.H, Hw = c.Hw, b = blockIdx.y;
+    const int x = blockIdx.x * VC_NT + threadIdx.x, lane = threadIdx.x & 31;
     const bool in = x < W;
     const int xc = in ? x : W - 1;             // out-of-range lanes shadow the last column and store nothing
-    const size_t fo = (size_t)blockIdx.y * P;
-    uint16_t* gp = g + fo;
-    constexpr int U = 8;    // rows whose loads are in flight together (the sweep itself is sequential)
-    unsigned d = 0xFFFFu;
-    for (int y0 = 0; y0 < H; y0 += U) {
-        bool srcv[U];
+    const size_t fo = (size_t)b * Hw * W;
+    uint32_t* vb = c.vbits + fo;
+    uint16_t* vu = c.vup + fo;
+    uint16_t* vd = c.vdn + fo;
+    // downward: the words, and the distance to the nearest source above each word
+    unsigned since = 0xFFFFu;                  // distance from the row above the current word to the nearest source at or above it
+    for (int yw = 0; yw < Hw; ++yw) {
+        unsigned w = 0;
+        const int ybase = yw << 5;
+        if (ybase + 32 <= H) {
 #pragma unroll
-        for (int k = 0; k < U; ++k) srcv[k] = (y0 + k < H) ? src.is_source(fo + (size_t)(y0 + k) * W + xc) : false;
-#pragma unroll
-        for (int k = 0; k < U; ++k) {
-            if (y0 + k < H) {
-                d = srcv[k] ? 0u : min(d + 1u, 0xFFFFu);
-                if (in) gp[(size_t)(y0 + k) * W + x] = (uint16_t)d;
-            }
+            for (int r = 0; r < 32; ++r) w |= (src.at(b, xc, ybase + r) ? 1u : 0u) << r;
+        } else {
+            for (int r = 0; ybase + r < H; ++r) w |= (src.at(b, xc, ybase + r) ? 1u : 0u) << r;
         }
+        if (in) {
+            vb[(size_t)yw * W + x] = w;
+            vu[(size_t)yw * W + x] = (uint16_t)min(since + 1u, 0xFFFFu);
+        }
+        since = w ? (unsigned)__clz(w) : min(since + 32u, 0xFFFFu);
     }
-    d = 0xFFFFu;
-    const int chunk = x >> 5, lane = threadIdx.x & 31;
-    uint16_t* gm = gmin ? gmin + (size_t)blockIdx.y * H * nchunks : nullptr;
-    for (int y0 = H - 1; y0 >= 0; y0 -= U) {
-        unsigned cur[U];
-#pragma unroll
-        for (int k = 0; k < U; ++k) cur[k] = (y0 - k >= 0) ? gp[(size_t)(y0 - k) * W + xc] : 0xFFFFu;
-#pragma unroll
-        for (int k = 0; k < U; ++k) {
-            if (y0 - k >= 0) {
-                d = min(cur[k], min(d + 1u, 0xFFFFu));
-                if (in) gp[(size_t)(y0 - k) * W + x] = (uint16_t)d;
-                if (gm) {
-                    const unsigned m = __reduce_min_sync(0xFFFFFFFFu, in ? d : 0xFFFFu);
-                    if (lane == 0 && chunk < nchunks) gm[(size_t)(y0 - k) * nchunks + chunk] = (uint16_t)m;
+    // upward: the distance to the nearest source below each word, and the chunk minima of g
+    const int chunk = x >> 5, nchunks = c.edt_nchunks;
+    const bool wr = want_min && lane == 0 && chunk < nchunks;
+    uint16_t* gm = c.edt_gmin + (size_t)b * H * nchunks + chunk;
+    uint16_t* g8 = c.edt_g8 + (size_t)b * c.H8 * nchunks + chunk;
+    unsigned below = 0xFFFFu;                  // distance from the current word's last row to the nearest source strictly below
+    unsigned m8 = 0xFFFFu;
+    for (int yw = Hw - 1; yw >= 0; --yw) {
+        const size_t o = (size_t)yw * W + xc;
+        const unsigned w = vb[o];              // written by this thread (or, for a shadow lane, by the last column's thread of
+        const unsigned up0 = vu[o];            // this very warp: same value in either order)
+        if (in) vd[(size_t)yw * W + x] = (uint16_t)below;
+        if (want_min) {
+            const int ybase = yw << 5;
+#pragma unroll 4
+            for (int r = 31; r >= 0; --r) {
+                const int y = ybase + r;
+                if (y >= H) continue;
+                unsigned g = 0u;
+                if (!((w >> r) & 1u)) {
+                    const unsigned mu = w << (31 - r), md = w >> r;
+                    const unsigned du = mu ? (unsigned)__clz(mu) : (unsigned)r + up0;
+                    const unsigned dd = md ? (unsigned)(__ffs(md) - 1) : (unsigned)(31 - r) + below;
+                    g = min(min(du, dd), 0xFFFFu);
                 }
+                const unsigned m = __reduce_min_sync(FULL, in ? g : 0xFFFFu);
+                m8 = min(m8, m);
+                if (wr) {
+                    gm[(size_t)y * nchunks] = (uint16_t)m;
+                    if ((y & 7) == 0) g8[(size_t)(y >> 3) * nchunks] = (uint16_t)m8;
+                }
+                if ((y & 7) == 0) m8 = 0xFFFFu;
             }
         }
+        below = w ? (unsigned)__ffs(w) : min(below + 32u, 0xFFFFu);
     }
 }
 
+// exact search for pixel x of a row whose squared column distances are in srow (shared memory): d2(x) = min over x' of
+// (x - x')^2 + g(x')^2, abandoned as soon as the running value drops below lb (such a pixel cannot be the maximum)
+__device__ __forceinline__ unsigned edt_row_search(const unsigned* srow, int W, int x, unsigned lb) {
+    unsigned bestd = srow[x];
+    if (bestd < lb) return bestd;
+    if (lb) {   // probes at doubling offsets: almost every pixel near a source drops below the bound here
+        for (unsigned k = 1; k * k < bestd; k <<= 1) {
+            const int xl = x - (int)k, xr = x + (int)k;
+            if (xl < 0 && xr >= W) break;
+            const unsigned kk = k * k;
+            if (xl >= 0) { const unsigned s = srow[xl]; if (s != 0xFFFFFFFFu) bestd = min(bestd, s + kk); }
+            if (xr < W) { const unsigned s = srow[xr]; if (s != 0xFFFFFFFFu) bestd = min(bestd, s + kk); }
+        }
+        if (bestd < lb) return bestd;
+    }
+    for (unsigned k = 1; k * k < bestd; ++k) {
+        const int xl = x - (int)k, xr = x + (int)k;
+        if (xl < 0 && xr >= W) break;
+        const unsigned kk = k * k;
+        if (xl >= 0) { const unsigned s = srow[xl]; if (s != 0xFFFFFFFFu) bestd = min(bestd, s + kk); }
+        if (xr < W) { const unsigned s = srow[xr]; if (s != 0xFFFFFFFFu) bestd = min(bestd, s + kk); }
+        if (bestd < lb) break;
+    }
+    return bestd;
+}
+
 constexpr int EDT_NT = 256;
-// pass 2: per row, d2(x) = min over x' of (x - x')^2 + g(x')^2.  The search around x stops as soon
-// as the horizontal offset alone exceeds the best distance found (Meijster's lower-envelope bound).
-//
-// When only the arg-max of the field is wanted (d2out == nullptr, the leaf-selection use) a pixel is
-// dropped as soon as its running upper bound falls below the largest exact distance found so far in
-// the frame (best[b], shared by all CTAs through atomicMax): such a pixel can neither be the maximum
-// nor tie with it, so the result is exactly the first maximum of the full field whatever the
-// scheduling.  CTAs walk rows `stride` apart (a permutation of the rows) so that the bound comes
-// from all over the frame early, and every CTA handles several rows to profit from it.
-__global__ void __launch_bounds__(EDT_NT) edt_row_kernel(const uint16_t* __restrict__ g, uint32_t* __restrict__ d2out,
-                                                          unsigned long long* __restrict__ best, int H, int W, size_t P,
-                                                          int row_stride, int yi_begin, int yi_end) {
+// Row pass, full field (d2out != nullptr: lg_edt_squared) or arg-max with pruning against the frame's running maximum
+// (small images, where the block search below has nothing to prune with).  One CTA per row at a time; rows are visited in a
+// permuted order so that the bound comes from all over the frame early.
+__global__ void __launch_bounds__(EDT_NT) edt_row_kernel(lg_context c, uint32_t* __restrict__ d2out,
+                                                          unsigned long long* __restrict__ best, int row_stride) {
     extern __shared__ unsigned srow[];   // g squared, 0xFFFFFFFF = no source in that column
     __shared__ unsigned long long sbest[EDT_NT / 32];
-    __shared__ unsigned schunk[128];     // minimum of srow over each 32-column chunk (rows up to 4096 wide)
-    __shared__ unsigned s_lb;            // pruning bound of the current row
-    constexpr int MAXV = 16;             // row values per thread held in registers: rows up to 4096 wide
-    const int b = blockIdx.x;
+    __shared__ unsigned s_lb;
+    const int b = blockIdx.x, W = c.W, H = c.H;
+    const size_t P = c.P;
+    const EdtCols cols = edt_cols_of(c, b);
     const bool prune = (d2out == nullptr) && (best != nullptr);
     unsigned long long mybest = 0;       // CTA-wide best so far (identical in every thread)
-    const int nv = (W + EDT_NT - 1) / EDT_NT;
-    // the next row's column distances are fetched while the current row is searched
-    unsigned short nxt[MAXV];
-    auto fetch = [&](int yi) {
-        if (yi < yi_end) {
-            const int y = (int)(((long long)yi * row_stride) % H);
-            const uint16_t* gp = g + (size_t)b * P + (size_t)y * W;
-#pragma unroll
-            for (int k = 0; k < MAXV; ++k) {
-                const int x = threadIdx.x + k * EDT_NT;
-                nxt[k] = (k < nv && x < W) ? gp[x] : (unsigned short)0xFFFFu;
-            }
-        }
-    };
-    fetch(yi_begin + blockIdx.y);
-    for (int yi = yi_begin + blockIdx.y; yi < yi_end; yi += gridDim.y) {
+    for (int yi = blockIdx.y; yi < H; yi += gridDim.y) {
         const int y = (int)(((long long)yi * row_stride) % H);
         int any = 0;
-#pragma unroll
-        for (int k = 0; k < MAXV; ++k) {
-            const int x = threadIdx.x + k * EDT_NT;
-            if (k < nv && x < W) {
-                const unsigned v = nxt[k];
-                srow[x] = (v == 0xFFFFu) ? 0xFFFFFFFFu : v * v;
-                any |= (v != 0xFFFFu);
-            }
+        for (int x = threadIdx.x; x < W; x += EDT_NT) {
+            const unsigned v = cols.g_of(x, y);
+            srow[x] = (v == 0xFFFFu) ? 0xFFFFFFFFu : v * v;
+            any |= (v != 0xFFFFu);
         }
-        // one thread samples the frame's running maximum: the bound must be the same for the whole CTA (it steers
-        // barriers and warp shuffles below), and other CTAs raise best[b] concurrently
         if (threadIdx.x == 0) {
             unsigned v = 0;
             if (prune) {
@@ -649,70 +763,23 @@ __global__ void __launch_bounds__(EDT_NT) edt_row_kernel(const uint16_t* __restr
         }
         any = __syncthreads_or(any);     // srow and s_lb complete; does the row see any source at all?
         const unsigned lb = s_lb;
-        fetch(yi + gridDim.y);
         unsigned long long rowbest = 0;
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        const int nchunks = (W + 31) >> 5;
-        if (any && lb) {   // minimum of every 32-column chunk: lets a warp discard a whole chunk at once
-            for (int j = warp; j < nchunks; j += EDT_NT / 32) {
-                const int x = (j << 5) + lane;
-                unsigned v = x < W ? srow[x] : 0xFFFFFFFFu;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) v = min(v, __shfl_xor_sync(0xFFFFFFFFu, v, d));
-                if (lane == 0) schunk[j] = v;
-            }
-            __syncthreads();
-        }
         if (any) {
-            for (int j = warp; j < nchunks; j += EDT_NT / 32) {
-                if (lb) {
-                    // every pixel of chunk j is at most 31 + 32*dj columns away from the best column of chunk j +- dj
-                    unsigned long long ub = (unsigned long long)schunk[j] + 31ull * 31ull;
-                    for (int dj = 1; dj < nchunks; ++dj) {
-                        const unsigned long long off = (unsigned long long)(32 * dj + 31) * (32 * dj + 31);
-                        if (off >= lb || ub < lb) break;
-                        if (j - dj >= 0) ub = min(ub, (unsigned long long)schunk[j - dj] + off);
-                        if (j + dj < nchunks) ub = min(ub, (unsigned long long)schunk[j + dj] + off);
-                    }
-                    if (ub < lb) continue;
-                }
-                const int x = (j << 5) + lane;
-                if (x >= W) continue;
-                unsigned bestd = srow[x];
+            for (int x = threadIdx.x; x < W; x += EDT_NT) {
+                const unsigned bestd = edt_row_search(srow, W, x, lb);
                 if (bestd < lb) continue;
-                if (lb) {   // probes at doubling offsets: almost every pixel near a source drops below the bound here
-                    for (unsigned k = 1; k * k < bestd; k <<= 1) {
-                        const int xl = x - (int)k, xr = x + (int)k;
-                        if (xl < 0 && xr >= W) break;
-                        const unsigned kk = k * k;
-                        if (xl >= 0) { unsigned s = srow[xl]; if (s != 0xFFFFFFFFu) bestd = min(bestd, s + kk); }
-                        if (xr < W) { unsigned s = srow[xr]; if (s != 0xFFFFFFFFu) bestd = min(bestd, s + kk); }
-                    }
-                    if (bestd < lb) continue;
-                }
-                for (unsigned k = 1; k * k < bestd; ++k) {
-                    int xl = x - (int)k, xr = x + (int)k;
-                    if (xl < 0 && xr >= W) break;
-                    unsigned kk = k * k;
-                    if (xl >= 0) { unsigned s = srow[xl]; if (s != 0xFFFFFFFFu) bestd = min(bestd, s + kk); }
-                    if (xr < W) { unsigned s = srow[xr]; if (s != 0xFFFFFFFFu) bestd = min(bestd, s + kk); }
-                    if (bestd < lb) break;
-                }
-                if (bestd < lb) continue;
-                size_t idx = (size_t)y * W + x;
+                const size_t idx = (size_t)y * W + x;
                 if (d2out) d2out[(size_t)b * P + idx] = bestd;
-                unsigned long long key = ((unsigned long long)bestd << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)idx);
-                rowbest = max(rowbest, key);
+                rowbest = max(rowbest, ((unsigned long long)bestd << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)idx));
             }
         } else if (d2out) {
             for (int x = threadIdx.x; x < W; x += EDT_NT) d2out[(size_t)b * P + (size_t)y * W + x] = 0xFFFFFFFFu;
         }
-        // the reduction only runs when some thread improved on the CTA's best (rare once the bound is tight);
-        // the barrier also protects srow against the next row's writers
+        // the reduction only runs when some thread improved on the CTA's best; the barrier also protects srow
         const int improved = __syncthreads_or(best != nullptr && rowbest > mybest);
         if (improved) {
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) rowbest = max(rowbest, __shfl_xor_sync(0xFFFFFFFFu, rowbest, d));
+            for (int d = 16; d > 0; d >>= 1) rowbest = max(rowbest, __shfl_xor_sync(FULL, rowbest, d));
             if ((threadIdx.x & 31) == 0) sbest[threadIdx.x >> 5] = rowbest;
             __syncthreads();
             for (int w = 0; w < EDT_NT / 32; ++w) mybest = max(mybest, sbest[w]);
@@ -722,127 +789,205 @@ __global__ void __launch_bounds__(EDT_NT) edt_row_kernel(const uint16_t* __restr
     }
 }
 
-// Arg-max search, main part: ONE WARP PER ROW.  A row is first judged by its chunk minima alone (gmin, 1/32 of the
-// data): chunk j cannot hold the maximum if min over j' of gmin(j')^2 + (32 |j - j'| + 31)^2 is below the frame's
-// running maximum.  Only rows with a surviving chunk load their column distances (into the warp's shared-memory
-// row) and run the exact search, for the surviving chunks only.  Exactness argument as for edt_row_kernel: a pixel
-// is only dropped when an upper bound of its distance is below an exact distance found elsewhere in the frame.
+// Arg-max search.  The first maximum of the field is found by branch and bound on upper bounds that come from the chunk
+// minima alone: every pixel of chunk j of row y is at most 31 + 32 dj columns away from the column of chunk j +- dj that
+// holds gmin, so d2 <= gmin(j')^2 + (32 |j - j'| + 31)^2 for every j'; for a block of 8 rows the same holds with
+// (g8(j') + 7) in place of gmin (the nearest source of the block's best column is at most 7 rows further from any other
+// row of the block).  A chunk whose bound is below the frame's running maximum (best[b], raised with atomicMax by every
+// warp that finds a larger exact distance) can neither hold the maximum nor tie with it, so the result is exactly the
+// first maximum of the full field whatever the schedule.
+//
+// mrow: chunk minima (linear, 0xFFFF = none) in shared memory; add: 0 for a row, 7 for a block of rows.  Returns in
+// alive[k] bit `lane`: chunk 32 k + lane may still hold a pixel at squared distance >= lb.
+__device__ __forceinline__ bool edt_alive_chunks(const unsigned* mrow, int nchunks, unsigned lb, unsigned add, int lane,
+                                                 unsigned (&alive)[4]) {
+    bool any_alive = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int j = 32 * k + lane;
+        bool keep = false;
+        if (j < nchunks) {
+            auto sq = [&](int jj) -> unsigned long long {
+                const unsigned v = mrow[jj];
+                if (v == 0xFFFFu) return ~0ull >> 1;
+                const unsigned long long t = (unsigned long long)v + add;
+                return t * t;
+            };
+            unsigned long long ub = sq(j) + 31ull * 31ull;
+            for (int dj = 1; dj < nchunks && ub >= lb; ++dj) {
+                const unsigned long long off = (unsigned long long)(32 * dj + 31) * (32 * dj + 31);
+                if (off >= lb) break;
+                if (j - dj >= 0) ub = min(ub, sq(j - dj) + off);
+                if (j + dj < nchunks) ub = min(ub, sq(j + dj) + off);
+            }
+            keep = ub >= lb;
+        }
+        alive[k] = __ballot_sync(FULL, keep);
+        any_alive |= alive[k] != 0u;
+    }
+    return any_alive;
+}
+
+// A lower bound to start from.  On the grid of cells (8 rows x 32 columns; a cell is occupied when it holds a source,
+// i.e. its g8 is 0) the kernel runs a small two-pass distance transform in shared memory - vertical distance to the
+// nearest occupied cell per cell column, then the lower envelope along the cell rows in pixel units - and every warp
+// evaluates the EXACT distance at the middle pixel of the best cell of its share.  The maximum of the true field is
+// within about a cell of the coarse one, so the search below starts with a bound that prunes nearly everything.
+// coarse == 0 (cell grid too large for shared memory): the cells are ranked by g8 alone.  One CTA per frame.
+constexpr int SEED_NT = 256;
+__global__ void __launch_bounds__(SEED_NT) edt_seed_kernel(lg_context c, int coarse) {
+    extern __shared__ uint16_t s_gc[];                  // [H8][nchunks] vertical distance in cells, 0xFFFF = column has no source
+    const int b = blockIdx.x, W = c.W, H = c.H, nchunks = c.edt_nchunks, H8 = c.H8;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const EdtCols cols = edt_cols_of(c, b);
+    const uint16_t* g8 = c.edt_g8 + (size_t)b * H8 * nchunks;
+    const int cells = H8 * nchunks;
+    unsigned long long bestv = 0;
+    int bestc = -1;
+    if (coarse) {
+        for (int j = tid; j < nchunks; j += SEED_NT) {
+            unsigned d = 0xFFFFu;
+            for (int i = 0; i < H8; ++i) {
+                d = g8[(size_t)i * nchunks + j] == 0 ? 0u : min(d + 1u, 0xFFFFu);
+                s_gc[i * nchunks + j] = (uint16_t)d;
+            }
+            d = 0xFFFFu;
+            for (int i = H8 - 1; i >= 0; --i) {
+                d = min((unsigned)s_gc[i * nchunks + j], min(d + 1u, 0xFFFFu));
+                s_gc[i * nchunks + j] = (uint16_t)d;
+            }
+        }
+        __syncthreads();
+        for (int cell = tid; cell < cells; cell += SEED_NT) {
+            const int i = cell / nchunks, j = cell - i * nchunks;
+            const uint16_t* row = s_gc + i * nchunks;
+            if (row[j] == 0) continue;                  // occupied: holds a source
+            unsigned long long d2 = ~0ull;
+            for (int jj = 0; jj < nchunks; ++jj) {
+                const unsigned v = row[jj];
+                if (v == 0xFFFFu) continue;
+                const long long dy = 8ll * v, dx = 32ll * (jj - j);
+                d2 = min(d2, (unsigned long long)(dy * dy + dx * dx));
+            }
+            if (d2 != ~0ull && d2 > bestv) { bestv = d2; bestc = cell; }
+        }
+    } else {
+        for (int cell = tid; cell < cells; cell += SEED_NT) {
+            const unsigned v = g8[cell];
+            if (v != 0xFFFFu && v > bestv) { bestv = v; bestc = cell; }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const unsigned long long ov = __shfl_xor_sync(FULL, bestv, d);
+        const int oc = __shfl_xor_sync(FULL, bestc, d);
+        if (ov > bestv || (ov == bestv && oc >= 0 && (bestc < 0 || oc < bestc))) { bestv = ov; bestc = oc; }
+    }
+    if (bestc < 0) return;                                  // warp-uniform
+    const int y = min((bestc / nchunks) * 8 + 4, H - 1), x = min((bestc % nchunks) * 32 + 16, W - 1);
+    // exact d2 at (x, y): min over x' of g(x', y)^2 + (x - x')^2
+    unsigned long long d2 = ~0ull;
+    for (int xx = lane; xx < W; xx += 32) {
+        const unsigned g = cols.g_of(xx, y);
+        if (g == 0xFFFFu) continue;
+        const long long dx = xx - x;
+        d2 = min(d2, (unsigned long long)g * g + (unsigned long long)(dx * dx));
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) d2 = min(d2, __shfl_xor_sync(FULL, d2, d));
+    if (lane == 0 && d2 != ~0ull && d2 > 0 && d2 <= 0xFFFFFFFFull) {
+        const unsigned idx = (unsigned)((size_t)y * W + x);
+        atomicMax(&c.edt_best[b], (d2 << 32) | (unsigned long long)(0xFFFFFFFFu - idx));
+    }
+}
+
+// Main part: ONE WARP PER BLOCK OF 8 ROWS.  The block is judged by its g8 row, each of its rows by its gmin row, and only
+// rows with a surviving chunk compute their column distances (into the warp's shared-memory row) and run the exact
+// search, for the surviving chunks only.
 constexpr int EDTW_NT = 256;
-__global__ void __launch_bounds__(EDTW_NT) edt_rowmax_kernel(const uint16_t* __restrict__ g, const uint16_t* __restrict__ gmin,
-                                                              unsigned long long* __restrict__ best, int nchunks, int H, int W,
-                                                              size_t P, int row_stride, int yi_begin, int yi_end) {
+__global__ void __launch_bounds__(EDTW_NT) edt_blockmax_kernel(lg_context c, int blk_stride) {
     extern __shared__ unsigned sm_rows[];            // per warp: W squared column distances, then 128 chunk minima
     const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int W = c.W, H = c.H, nchunks = c.edt_nchunks, H8 = c.H8;
     unsigned* srow = sm_rows + (size_t)warp * (W + 128);
     unsigned* mrow = srow + W;
-    const uint16_t* gmf = gmin + (size_t)b * H * nchunks;
+    const EdtCols cols = edt_cols_of(c, b);
+    const uint16_t* gmf = c.edt_gmin + (size_t)b * H * nchunks;
+    const uint16_t* g8f = c.edt_g8 + (size_t)b * H8 * nchunks;
+    unsigned long long* best = c.edt_best;
     unsigned long long mybest = 0;                   // this warp's best (identical in all lanes)
-    const int rows_per_pass = gridDim.y * (EDTW_NT / 32);
-    for (int yi = yi_begin + blockIdx.y * (EDTW_NT / 32) + warp; yi < yi_end; yi += rows_per_pass) {
-        const int y = (int)(((long long)yi * row_stride) % H);
+    const int per_pass = gridDim.y * (EDTW_NT / 32);
+    auto bound = [&]() -> unsigned {
         unsigned long long gb = 0;
         if (lane == 0) gb = *reinterpret_cast<volatile unsigned long long*>(&best[b]);
-        gb = __shfl_sync(0xFFFFFFFFu, gb, 0);
-        const unsigned lb = (unsigned)(max(gb, mybest) >> 32);
-        __syncwarp();
-        bool has_source = false;
-        for (int j = lane; j < nchunks; j += 32) {
-            const unsigned v = gmf[(size_t)y * nchunks + j];
-            mrow[j] = (v == 0xFFFFu) ? 0xFFFFFFFFu : v * v;
-            has_source |= v != 0xFFFFu;
+        gb = __shfl_sync(FULL, gb, 0);
+        return (unsigned)(max(gb, mybest) >> 32);
+    };
+    for (int bi = blockIdx.y * (EDTW_NT / 32) + warp; bi < H8; bi += per_pass) {
+        const int blk = (int)(((long long)bi * blk_stride) % H8);
+        unsigned lb = bound();
+        unsigned alive[4];
+        if (lb) {                                    // with no bound yet nothing can be dropped
+            __syncwarp();
+            bool has_source = false;
+            for (int j = lane; j < nchunks; j += 32) { const unsigned v = g8f[(size_t)blk * nchunks + j]; mrow[j] = v; has_source |= v != 0xFFFFu; }
+            if (!__any_sync(FULL, has_source)) continue;
+            __syncwarp();
+            if (!edt_alive_chunks(mrow, nchunks, lb, 7u, lane, alive)) continue;
         }
-        if (!__any_sync(0xFFFFFFFFu, has_source)) continue;      // no source in any column of this row: nothing to rank
-        __syncwarp();
-        // chunks that may still hold a pixel at distance >= lb
-        unsigned alive[4] = {0u, 0u, 0u, 0u};        // bit `lane` of alive[k]: chunk 32 k + lane survives
-        bool any_alive = false;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int j = 32 * k + lane;
-            bool keep = false;
-            if (j < nchunks) {
-                unsigned long long ub = (unsigned long long)mrow[j] + 31ull * 31ull;
-                for (int dj = 1; dj < nchunks && ub >= lb; ++dj) {
-                    const unsigned long long off = (unsigned long long)(32 * dj + 31) * (32 * dj + 31);
-                    if (off >= lb) break;
-                    if (j - dj >= 0) ub = min(ub, (unsigned long long)mrow[j - dj] + off);
-                    if (j + dj < nchunks) ub = min(ub, (unsigned long long)mrow[j + dj] + off);
-                }
-                keep = ub >= lb;
+        const int y_end = min(blk * 8 + 8, H);
+        for (int y = blk * 8; y < y_end; ++y) {
+            lb = bound();
+            __syncwarp();
+            bool has_source = false;
+            for (int j = lane; j < nchunks; j += 32) { const unsigned v = gmf[(size_t)y * nchunks + j]; mrow[j] = v; has_source |= v != 0xFFFFu; }
+            if (!__any_sync(FULL, has_source)) continue;      // no source in any column of this row: nothing to rank
+            __syncwarp();
+            if (!edt_alive_chunks(mrow, nchunks, lb, 0u, lane, alive)) continue;
+            for (int x = lane; x < W; x += 32) {
+                const unsigned v = cols.g_of(x, y);
+                srow[x] = (v == 0xFFFFu) ? 0xFFFFFFFFu : v * v;
             }
-            alive[k] = __ballot_sync(0xFFFFFFFFu, keep);
-            any_alive |= alive[k] != 0u;
-        }
-        if (!any_alive) continue;
-        // exact search on the surviving chunks
-        const uint16_t* gp = g + (size_t)b * P + (size_t)y * W;
-        for (int x = lane; x < W; x += 32) {
-            const unsigned v = gp[x];
-            srow[x] = (v == 0xFFFFu) ? 0xFFFFFFFFu : v * v;
-        }
-        __syncwarp();
-        unsigned long long rowbest = 0;
+            __syncwarp();
+            unsigned long long rowbest = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            unsigned rem = alive[k];
-            while (rem) {
-                const int j = 32 * k + (__ffs(rem) - 1);
-                rem &= rem - 1;
-                const int x = (j << 5) + lane;
-                if (x >= W) continue;
-                unsigned bestd = srow[x];
-                if (bestd < lb) continue;
-                if (lb) {
-                    for (unsigned kk = 1; kk * kk < bestd; kk <<= 1) {
-                        const int xl = x - (int)kk, xr = x + (int)kk;
-                        if (xl < 0 && xr >= W) break;
-                        const unsigned q = kk * kk;
-                        if (xl >= 0) { const unsigned t = srow[xl]; if (t != 0xFFFFFFFFu) bestd = min(bestd, t + q); }
-                        if (xr < W) { const unsigned t = srow[xr]; if (t != 0xFFFFFFFFu) bestd = min(bestd, t + q); }
-                    }
+            for (int k = 0; k < 4; ++k) {
+                unsigned rem = alive[k];
+                while (rem) {
+                    const int j = 32 * k + (__ffs(rem) - 1);
+                    rem &= rem - 1;
+                    const int x = (j << 5) + lane;
+                    if (x >= W) continue;
+                    const unsigned bestd = edt_row_search(srow, W, x, lb);
                     if (bestd < lb) continue;
+                    const unsigned idx = (unsigned)((size_t)y * W + x);
+                    rowbest = max(rowbest, ((unsigned long long)bestd << 32) | (unsigned long long)(0xFFFFFFFFu - idx));
                 }
-                for (unsigned kk = 1; kk * kk < bestd; ++kk) {
-                    const int xl = x - (int)kk, xr = x + (int)kk;
-                    if (xl < 0 && xr >= W) break;
-                    const unsigned q = kk * kk;
-                    if (xl >= 0) { const unsigned t = srow[xl]; if (t != 0xFFFFFFFFu) bestd = min(bestd, t + q); }
-                    if (xr < W) { const unsigned t = srow[xr]; if (t != 0xFFFFFFFFu) bestd = min(bestd, t + q); }
-                    if (bestd < lb) break;
-                }
-                if (bestd < lb) continue;
-                const unsigned idx = (unsigned)((size_t)y * W + x);
-                rowbest = max(rowbest, ((unsigned long long)bestd << 32) | (unsigned long long)(0xFFFFFFFFu - idx));
             }
-        }
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) rowbest = max(rowbest, __shfl_xor_sync(0xFFFFFFFFu, rowbest, d));
-        if (rowbest > mybest) {
-            mybest = rowbest;
-            if (lane == 0 && mybest > *reinterpret_cast<volatile unsigned long long*>(&best[b])) atomicMax(&best[b], mybest);
+            for (int d = 16; d > 0; d >>= 1) rowbest = max(rowbest, __shfl_xor_sync(FULL, rowbest, d));
+            if (rowbest > mybest) {
+                mybest = rowbest;
+                if (lane == 0 && mybest > *reinterpret_cast<volatile unsigned long long*>(&best[b])) atomicMax(&best[b], mybest);
+            }
         }
     }
 }
 
-// rows are visited in the order (i * stride) mod H: stride ~ 0.618 H, coprime with H
-static int edt_row_stride(int H) {
+// items are visited in the order (i * stride) mod n: stride ~ 0.618 n, coprime with n
+static int golden_stride(int n) {
     auto gcd = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
-    int s = (int)(H * 0.6180339887);
+    int s = (int)(n * 0.6180339887);
     if (s < 1) s = 1;
-    while (gcd(s, H) != 1) ++s;
-    return s % H ? s % H : 1;
-}
-static dim3 edt_row_grid(int n, int H) {
-    int per_frame = (148 * 8 * 2 + n - 1) / n;     // ~two waves of 8 CTAs per SM over the whole batch
-    if (per_frame > H) per_frame = H;
-    if (per_frame < 1) per_frame = 1;
-    return dim3(n, per_frame);
+    while (gcd(s, n) != 1) ++s;
+    return s % n ? s % n : 1;
 }
 
 __global__ void edt_argmax_out_kernel(const unsigned long long* best, int32_t* argmax, int n) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < n) argmax[b] = (int32_t)(0xFFFFFFFFu - (unsigned)(best[b] & 0xFFFFFFFFull));
 }
+
 
 // ---------------------------------------------------------------------------------------------------
 // the pick
@@ -1008,29 +1153,33 @@ __global__ void __launch_bounds__(32) select_leaf_kernel(lg_context c, lg_camera
 
 }  // namespace
 
-// row pass for n frames; d2 == nullptr: arg-max only (pruned search).  The arg-max search first runs a few well
-// spread rows per frame one after the other (edt_row_kernel, one CTA per frame: the first row is searched in full,
-// the following ones against the bound it leaves), then all remaining rows with one warp per row.
-static int run_edt_rows(lg_context* c, int n, uint32_t* d2, cudaStream_t st) {
-    const int stride = edt_row_stride(c->H);
-    const size_t sm = c->W * sizeof(unsigned);
-    if (d2 || c->H < 64) {
-        edt_row_kernel<<<edt_row_grid(n, c->H), EDT_NT, sm, st>>>(c->edt_g, d2, c->edt_best, c->H, c->W, c->P, stride, 0, c->H);
+// column pass + arg-max search of the union distance transform for n frames, on `st`
+template <class SRC>
+static int run_edt_argmax(lg_context* c, SRC src, int n, cudaStream_t st, bool mark) {
+    const bool small = c->H < 64;      // too few 8-row blocks to prune with: plain pruned row search
+    edt_vcol_kernel<SRC><<<dim3((c->W + VC_NT - 1) / VC_NT, n), VC_NT, 0, st>>>(*c, src, small ? 0 : 1);
+    LG_LAUNCH_CHECK();
+    if (mark) lg_mark(c, LG_M_EDT_COL, st);
+    if (small) {
+        int per_frame = (148 * 8 * 2 + n - 1) / n;
+        per_frame = per_frame < 1 ? 1 : (per_frame > c->H ? c->H : per_frame);
+        edt_row_kernel<<<dim3(n, per_frame), EDT_NT, c->W * sizeof(unsigned), st>>>(*c, nullptr, c->edt_best, golden_stride(c->H));
         LG_LAUNCH_CHECK();
         return LG_OK;
     }
-    const int seed = 16;
-    int seed_ctas = 296 / n;                         // small batches: spread the seed rows over a few CTAs per frame
-    seed_ctas = seed_ctas < 1 ? 1 : (seed_ctas > seed ? seed : seed_ctas);
-    edt_row_kernel<<<dim3(n, seed_ctas), EDT_NT, sm, st>>>(c->edt_g, nullptr, c->edt_best, c->H, c->W, c->P, stride, 0, seed);
-    LG_LAUNCH_CHECK();
+    {
+        const size_t sm_seed = (size_t)c->H8 * c->edt_nchunks * sizeof(uint16_t);
+        const int coarse = sm_seed <= 200 * 1024;
+        if (coarse) LG_ENSURE_SMEM(edt_seed_kernel, sm_seed);
+        edt_seed_kernel<<<n, SEED_NT, coarse ? sm_seed : 0, st>>>(*c, coarse);
+        LG_LAUNCH_CHECK();
+    }
     const size_t smw = (size_t)(EDTW_NT / 32) * (c->W + 128) * sizeof(unsigned);
-    LG_ENSURE_SMEM(edt_rowmax_kernel, smw);
+    LG_ENSURE_SMEM(edt_blockmax_kernel, smw);
     int per_frame = (148 * 4 * 2 + n - 1) / n;       // about two waves of CTAs over the batch
-    const int max_ctas = (c->H - seed + EDTW_NT / 32 - 1) / (EDTW_NT / 32);
+    const int max_ctas = (c->H8 + EDTW_NT / 32 - 1) / (EDTW_NT / 32);
     per_frame = per_frame < 1 ? 1 : (per_frame > max_ctas ? max_ctas : per_frame);
-    edt_rowmax_kernel<<<dim3(n, per_frame), EDTW_NT, smw, st>>>(c->edt_g, c->edt_gmin, c->edt_best, c->edt_nchunks, c->H, c->W,
-                                                                 c->P, stride, seed, c->H);
+    edt_blockmax_kernel<<<dim3(n, per_frame), EDTW_NT, smw, st>>>(*c, golden_stride(c->H8));
     LG_LAUNCH_CHECK();
     return LG_OK;
 }
@@ -1038,35 +1187,45 @@ static int run_edt_rows(lg_context* c, int n, uint32_t* d2, cudaStream_t st) {
 int lg_run_stage1(lg_context* c, const int16_t* labels, const float* depth, int n, lg_camera cam, cudaStream_t st) {
     clear_tables_kernel<<<64, 256, 0, st>>>(*c, n);
     LG_LAUNCH_CHECK();
-    const int tiles = (int)((c->P + ST_NT * ST_PX - 1) / (ST_NT * ST_PX));
     if (!c->ray_valid || c->ray_cam.f != cam.f || c->ray_cam.cx != cam.cx || c->ray_cam.cy != cam.cy) {
-        ray_table_kernel<<<(c->W + 127) / 128, 128, 0, st>>>(c->ray_tab, c->H, c->W, cam);
+        ray_table_kernel<<<(c->H + 7) / 8, 256, 0, st>>>(c->ray_tab, c->H, c->W, cam);
         LG_LAUNCH_CHECK();
         c->ray_cam = cam;
         c->ray_valid = 1;
     }
-    // per-leaf statistics + column pass of the union distance transform in one walk over the columns
-    LG_ENSURE_SMEM(leaf_stats_kernel, c->L * sizeof(SmemLeaf) + (size_t)STC_BND * STC_NT * sizeof(uint16_t));
-    leaf_stats_kernel<<<dim3((c->W + STC_NT - 1) / STC_NT, n), STC_NT,
-                        c->L * sizeof(SmemLeaf) + (size_t)STC_BND * STC_NT * sizeof(uint16_t), st>>>(*c, labels, depth);
-    LG_LAUNCH_CHECK();
+    // the one pass over labels + depth: per-leaf statistics, grouped depth values, union bit mask
+    {
+        const size_t smem = c->L * (sizeof(SmemLeaf) + 2 * sizeof(unsigned));
+        long long rpc = ((long long)c->H * n + 8191) / 8192;                // several thousand CTAs over the batch
+        rpc = rpc < 1 ? 1 : (rpc > 16 ? 16 : rpc);
+        const dim3 grid((unsigned)((c->H + rpc - 1) / rpc), n);
+        const int nt = (((c->W + 7) / 8 + 31) / 32) * 32;                    // one thread per 8 pixels of a row
+        const bool vec = (c->W % 8 == 0) && ((reinterpret_cast<uintptr_t>(labels) | reinterpret_cast<uintptr_t>(depth)) % 16 == 0);
+        if (vec) {
+            LG_ENSURE_SMEM(leaf_rows_kernel<true>, smem);
+            leaf_rows_kernel<true><<<grid, nt, smem, st>>>(*c, labels, depth, (int)rpc);
+        } else {
+            LG_ENSURE_SMEM(leaf_rows_kernel<false>, smem);
+            leaf_rows_kernel<false><<<grid, nt, smem, st>>>(*c, labels, depth, (int)rpc);
+        }
+        LG_LAUNCH_CHECK();
+    }
     lg_mark(c, LG_M_STATS, st);
-    // the row pass (arg-max only) is independent of the medians: it runs beside scatter + median
+    // the distance transform of the union (arg-max only) is independent of the medians: it runs beside them
     cudaStream_t aux = lg_fork(c, 0, st);
-    lg_mark(c, LG_M_EDT_COL, aux);
-    int rc = run_edt_rows(c, n, nullptr, aux);
-    if (rc) return rc;
+    int rc = run_edt_argmax(c, SrcUnionBits{c->ubits, c->ub_stride, (c->W + 7) / 8}, n, aux, true);
     lg_mark(c, LG_M_EDT_ROW, aux);
-    leaf_offsets_kernel<<<(n + 63) / 64, 64, 0, st>>>(*c, n);
-    LG_LAUNCH_CHECK();
-    leaf_scatter_kernel<<<dim3(tiles, n), ST_NT, c->L * sizeof(unsigned), st>>>(*c, labels, depth);
-    LG_LAUNCH_CHECK();
-    lg_mark(c, LG_M_SCATTER, st);
-    LG_ENSURE_SMEM(leaf_median_kernel, MED_CAP * sizeof(unsigned));
-    leaf_median_kernel<<<dim3(c->L, n), MED_NT, MED_CAP * sizeof(unsigned), st>>>(*c);
-    LG_LAUNCH_CHECK();
+    if (!rc) {
+        rc = lg_ensure_smem_impl((const void*)leaf_median_kernel, MED_CAP * sizeof(unsigned));
+        if (!rc) {
+            leaf_median_kernel<<<dim3(c->L, n), MED_NT, MED_CAP * sizeof(unsigned), st>>>(*c);
+            ++g_lg_launches;
+            if (cudaGetLastError() != cudaSuccess) { lg_set_error("leaf_median_kernel launch failed"); rc = LG_E_CUDA; }
+        }
+    }
     lg_mark(c, LG_M_MEDIAN, st);
-    return lg_join(c, 0, aux, st);
+    const int rcj = lg_join(c, 0, aux, st);        // also on an error path: the side stream must not stay unordered
+    return rc ? rc : rcj;
 }
 
 int lg_run_select(lg_context* c, int n, lg_camera cam, int32_t* leaf_out, lg_leaf_record* rec_out, cudaStream_t st) {
@@ -1082,12 +1241,18 @@ extern "C" int lg_edt_squared(lg_context* c, const uint8_t* mask, int n, uint32_
     if (n > c->B) return LG_E_CAPACITY;
     cudaStream_t st = (cudaStream_t)stream;
     LG_CUDA(cudaMemsetAsync(c->edt_best, 0, sizeof(unsigned long long) * n, st));
-    EdtSrc src{nullptr, mask};
-    edt_col_kernel<<<dim3((c->W + 127) / 128, n), 128, 0, st>>>(src, c->edt_g, d2 ? nullptr : c->edt_gmin, c->edt_nchunks, c->H, c->W,
-                                                                c->P);
-    LG_LAUNCH_CHECK();
-    int rc = run_edt_rows(c, n, d2, st);
-    if (rc) return rc;
+    const SrcMaskZero src{mask, c->P, c->W};
+    if (d2) {       // the full field: every row, no pruning
+        edt_vcol_kernel<SrcMaskZero><<<dim3((c->W + VC_NT - 1) / VC_NT, n), VC_NT, 0, st>>>(*c, src, 0);
+        LG_LAUNCH_CHECK();
+        int per_frame = (148 * 8 * 2 + n - 1) / n;
+        per_frame = per_frame < 1 ? 1 : (per_frame > c->H ? c->H : per_frame);
+        edt_row_kernel<<<dim3(n, per_frame), EDT_NT, c->W * sizeof(unsigned), st>>>(*c, d2, c->edt_best, golden_stride(c->H));
+        LG_LAUNCH_CHECK();
+    } else {
+        int rc = run_edt_argmax(c, src, n, st, false);
+        if (rc) return rc;
+    }
     if (argmax) {
         edt_argmax_out_kernel<<<(n + 63) / 64, 64, 0, st>>>(c->edt_best, argmax, n);
         LG_LAUNCH_CHECK();
