@@ -110,16 +110,19 @@ extern "C" int lg_create(lg_context** out, int max_frames, int height, int width
     auto A = [&](auto pp, size_t count) { if (!rc) rc = dev_alloc(c, pp, count); };
     A(&c->cnt, B * L); A(&c->sx, B * L); A(&c->sy, B * L); A(&c->sdep, B * L); A(&c->sdist, B * L);
     A(&c->bx0, B * L); A(&c->bx1, B * L); A(&c->by0, B * L); A(&c->by1, B * L); A(&c->border, B * L);
-    A(&c->kmin, B * L); A(&c->kmax, B * L); A(&c->ray_tab, P);
-    A(&c->first_leaf, B); A(&c->seg, B * P); A(&c->median, B * L);
+    A(&c->krange, B * 2); A(&c->ray_tab, P);
+    c->seg_stride = (P + 7) & ~(size_t)7;
+    A(&c->first_leaf, B); A(&c->seg, B * c->seg_stride); A(&c->median, B * L);
     c->lstride = (int)((L + 1 + 7) & ~(size_t)7);
-    A(&c->tile_off, B * (size_t)height * c->lstride);
-    c->ub_stride = ((size_t)height * ((width + 7) / 8) + 15) & ~(size_t)15;
-    A(&c->ubits, B * c->ub_stride);
-    c->edt_nchunks = (width + 31) / 32;
-    c->Hw = (height + 31) / 32; c->H8 = (height + 7) / 8;
+    c->n_bands = (height + LG_BAND - 1) / LG_BAND;
+    A(&c->band_off, B * (size_t)c->n_bands * 2 * c->lstride);
+    c->ub_pitch = (((width + 7) / 8) + 3) & ~3;
+    c->ub_stride = ((size_t)height * c->ub_pitch + 15) & ~(size_t)15;
+    A(&c->ubits, B * c->ub_stride); A(&c->cellocc, B * (size_t)c->n_bands * c->ub_pitch);
+    c->am_cs = lg_edt_cell_size(height, width);
+    c->Hw = (height + 31) / 32;
     A(&c->vbits, B * (size_t)c->Hw * width); A(&c->vup, B * (size_t)c->Hw * width); A(&c->vdn, B * (size_t)c->Hw * width);
-    A(&c->edt_gmin, B * (size_t)height * c->edt_nchunks); A(&c->edt_g8, B * (size_t)c->H8 * c->edt_nchunks); A(&c->edt_best, B); A(&c->leaf_id, B); A(&c->records, B * L); A(&c->status, B); A(&c->region, B);
+    A(&c->edt_best, B); A(&c->leaf_id, B); A(&c->records, B * L); A(&c->status, B); A(&c->region, B);
     A(&c->dt_fwd, 2 * B * P); A(&c->di, B * P); A(&c->dt_max, B * 2);
     A(&c->bnd_list, B * (size_t)LG_BND_CAP); A(&c->bnd_count, B); A(&c->need_full, B);
     c->bits_stride = (size_t)((width + 2 + 31) / 32) * (height + 2);
@@ -159,6 +162,7 @@ extern "C" int lg_create(lg_context** out, int max_frames, int height, int width
     cudaError_t e = cudaMemset(c->results, 0, sizeof(lg_frame_result) * B);
     if (e == cudaSuccess) e = cudaMemset(c->dt_max, 0, sizeof(uint32_t) * 2 * B);
     if (e == cudaSuccess) e = cudaMemset(c->orient, 0, sizeof(LgOrient) * B);
+    if (e == cudaSuccess) e = cudaMemset(c->ubits, 0, B * c->ub_stride);     // the padding bits of every row stay zero
     if (e != cudaSuccess) { lg_set_error("lg_create: %s", cudaGetErrorString(e)); lg_destroy(c); return LG_E_CUDA; }
     *out = c;
     return LG_OK;

@@ -20,6 +20,7 @@
 #define LG_REGION_PAD 16 // score maps are produced on the leaf bbox grown by half a patch
 #define LG_SE_STEM 30
 #define LG_SE_PRE 31
+#define LG_BAND 8            // rows per band of the stage-1 pass (8 x 4096 pixels still fit a u16 offset)
 #define LG_PROF_MARKS 20
 #define LG_PROF_RING 32
 #define LG_BND_CAP 16384
@@ -87,25 +88,27 @@ struct lg_context {
     uint32_t* cnt;
     unsigned long long *sx, *sy, *sdep, *sdist;
     uint32_t *bx0, *bx1, *by0, *by1, *border;
-    uint32_t *kmin, *kmax;         // [B][L] smallest / largest depth key of the label (median search range)
-    unsigned long long* ray_tab;   // [P] viewing-ray length per unit depth, 2^36 fixed point, for ray_cam
+    uint32_t* krange;              // [B][2] bounds of the depth keys of the frame's leaf pixels (median search range)
+    unsigned long long* ray_tab;   // [P] summed-area table of the viewing-ray length per unit depth, 2^36 fixed point, for ray_cam
     lg_camera ray_cam;
     int ray_valid;
     uint32_t* first_leaf;          // [B] flat index of the first pixel with label >= 1
-    float* seg;                    // [B][P] depth values of the leaf pixels, grouped by label inside every image row
-    uint16_t* tile_off;            // [B][H][lstride] per row: offset of every label's sub-block, entry L = total
-    int lstride;
-    uint8_t* ubits;                // [B][H][ceil(W/8)] (frame stride ub_stride) bit x%8 of byte x/8: pixel belongs to a leaf
+    float* seg;                    // [B][seg_stride] depth values of the leaf pixels, grouped by label inside every band of LG_BAND rows
+    size_t seg_stride;             // P rounded up to 8 values: every band's part starts 32-byte aligned
+    uint16_t* band_off;            // [B][n_bands][2][lstride] per band: offsets of every label's block part (in blocks of 64
+                                   // values) and pixel part (in values), entry L = total
+    int n_bands, lstride;
+    uint8_t* ubits;                // [B][H][ub_pitch] (frame stride ub_stride) bit x%8 of byte x/8: pixel belongs to a leaf
+    uint8_t* cellocc;              // [B][n_bands][ub_pitch] 1: the 8 x 8 block holds a leaf pixel
     size_t ub_stride;
+    int ub_pitch;                  // bytes per row of ubits, a multiple of 4, padding bits zero
+    int am_cs;                     // cell size of the distance-transform search (lg_edt_cell_size)
     float* median;                 // [B][L]
-    // column pass of the exact distance transform (of the leaf union, or of a caller's mask): per column vertical bit
+    // column pass of the exact distance transform of a caller's mask (lg_edt_squared): per column vertical bit
     // words of the sources and the distance to the nearest source above / below every word
     uint32_t* vbits;               // [B][Hw][W]
     uint16_t *vup, *vdn;           // [B][Hw][W]
-    int Hw, H8;                    // ceil(H / 32), ceil(H / 8)
-    uint16_t* edt_gmin;            // [B][H][edt_nchunks] minimum of the column distance over each chunk of 32 columns
-    uint16_t* edt_g8;              // [B][H8][edt_nchunks] the same over blocks of 8 rows
-    int edt_nchunks;
+    int Hw;                        // ceil(H / 32)
     unsigned long long* edt_best;  // [B] packed (d2 << 32 | ~index)
     int32_t* leaf_id;              // [B]
     lg_leaf_record* records;       // [B][L]
@@ -195,6 +198,7 @@ static inline void lg_mark(lg_context* c, int id, cudaStream_t st) {
 
 // stage launchers (defined across the .cu files); all asynchronous on `st`
 int lg_run_stage1(lg_context* c, const int16_t* labels, const float* depth, int n, lg_camera cam, cudaStream_t st);
+int lg_edt_cell_size(int H, int W);
 int lg_run_select(lg_context* c, int n, lg_camera cam, int32_t* leaf_out, lg_leaf_record* rec_out, cudaStream_t st);
 // aux = lg_fork(c, k, st): stream for the side branch (st itself when overlap is off); lg_join makes st wait for it
 cudaStream_t lg_fork(lg_context* c, int k, cudaStream_t st);
