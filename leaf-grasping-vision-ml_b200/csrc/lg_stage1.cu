@@ -650,13 +650,17 @@ __global__ void __launch_bounds__(MED_NT) leaf_median_kernel(lg_context c) {
     const bool need_hi = !(n & 1);
     // candidates: the keys with (key >> s) == p; `below` elements are smaller than all of them, m are candidates
     int s = kmax > kmin ? 32 - __clz(kmax - kmin) : 0;    // number of significant bits of a relative key
+    const int s_top = s;
     unsigned p = 0, below = 0, m = n;
     auto match = [&](unsigned key) { return s >= 32 ? true : (key >> s) == p; };
     while (m > MED_CAP && s > 0) {
         const int nbits = min(MED_BITS, s), s2 = s - nbits;
         const unsigned dmask = (1u << nbits) - 1u;
         clear_hist();
-        for_each_key([&](unsigned key, bool ok) { if (ok && match(key)) atomicAdd(&S.hist[(key >> s2) & dmask], 1u); });
+        if (s == s_top)     // first pass: every key is a candidate and has no bit above the digit
+            for_each_key([&](unsigned key, bool ok) { if (ok) atomicAdd(&S.hist[key >> s2], 1u); });
+        else
+            for_each_key([&](unsigned key, bool ok) { if (ok && match(key)) atomicAdd(&S.hist[(key >> s2) & dmask], 1u); });
         __syncthreads();
         block_scan_pick(k_lo - below);
         p = s >= 32 ? S.sel[0] : ((p << nbits) | S.sel[0]);
@@ -671,17 +675,23 @@ __global__ void __launch_bounds__(MED_NT) leaf_median_kernel(lg_context c) {
         klo = p;
         if (need_hi && below + m > k_lo + 1) { khi = p; have_hi = true; }
     } else {
-        // the candidates into shared memory
-        for_each_key([&](unsigned key, bool ok) {
-            const bool hit = ok && match(key);
-            const unsigned ball = __ballot_sync(FULL, hit);
-            if (ball) {
-                unsigned base = 0;
-                if (lane == 0) base = atomicAdd(&S.n_keys, __popc(ball));
-                base = __shfl_sync(FULL, base, 0);
-                if (hit) S.keys[0][base + __popc(ball & ((1u << lane) - 1u))] = key;
-            }
-        });
+        // the candidates into shared memory: all values of a small label (one cursor bump per warp), or the few of the
+        // median's bin (one in a few hundred values: a plain atomic per hit)
+        if (m == n) {
+            for_each_key([&](unsigned key, bool ok) {
+                const unsigned ball = __ballot_sync(FULL, ok);
+                if (ball) {
+                    unsigned base = 0;
+                    if (lane == 0) base = atomicAdd(&S.n_keys, __popc(ball));
+                    base = __shfl_sync(FULL, base, 0);
+                    if (ok) S.keys[0][base + __popc(ball & ((1u << lane) - 1u))] = key;
+                }
+            });
+        } else {
+            const unsigned pp = p;
+            const int sh = s;               // < 32 here: a histogram pass has narrowed the range
+            for_each_key([&](unsigned key, bool ok) { if (ok && (key >> sh) == pp) S.keys[0][atomicAdd(&S.n_keys, 1u)] = key; });
+        }
         __syncthreads();
         int cur = 0;
         unsigned r = k_lo - below;              // rank among the candidates
@@ -927,64 +937,94 @@ __device__ __forceinline__ unsigned isqrt_floor(unsigned v) {
     return r;
 }
 
+// One row of the exact search below: where to look (issue: computes the ring's two column intervals and loads up to four
+// words of the row's bit mask per side - all loads independent) and what was found (resolve).
+struct AmRow {
+    const uint32_t* rw;
+    unsigned a[4], c[4], dy2;
+    int hx, xmin, xmax, wl, wr, wmin, wmax;
+    bool act_l, act_r;
+    unsigned mask_l, mask_r;
+};
+__device__ __forceinline__ void am_row_issue(AmRow& q, const AmBits& B, int x, int y, int i, unsigned R, unsigned best, unsigned L2) {
+    const int ady = (i + 1) >> 1;
+    const int yy = (i & 1) ? y + ady : y - ady;
+    q.act_l = q.act_r = false;
+    q.hx = -1;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { q.a[u] = 0; q.c[u] = 0; }
+    if ((unsigned)ady > R || yy < 0 || yy >= B.H) return;
+    q.dy2 = (unsigned)(ady * ady);
+    // dx <= hx  <=  dx^2 + dy^2 < best;  dx < lx  =>  dx^2 + dy^2 < L^2: no source there.  Both roots may be off by
+    // one towards the safe side (a few more columns looked at; a candidate that is no improvement changes nothing).
+    q.hx = (int)__fsqrt_ru((float)(best - 1u - q.dy2)) + 1;
+    const int lx = q.dy2 < L2 ? max((int)__fsqrt_rd((float)(L2 - q.dy2)) - 1, 0) : 0;
+    q.rw = reinterpret_cast<const uint32_t*>(B.bits + (size_t)yy * B.pitch);
+    q.xmin = max(x - q.hx, 0); q.xmax = min(x + q.hx, B.W - 1);
+    const int xl = x - lx, xr = x + lx;                            // first columns worth a look on either side
+    q.act_l = xl >= q.xmin; q.act_r = xr <= q.xmax;
+    q.wl = q.act_l ? xl >> 5 : 0; q.wr = q.act_r ? xr >> 5 : 0;
+    q.mask_l = q.act_l ? 0xFFFFFFFFu >> (31 - (xl & 31)) : 0u; q.mask_r = q.act_r ? 0xFFFFFFFFu << (xr & 31) : 0u;
+    q.wmin = q.xmin >> 5; q.wmax = q.xmax >> 5;
+    if (q.act_l) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (q.wl - u >= q.wmin) q.a[u] = q.rw[q.wl - u];
+    }
+    if (q.act_r) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (q.wr + u <= q.wmax) q.c[u] = q.rw[q.wr + u];
+    }
+}
+__device__ __forceinline__ unsigned am_row_resolve(AmRow& q, int x) {
+    if (q.hx < 0) return 0xFFFFFFFFu;
+    int col_l = -1, col_r = 0x7FFFFFFF;
+    while (q.act_l || q.act_r) {                       // one turn unless the ring covers more than four words of the row
+        if (q.act_l) {
+            q.a[0] &= q.mask_l; q.mask_l = 0xFFFFFFFFu;
+#pragma unroll
+            for (int u = 3; u >= 0; --u) if (q.a[u]) col_l = 32 * (q.wl - u) + 31 - __clz(q.a[u]);
+            q.wl -= 4;
+            q.act_l = col_l < 0 && q.wl >= q.wmin;
+        }
+        if (q.act_r) {
+            q.c[0] &= q.mask_r; q.mask_r = 0xFFFFFFFFu;
+#pragma unroll
+            for (int u = 3; u >= 0; --u) if (q.c[u]) col_r = 32 * (q.wr + u) + __ffs(q.c[u]) - 1;
+            q.wr += 4;
+            q.act_r = col_r == 0x7FFFFFFF && q.wr <= q.wmax;
+        }
+        if (q.act_l) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) q.a[u] = q.wl - u >= q.wmin ? q.rw[q.wl - u] : 0u;
+        }
+        if (q.act_r) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) q.c[u] = q.wr + u <= q.wmax ? q.rw[q.wr + u] : 0u;
+        }
+    }
+    int nd = 0x7FFFFFFF;
+    if (col_l >= q.xmin) nd = x - col_l;
+    if (col_r <= q.xmax) nd = min(nd, col_r - x);
+    return nd <= q.hx ? q.dy2 + (unsigned)nd * (unsigned)nd : 0xFFFFFFFFu;      // nd < W <= 4096: no overflow
+}
+
 // Exact squared distance from pixel (x, y) to the nearest source, given that a source exists within distance U and none
 // is nearer than L (both in pixels; L = 0 and any valid U always work).  Stops early and returns some value < stop2 - still
 // the squared distance to SOME source - as soon as the distance is known to be below stop2.  All lanes of the warp call
-// with the same arguments and get the same result.
+// with the same arguments and get the same result.  A lane takes two rows per turn; their loads are in flight together.
+template <int ROWS>
 __device__ __forceinline__ unsigned am_exact_d2(const AmBits& B, int x, int y, unsigned U, unsigned L, unsigned stop2, int lane) {
     unsigned best = U >= 0xFFFFu ? 0xFFFFFFFFu : U * U + 1u;     // strictly-better search: a source at exactly U must be found
     const unsigned L2 = L >= 0xFFFFu ? 0u : L * L;
-    for (int i0 = 0;; i0 += 32) {
+    for (int i0 = 0;; i0 += 32 * ROWS) {
         const unsigned R = isqrt_floor(best - 1u);       // rows with |dy| <= R can still improve
         if ((unsigned)((i0 + 1) >> 1) > R) break;
-        const int i = i0 + lane;
-        const int ady = (i + 1) >> 1;
-        const int yy = (i & 1) ? y + ady : y - ady;
+        AmRow q[ROWS];
+#pragma unroll
+        for (int k = 0; k < ROWS; ++k) am_row_issue(q[k], B, x, y, i0 + 32 * k + lane, R, best, L2);
         unsigned cand = 0xFFFFFFFFu;
-        if ((unsigned)ady <= R && yy >= 0 && yy < B.H) {
-            const unsigned dy2 = (unsigned)(ady * ady);
-            // dx <= hx  <=  dx^2 + dy^2 < best;  dx < lx  =>  dx^2 + dy^2 < L^2: no source there.  Both roots may be off by
-            // one towards the safe side (a few more columns looked at; a candidate that is no improvement changes nothing).
-            const int hx = (int)__fsqrt_ru((float)(best - 1u - dy2)) + 1;
-            const int lx = dy2 < L2 ? max((int)__fsqrt_rd((float)(L2 - dy2)) - 1, 0) : 0;
-            const uint32_t* rw = reinterpret_cast<const uint32_t*>(B.bits + (size_t)yy * B.pitch);
-            const int xmin = max(x - hx, 0), xmax = min(x + hx, B.W - 1);
-            const int xl = x - lx, xr = x + lx;                            // first columns worth a look on either side
-            bool act_l = xl >= xmin, act_r = xr <= xmax;
-            int wl = act_l ? xl >> 5 : 0, wr = act_r ? xr >> 5 : 0;
-            unsigned mask_l = act_l ? 0xFFFFFFFFu >> (31 - (xl & 31)) : 0u, mask_r = act_r ? 0xFFFFFFFFu << (xr & 31) : 0u;
-            const int wmin = xmin >> 5, wmax = xmax >> 5;
-            int col_l = -1, col_r = 0x7FFFFFFF;
-            while (act_l || act_r) {                       // four words per side and step; the loads of a step are independent
-                unsigned a[4] = {0, 0, 0, 0}, c[4] = {0, 0, 0, 0};
-                if (act_l) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) if (wl - u >= wmin) a[u] = rw[wl - u];
-                }
-                if (act_r) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) if (wr + u <= wmax) c[u] = rw[wr + u];
-                }
-                if (act_l) {
-                    a[0] &= mask_l; mask_l = 0xFFFFFFFFu;
-#pragma unroll
-                    for (int u = 3; u >= 0; --u) if (a[u]) col_l = 32 * (wl - u) + 31 - __clz(a[u]);
-                    wl -= 4;
-                    act_l = col_l < 0 && wl >= wmin;
-                }
-                if (act_r) {
-                    c[0] &= mask_r; mask_r = 0xFFFFFFFFu;
-#pragma unroll
-                    for (int u = 3; u >= 0; --u) if (c[u]) col_r = 32 * (wr + u) + __ffs(c[u]) - 1;
-                    wr += 4;
-                    act_r = col_r == 0x7FFFFFFF && wr <= wmax;
-                }
-            }
-            int nd = 0x7FFFFFFF;
-            if (col_l >= xmin) nd = x - col_l;
-            if (col_r <= xmax) nd = min(nd, col_r - x);
-            if (nd <= hx) cand = dy2 + (unsigned)nd * (unsigned)nd;       // hx < 65538: no overflow
-        }
+        for (int k = 0; k < ROWS; ++k) cand = min(cand, am_row_resolve(q[k], x));
         cand = __reduce_min_sync(FULL, cand);
         best = min(best, cand);
         if (best < stop2) return best;
@@ -1003,6 +1043,7 @@ struct AmShared {
 };
 
 // bits: [n][H][pitch] source bit mask; occ: [n][n_bands][pitch] occupancy of the 8 x 8 blocks; best: [n] packed result
+template <int ROWS>
 __global__ void __launch_bounds__(AM_NT) edt_argmax_kernel(const uint8_t* __restrict__ bits_all, size_t bits_stride, int pitch,
                                                             const uint8_t* __restrict__ occ_all, int n_bands, int W, int H,
                                                             int cs /* cell size: 8, 16, 32, ... */, unsigned long long* __restrict__ best_out,
@@ -1017,15 +1058,26 @@ __global__ void __launch_bounds__(AM_NT) edt_argmax_kernel(const uint8_t* __rest
     const uint8_t* occ = occ_all + (size_t)b * n_bands * pitch;
     if (tid == 0) { S.best = 0ull; S.dmax = 0; S.n_items[0] = 0; S.n_items[1] = 0; S.next_item = 0; }
     __syncthreads();
+    long long t_prev = clock64();
+    int t_slot = 8;
+    auto stamp = [&]() { if (dbg && tid == 0 && b == 0) { const long long t = clock64(); if (t_slot < 30) dbg[t_slot++] = (unsigned)(t - t_prev); t_prev = t; } };
     // ---- cells: occupancy = OR over the 8 x 8 blocks of the cell, then the vertical pass (one thread per cell column)
     const int k8 = cs >> 3;              // blocks per cell side
     const int bw8 = (W + 7) >> 3;
     int any = 0;
+#pragma unroll 4
     for (int cidx = tid; cidx < cells; cidx += AM_NT) {
         const int i = cidx / cw, j = cidx - i * cw;
         unsigned o = 0;
-        for (int bi = i * k8; bi < min((i + 1) * k8, n_bands); ++bi)
-            for (int bj = j * k8; bj < min((j + 1) * k8, bw8); ++bj) o |= occ[(size_t)bi * pitch + bj];
+        if (k8 == 2) {                   // 16 x 16 cells: two 16-bit loads (the pitch is even, so is the first block column)
+            const int bi = 2 * i, bj = 2 * j;
+            o = *reinterpret_cast<const uint16_t*>(occ + (size_t)bi * pitch + bj);
+            if (bi + 1 < n_bands) o |= *reinterpret_cast<const uint16_t*>(occ + (size_t)(bi + 1) * pitch + bj);
+            if (bj + 1 >= bw8) o &= 0xFFu;
+        } else {
+            for (int bi = i * k8; bi < min((i + 1) * k8, n_bands); ++bi)
+                for (int bj = j * k8; bj < min((j + 1) * k8, bw8); ++bj) o |= occ[(size_t)bi * pitch + bj];
+        }
         dv[cidx] = o ? 0u : 0xFFu;
         any |= o != 0;
     }
@@ -1067,6 +1119,7 @@ __global__ void __launch_bounds__(AM_NT) edt_argmax_kernel(const uint8_t* __rest
     my_dmax = __reduce_max_sync(FULL, my_dmax);
     if (lane == 0) atomicMax(&S.dmax, my_dmax);
     __syncthreads();
+    stamp();    // coarse done
     // Every pixel of the farthest cell is at least s (sqrt(Dmax) - sqrt 2) away: the search starts with that bound.
     const double SQ2 = 1.41421356237309515;
     const double r_max = sqrt((double)S.dmax);
@@ -1091,7 +1144,7 @@ __global__ void __launch_bounds__(AM_NT) edt_argmax_kernel(const uint8_t* __rest
         const double lbd = sqrt((double)(unsigned)(cur >> 32));
         stop2 = 0;
         if (lbd - rad - 1e-6 > 0.0) { const double t = lbd - rad - 1e-6; stop2 = (unsigned)floor(t * t); }
-        const unsigned d2 = am_exact_d2(B, px, py, U, L, stop2, lane);
+        const unsigned d2 = am_exact_d2<ROWS>(B, px, py, U, L, stop2, lane);
         if (d2 >= stop2) {
             const unsigned idx = (unsigned)((size_t)py * W + px);
             const unsigned long long packed = ((unsigned long long)d2 << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
@@ -1159,13 +1212,13 @@ __global__ void __launch_bounds__(AM_NT) edt_argmax_kernel(const uint8_t* __rest
             if (t > 0.0) thr2 = max(thr2, (unsigned)floor(t * t));
         }
         for (int g = warp; g < groups; g += AM_NT / 32) {
-            const int cidx = g * 32 + lane;
+            const int cidx = lane * groups + g;               // neighbouring cells (the top ones are) go to different warps
             const unsigned dcell = cidx < cells ? (unsigned)D[cidx] : 0xFFFFu;
             unsigned todo = __ballot_sync(FULL, dcell >= thr2 && dcell < hi2);
             while (todo) {
                 const int src = __ffs(todo) - 1;
                 todo &= todo - 1;
-                const int cc = g * 32 + src;
+                const int cc = src * groups + g;
                 const int ci = cc / cw, cj = cc - ci * cw;
                 const double rc = sqrt((double)__shfl_sync(FULL, dcell, src));
                 const unsigned U0 = (unsigned)ceil((double)cs * (rc + SQ2) + 1e-6);
@@ -1181,6 +1234,7 @@ __global__ void __launch_bounds__(AM_NT) edt_argmax_kernel(const uint8_t* __rest
             }
         }
         __syncthreads();
+        stamp();    // one round
         if (lo2 == 0u) break;
         if ((double)cs * (sqrt((double)lo2) + SQ2) + 1e-6 < lower_bound()) break;    // uniform: S.best is stable here
         hi2 = lo2;
@@ -1229,6 +1283,7 @@ __global__ void __launch_bounds__(AM_NT) edt_argmax_kernel(const uint8_t* __rest
         }
     }
     __syncthreads();
+    stamp();    // list built
     for (int lg = lg0 - 1; lg >= 0; --lg) {
         const unsigned n_cur = min(S.n_items[cur], (unsigned)AM_ITEMS);
         if (n_cur == 0) break;                                  // uniform
@@ -1249,6 +1304,7 @@ __global__ void __launch_bounds__(AM_NT) edt_argmax_kernel(const uint8_t* __rest
             if (lane == 0) S.items[cur][it][1] = d2 >= stop2 ? (0x80000000u | d2 >> 0) : 0u;   // exact d2 (< 2^31: d < 46340) or dropped
         }
         __syncthreads();
+        stamp();    // level measured
         if (tid == 0) { S.next_item = 0; S.n_items[cur ^ 1] = 0; }
         __syncthreads();
         if (lg == 0) break;
@@ -1298,6 +1354,7 @@ __global__ void __launch_bounds__(AM_NT) edt_argmax_kernel(const uint8_t* __rest
             }
         }
         __syncthreads();
+        stamp();    // level quartered
         cur ^= 1;
     }
     __syncthreads();
@@ -1508,18 +1565,28 @@ static int run_edt_argmax(lg_context* c, int n, cudaStream_t st) {
     const int cs = c->am_cs;
     const int cells = ((c->W + cs - 1) / cs) * ((c->H + cs - 1) / cs);
     const size_t smem = sizeof(AmShared) + (size_t)cells * 3;
-    LG_ENSURE_SMEM(edt_argmax_kernel, smem);
     static unsigned* dbg = nullptr;
     static int dbg_on = -1;
-    if (dbg_on < 0) { const char* e = getenv("LG_AM_DEBUG"); dbg_on = e && e[0] == '1'; if (dbg_on) { cudaMalloc(&dbg, 64); } }
-    if (dbg_on) cudaMemsetAsync(dbg, 0, 64, st);
-    edt_argmax_kernel<<<n, AM_NT, smem, st>>>(c->ubits, c->ub_stride, c->ub_pitch, c->cellocc, c->n_bands, c->W, c->H, cs, c->edt_best, dbg_on ? dbg : nullptr);
+    if (dbg_on < 0) { const char* e = getenv("LG_AM_DEBUG"); dbg_on = e && e[0] == '1'; if (dbg_on) { cudaMalloc(&dbg, 128); } }
+    if (dbg_on) cudaMemsetAsync(dbg, 0, 128, st);
+    static int rows = 0;
+    if (!rows) { const char* e = getenv("LG_AM_ROWS"); rows = e && e[0] == '1' ? 1 : 2; }    // A/B switch; two rows per lane measured faster
+    if (rows == 2) {
+        LG_ENSURE_SMEM(edt_argmax_kernel<2>, smem);
+        edt_argmax_kernel<2><<<n, AM_NT, smem, st>>>(c->ubits, c->ub_stride, c->ub_pitch, c->cellocc, c->n_bands, c->W, c->H, cs, c->edt_best, dbg_on ? dbg : nullptr);
+    } else {
+        LG_ENSURE_SMEM(edt_argmax_kernel<1>, smem);
+        edt_argmax_kernel<1><<<n, AM_NT, smem, st>>>(c->ubits, c->ub_stride, c->ub_pitch, c->cellocc, c->n_bands, c->W, c->H, cs, c->edt_best, dbg_on ? dbg : nullptr);
+    }
     LG_LAUNCH_CHECK();
     if (dbg_on) {
-        unsigned h[16];
+        unsigned h[32];
         cudaStreamSynchronize(st);
-        cudaMemcpy(h, dbg, 64, cudaMemcpyDeviceToHost);
+        cudaMemcpy(h, dbg, 128, cudaMemcpyDeviceToHost);
         fprintf(stderr, "[am] frames %d cs %d: level-0 evals %u, below %u (by size 1:%u 2:%u 4:%u 8:%u 16:%u 32+:%u)\n", n, cs, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+        fprintf(stderr, "[am] frame 0 phase cycles:");
+        for (int i = 8; i < 30; ++i) fprintf(stderr, " %u", h[i]);
+        fprintf(stderr, "\n");
     }
     return LG_OK;
 }
