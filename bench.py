@@ -353,6 +353,13 @@ class Dist:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
+    def sum_over_ranks(self, v):
+        if self.world == 1:
+            return float(v)
+        t = self.torch.tensor([float(v)], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
     def finish(self):
         if self.world > 1:
             self.dist.destroy_process_group()
@@ -444,6 +451,19 @@ def run_frames(args, D, config, spec_name, B, chunks_per_step, unique, want_cpu,
     out_host = run_steps(steps, True)
     D.barrier()
     e2e_s = D.max_over_ranks(time.perf_counter() - t0)
+    # ---- what the box allows end to end: the same pinned buffers copied to the GPUs by all ranks at once, nothing else
+    # running (tools/h2d_ceiling.py measures the same thing standalone, with a solo leg beside it)
+    lab_d.copy_(lab_h, non_blocking=True); dep_d.copy_(dep_h, non_blocking=True)
+    torch.cuda.synchronize()
+    D.barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        lab_d.copy_(lab_h, non_blocking=True); dep_d.copy_(dep_h, non_blocking=True)
+    torch.cuda.synchronize()
+    own_s = time.perf_counter() - t0
+    ceil_s = D.max_over_ranks(own_s)
+    h2d_ceiling_gbs = 3 * B * P * 6 * world / ceil_s / 1e9            # equal shards: the slowest link sets the pace
+    h2d_links_gbs = D.sum_over_ranks(3 * B * P * 6 / own_s / 1e9)      # every link at its own pace
     if rank != 0:
         eng.close()
         return None
@@ -558,7 +578,12 @@ def run_frames(args, D, config, spec_name, B, chunks_per_step, unique, want_cpu,
                    f"{hostmem.numa_node_of_cpus(cpus)}" if cpus else "unbound"},
         "e2e": {"value": frames_per_step * steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(B * cps * P * 6),
                 "d2h_bytes_per_step": int(B * cps * N.FRAME_RESULT.itemsize),
-                "h2d_gbs_per_gpu": round(B * cps * P * 6 * steps / e2e_s / 1e9, 1)},
+                "h2d_gbs_per_gpu": round(B * cps * P * 6 * steps / e2e_s / 1e9, 1),
+                # all ranks copying the same inputs at once and doing nothing else, measured in this run: the ceiling of e2e
+                "h2d_ceiling_gbs": round(h2d_ceiling_gbs, 1),
+                "h2d_sum_of_links_gbs": round(h2d_links_gbs, 1),      # > ceiling when the links are not equally fast
+                "frames_per_s_at_h2d_ceiling": round(h2d_ceiling_gbs * 1e9 / (P * 6), 0),
+                "frac_of_h2d_ceiling": round(frames_per_step * steps / e2e_s / (h2d_ceiling_gbs * 1e9 / (P * 6)), 3)},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "consistency": check,
     }
     return line
