@@ -31,6 +31,9 @@ struct ChamferArgs {
     uint32_t* out_max;        // [n][nvar] (may be null)
     const uint32_t* need_full; // [n] (may be null): variant 1 only runs for frames whose entry is non-zero
     size_t P;
+    int warp_path;            // 1: rectangles up to CHW_MAXW wide (variant 0, rect_mode) are left to chamfer_warp_kernel
+    int nvar;                 // variants per frame (layout of out_max)
+    int var_base;             // first variant of this launch (variant = blockIdx.y + var_base)
 };
 
 // LPT = source / forward values each thread fetches per row (row width <= LPT * CH_NT), D = rows fetched ahead.
@@ -41,7 +44,7 @@ __global__ void __launch_bounds__(CH_NT, LPT <= 3 ? 2 : 1) chamfer_kernel(Chamfe
     extern __shared__ int smem[];
     __shared__ int wtot[2][CH_NT / 32];
     __shared__ unsigned smax[CH_NT / 32];
-    const int b = blockIdx.x, var = blockIdx.y, nvar = gridDim.y;
+    const int b = blockIdx.x, var = blockIdx.y + A.var_base, nvar = A.nvar;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = A.W, H = A.H;
     if (var == 1 && A.need_full && A.need_full[b] == 0) return;   // outside_max_kernel already produced this frame's maximum
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(512) chamfer8_kernel(ChamferArgs A) {
     extern __shared__ __align__(16) int smem[];
     __shared__ int wtot[2][16];
     __shared__ unsigned smax[16];
-    const int b = blockIdx.x, var = blockIdx.y, nvar = gridDim.y;
+    const int b = blockIdx.x, var = blockIdx.y + A.var_base, nvar = A.nvar;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int W = A.W, H = A.H;
     if (var == 1 && A.need_full && A.need_full[b] == 0) return;   // outside_max_kernel already produced this frame's maximum
@@ -272,6 +275,7 @@ __global__ void __launch_bounds__(512) chamfer8_kernel(ChamferArgs A) {
         }
     }
     const int w = rx1 - rx0, h = ry1 - ry0;
+    if (A.warp_path && A.rect_mode && var == 0 && w <= 512) return;    // chamfer_warp_kernel's
     const int wpad = w + 8;                            // stored position = lx + 2; borders at 0,1 and w+2,w+3
     int* ring = smem;                                  // 3 rows
     const size_t fo = (size_t)b * A.P;
@@ -435,6 +439,185 @@ __global__ void __launch_bounds__(512) chamfer8_kernel(ChamferArgs A) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// One warp per leaf rectangle (up to 512 pixels wide: every leaf of a 1440 x 1080 frame).  The sweeps are a chain of
+// row steps, and with a CTA per rectangle every step paid two block barriers and a trip through shared memory for a
+// row that two warps could hold.  Here a lane owns 16 consecutive pixels and keeps the two previous rows in REGISTERS
+// (plus two halo pixels on either side, fetched with four shuffles when the row was produced); the running minimum along
+// the row is 16 dependent steps in the lane, a five-step warp scan of the lane totals, and no barrier at all.  Source
+// flags / forward values are fetched two rows ahead.  Same arithmetic, same order of minima as chamfer8_kernel: the
+// result is bit-identical.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int CHW_PX = 16;
+constexpr int CHW_MAXW = 32 * CHW_PX;
+constexpr int CHW_D = 3;            // rows fetched ahead = rows per turn of the unrolled loop
+
+template <bool LABELS>
+__global__ void __launch_bounds__(32) chamfer_warp_kernel(ChamferArgs A) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const int W = A.W, H = A.H;
+    int id = 1;
+    if (LABELS) {
+        id = A.src.leaf_id[b];
+        if (id < 0) {
+            if (A.out_max && lane == 0) A.out_max[b * A.nvar] = 0;
+            return;
+        }
+    }
+    const LgRegion r = A.region[b];
+    if (!r.ok) {
+        if (A.out_max && lane == 0) A.out_max[b * A.nvar] = 0;
+        return;
+    }
+    const bool invert = (A.invert_base & 1) != 0;
+    const int rx0 = max(0, r.x0 - 1) & ~7, rx1 = min(W, (r.x1 + 1 + 7) & ~7);
+    const int ry0 = max(0, r.y0 - 1), ry1 = min(H, r.y1 + 1);
+    const int w = rx1 - rx0, h = ry1 - ry0;
+    if (w > CHW_MAXW) return;                           // chamfer8_kernel's
+    const size_t fo = (size_t)b * A.P;
+    int32_t* fwd = A.fwd + (size_t)b * A.P;             // variant 0
+    float* of = A.out_f32 ? A.out_f32 + fo : nullptr;
+    uint32_t* oq = A.out_q16 ? A.out_q16 + fo : nullptr;
+    unsigned my_max = 0;
+    const int lx0 = lane * CHW_PX;
+    const int nv = max(0, min(CHW_PX, w - lx0));        // valid pixels of this lane: 16, 8 or 0 (w is a multiple of 8)
+
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool flip = pass == 1;
+        // physical start of this lane's 16 pixels (ascending addresses; logical order is reversed when flipped)
+        const int xphys = flip ? (rx1 - CHW_PX - lx0) : (rx0 + lx0);
+        auto rowoff = [&](int ly) -> long long { return (long long)(flip ? (ry1 - 1 - ly) : (ry0 + ly)) * W + xphys; };
+        // a flipped lane with 8 valid pixels owns the UPPER half of its 16 physical positions
+        uint4 pre[CHW_D][4];
+        auto fetch = [&](int ly, uint4* dst) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dst[k] = make_uint4(0, 0, 0, 0);
+            if (nv == 0 || ly >= h) return;
+            const long long p = rowoff(ly);
+            if (pass == 0) {
+                if (LABELS) {
+                    dst[0] = *reinterpret_cast<const uint4*>(A.src.labels + fo + p);
+                    if (nv > 8) dst[1] = *reinterpret_cast<const uint4*>(A.src.labels + fo + p + 8);
+                } else {
+                    const uint2 m0 = *reinterpret_cast<const uint2*>(A.src.mask + fo + p);
+                    dst[0].x = m0.x; dst[0].y = m0.y;
+                    if (nv > 8) { const uint2 m1 = *reinterpret_cast<const uint2*>(A.src.mask + fo + p + 8); dst[0].z = m1.x; dst[0].w = m1.y; }
+                }
+            } else {
+                if (nv > 8) {
+                    dst[0] = *reinterpret_cast<const uint4*>(fwd + p);
+                    dst[1] = *reinterpret_cast<const uint4*>(fwd + p + 4);
+                }
+                dst[2] = *reinterpret_cast<const uint4*>(fwd + p + 8);
+                dst[3] = *reinterpret_cast<const uint4*>(fwd + p + 12);
+            }
+        };
+        // Three row buffers with halos (index i + 2 = logical pixel lx0 + i, i in [-2, 18)) rotate through the roles
+        // "row before last", "last row", "this row"; the row loop is unrolled by three so that the rotation costs nothing.
+        int ra[CHW_PX + 4], rb[CHW_PX + 4], rc[CHW_PX + 4];
+#pragma unroll
+        for (int i = 0; i < CHW_PX + 4; ++i) { ra[i] = LG_CH_INF; rb[i] = LG_CH_INF; rc[i] = LG_CH_INF; }
+#pragma unroll
+        for (int d = 0; d < CHW_D; ++d) fetch(d, pre[d]);
+        auto row_step = [&](int ly, uint4* mine, const int (&p1)[CHW_PX + 4], const int (&p2)[CHW_PX + 4], int (&cur)[CHW_PX + 4]) {
+            // this row's source flags (pass 0) or forward values (pass 1), in logical order
+            int sv[CHW_PX];
+            {
+                const unsigned q[16] = {mine[0].x, mine[0].y, mine[0].z, mine[0].w, mine[1].x, mine[1].y, mine[1].z, mine[1].w,
+                                        mine[2].x, mine[2].y, mine[2].z, mine[2].w, mine[3].x, mine[3].y, mine[3].z, mine[3].w};
+                if (pass == 0) {
+#pragma unroll
+                    for (int k = 0; k < CHW_PX; ++k) {
+                        bool leaf;
+                        if (LABELS) leaf = (int)(int16_t)((q[k >> 1] >> (16 * (k & 1))) & 0xFFFFu) == id;
+                        else leaf = ((q[k >> 2] >> (8 * (k & 3))) & 0xFFu) != 0;
+                        sv[k] = (leaf != invert) ? 1 : 0;
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < CHW_PX; ++k) sv[k] = (int)q[15 - k];     // reversed: logical order
+                }
+            }
+            fetch(ly + CHW_D, mine);
+            int pv[CHW_PX];
+            int run = 0x7FFFFFFF;
+#pragma unroll
+            for (int i = 0; i < CHW_PX; ++i) {
+                // taps at columns -2..+2 of pixel i are p[i..i+4]
+                int m = min(min(p2[i + 1], p2[i + 3]), min(p1[i], p1[i + 4])) + LG_CH_C;
+                m = min(m, min(p1[i + 1], p1[i + 3]) + LG_CH_B);
+                m = min(m, p1[i + 2] + LG_CH_A);
+                int u;
+                if (pass == 0) u = sv[i] ? min(m, LG_CH_INF) : 0;
+                else u = min(sv[i], m);
+                if (i >= nv) u = LG_CH_INF;                                      // beyond the rectangle
+                run = min(run, u - LG_CH_A * (lx0 + i));
+                pv[i] = run;
+            }
+            int incl = run;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= d) incl = min(incl, t);
+            }
+            int excl = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+            if (lane == 0) excl = 0x7FFFFFFF;
+#pragma unroll
+            for (int i = 0; i < CHW_PX; ++i) {
+                int t = min(pv[i], excl);
+                t = (t > LG_CH_INF) ? LG_CH_INF : min(t + LG_CH_A * (lx0 + i), LG_CH_INF);
+                cur[i + 2] = i < nv ? t : LG_CH_INF;
+            }
+            {   // the new row's halos come from the neighbouring lanes
+                const int l14 = __shfl_up_sync(0xFFFFFFFFu, cur[CHW_PX], 1), l15 = __shfl_up_sync(0xFFFFFFFFu, cur[CHW_PX + 1], 1);
+                const int r0 = __shfl_down_sync(0xFFFFFFFFu, cur[2], 1), r1 = __shfl_down_sync(0xFFFFFFFFu, cur[3], 1);
+                cur[0] = lane == 0 ? LG_CH_INF : l14; cur[1] = lane == 0 ? LG_CH_INF : l15;
+                cur[CHW_PX + 2] = lane == 31 ? LG_CH_INF : r0; cur[CHW_PX + 3] = lane == 31 ? LG_CH_INF : r1;
+            }
+            if (nv > 0) {
+                const long long p = rowoff(ly);
+                if (pass == 0) {
+                    *reinterpret_cast<int4*>(fwd + p) = make_int4(cur[2], cur[3], cur[4], cur[5]);
+                    *reinterpret_cast<int4*>(fwd + p + 4) = make_int4(cur[6], cur[7], cur[8], cur[9]);
+                    if (nv > 8) {
+                        *reinterpret_cast<int4*>(fwd + p + 8) = make_int4(cur[10], cur[11], cur[12], cur[13]);
+                        *reinterpret_cast<int4*>(fwd + p + 12) = make_int4(cur[14], cur[15], cur[16], cur[17]);
+                    }
+                } else {
+                    unsigned q[CHW_PX];
+#pragma unroll
+                    for (int i = 0; i < CHW_PX; ++i) {                          // ascending addresses
+                        const int o = cur[2 + 15 - i];
+                        q[i] = (o >= LG_CH_INF) ? LG_CH_DIST_MAX : (unsigned)o;
+                        if (15 - i < nv) my_max = max(my_max, q[i]);
+                    }
+                    const float sc = 1.0f / 65536.0f;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        if (nv <= 8 && g < 2) continue;                         // the lower half lies outside the rectangle
+                        if (oq) *reinterpret_cast<uint4*>(oq + p + 4 * g) = make_uint4(q[4 * g], q[4 * g + 1], q[4 * g + 2], q[4 * g + 3]);
+                        if (of) *reinterpret_cast<float4*>(of + p + 4 * g) =
+                            make_float4(__fmul_rn((float)q[4 * g], sc), __fmul_rn((float)q[4 * g + 1], sc),
+                                        __fmul_rn((float)q[4 * g + 2], sc), __fmul_rn((float)q[4 * g + 3], sc));
+                    }
+                }
+            }
+        };
+        for (int ly0 = 0; ly0 < h; ly0 += 3) {
+            row_step(ly0, pre[0], rc, rb, ra);                  // (last row, row before last) -> this row
+            if (ly0 + 1 < h) row_step(ly0 + 1, pre[1], ra, rc, rb);
+            if (ly0 + 2 < h) row_step(ly0 + 2, pre[2], rb, ra, rc);
+        }
+        __syncwarp();
+        __threadfence_block();          // pass 1 reads the forward field other lanes wrote
+    }
+    if (A.out_max) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) my_max = max(my_max, __shfl_xor_sync(0xFFFFFFFFu, my_max, d));
+        if (lane == 0) A.out_max[b * A.nvar] = my_max;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Maximum of the OUTSIDE transform without running it.
 //
 // The two-sweep 5x5 chamfer transform computes, for every pixel p, min over source pixels q of the chamfer norm
@@ -573,7 +756,7 @@ __global__ void __launch_bounds__(OM_NT) outside_max_kernel(lg_context c) {
 
 }  // namespace
 
-int lg_run_chamfer(lg_context* c, LgMaskSrc src, int n, int rect_mode, int invert_base, int nvar,
+int lg_run_chamfer(lg_context* c, LgMaskSrc src, int n, int rect_mode, int invert_base, int nvar, int var_first, int var_count,
                    float* out0, uint32_t* q0, uint32_t* out_max, const uint32_t* need_full, cudaStream_t st) {
     if (c->W > CH_NT * CH_MAXI) {
         lg_set_error("chamfer transform supports widths up to %d", CH_NT * CH_MAXI);
@@ -582,7 +765,7 @@ int lg_run_chamfer(lg_context* c, LgMaskSrc src, int n, int rect_mode, int inver
     ChamferArgs A;
     A.src = src; A.region = c->region; A.n = n; A.H = c->H; A.W = c->W; A.rect_mode = rect_mode;
     A.invert_base = invert_base; A.fwd = c->dt_fwd; A.out_f32 = out0; A.out_q16 = q0; A.out_max = out_max; A.P = c->P;
-    A.need_full = need_full;
+    A.need_full = need_full; A.warp_path = 0; A.nvar = nvar; A.var_base = var_first;
     // fast path: 8 pixels per thread, vector loads/stores -> needs 16-byte aligned rows
     const bool aligned = (c->W % 8 == 0) &&
                          ((reinterpret_cast<uintptr_t>(src.labels) | reinterpret_cast<uintptr_t>(src.mask) |
@@ -590,20 +773,31 @@ int lg_run_chamfer(lg_context* c, LgMaskSrc src, int n, int rect_mode, int inver
                          (src.labels || c->P % 8 == 0);
     static const bool force_generic = getenv("LG_CHAMFER_GENERIC") != nullptr;
     if (aligned && !force_generic) {
+        static const bool no_warp = getenv("LG_CHAMFER_NO_WARP") != nullptr;    // A/B switch
+        A.warp_path = (rect_mode && !no_warp) ? 1 : 0;
+        if (A.warp_path && var_first == 0) {      // the leaf rectangles that one warp can hold (all of them at 1440 x 1080)
+            // The kernel uses no shared memory, but it runs beside kernels that do (orientation, outside maximum): ask for
+            // the large carve-out so that an SM it occupies does not have to drain before it can take their CTAs.
+            LG_PREFER_LARGE_SMEM(chamfer_warp_kernel<true>);
+            LG_PREFER_LARGE_SMEM(chamfer_warp_kernel<false>);
+            if (src.labels) chamfer_warp_kernel<true><<<n, 32, 0, st>>>(A);
+            else chamfer_warp_kernel<false><<<n, 32, 0, st>>>(A);
+            LG_LAUNCH_CHECK();
+        }
         const int threads = ((c->W / 8 + 31) / 32) * 32;
         const size_t sm8 = (size_t)3 * (c->W + 8) * sizeof(int);
         LG_ENSURE_SMEM(chamfer8_kernel<true>, sm8);
         LG_ENSURE_SMEM(chamfer8_kernel<false>, sm8);
-        if (src.labels) chamfer8_kernel<true><<<dim3(n, nvar), threads, sm8, st>>>(A);
-        else chamfer8_kernel<false><<<dim3(n, nvar), threads, sm8, st>>>(A);
+        if (src.labels) chamfer8_kernel<true><<<dim3(n, var_count), threads, sm8, st>>>(A);
+        else chamfer8_kernel<false><<<dim3(n, var_count), threads, sm8, st>>>(A);
         LG_LAUNCH_CHECK();
         return LG_OK;
     }
     size_t sm = (size_t)(3 * (c->W + 4) + 2 * c->W) * sizeof(int);
     LG_ENSURE_SMEM((chamfer_kernel<3, 4>), sm);
     LG_ENSURE_SMEM((chamfer_kernel<CH_MAXI, 2>), sm);
-    if (c->W <= 3 * CH_NT) chamfer_kernel<3, 4><<<dim3(n, nvar), CH_NT, sm, st>>>(A);
-    else chamfer_kernel<CH_MAXI, 2><<<dim3(n, nvar), CH_NT, sm, st>>>(A);
+    if (c->W <= 3 * CH_NT) chamfer_kernel<3, 4><<<dim3(n, var_count), CH_NT, sm, st>>>(A);
+    else chamfer_kernel<CH_MAXI, 2><<<dim3(n, var_count), CH_NT, sm, st>>>(A);
     LG_LAUNCH_CHECK();
     return LG_OK;
 }
@@ -612,6 +806,8 @@ int lg_run_chamfer(lg_context* c, LgMaskSrc src, int n, int rect_mode, int inver
 // and handled by variant 1 of the sweep kernels)
 int lg_run_outside_max(lg_context* c, LgMaskSrc src, int n, cudaStream_t st) {
     LG_CUDA(cudaMemsetAsync(c->bnd_count, 0, sizeof(uint32_t) * n, st));
+    LG_PREFER_LARGE_SMEM(leaf_boundary_kernel);
+    LG_PREFER_LARGE_SMEM(outside_max_kernel);
     leaf_boundary_kernel<<<dim3(16, n), BND_NT, 0, st>>>(*c, src);
     LG_LAUNCH_CHECK();
     outside_max_kernel<<<n, OM_NT, 0, st>>>(*c);
@@ -624,5 +820,5 @@ extern "C" int lg_chamfer_transform(lg_context* c, const uint8_t* mask, int n, i
     if (!c || !mask || n < 1) return LG_E_ARG;
     if (n > c->B) return LG_E_CAPACITY;
     LgMaskSrc src{nullptr, mask, nullptr};
-    return lg_run_chamfer(c, src, n, 0, invert ? 1 : 0, 1, dist, q16, max_q16, nullptr, (cudaStream_t)stream);
+    return lg_run_chamfer(c, src, n, 0, invert ? 1 : 0, 1, 0, 1, dist, q16, max_q16, nullptr, (cudaStream_t)stream);
 }

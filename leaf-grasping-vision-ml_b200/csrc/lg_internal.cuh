@@ -185,6 +185,12 @@ int lg_ensure_smem_impl(const void* kernel, size_t bytes);
         int rc__ = lg_ensure_smem_impl((const void*)(kernel), (size_t)(bytes)); \
         if (rc__) return rc__;                                               \
     } while (0)
+int lg_prefer_large_smem_impl(const void* kernel);
+#define LG_PREFER_LARGE_SMEM(kernel)                                 \
+    do {                                                             \
+        int rc__ = lg_prefer_large_smem_impl((const void*)(kernel)); \
+        if (rc__) return rc__;                                       \
+    } while (0)
 extern unsigned long long g_lg_launches;
 #define LG_LAUNCH_CHECK()            \
     do {                             \
@@ -203,7 +209,8 @@ int lg_run_select(lg_context* c, int n, lg_camera cam, int32_t* leaf_out, lg_lea
 // aux = lg_fork(c, k, st): stream for the side branch (st itself when overlap is off); lg_join makes st wait for it
 cudaStream_t lg_fork(lg_context* c, int k, cudaStream_t st);
 int lg_join(lg_context* c, int k, cudaStream_t aux, cudaStream_t st);
-int lg_run_chamfer(lg_context* c, LgMaskSrc src, int n, int rect_mode, int invert_base, int nvar,
+// variants var_first .. var_first + var_count - 1 of the nvar a frame has (0: the mask as given, 1: its complement)
+int lg_run_chamfer(lg_context* c, LgMaskSrc src, int n, int rect_mode, int invert_base, int nvar, int var_first, int var_count,
                    float* out0, uint32_t* q0, uint32_t* out_max, const uint32_t* need_full, cudaStream_t st);
 int lg_run_outside_max(lg_context* c, LgMaskSrc src, int n, cudaStream_t st);
 int lg_run_orientation(lg_context* c, LgMaskSrc src, int n, cudaStream_t st);

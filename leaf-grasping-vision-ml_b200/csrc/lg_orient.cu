@@ -527,6 +527,7 @@ __global__ void mask_clear_kernel(lg_context c, int n) {
 
 int lg_run_orientation(lg_context* c, LgMaskSrc src, int n, cudaStream_t st) {
     LG_ENSURE_SMEM(orient_kernel, OR_SMEM);
+    LG_PREFER_LARGE_SMEM(orient_kernel);
     orient_kernel<<<n, OR_NT, OR_SMEM, st>>>(*c, src, n);
     LG_LAUNCH_CHECK();
     return LG_OK;

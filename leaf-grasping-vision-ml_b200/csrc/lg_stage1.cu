@@ -1571,6 +1571,8 @@ static int run_edt_argmax(lg_context* c, int n, cudaStream_t st) {
     if (dbg_on) cudaMemsetAsync(dbg, 0, 128, st);
     static int rows = 0;
     if (!rows) { const char* e = getenv("LG_AM_ROWS"); rows = e && e[0] == '1' ? 1 : 2; }    // A/B switch; two rows per lane measured faster
+    LG_PREFER_LARGE_SMEM(edt_argmax_kernel<1>);       // runs beside the median kernel
+    LG_PREFER_LARGE_SMEM(edt_argmax_kernel<2>);
     if (rows == 2) {
         LG_ENSURE_SMEM(edt_argmax_kernel<2>, smem);
         edt_argmax_kernel<2><<<n, AM_NT, smem, st>>>(c->ubits, c->ub_stride, c->ub_pitch, c->cellocc, c->n_bands, c->W, c->H, cs, c->edt_best, dbg_on ? dbg : nullptr);
@@ -1633,6 +1635,7 @@ int lg_run_stage1(lg_context* c, const int16_t* labels, const float* depth, int 
     lg_mark(c, LG_M_EDT_ROW, aux);
     if (!rc) {
         rc = lg_ensure_smem_impl((const void*)leaf_median_kernel, sizeof(MedShared));
+        if (!rc) rc = lg_prefer_large_smem_impl((const void*)leaf_median_kernel);
         if (!rc) {
             leaf_median_kernel<<<dim3(c->L, n), MED_NT, sizeof(MedShared), st>>>(*c);
             ++g_lg_launches;
