@@ -400,6 +400,7 @@ def run_frames(args, D, config, spec_name, B, chunks_per_step, unique, want_cpu,
     eng = GraspEngine(B, H, W, 128, device=dev, lanes=args.lanes)
     n_prof = eng.lane_split(B)[0][1]          # frames the profiled (main) context handles per call
     eng.set_cnn_weights(pack_weights(synth.seeded_state_dict(CNN_SEED)))
+    eng.set_patch_export(False)      # throughput mode: the gather writes the CNN's input layout, no float32 patch tensor
     lib = N.lib()
     steps, cps = args.steps, chunks_per_step
     # candidate records of every frame of the timed region, written by the fusion kernel; ONE all-gather at the end

@@ -238,6 +238,11 @@ int lg_leaf_orientation(lg_context* ctx, const uint8_t* mask, int frames, double
  * call fed to the CNN (rows of candidates without an ML score are zero). */
 int lg_patches(lg_context* ctx, float* patches_out, int frames, void* stream);
 
+/* Drop-in mode (on = 1, the default) keeps that float32 patch tensor - what get_ml_score (grasp_point_selector.py:59-127)
+ * builds per candidate - for lg_patches.  Throughput mode (on = 0): with the bf16 tensor-core CNN the gather kernel writes
+ * the CNN's input layout directly and no float32 patch tensor exists (lg_patches then fails); results are identical. */
+int lg_set_patch_export(lg_context* ctx, int on);
+
 /* ImageProcessor.smooth_depth (image_processor.py:56-64): reflect padding by 2 + the 5x5 Gaussian (sigma = 5/6, float32
  * taps) on n float32 images of height x width (>= 3 x 3), any size, no context needed.  out float32 [n][height][width]. */
 int lg_smooth_depth(const float* depth, int n, int height, int width, float* out, void* stream);

@@ -90,6 +90,7 @@ SYMBOLS = {
     "lg_stage_times": (C.c_int, [_P, _P, C.c_int]),
     "lg_stage_times_mean": (C.c_int, [_P, _P, C.c_int, _P]),
     "lg_set_overlap": (C.c_int, [_P, C.c_int]),
+    "lg_set_patch_export": (C.c_int, [_P, C.c_int]),
     "lg_launch_count": (C.c_uint64, []),
     "lg_sizeof_frame_result": (C.c_uint64, []),
     "lg_sizeof_leaf_record": (C.c_uint64, []),

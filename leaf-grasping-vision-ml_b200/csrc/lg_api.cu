@@ -119,6 +119,7 @@ extern "C" int lg_create(lg_context** out, int max_frames, int height, int width
     if (!c) return LG_E_ARG;
     memset(c, 0, sizeof(*c));
     c->B = max_frames; c->H = height; c->W = width; c->L = max_labels;
+    c->patch_export = 1;
     c->P = (size_t)height * width;
     c->allocs = new (std::nothrow) std::vector<void*>();
     if (!c->allocs) { delete c; return LG_E_ARG; }
@@ -327,9 +328,11 @@ static int process_batch_impl(lg_context* c, const int16_t* labels, const float*
     lg_mark(c, LG_M_NMS, st);
     const int have_ml = c->cnn.loaded;
     if (have_ml) {
-        TRY(lg_run_gather(c, src, depth, frames, *cam, st));
+        // throughput mode (lg_set_patch_export(ctx, 0)): the gather writes the tensor-core CNN's input directly
+        const int packed = use_bf16_cnn && !c->patch_export && c->cnn.is_default && frames * LG_TOP_K <= c->cnn_cap;
+        TRY(lg_run_gather(c, src, depth, frames, *cam, packed, st));
         lg_mark(c, LG_M_GATHER, st);
-        TRY(lg_run_cnn(c, c->patches, frames * LG_TOP_K, c->cnn_count, c->logits, use_bf16_cnn, st));
+        TRY(lg_run_cnn(c, packed ? nullptr : c->patches, frames * LG_TOP_K, c->cnn_count, c->logits, use_bf16_cnn, st));
         lg_mark(c, LG_M_CNN, st);
     }
     TRY(lg_run_fuse(c, src, depth, frames, *cam, have_ml, results, rec_out, st));
@@ -417,7 +420,7 @@ extern "C" int lg_select_grasp_point(lg_context* c, const uint8_t* mask, const f
     TRY(lg_run_nms(c, frames, st));
     const int have_ml = c->cnn.loaded;
     if (have_ml) {
-        TRY(lg_run_gather(c, src, depth, frames, *cam, st));
+        TRY(lg_run_gather(c, src, depth, frames, *cam, 0, st));
         TRY(lg_run_cnn(c, c->patches, frames * LG_TOP_K, c->cnn_count, c->logits, use_bf16_cnn, st));
     }
     TRY(lg_run_fuse(c, src, depth, frames, *cam, have_ml, results, nullptr, st));
@@ -434,8 +437,18 @@ extern "C" int lg_leaf_orientation(lg_context* c, const uint8_t* mask, int frame
     return lg_run_export_orient(c, frames, out5, st);
 }
 
+extern "C" int lg_set_patch_export(lg_context* c, int on) {
+    if (!c) return LG_E_ARG;
+    c->patch_export = on ? 1 : 0;
+    return LG_OK;
+}
+
 extern "C" int lg_patches(lg_context* c, float* patches_out, int frames, void* stream) {
     if (!c || !patches_out || frames < 1 || frames > c->B) return LG_E_ARG;
+    if (!c->patches_valid) {
+        lg_set_error("lg_patches: the last call ran in throughput mode (lg_set_patch_export(ctx, 0)): no float32 patch tensor was written");
+        return LG_E_ARG;
+    }
     return lg_run_export_patches(c, patches_out, frames, (cudaStream_t)stream);
 }
 

@@ -419,6 +419,7 @@ int lg_run_cnn(lg_context* c, const float* patches, int n, const int32_t* n_dev,
         return run_cnn_generic(c, patches, n, logits, st);
     }
     if (use_bf16) return lg_run_cnn_bf16(c, patches, n, n_dev, logits, st);
+    if (!patches) { lg_set_error("the fp32 CNN needs the float32 patch tensor"); return LG_E_ARG; }
     // the fp32 anchor path sizes its grids on the host: with a device-side count it simply runs all n slots
     const float* blob = c->cnn.blob;
     const int cap = min(c->cnn_cap, 32768);               // patches ride on gridDim.z (<= 65535)

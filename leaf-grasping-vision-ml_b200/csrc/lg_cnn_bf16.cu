@@ -660,8 +660,12 @@ int lg_cnn_prepare_bf16(lg_context* c) {
 static int run_cnn_bf16(lg_context* c, const float* patches, int n, const int32_t* n_dev, float* logits, int stop_layer,
                         float* feat_out, cudaStream_t st);
 
+// geometry of the layer-0 input, for the gather kernel that writes it directly (lg_score.cu)
+long long lg_cnn_input_plane_rows(long long n_patches) { return rows_per_plane(32, n_patches); }
+int lg_cnn_input_lead() { return LEAD; }
+
 int lg_run_cnn_bf16(lg_context* c, const float* patches, int n, const int32_t* n_dev, float* logits, cudaStream_t st) {
-    if (n_dev && n > c->cnn_cap) { lg_set_error("device-side patch count needs n <= %d", c->cnn_cap); return LG_E_CAPACITY; }
+    if ((n_dev || !patches) && n > c->cnn_cap) { lg_set_error("device-side patch count needs n <= %d", c->cnn_cap); return LG_E_CAPACITY; }
     return run_cnn_bf16(c, patches, n, n_dev, logits, -1, nullptr, st);
 }
 
@@ -703,7 +707,7 @@ static int run_cnn_bf16(lg_context* c, const float* patches, int n, const int32_
         const int m = n - done < c->cnn_cap ? n - done : c->cnn_cap;
         uint4* buf[2] = {reinterpret_cast<uint4*>(c->cnn_act0), reinterpret_cast<uint4*>(c->cnn_act1)};
         int cur = 0;   // buffer holding the current layer's input
-        {
+        if (patches) {     // null: the gather kernel wrote the packed input into buf[0] itself
             const long long R = rows_per_plane(32, m);
             const long long total = (long long)m * 33 * 33 + 34 + LEAD;
             const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);

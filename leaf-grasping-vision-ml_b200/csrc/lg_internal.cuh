@@ -139,6 +139,8 @@ struct lg_context {
     float* logits;                           // [B*20], indexed by compact slot
     int32_t* slot_map;                       // [B*20] compact patch index of every (frame, candidate), -1 = no ML score
     int32_t* cnn_count;                      // [1] number of valid slots of the current batch
+    int patch_export;                        // 1 (default): the float32 patch tensor is kept for lg_patches; 0: throughput mode
+    int patches_valid;                       // the last gather wrote c->patches
     lg_frame_result* results;                // [B]
     float* rec_out;                          // caller-owned [frames][20][4] candidate records (lg_set_record_output), or null
     // CNN scratch
@@ -217,7 +219,8 @@ int lg_run_orientation(lg_context* c, LgMaskSrc src, int n, cudaStream_t st);
 int lg_run_scores(lg_context* c, LgMaskSrc src, const float* depth, int n, lg_camera cam, int full,
                   double* iso_out, cudaStream_t st);
 int lg_run_nms(lg_context* c, int n, cudaStream_t st);
-int lg_run_gather(lg_context* c, LgMaskSrc src, const float* depth, int n, lg_camera cam, cudaStream_t st);
+// packed != 0: the patches go straight into the tensor-core CNN's input layout (no float32 patch tensor: lg_patches has nothing to export)
+int lg_run_gather(lg_context* c, LgMaskSrc src, const float* depth, int n, lg_camera cam, int packed, cudaStream_t st);
 // n patches; n_dev (device int, may be null) = the number actually present (<= n): the kernels read it on the device
 int lg_run_cnn(lg_context* c, const float* patches, int n, const int32_t* n_dev, float* logits, int use_bf16, cudaStream_t st);
 int lg_run_export_patches(lg_context* c, float* out, int n, cudaStream_t st);

@@ -12,6 +12,8 @@
 //   fuse_kernel    ML rescale + confidence weighting + 3-D / pre-grasp points    (:133-136, 205-249, 152-180, 754-826)
 #include <math_constants.h>
 
+#include <cuda_bf16.h>
+
 #include "lg_internal.cuh"
 
 namespace {
@@ -463,12 +465,32 @@ __global__ void __launch_bounds__(CS_NT) compact_slots_kernel(lg_context c, int 
 }
 
 constexpr int GA_NT = 256;
-__global__ void __launch_bounds__(GA_NT) gather_kernel(lg_context c, LgMaskSrc src, const float* __restrict__ depth) {
+// PACKED = false: float32 [slot][9][32][32] into c.patches (the fp32 CNN, lg_patches).  PACKED = true: straight into the
+// input layout of the tensor-core convolutions (lg_cnn_bf16.cu: two planes of 16-byte units - channels 0-7 | channel 8 and
+// zeros - at position lead + slot * 33 * 33 + (y + 1) * 33 + (x + 1), row 0 / column 0 of every patch zero), so that no
+// fp32 patch tensor is written and re-read on the way to the CNN.
+template <bool PACKED>
+__global__ void __launch_bounds__(GA_NT) gather_kernel(lg_context c, LgMaskSrc src, const float* __restrict__ depth,
+                                                        uint4* __restrict__ packed, long long plane_rows, int lead) {
     const int k = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     lg_frame_result* res = &c.results[b];
     const int slot = c.slot_map[b * LG_TOP_K + k];
     if (slot < 0) return;                      // no ML score for this candidate: nothing to build
     float* out = c.patches + (size_t)slot * (LG_CHANNELS * LG_PATCH * LG_PATCH);
+    constexpr int PITCH = LG_PATCH + 1, PP = PITCH * PITCH;
+    uint4* pk = PACKED ? packed + lead + (long long)slot * PP : nullptr;
+    if (PACKED) {
+        // the zero halo of this patch (row 0, column 0), the PITCH + 1 positions behind it (halo of the next patch, or the
+        // tail the convolutions read past the last one), and - by the first patch - the lead rows
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        long long pos = -1;
+        if (tid < PITCH) pos = tid;
+        else if (tid < PITCH + LG_PATCH) pos = (long long)(tid - PITCH + 1) * PITCH;
+        else if (tid < 2 * PITCH + LG_PATCH + 1) pos = PP + (tid - PITCH - LG_PATCH);
+        if (pos >= 0) { pk[pos] = z; pk[plane_rows + pos] = z; }
+        if (slot == 0)
+            for (int i = tid; i < lead; i += GA_NT) { packed[i] = z; packed[plane_rows + i] = z; }
+    }
     const LgRegion r = c.region[b];
     const int W = c.W, H = c.H;
     __shared__ float smn[GA_NT / 32][LG_CHANNELS], smx[GA_NT / 32][LG_CHANNELS];
@@ -525,7 +547,18 @@ __global__ void __launch_bounds__(GA_NT) gather_kernel(lg_context c, LgMaskSrc s
         for (int q = 0; q < 4; ++q) {
             float val = v[ch][q];
             if (norm) val = __fdiv_rn(__fsub_rn(val, lo), den);
-            out[ch * (LG_PATCH * LG_PATCH) + tid + q * GA_NT] = val;
+            if (PACKED) v[ch][q] = val;
+            else out[ch * (LG_PATCH * LG_PATCH) + tid + q * GA_NT] = val;
+        }
+    }
+    if (PACKED) {
+        auto pack2 = [](float a, float b2) -> unsigned { __nv_bfloat162 h = __floats2bfloat162_rn(a, b2); return *reinterpret_cast<unsigned*>(&h); };
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int pi = tid + q * GA_NT;
+            const long long pos = (long long)((pi >> 5) + 1) * PITCH + (pi & 31) + 1;
+            pk[pos] = make_uint4(pack2(v[0][q], v[1][q]), pack2(v[2][q], v[3][q]), pack2(v[4][q], v[5][q]), pack2(v[6][q], v[7][q]));
+            pk[plane_rows + pos] = make_uint4(pack2(v[8][q], 0.f), 0u, 0u, 0u);
         }
     }
 }
@@ -750,12 +783,21 @@ int lg_run_nms(lg_context* c, int n, cudaStream_t st) {
     return LG_OK;
 }
 
-int lg_run_gather(lg_context* c, LgMaskSrc src, const float* depth, int n, lg_camera cam, cudaStream_t st) {
+long long lg_cnn_input_plane_rows(long long n_patches);
+int lg_cnn_input_lead();
+
+// packed != 0: write the tensor-core CNN's input (c->cnn_act0) instead of the float32 patch tensor
+int lg_run_gather(lg_context* c, LgMaskSrc src, const float* depth, int n, lg_camera cam, int packed, cudaStream_t st) {
     (void)cam;
     compact_slots_kernel<<<1, CS_NT, 0, st>>>(*c, n);
     LG_LAUNCH_CHECK();
-    gather_kernel<<<dim3(LG_TOP_K, n), GA_NT, 0, st>>>(*c, src, depth);
+    if (packed)
+        gather_kernel<true><<<dim3(LG_TOP_K, n), GA_NT, 0, st>>>(*c, src, depth, reinterpret_cast<uint4*>(c->cnn_act0),
+                                                                 lg_cnn_input_plane_rows((long long)n * LG_TOP_K), lg_cnn_input_lead());
+    else
+        gather_kernel<false><<<dim3(LG_TOP_K, n), GA_NT, 0, st>>>(*c, src, depth, nullptr, 0, 0);
     LG_LAUNCH_CHECK();
+    c->patches_valid = packed ? 0 : 1;
     return LG_OK;
 }
 

@@ -76,6 +76,12 @@ class GraspEngine:
         for ctx in self._all_ctx():
             N.check(self.lib.lg_set_overlap(ctx, int(bool(on))), "lg_set_overlap")
 
+    def set_patch_export(self, on: bool):
+        """Drop-in mode (default) keeps the float32 patch tensor of the last call for last_patches(); throughput mode
+        (False) lets the gather kernel write the tensor-core CNN's input directly (bf16 CNN only; same results)."""
+        for ctx in self._all_ctx():
+            N.check(self.lib.lg_set_patch_export(ctx, int(bool(on))), "lg_set_patch_export")
+
     @property
     def context_bytes(self) -> int:
         return sum(int(self.lib.lg_context_bytes(ctx)) for ctx in self._all_ctx())

@@ -255,3 +255,29 @@ def test_wide_sweep_against_strict_oracle(spec_name, first, count, blob):
         np.testing.assert_allclose(r["pre_grasp"], o["pre_grasp"], rtol=1e-9)
         n_checked += 1
     assert n_checked >= count * 3 // 4
+
+
+def test_throughput_mode_gather_writes_cnn_input_directly(blob):
+    """lg_set_patch_export(ctx, 0): the gather kernel writes the bf16 tensor-core CNN's input layout itself (no float32
+    patch tensor, no pack kernel).  Same values rounded once to bf16 either way: logits, candidates and picks are identical
+    to the drop-in mode bit for bit, and lg_patches reports that there is nothing to export."""
+    spec = synth.CFG2
+    lab, dep = synth.make_batch(spec, SEED, 20, 6)
+    eng = _engine(6, spec.height, spec.width, 128)
+    eng.set_cnn_weights(blob)
+    cam = _cam(spec)
+    lt, dt = torch.from_numpy(lab).cuda(), torch.from_numpy(dep).cuda()
+    a = eng.process_batch(lt, dt, cam, True).copy()
+    eng.last_patches(6)                                   # drop-in mode: available
+    eng.set_patch_export(False)
+    b = eng.process_batch(lt, dt, cam, True).copy()
+    for f in ("leaf_id", "n_candidates", "cand_x", "cand_y", "ml_valid", "best_index", "grasp_x", "grasp_y"):
+        assert np.array_equal(a[f], b[f]), f
+    ok = a["ml_valid"] > 0
+    assert ok.any() and np.array_equal(a["logit"][ok], b["logit"][ok])
+    with pytest.raises(Exception):
+        eng.last_patches(6)
+    c = eng.process_batch(lt, dt, cam, False)             # the fp32 CNN always takes the float32 patches
+    assert np.array_equal(a["cand_x"], c["cand_x"])
+    eng.last_patches(6)
+    eng.close()

@@ -17,6 +17,8 @@ lab = np.concatenate([lab] * (B // U)); dep = np.concatenate([dep] * (B // U))
 lt, dt = torch.from_numpy(lab).cuda(), torch.from_numpy(dep).cuda()
 eng = GraspEngine(B, spec.height, spec.width, 128)
 eng.set_cnn_weights(pack_weights(O.seeded_state_dict(1234)))
+if os.environ.get('LG_PATCH_EXPORT', '0') != '1':
+    eng.set_patch_export(False)
 cam = camera_from_projection(synth.projection_matrix(spec))
 lib = N.lib()
 names = ["leaf_stats", "scatter", "median", "edt_columns", "edt_rows", "select", "chamfer", "orientation", "score_maps",
