@@ -5,7 +5,8 @@ reference checkpoint (``checkpoint['model_state_dict']``, grasp_point_selector.p
 architecture the reference can build (attention 'spatial' / 'channel' / 'hybrid' / 'none', any encoder filter list of
 the sweep in train_model_mlflow.py:173-182).  ``forward`` in eval mode runs the hand-written CUDA kernels
 (csrc/lg_cnn*.cu) on BatchNorm-folded weights; there is no torch / cuDNN forward behind it.  The default architecture
-(the one the live node builds) can run on the tensor cores (``use_bf16``); the variants use the fp32 kernels.
+(the one the live node builds) and its attention variants (same encoder [64, 128, 256]) can run on the tensor cores
+(``use_bf16``); the other encoders use the fp32 kernels.
 Training is out of scope: calling it in training mode raises.
 """
 from __future__ import annotations
@@ -145,6 +146,11 @@ class GraspPointCNN(nn.Module):
     def is_default_architecture(self) -> bool:
         return self.attention_type == "spatial" and self.encoder_filters == [64, 128, 256]
 
+    @property
+    def has_tensor_core_path(self) -> bool:
+        """The tcgen05 convolutions are built for the encoder [64, 128, 256]; the attention type only changes the fp32 tail."""
+        return self.encoder_filters == [64, 128, 256]
+
     def _version(self):
         return tuple(int(t._version) for t in self.state_dict().values())
 
@@ -165,4 +171,4 @@ class GraspPointCNN(nn.Module):
             self._engine.set_cnn_weights(self.packed(), None if self.is_default_architecture else self._config)
             self._packed_version = ver
         xin = x.detach().to(dev, torch.float32).contiguous()
-        return self._engine.cnn_forward(xin, self.use_bf16 and self.is_default_architecture).reshape(-1, 1).to(x.device)
+        return self._engine.cnn_forward(xin, self.use_bf16 and self.has_tensor_core_path).reshape(-1, 1).to(x.device)

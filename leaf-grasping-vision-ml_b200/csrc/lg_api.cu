@@ -241,9 +241,10 @@ extern "C" int lg_set_cnn_model(lg_context* c, const lg_cnn_config* cfg, const f
     c->cnn.n_floats = n_floats;
     c->cnn.cfg = *cfg;
     c->cnn.is_default = lg_cnn_config_is_default(cfg) ? 1 : 0;
+    c->cnn.bf16_convs = (cfg->n_blocks == 3 && cfg->filters[0] == 64 && cfg->filters[1] == 128 && cfg->filters[2] == 256) ? 1 : 0;
     c->cnn.loaded = 1;
     TRY(ensure_cnn_scratch(c));
-    return c->cnn.is_default ? lg_cnn_prepare_bf16(c) : LG_OK;
+    return c->cnn.bf16_convs ? lg_cnn_prepare_bf16(c) : LG_OK;
 }
 
 extern "C" int lg_set_cnn_weights(lg_context* c, const float* blob_host, uint64_t n_floats) {

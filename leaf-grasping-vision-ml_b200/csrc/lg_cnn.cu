@@ -389,6 +389,16 @@ static int run_cnn_generic(lg_context* c, const float* patches, int n, float* lo
 }
 
 int lg_run_cnn_bf16(lg_context* c, const float* patches, int n, const int32_t* n_dev, float* logits, cudaStream_t st);
+int lg_run_cnn_bf16_variant(lg_context* c, const float* patches, int n, float* logits, cudaStream_t st);
+
+// the generic tail (any attention type) on fp32 NHWC features [m][S2][C]; w = the blob behind the convolution weights
+int lg_launch_cnn_tail_generic(const float* feat, const float* w, float* logits, int C, int S2, int attention, int m, cudaStream_t st) {
+    const size_t tail_smem = ((size_t)S2 * C + S2 + 3 * (size_t)C) * sizeof(float);
+    LG_ENSURE_SMEM(cnn_tail_generic_kernel, tail_smem);
+    cnn_tail_generic_kernel<<<m, 256, tail_smem, st>>>(feat, w, logits, C, S2, attention);
+    LG_LAUNCH_CHECK();
+    return LG_OK;
+}
 
 // attention + average + MLP on fp32 NHWC [n][4][4][256] features (shared by the fp32 and the bf16 conv paths)
 int lg_launch_cnn_tail(const float* feat, const float* blob_tail, float* logits, int n, const int32_t* n_dev, cudaStream_t st) {
@@ -413,7 +423,9 @@ int lg_run_cnn(lg_context* c, const float* patches, int n, const int32_t* n_dev,
     }
     if (!c->cnn.is_default) {
         if (use_bf16) {
-            lg_set_error("the bf16 tensor-core path covers the default GraspPointCNN architecture only; use the fp32 path");
+            // the attention variants of the default encoder: tensor-core convolutions, generic fp32 tail
+            if (c->cnn.bf16_convs && patches) return lg_run_cnn_bf16_variant(c, patches, n, logits, st);
+            lg_set_error("the bf16 tensor-core path covers the encoder [64, 128, 256] only; use the fp32 path");
             return LG_E_ARG;
         }
         return run_cnn_generic(c, patches, n, logits, st);

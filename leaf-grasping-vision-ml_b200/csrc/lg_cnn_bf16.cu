@@ -658,7 +658,14 @@ int lg_cnn_prepare_bf16(lg_context* c) {
 }
 
 static int run_cnn_bf16(lg_context* c, const float* patches, int n, const int32_t* n_dev, float* logits, int stop_layer,
-                        float* feat_out, cudaStream_t st);
+                        float* feat_out, cudaStream_t st, int generic_tail = 0);
+int lg_launch_cnn_tail_generic(const float* feat, const float* w, float* logits, int C, int S2, int attention, int m, cudaStream_t st);
+
+// encoder [64, 128, 256] with another attention type (model.py:30-60): the convolutions as for the default architecture,
+// then the pooled fp32 features go through the generic tail of the fp32 path
+int lg_run_cnn_bf16_variant(lg_context* c, const float* patches, int n, float* logits, cudaStream_t st) {
+    return run_cnn_bf16(c, patches, n, nullptr, logits, -1, nullptr, st, 1);
+}
 
 // geometry of the layer-0 input, for the gather kernel that writes it directly (lg_score.cu)
 long long lg_cnn_input_plane_rows(long long n_patches) { return rows_per_plane(32, n_patches); }
@@ -677,7 +684,7 @@ extern "C" int lg_cnn_bf16_features(lg_context* c, const float* patches, int n, 
 }
 
 static int run_cnn_bf16(lg_context* c, const float* patches, int n, const int32_t* n_dev, float* logits, int stop_layer,
-                        float* feat_out, cudaStream_t st) {
+                        float* feat_out, cudaStream_t st, int generic_tail) {
     if (!c->cnn.bf16_blob) { lg_set_error("bf16 CNN weights are not prepared"); return LG_E_ARG; }
     static int sms = 0, issuers = 4, fuse_pool = 1;
     if (!sms) {
@@ -729,7 +736,7 @@ static int run_cnn_bf16(lg_context* c, const float* patches, int n, const int32_
             else rc = fused_pool ? launch_conv<8, 128, true>(A, L.S, sms, st) : launch_conv<8, 128, false>(A, L.S, sms, st);
             if (rc) return rc;
             cur ^= 1;
-            if (l == 5 && stop_layer != 5) break;   // the tail kernel pools the last layer's output while it loads it
+            if (l == 5 && stop_layer != 5 && !generic_tail) break;   // the tail kernel pools the last layer's output while it loads it
             if ((l & 1) && !fused_pool) {   // max-pool after the second conv of each block
                 const int planes = L.cout / 8;
                 if (l == 5) {
@@ -756,7 +763,14 @@ static int run_cnn_bf16(lg_context* c, const float* patches, int n, const int32_
                 return LG_OK;
             }
         }
-        int rc = lg_launch_cnn_tail_bf16(buf[cur], rows_per_plane(8, m), LEAD, tail, logits + done, m, n_dev, st);
+        int rc;
+        if (generic_tail) {     // buf[cur]: pooled fp32 NHWC [m][4][4][256]; the tail's weights follow the six convolutions
+            const float* w = c->cnn.blob;
+            for (int l = 0; l < 6; ++l) w += 9ull * kLayers[l].cin * kLayers[l].cout + kLayers[l].cout;
+            rc = lg_launch_cnn_tail_generic(reinterpret_cast<const float*>(buf[cur]), w, logits + done, 256, 16, c->cnn.cfg.attention, m, st);
+        } else {
+            rc = lg_launch_cnn_tail_bf16(buf[cur], rows_per_plane(8, m), LEAD, tail, logits + done, m, n_dev, st);
+        }
         if (rc) return rc;
     }
     return LG_OK;

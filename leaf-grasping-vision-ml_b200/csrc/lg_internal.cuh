@@ -67,6 +67,7 @@ struct LgCnn {
     int loaded;
     lg_cnn_config cfg;  // architecture the blob belongs to
     int is_default;     // 3 blocks [64,128,256], spatial attention: the one the live node builds
+    int bf16_convs;     // encoder [64,128,256] with ANY attention: the six convolutions can run on the tensor cores
 };
 
 // Per-stage timing (lg_set_profiling): a ring of event sets, so that the stage times of up to LG_PROF_RING consecutive calls

@@ -198,9 +198,9 @@ __device__ __forceinline__ void load_labels8(const int16_t* __restrict__ lp, siz
     }
 }
 
-template <bool VEC>
-__global__ void __launch_bounds__(512, 2) leaf_band_kernel(lg_context c, const int16_t* __restrict__ labels,
-                                                           const float* __restrict__ depth) {
+template <bool VEC, int MAX_NT, int MIN_CTAS>
+__global__ void __launch_bounds__(MAX_NT, MIN_CTAS) leaf_band_kernel(lg_context c, const int16_t* __restrict__ labels,
+                                                                     const float* __restrict__ depth) {
     extern __shared__ __align__(16) unsigned char bs_smem[];
     __shared__ unsigned s_first, s_bad, s_umin, s_umax, s_nq;
     const int L = c.L, W = c.W, H = c.H, NT = blockDim.x;
@@ -1619,12 +1619,20 @@ int lg_run_stage1(lg_context* c, const int16_t* labels, const float* depth, int 
         const size_t smem = (size_t)LG_BAND * nt * sizeof(uint4) + c->L * (sizeof(SmemLeaf) + 2 * sizeof(unsigned)) + (size_t)nt * sizeof(unsigned short);
         const dim3 grid((unsigned)c->n_bands, n);
         const bool vec = (c->W % 8 == 0) && ((reinterpret_cast<uintptr_t>(labels) | reinterpret_cast<uintptr_t>(depth)) % 16 == 0);
-        if (vec) {
-            LG_ENSURE_SMEM(leaf_band_kernel<true>, smem);
-            leaf_band_kernel<true><<<grid, nt, smem, st>>>(*c, labels, depth);
+        static int ctas = 0;      // A/B switch: resident CTAs the register allocation aims at for frames up to 1536 wide
+        if (!ctas) { const char* e = getenv("LG_BAND_CTAS"); ctas = e ? atoi(e) : 6; }
+        if (vec && nt <= 192 && ctas == 7) {
+            LG_ENSURE_SMEM((leaf_band_kernel<true, 192, 7>), smem);
+            leaf_band_kernel<true, 192, 7><<<grid, nt, smem, st>>>(*c, labels, depth);
+        } else if (vec && nt <= 192 && ctas == 6) {
+            LG_ENSURE_SMEM((leaf_band_kernel<true, 192, 6>), smem);
+            leaf_band_kernel<true, 192, 6><<<grid, nt, smem, st>>>(*c, labels, depth);
+        } else if (vec) {
+            LG_ENSURE_SMEM((leaf_band_kernel<true, 512, 2>), smem);
+            leaf_band_kernel<true, 512, 2><<<grid, nt, smem, st>>>(*c, labels, depth);
         } else {
-            LG_ENSURE_SMEM(leaf_band_kernel<false>, smem);
-            leaf_band_kernel<false><<<grid, nt, smem, st>>>(*c, labels, depth);
+            LG_ENSURE_SMEM((leaf_band_kernel<false, 512, 2>), smem);
+            leaf_band_kernel<false, 512, 2><<<grid, nt, smem, st>>>(*c, labels, depth);
         }
         LG_LAUNCH_CHECK();
     }

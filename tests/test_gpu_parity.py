@@ -404,10 +404,21 @@ def test_cnn_architecture_variants_against_reference_logits():
         net = GraspPointCNN(in_channels=9, attention_type=v["attention_type"], encoder_filters=v["encoder_filters"])
         net.load_state_dict(O.seeded_state_dict_from_shapes(v["shapes"], v["seed"]))
         net.eval()
-        net.use_bf16 = True          # ignored for non-default architectures: they run the fp32 kernels
+        net.use_bf16 = False
         with torch.no_grad():
             y = net(x).reshape(-1).cpu().numpy()
         np.testing.assert_allclose(y, gold[f"logits_{i}"], atol=2e-4, rtol=2e-4, err_msg=str((v["attention_type"], v["encoder_filters"])))
+        # the attention variants of the encoder [64, 128, 256] also run their convolutions on the tensor cores (bf16);
+        # for the other encoders the switch is ignored and the fp32 kernels run
+        net.use_bf16 = True
+        with torch.no_grad():
+            y16 = net(x).reshape(-1).cpu().numpy()
+        if v["encoder_filters"] == [64, 128, 256]:
+            assert not np.array_equal(y16, y)
+            np.testing.assert_allclose(y16, gold[f"logits_{i}"], atol=1e-2, err_msg="bf16 " + str(v["attention_type"]))
+        else:
+            np.testing.assert_array_equal(y16, y)
+        net.use_bf16 = False
         # a batch that does not fit one activation chunk gives the same rows
         with torch.no_grad():
             yb = net(x.repeat(500, 1, 1, 1)).reshape(500, -1).cpu().numpy()
