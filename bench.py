@@ -396,6 +396,8 @@ def run_frames(args, D, config, spec_name, B, chunks_per_step, unique, want_cpu,
     D.init_cuda()
     dev = D.dev
     lab_d, dep_d = lab_h.to(dev), dep_h.to(dev)
+    pinned_ok = (N.lib().lg_host_memory_is_pinned(C.c_void_p(lab_h.data_ptr())) == 1 and
+                 N.lib().lg_host_memory_is_pinned(C.c_void_p(dep_h.data_ptr())) == 1)
 
     eng = GraspEngine(B, H, W, 128, device=dev, lanes=args.lanes)
     n_prof = eng.lane_split(B)[0][1]          # frames the profiled (main) context handles per call
@@ -580,6 +582,7 @@ def run_frames(args, D, config, spec_name, B, chunks_per_step, unique, want_cpu,
         "e2e": {"value": frames_per_step * steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(B * cps * P * 6),
                 "d2h_bytes_per_step": int(B * cps * N.FRAME_RESULT.itemsize),
                 "h2d_gbs_per_gpu": round(B * cps * P * 6 * steps / e2e_s / 1e9, 1),
+                "host_buffers_pinned": bool(pinned_ok),
                 # all ranks copying the same inputs at once and doing nothing else, measured in this run: the ceiling of e2e
                 "h2d_ceiling_gbs": round(h2d_ceiling_gbs, 1),
                 "h2d_sum_of_links_gbs": round(h2d_links_gbs, 1),      # > ceiling when the links are not equally fast

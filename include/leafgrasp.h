@@ -121,12 +121,23 @@ uint64_t lg_cnn_model_floats(const lg_cnn_config* cfg);   /* 0 for an unsupporte
 int lg_process_batch(lg_context* ctx, const int16_t* labels, const float* depth, int frames,
                      const lg_camera* cam_host, lg_frame_result* results, int use_bf16_cnn, void* stream);
 
-/* Same, but labels/depth/results are HOST buffers (pinned for speed): copies in, runs, copies the
- * results back and synchronises the stream.  This is the call the drop-in Python classes and the
- * end-to-end benchmark make. */
+/* Same, but labels/depth/results are HOST buffers: copies in (32-frame chunks on a copy stream, each chunk processed
+ * as soon as it has landed), runs, copies the results back and synchronises the stream.  This is the call the
+ * end-to-end benchmark makes.  The inputs should be PINNED (cudaHostAlloc / cudaHostRegister / torch pin_memory):
+ * pageable memory is accepted, but CUDA then stages every copy through its own pinned buffer and the copies no longer
+ * overlap the kernels; lg_host_memory_is_pinned tells which kind a pointer is. */
 int lg_process_batch_host(lg_context* ctx, const int16_t* labels_host, const float* depth_host, int frames,
                           const lg_camera* cam_host, lg_frame_result* results_host, int use_bf16_cnn,
                           void* stream);
+
+/* Weights of the traditional score, traditional = (approach * a + sdf_score * s + flatness * f + accessibility * c) *
+ * (1 - stem_penalty) (grasp_point_selector.py:272-277).  The default is what the reference's CODE uses, 0.4 / 0.3 / 0.2 /
+ * 0.1, and every parity test runs with it; the reference's README.md:83-87 advertises another set (approach 0.40, edge =
+ * sdf 0.20, flatness 0.25, accessibility 0.15), which SURVEY.md 8(a') asks to be selectable: pass it here. */
+int lg_set_score_weights(lg_context* ctx, double approach, double sdf, double flatness, double accessibility);
+
+/* 1: page-locked host memory known to CUDA, 0: pageable (or not host memory), < 0: error. */
+int lg_host_memory_is_pinned(const void* host_ptr);
 
 /* Candidate records for the multi-GPU aggregation (the only exchange between ranks is one all-gather of
  * fixed-size records): when `records` (DEVICE float32 [frames][LG_TOP_K][4], caller-owned, NULL = off) is set, every

@@ -91,6 +91,8 @@ SYMBOLS = {
     "lg_stage_times_mean": (C.c_int, [_P, _P, C.c_int, _P]),
     "lg_set_overlap": (C.c_int, [_P, C.c_int]),
     "lg_set_patch_export": (C.c_int, [_P, C.c_int]),
+    "lg_host_memory_is_pinned": (C.c_int, [_P]),
+    "lg_set_score_weights": (C.c_int, [_P, C.c_double, C.c_double, C.c_double, C.c_double]),
     "lg_launch_count": (C.c_uint64, []),
     "lg_sizeof_frame_result": (C.c_uint64, []),
     "lg_sizeof_leaf_record": (C.c_uint64, []),

@@ -23,7 +23,7 @@ int lg_run_export_orient(lg_context* c, int n, double* out5, cudaStream_t st);
 int lg_run_normalize_patches(const float* raw, int n, float* out, cudaStream_t st);
 
 static thread_local char g_err[512] = "";
-unsigned long long g_lg_launches = 0;
+std::atomic<unsigned long long> g_lg_launches{0};
 
 void lg_set_error(const char* fmt, ...) {
     va_list ap;
@@ -120,6 +120,7 @@ extern "C" int lg_create(lg_context** out, int max_frames, int height, int width
     memset(c, 0, sizeof(*c));
     c->B = max_frames; c->H = height; c->W = width; c->L = max_labels;
     c->patch_export = 1;
+    c->w_trad[0] = 0.4; c->w_trad[1] = 0.3; c->w_trad[2] = 0.2; c->w_trad[3] = 0.1;
     c->P = (size_t)height * width;
     c->allocs = new (std::nothrow) std::vector<void*>();
     if (!c->allocs) { delete c; return LG_E_ARG; }
@@ -159,7 +160,7 @@ extern "C" int lg_create(lg_context** out, int max_frames, int height, int width
     // runs the CNN (OptimalLeafSelector's) does not pay for them
     c->cnn_cap = (int)(B * LG_TOP_K < 2048 ? 2048 : B * LG_TOP_K);
     c->cnn_act_bytes = (size_t)c->cnn_cap * 32 * 32 * 64 * sizeof(float);
-    A(&c->in_labels, B * P); A(&c->in_depth, B * P); A(&c->results_all, B);
+    // (the staging buffers of the host entry point - 9.3 MB per 1440 x 1080 frame - are allocated by its first call)
     if (rc) { lg_destroy(c); return rc; }
     {
         cudaError_t e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
@@ -357,6 +358,12 @@ extern "C" int lg_process_batch_host(lg_context* c, const int16_t* labels_host, 
     TRY(check_batch(c, labels_host, depth_host, frames));
     if (!results_host || !cam) return LG_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
+    if (!c->in_labels) {     // first host call of this context: device staging for a full batch
+        const size_t Bc = (size_t)c->B;
+        TRY(dev_alloc(c, &c->in_labels, Bc * c->P));
+        TRY(dev_alloc(c, &c->in_depth, Bc * c->P));
+        TRY(dev_alloc(c, &c->results_all, Bc));
+    }
     // Host-to-device copies run chunk by chunk on their own stream; chunk k is processed on the caller's stream
     // as soon as it has landed, while chunk k+1 is still crossing PCIe (the copies are the longer leg).
     int chunk = LG_HOST_CHUNK_FRAMES;
@@ -381,6 +388,22 @@ extern "C" int lg_process_batch_host(lg_context* c, const int16_t* labels_host, 
     LG_CUDA(cudaMemcpyAsync(results_host, c->results_all, sizeof(lg_frame_result) * frames, cudaMemcpyDeviceToHost, st));
     LG_CUDA(cudaStreamSynchronize(st));
     return LG_OK;
+}
+
+extern "C" int lg_set_score_weights(lg_context* c, double approach, double sdf, double flatness, double accessibility) {
+    if (!c || !(approach >= 0) || !(sdf >= 0) || !(flatness >= 0) || !(accessibility >= 0)) {
+        lg_set_error("lg_set_score_weights: weights must be non-negative numbers");
+        return LG_E_ARG;
+    }
+    c->w_trad[0] = approach; c->w_trad[1] = sdf; c->w_trad[2] = flatness; c->w_trad[3] = accessibility;
+    return LG_OK;
+}
+
+extern "C" int lg_host_memory_is_pinned(const void* host_ptr) {
+    if (!host_ptr) return LG_E_ARG;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, host_ptr) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return a.type == cudaMemoryTypeHost ? 1 : 0;
 }
 
 extern "C" int lg_score_maps(lg_context* c, const uint8_t* mask, const float* depth, int frames, const lg_camera* cam,
@@ -569,7 +592,7 @@ extern "C" int lg_stage_times_mean(lg_context* c, float* ms, int n, int* calls_o
     return LG_OK;
 }
 
-extern "C" uint64_t lg_launch_count(void) { return g_lg_launches; }
+extern "C" uint64_t lg_launch_count(void) { return g_lg_launches.load(); }
 
 extern "C" int lg_set_overlap(lg_context* c, int on) {
     if (!c) return LG_E_ARG;

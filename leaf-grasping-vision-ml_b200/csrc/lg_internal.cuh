@@ -1,6 +1,8 @@
 // Internal declarations shared by the translation units of liblgb200.so (not part of the C-ABI).
 #pragma once
 #include <cuda_runtime.h>
+
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -165,6 +167,8 @@ struct lg_context {
     int overlap;
     // optional per-stage timing (lg_set_profiling): events recorded on the stream the stage runs on
     LgProf* prof;                            // host-side state, kept out of this struct: kernels take the struct by value
+    // weights of the traditional score: approach, sdf_score, flatness, accessibility (grasp_point_selector.py:272-277)
+    double w_trad[4];
     // constants
     float gauss[25];
     int se30_a[LG_SE_STEM], se30_b[LG_SE_STEM];   // per structuring-element row: first / last+1 column
@@ -194,7 +198,7 @@ int lg_prefer_large_smem_impl(const void* kernel);
         int rc__ = lg_prefer_large_smem_impl((const void*)(kernel)); \
         if (rc__) return rc__;                                       \
     } while (0)
-extern unsigned long long g_lg_launches;
+extern std::atomic<unsigned long long> g_lg_launches;    // host threads may each drive a context
 #define LG_LAUNCH_CHECK()            \
     do {                             \
         ++g_lg_launches;             \

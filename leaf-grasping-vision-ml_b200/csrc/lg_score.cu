@@ -161,7 +161,9 @@ __global__ void __launch_bounds__(SC_TW * SC_TH) score_kernel(lg_context c, LgMa
             }
         }
         // combination (:272-277); evaluated for every pixel like the reference (flatness is not masked)
-        trad = (((0.4 * approach + 0.3 * sdf_score) + (double)__fmul_rn(0.2f, flat)) + 0.1 * access) *
+        // (weights: 0.4 / 0.3 / 0.2 / 0.1 unless lg_set_score_weights changed them; the flatness term is a float32 product
+        // in the reference, float32 map times Python scalar)
+        trad = (((c.w_trad[0] * approach + c.w_trad[1] * sdf_score) + (double)__fmul_rn((float)c.w_trad[2], flat)) + c.w_trad[3] * access) *
                (double)__fsub_rn(1.f, stem);
         const bool valid = (di > 20.f) && M && (stem < 0.8f);
         c.m_sdf[fo + p] = sdf_score; c.m_app[fo + p] = approach; c.m_acc[fo + p] = access; c.m_trad[fo + p] = trad;

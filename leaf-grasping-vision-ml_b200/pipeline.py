@@ -76,6 +76,16 @@ class GraspEngine:
         for ctx in self._all_ctx():
             N.check(self.lib.lg_set_overlap(ctx, int(bool(on))), "lg_set_overlap")
 
+    CODE_WEIGHTS = dict(approach=0.4, sdf=0.3, flatness=0.2, accessibility=0.1)       # grasp_point_selector.py:272-277
+    README_WEIGHTS = dict(approach=0.40, sdf=0.20, flatness=0.25, accessibility=0.15)   # reference README.md:83-87
+
+    def set_score_weights(self, approach=0.4, sdf=0.3, flatness=0.2, accessibility=0.1):
+        """Weights of the traditional score.  Default: the reference's code; GraspEngine.README_WEIGHTS is the set its
+        README advertises (SURVEY.md 8a': selectable, not parity-tested against the reference - its code never uses it)."""
+        for ctx in self._all_ctx():
+            N.check(self.lib.lg_set_score_weights(ctx, float(approach), float(sdf), float(flatness), float(accessibility)),
+                    "lg_set_score_weights")
+
     def set_patch_export(self, on: bool):
         """Drop-in mode (default) keeps the float32 patch tensor of the last call for last_patches(); throughput mode
         (False) lets the gather kernel write the tensor-core CNN's input directly (bf16 CNN only; same results)."""

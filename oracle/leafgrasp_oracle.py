@@ -62,6 +62,7 @@ NMS_RADIUS = 10                # grasp_point_selector.py:198
 PATCH = 32                     # grasp_point_selector.py:66
 STEM_SE = 30                   # grasp_point_selector.py:696
 PREGRASP_SE = 31               # grasp_point_selector.py:777-778
+TRAD_WEIGHTS = (0.4, 0.3, 0.2, 0.1)           # approach, sdf_score, flatness, accessibility (grasp_point_selector.py:272-277)
 CH_A, CH_B, CH_C = 65536, 91750, 143976     # OpenCV DIST_L2 5x5 weights 1, 1.4, 2.1969 in Q16
 CH_DIST_MAX = 0xFFFFFFFF - CH_C             # OpenCV's saturation value (probed: all-ones image)
 SCORE_CHANNELS = ("sdf_score", "approach_score", "flatness_map", "isolation_map",
@@ -624,8 +625,9 @@ def score_maps(mask_u8, depth, f, cx, cy, arith="reference", use_cv2=True):
         "accessibility_map": accessibility_map(mask_u8, cx, cy, arith),
         "stem_penalty": stem_penalty_map(mask_u8, use_cv2),
     }
-    s["traditional_score"] = (0.4 * s["approach_score"] + 0.3 * s["sdf_score"] +
-                              0.2 * s["flatness_map"] + 0.1 * s["accessibility_map"]) * (1 - s["stem_penalty"])
+    wa, ws, wf, wc = TRAD_WEIGHTS      # module-level so that a test can restate the README's set (SURVEY.md 8a')
+    s["traditional_score"] = (wa * s["approach_score"] + ws * s["sdf_score"] +
+                              wf * s["flatness_map"] + wc * s["accessibility_map"]) * (1 - s["stem_penalty"])
     s["_parts"] = parts
     return s
 

@@ -281,3 +281,34 @@ def test_throughput_mode_gather_writes_cnn_input_directly(blob):
     assert np.array_equal(a["cand_x"], c["cand_x"])
     eng.last_patches(6)
     eng.close()
+
+
+def test_readme_weight_set_is_selectable():
+    """SURVEY.md 8(a'): the weights of the traditional score are runtime parameters; the default is the reference's code
+    (0.4 / 0.3 / 0.2 / 0.1, every parity test), the README's set (README.md:83-87) can be selected.  Checked against the
+    oracle with the same weights: the component maps do not change, the traditional score follows the new weights."""
+    from leafgrasp_b200 import GraspEngine
+    spec = synth.SMALL
+    P = synth.projection_matrix(spec)
+    lab, dep = synth.make_frame(spec, SEED, 1)
+    leaf = O.select_optimal_leaf(lab, dep, P[0, 0], P[0, 2], P[1, 2])["leaf_id"]
+    mask = (lab == leaf).astype(np.uint8)
+    eng = _engine(1, spec.height, spec.width, 2)
+    base = eng.score_maps(torch.from_numpy(mask), torch.from_numpy(dep), _cam(spec))
+    w = GraspEngine.README_WEIGHTS
+    eng.set_score_weights(**w)
+    got = eng.score_maps(torch.from_numpy(mask), torch.from_numpy(dep), _cam(spec))
+    old = O.TRAD_WEIGHTS
+    O.TRAD_WEIGHTS = (w["approach"], w["sdf"], w["flatness"], w["accessibility"])
+    try:
+        ref = O.score_maps(mask, dep, P[0, 0], P[0, 2], P[1, 2], "strict")
+    finally:
+        O.TRAD_WEIGHTS = old
+    for k in ("sdf_score", "approach_score", "accessibility_map", "flatness_map", "stem_penalty"):
+        assert torch.equal(got[k], base[k]), k
+    np.testing.assert_allclose(got["traditional_score"][0].cpu().numpy(), ref["traditional_score"], rtol=1e-9, atol=1e-12)
+    assert not torch.equal(got["traditional_score"], base["traditional_score"])
+    eng.set_score_weights(**GraspEngine.CODE_WEIGHTS)
+    again = eng.score_maps(torch.from_numpy(mask), torch.from_numpy(dep), _cam(spec))
+    assert torch.equal(again["traditional_score"], base["traditional_score"])
+    eng.close()
