@@ -920,7 +920,7 @@ __global__ void __launch_bounds__(EDT_NT) edt_row_kernel(lg_context c, uint32_t*
 //
 // Around the maximum the field falls off with slope ~1, so only the nodes within `rad` of it survive on every level: a
 // frame costs on the order of a hundred exact evaluations instead of a transform of all its pixels.
-constexpr int AM_NT = 512;
+constexpr int AM_MAX_NT = 512;
 constexpr int AM_MAX_CELLS = 8192;
 constexpr int AM_ITEMS = 1536;          // nodes of one level of the search
 constexpr int AM_STACK = 48;            // per-warp node stack of the overflow path (depth first: at most 3 entries per level + 4)
@@ -1039,12 +1039,12 @@ struct AmShared {
     unsigned dmax;                 // largest cell distance (squared, in cells)
     unsigned n_items[2], next_item;
     unsigned items[2][AM_ITEMS][2];
-    unsigned stack[AM_NT / 32][AM_STACK][2];
+    unsigned stack[AM_MAX_NT / 32][AM_STACK][2];
 };
 
 // bits: [n][H][pitch] source bit mask; occ: [n][n_bands][pitch] occupancy of the 8 x 8 blocks; best: [n] packed result
-template <int ROWS>
-__global__ void __launch_bounds__(AM_NT) edt_argmax_kernel(const uint8_t* __restrict__ bits_all, size_t bits_stride, int pitch,
+template <int ROWS, int AM_NT>
+__global__ void __launch_bounds__(AM_NT, 2) edt_argmax_kernel(const uint8_t* __restrict__ bits_all, size_t bits_stride, int pitch,
                                                             const uint8_t* __restrict__ occ_all, int n_bands, int W, int H,
                                                             int cs /* cell size: 8, 16, 32, ... */, unsigned long long* __restrict__ best_out,
                                                             unsigned* dbg) {
@@ -1569,16 +1569,19 @@ static int run_edt_argmax(lg_context* c, int n, cudaStream_t st) {
     static int dbg_on = -1;
     if (dbg_on < 0) { const char* e = getenv("LG_AM_DEBUG"); dbg_on = e && e[0] == '1'; if (dbg_on) { cudaMalloc(&dbg, 128); } }
     if (dbg_on) cudaMemsetAsync(dbg, 0, 128, st);
+    // One row per lane and 16 warps per frame, compiled for two CTAs per SM (64 registers) so that a batch of 256 frames is
+    // resident at once.  A/B switch LG_AM_ROWS=2: two rows per lane (124 registers), 8 warps per frame - measured slower
+    // (0.54 vs 0.46 ms per 256 frames).
     static int rows = 0;
-    if (!rows) { const char* e = getenv("LG_AM_ROWS"); rows = e && e[0] == '1' ? 1 : 2; }    // A/B switch; two rows per lane measured faster
-    LG_PREFER_LARGE_SMEM(edt_argmax_kernel<1>);       // runs beside the median kernel
-    LG_PREFER_LARGE_SMEM(edt_argmax_kernel<2>);
+    if (!rows) { const char* e = getenv("LG_AM_ROWS"); rows = e && e[0] == '2' ? 2 : 1; }
+    LG_PREFER_LARGE_SMEM((edt_argmax_kernel<1, 512>));       // runs beside the median kernel
+    LG_PREFER_LARGE_SMEM((edt_argmax_kernel<2, 256>));
     if (rows == 2) {
-        LG_ENSURE_SMEM(edt_argmax_kernel<2>, smem);
-        edt_argmax_kernel<2><<<n, AM_NT, smem, st>>>(c->ubits, c->ub_stride, c->ub_pitch, c->cellocc, c->n_bands, c->W, c->H, cs, c->edt_best, dbg_on ? dbg : nullptr);
+        LG_ENSURE_SMEM((edt_argmax_kernel<2, 256>), smem);
+        edt_argmax_kernel<2, 256><<<n, 256, smem, st>>>(c->ubits, c->ub_stride, c->ub_pitch, c->cellocc, c->n_bands, c->W, c->H, cs, c->edt_best, dbg_on ? dbg : nullptr);
     } else {
-        LG_ENSURE_SMEM(edt_argmax_kernel<1>, smem);
-        edt_argmax_kernel<1><<<n, AM_NT, smem, st>>>(c->ubits, c->ub_stride, c->ub_pitch, c->cellocc, c->n_bands, c->W, c->H, cs, c->edt_best, dbg_on ? dbg : nullptr);
+        LG_ENSURE_SMEM((edt_argmax_kernel<1, 512>), smem);
+        edt_argmax_kernel<1, 512><<<n, 512, smem, st>>>(c->ubits, c->ub_stride, c->ub_pitch, c->cellocc, c->n_bands, c->W, c->H, cs, c->edt_best, dbg_on ? dbg : nullptr);
     }
     LG_LAUNCH_CHECK();
     if (dbg_on) {

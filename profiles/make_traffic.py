@@ -2,18 +2,17 @@
 """profiles/traffic.json: DRAM bytes per launch of every bench stage, from the committed `ncu --set full` summaries
 (profiles/summarize_ncu.py output) of ONE step of `python bench.py` at the default batch (256 frames).
 
-    python profiles/make_traffic.py 256 profiles/r1y_ncu_full_stats_conv.csv profiles/r1y_ncu_full_other.csv
+    python profiles/make_traffic.py 256 profiles/r4/ncu_full_step.csv
 """
 import csv
 import json
 import os
 import sys
 
-STAGE_OF = [("leaf_stats", "leaf_stats"), ("leaf_scatter", "scatter"), ("leaf_offsets", "scatter"), ("leaf_median", "median"),
-            ("edt_row", "edt_rows"), ("select_leaf", "select"), ("chamfer", "chamfer"), ("outside_max", "chamfer"),
-            ("leaf_boundary", "chamfer"), ("orient", "orientation"), ("score_kernel", "score_maps"), ("nms_kernel", "candidates"),
-            ("gather_kernel", "patches"), ("compact_slots", "patches"), ("conv3x3_umma", "cnn"), ("pool2x2", "cnn"),
-            ("pack_input", "cnn"), ("cnn_tail", "cnn"), ("fuse_kernel", "fuse")]
+STAGE_OF = [("leaf_band", "leaf_stats"), ("leaf_median", "median"), ("edt_argmax", "edt_rows"), ("select_leaf", "select"),
+            ("chamfer", "chamfer"), ("outside_max", "orientation"), ("leaf_boundary", "orientation"), ("orient", "orientation"),
+            ("score_kernel", "score_maps"), ("nms_kernel", "candidates"), ("gather_kernel", "patches"), ("compact_slots", "patches"),
+            ("conv3x3_umma", "cnn"), ("pool2x2", "cnn"), ("pack_input", "cnn"), ("cnn_tail", "cnn"), ("fuse_kernel", "fuse")]
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 
