@@ -454,6 +454,7 @@ def run_frames(args, D, config, spec_name, B, chunks_per_step, unique, want_cpu,
     out_host = run_steps(steps, True)
     D.barrier()
     e2e_s = D.max_over_ranks(time.perf_counter() - t0)
+    h2d_call, d2h_call = eng.host_call_bytes()        # what one host call really moved (labels cross the link run-length encoded)
     # ---- what the box allows end to end: the same pinned buffers copied to the GPUs by all ranks at once, nothing else
     # running (tools/h2d_ceiling.py measures the same thing standalone, with a solo leg beside it)
     lab_d.copy_(lab_h, non_blocking=True); dep_d.copy_(dep_h, non_blocking=True)
@@ -579,15 +580,19 @@ def run_frames(args, D, config, spec_name, B, chunks_per_step, unique, want_cpu,
                    "lanes_per_gpu": args.lanes, "cnn": args.cnn, "picked": int((records["n_candidates"] > 0).sum()),
                    "context_gb": round(ctx_gb, 2), "cpu_affinity": f"{len(cpus)} CPUs of NUMA node(s) "
                    f"{hostmem.numa_node_of_cpus(cpus)}" if cpus else "unbound"},
-        "e2e": {"value": frames_per_step * steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(B * cps * P * 6),
-                "d2h_bytes_per_step": int(B * cps * N.FRAME_RESULT.itemsize),
-                "h2d_gbs_per_gpu": round(B * cps * P * 6 * steps / e2e_s / 1e9, 1),
+        "e2e": {"value": frames_per_step * steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d_call * cps),
+                "d2h_bytes_per_step": int(d2h_call * cps),
+                "host_input_bytes_per_step": int(B * cps * P * 6),      # the caller's buffers: int16 labels + float32 depth
+                "labels_on_the_link": "run-length encoded by host threads inside the call, expanded on the device (lossless)"
+                if h2d_call < B * P * 6 else "raw",
+                "h2d_gbs_per_gpu": round(h2d_call * cps * steps / e2e_s / 1e9, 1),
                 "host_buffers_pinned": bool(pinned_ok),
                 # all ranks copying the same inputs at once and doing nothing else, measured in this run: the ceiling of e2e
                 "h2d_ceiling_gbs": round(h2d_ceiling_gbs, 1),
                 "h2d_sum_of_links_gbs": round(h2d_links_gbs, 1),      # > ceiling when the links are not equally fast
-                "frames_per_s_at_h2d_ceiling": round(h2d_ceiling_gbs * 1e9 / (P * 6), 0),
-                "frac_of_h2d_ceiling": round(frames_per_step * steps / e2e_s / (h2d_ceiling_gbs * 1e9 / (P * 6)), 3)},
+                # the ceiling in frames: the link rate over the bytes a frame really puts on the link
+                "frames_per_s_at_h2d_ceiling": round(h2d_ceiling_gbs * 1e9 / (h2d_call / B), 0),
+                "frac_of_h2d_ceiling": round(frames_per_step * steps / e2e_s / (h2d_ceiling_gbs * 1e9 / (h2d_call / B)), 3)},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "consistency": check,
     }
     return line

@@ -136,6 +136,13 @@ int lg_process_batch_host(lg_context* ctx, const int16_t* labels_host, const flo
  * sdf 0.20, flatness 0.25, accessibility 0.15), which SURVEY.md 8(a') asks to be selectable: pass it here. */
 int lg_set_score_weights(lg_context* ctx, double approach, double sdf, double flatness, double accessibility);
 
+/* The label image is piecewise constant, so lg_process_batch_host run-length encodes it with host threads inside the call
+ * (lossless; a frame with more than H*W/16 runs is copied as it is) and a kernel expands it on the device: ~0.1 MB instead
+ * of 3.1 MB per 1440 x 1080 frame cross the host-to-device link, which bounds the call.  on = 0 copies the labels raw.
+ * lg_host_call_bytes: bytes the last lg_process_batch_host call copied to / from the device. */
+int lg_set_host_label_rle(lg_context* ctx, int on);
+int lg_host_call_bytes(const lg_context* ctx, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
+
 /* 1: page-locked host memory known to CUDA, 0: pageable (or not host memory), < 0: error. */
 int lg_host_memory_is_pinned(const void* host_ptr);
 

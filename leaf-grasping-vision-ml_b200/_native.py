@@ -92,6 +92,8 @@ SYMBOLS = {
     "lg_set_overlap": (C.c_int, [_P, C.c_int]),
     "lg_set_patch_export": (C.c_int, [_P, C.c_int]),
     "lg_host_memory_is_pinned": (C.c_int, [_P]),
+    "lg_set_host_label_rle": (C.c_int, [_P, C.c_int]),
+    "lg_host_call_bytes": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "lg_set_score_weights": (C.c_int, [_P, C.c_double, C.c_double, C.c_double, C.c_double]),
     "lg_launch_count": (C.c_uint64, []),
     "lg_sizeof_frame_result": (C.c_uint64, []),

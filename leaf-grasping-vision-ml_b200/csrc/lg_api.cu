@@ -120,6 +120,7 @@ extern "C" int lg_create(lg_context** out, int max_frames, int height, int width
     memset(c, 0, sizeof(*c));
     c->B = max_frames; c->H = height; c->W = width; c->L = max_labels;
     c->patch_export = 1;
+    c->host_rle = 1;
     c->w_trad[0] = 0.4; c->w_trad[1] = 0.3; c->w_trad[2] = 0.2; c->w_trad[3] = 0.1;
     c->P = (size_t)height * width;
     c->allocs = new (std::nothrow) std::vector<void*>();
@@ -193,6 +194,7 @@ extern "C" int lg_create(lg_context** out, int max_frames, int height, int width
 
 extern "C" void lg_destroy(lg_context* c) {
     if (!c) return;
+    lg_host_pipe_destroy(c);
     if (c->allocs) {
         std::vector<void*>* v = static_cast<std::vector<void*>*>(c->allocs);
         for (void* p : *v)
@@ -353,40 +355,15 @@ extern "C" int lg_set_record_output(lg_context* c, float* records) {
     return LG_OK;
 }
 
-extern "C" int lg_process_batch_host(lg_context* c, const int16_t* labels_host, const float* depth_host, int frames,
-                                     const lg_camera* cam, lg_frame_result* results_host, int use_bf16_cnn, void* stream) {
-    TRY(check_batch(c, labels_host, depth_host, frames));
-    if (!results_host || !cam) return LG_E_ARG;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (!c->in_labels) {     // first host call of this context: device staging for a full batch
-        const size_t Bc = (size_t)c->B;
-        TRY(dev_alloc(c, &c->in_labels, Bc * c->P));
-        TRY(dev_alloc(c, &c->in_depth, Bc * c->P));
-        TRY(dev_alloc(c, &c->results_all, Bc));
-    }
-    // Host-to-device copies run chunk by chunk on their own stream; chunk k is processed on the caller's stream
-    // as soon as it has landed, while chunk k+1 is still crossing PCIe (the copies are the longer leg).
-    int chunk = LG_HOST_CHUNK_FRAMES;
-    while ((frames + chunk - 1) / chunk > LG_MAX_HOST_CHUNKS) chunk *= 2;
-    const int n_chunks = (frames + chunk - 1) / chunk;
-    LG_CUDA(cudaEventRecord(c->copy_gate, st));                 // staging is free once earlier work on st is done
-    LG_CUDA(cudaStreamWaitEvent(c->copy_stream, c->copy_gate, 0));
-    for (int k = 0; k < n_chunks; ++k) {
-        const size_t off = (size_t)k * chunk * c->P;
-        const size_t n = (size_t)(frames - k * chunk < chunk ? frames - k * chunk : chunk) * c->P;
-        LG_CUDA(cudaMemcpyAsync(c->in_labels + off, labels_host + off, n * sizeof(int16_t), cudaMemcpyHostToDevice, c->copy_stream));
-        LG_CUDA(cudaMemcpyAsync(c->in_depth + off, depth_host + off, n * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
-        LG_CUDA(cudaEventRecord(c->copy_ev[k], c->copy_stream));
-    }
-    for (int k = 0; k < n_chunks; ++k) {
-        const size_t off = (size_t)k * chunk * c->P;
-        const int m = frames - k * chunk < chunk ? frames - k * chunk : chunk;
-        LG_CUDA(cudaStreamWaitEvent(st, c->copy_ev[k], 0));
-        TRY(process_batch_impl(c, c->in_labels + off, c->in_depth + off, m, cam, c->results_all + (size_t)k * chunk,
-                               c->rec_out ? c->rec_out + (size_t)k * chunk * LG_TOP_K * 4 : nullptr, use_bf16_cnn, stream));
-    }
-    LG_CUDA(cudaMemcpyAsync(results_host, c->results_all, sizeof(lg_frame_result) * frames, cudaMemcpyDeviceToHost, st));
-    LG_CUDA(cudaStreamSynchronize(st));
+// (lg_process_batch_host: lg_host.cu)
+int lg_process_batch_device_impl(lg_context* c, const int16_t* labels, const float* depth, int frames, const lg_camera* cam,
+                                 lg_frame_result* results, float* rec_out, int use_bf16_cnn, void* stream) {
+    return process_batch_impl(c, labels, depth, frames, cam, results, rec_out, use_bf16_cnn, stream);
+}
+int lg_context_dev_alloc(lg_context* c, void** p, size_t bytes) {
+    unsigned char* q = nullptr;
+    TRY(dev_alloc(c, &q, bytes));
+    *p = q;
     return LG_OK;
 }
 

@@ -157,6 +157,9 @@ struct lg_context {
     int16_t* in_labels;
     float* in_depth;
     lg_frame_result* results_all;            // [B] results of all chunks of one host call
+    void* host_pipe;                         // lg_host.cu: host thread pool + run-length staging of the host entry point
+    int host_rle;                            // 1 (default): labels cross the link run-length encoded
+    uint64_t last_h2d_bytes, last_d2h_bytes; // what the last lg_process_batch_host call moved
     cudaStream_t copy_stream;
     cudaEvent_t copy_ev[LG_MAX_HOST_CHUNKS];
     cudaEvent_t copy_gate;                   // the caller's stream reached the start of this host call
@@ -176,6 +179,7 @@ struct lg_context {
 };
 
 void lg_set_error(const char* fmt, ...);
+void lg_host_pipe_destroy(lg_context* c);
 #define LG_CUDA(expr)                                                                       \
     do {                                                                                    \
         cudaError_t e__ = (expr);                                                           \

@@ -86,6 +86,17 @@ class GraspEngine:
             N.check(self.lib.lg_set_score_weights(ctx, float(approach), float(sdf), float(flatness), float(accessibility)),
                     "lg_set_score_weights")
 
+    def set_host_label_rle(self, on: bool):
+        """process_batch_host: run-length encode the label images on the host inside the call (default) or copy them raw."""
+        for ctx in self._all_ctx():
+            N.check(self.lib.lg_set_host_label_rle(ctx, int(bool(on))), "lg_set_host_label_rle")
+
+    def host_call_bytes(self):
+        """(host-to-device, device-to-host) bytes of the last process_batch_host call."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        N.check(self.lib.lg_host_call_bytes(self._ctx, C.byref(a), C.byref(b)), "lg_host_call_bytes")
+        return int(a.value), int(b.value)
+
     def set_patch_export(self, on: bool):
         """Drop-in mode (default) keeps the float32 patch tensor of the last call for last_patches(); throughput mode
         (False) lets the gather kernel write the tensor-core CNN's input directly (bf16 CNN only; same results)."""

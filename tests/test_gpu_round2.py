@@ -312,3 +312,34 @@ def test_readme_weight_set_is_selectable():
     again = eng.score_maps(torch.from_numpy(mask), torch.from_numpy(dep), _cam(spec))
     assert torch.equal(again["traditional_score"], base["traditional_score"])
     eng.close()
+
+
+def test_host_call_run_length_encodes_labels_losslessly(blob):
+    """lg_process_batch_host sends the label images run-length encoded (host threads inside the call, expansion kernel on the
+    device).  Lossless: every field of the results equals the device-resident call's and the raw-copy call's, the link
+    carries depth + ~3 % of the label bytes, and a frame of label noise (more runs than the staging holds) goes raw."""
+    spec = synth.CFG2
+    n = 40                                                     # two chunks of 32
+    lab, dep = synth.make_batch(spec, SEED, 500, n)
+    rng = np.random.default_rng(5)
+    lab[7] = rng.integers(0, 3, size=lab[7].shape).astype(np.int16)      # noise: ~1 M runs
+    eng = _engine(n, spec.height, spec.width, 128)
+    eng.set_cnn_weights(blob)
+    cam = _cam(spec)
+    lt, dt = torch.from_numpy(lab).pin_memory(), torch.from_numpy(dep).pin_memory()
+    dev = eng.process_batch(lt.cuda(), dt.cuda(), cam, True).copy()
+    a = eng.process_batch_host(lt, dt, cam, True).copy()
+    h2d_rle, d2h = eng.host_call_bytes()
+    eng.set_host_label_rle(False)
+    b = eng.process_batch_host(lt, dt, cam, True).copy()
+    h2d_raw, _ = eng.host_call_bytes()
+    P = spec.height * spec.width
+    assert h2d_raw == n * P * 6 and d2h == n * a.dtype.itemsize
+    assert n * P * 4 + P * 2 < h2d_rle < n * P * 4 + P * 2 + (n - 1) * P * 2 * 0.06      # depth + one raw frame + ~3 % of the rest
+    for name in a.dtype.names:
+        x, y, z = a[name], b[name], dev[name]
+        if x.dtype.kind == "f":
+            assert np.array_equal(x, y, equal_nan=True) and np.array_equal(x, z, equal_nan=True), name
+        else:
+            assert np.array_equal(x, y) and np.array_equal(x, z), name
+    eng.close()
