@@ -175,8 +175,13 @@ int ensure_pipe(lg_context* c, int chunk) {
         hp = new (std::nothrow) HostPipe();
         if (!hp) return LG_E_ARG;
         c->host_pipe = hp;
+        // host threads of the label encoder: the CPUs this process may use, shared with the other ranks of the node when a
+        // launcher says how many there are (torchrun: LOCAL_WORLD_SIZE); LG_HOST_THREADS overrides
         int t = allowed_cpus();
+        const char* lw = getenv("LOCAL_WORLD_SIZE");
+        if (lw && atoi(lw) > 1) t /= atoi(lw);
         if (t > 16) t = 16;
+        if (t < 2) t = 2;
         const char* e = getenv("LG_HOST_THREADS");
         if (e && atoi(e) > 0) t = atoi(e);
         hp->threads = t;
