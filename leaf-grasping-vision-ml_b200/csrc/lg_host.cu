@@ -98,7 +98,8 @@ struct HostPipe {
     int chunk_cap = 0;                  // frames per staging slot
     uint32_t run_cap = 0;               // runs per frame the staging holds
     uint32_t* h_runs[RLE_SLOTS] = {};   // pinned [chunk_cap][run_cap]
-    uint32_t* h_rowoff[RLE_SLOTS] = {}; // pinned [chunk_cap][H + 1]; rowoff[f][0] = 0xFFFFFFFF: frame f was copied raw
+    uint32_t* h_pack[RLE_SLOTS] = {};   // pinned [chunk_cap * run_cap]: the chunk's runs packed back to back (what is copied)
+    uint32_t* h_rowoff[RLE_SLOTS] = {}; // pinned [chunk_cap][H + 2]: row offsets, [H + 1] = the frame's start in the packed runs; [0] = 0xFFFFFFFF: frame copied raw
     uint32_t* d_runs[RLE_SLOTS] = {};
     uint32_t* d_rowoff[RLE_SLOTS] = {};
     cudaEvent_t copied[RLE_SLOTS] = {};     // the slot's host buffers have been read
@@ -133,16 +134,16 @@ uint32_t encode_frame(const int16_t* lab, int H, int W, uint32_t* runs, uint32_t
 }
 
 // one warp per image row: the row's runs (first column | label << 16) back into int16 labels
-__global__ void __launch_bounds__(256) expand_labels_kernel(const uint32_t* __restrict__ runs_all, uint32_t run_cap,
+__global__ void __launch_bounds__(256) expand_labels_kernel(const uint32_t* __restrict__ runs_all,
                                                             const uint32_t* __restrict__ rowoff_all, int16_t* __restrict__ out,
                                                             size_t P, int H, int W) {
     const int f = blockIdx.y, lane = threadIdx.x & 31;
     const int y = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (y >= H) return;
-    const uint32_t* ro = rowoff_all + (size_t)f * (H + 1);
+    const uint32_t* ro = rowoff_all + (size_t)f * (H + 2);
     if (ro[0] == 0xFFFFFFFFu) return;            // this frame's labels were copied as they are
     const uint32_t a = ro[y], b = ro[y + 1];
-    const uint32_t* runs = runs_all + (size_t)f * run_cap;
+    const uint32_t* runs = runs_all + ro[H + 1];      // the chunk's runs are packed: this frame's start at ro[H + 1]
     int16_t* orow = out + (size_t)f * P + (size_t)y * W;
     for (uint32_t j0 = a; j0 < b; j0 += 32) {
         const uint32_t mine = j0 + lane < b ? runs[j0 + lane] : 0u;
@@ -197,14 +198,16 @@ int ensure_pipe(lg_context* c, int chunk) {
     for (int s = 0; s < RLE_SLOTS; ++s) {
         if (hp->h_runs[s]) cudaFreeHost(hp->h_runs[s]);
         if (hp->h_rowoff[s]) cudaFreeHost(hp->h_rowoff[s]);
-        hp->h_runs[s] = nullptr; hp->h_rowoff[s] = nullptr;
+        if (hp->h_pack[s]) cudaFreeHost(hp->h_pack[s]);
+        hp->h_runs[s] = nullptr; hp->h_rowoff[s] = nullptr; hp->h_pack[s] = nullptr;
         LG_CUDA(cudaHostAlloc((void**)&hp->h_runs[s], (size_t)chunk * hp->run_cap * sizeof(uint32_t), cudaHostAllocDefault));
-        LG_CUDA(cudaHostAlloc((void**)&hp->h_rowoff[s], (size_t)chunk * (c->H + 1) * sizeof(uint32_t), cudaHostAllocDefault));
+        LG_CUDA(cudaHostAlloc((void**)&hp->h_pack[s], (size_t)chunk * hp->run_cap * sizeof(uint32_t), cudaHostAllocDefault));
+        LG_CUDA(cudaHostAlloc((void**)&hp->h_rowoff[s], (size_t)chunk * (c->H + 2) * sizeof(uint32_t), cudaHostAllocDefault));
         void* p = nullptr;
         int rc = lg_context_dev_alloc(c, &p, (size_t)chunk * hp->run_cap * sizeof(uint32_t));
         if (rc) return rc;
         hp->d_runs[s] = static_cast<uint32_t*>(p);
-        rc = lg_context_dev_alloc(c, &p, (size_t)chunk * (c->H + 1) * sizeof(uint32_t));
+        rc = lg_context_dev_alloc(c, &p, (size_t)chunk * (c->H + 2) * sizeof(uint32_t));
         if (rc) return rc;
         hp->d_rowoff[s] = static_cast<uint32_t*>(p);
         hp->used[s] = false;
@@ -222,6 +225,7 @@ void lg_host_pipe_destroy(lg_context* c) {
     for (int s = 0; s < RLE_SLOTS; ++s) {
         if (hp->h_runs[s]) cudaFreeHost(hp->h_runs[s]);
         if (hp->h_rowoff[s]) cudaFreeHost(hp->h_rowoff[s]);
+        if (hp->h_pack[s]) cudaFreeHost(hp->h_pack[s]);
         if (hp->copied[s]) cudaEventDestroy(hp->copied[s]);
         if (hp->expanded[s]) cudaEventDestroy(hp->expanded[s]);
     }
@@ -261,7 +265,8 @@ extern "C" int lg_process_batch_host(lg_context* c, const int16_t* labels_host, 
         if (rc) return rc;
         c->results_all = static_cast<lg_frame_result*>(p);
     }
-    int chunk = LG_HOST_CHUNK_FRAMES;
+    static const int chunk0 = [] { const char* e = getenv("LG_HOST_CHUNK"); const int v = e ? atoi(e) : 0; return v >= 1 ? v : LG_HOST_CHUNK_FRAMES; }();
+    int chunk = chunk0;
     while ((frames + chunk - 1) / chunk > LG_MAX_HOST_CHUNKS) chunk *= 2;
     const int n_chunks = (frames + chunk - 1) / chunk;
     static const bool env_off = [] { const char* e = getenv("LG_HOST_RLE"); return e && e[0] == '0'; }();
@@ -294,31 +299,41 @@ extern "C" int lg_process_batch_host(lg_context* c, const int16_t* labels_host, 
             uint32_t* runs = hp->h_runs[slot];
             uint32_t* rowoff = hp->h_rowoff[slot];
             const uint32_t cap = hp->run_cap;
-            std::vector<uint32_t> n_runs((size_t)m);
+            std::vector<uint32_t> n_runs((size_t)m), base((size_t)m + 1);
             const std::function<void(int)> job = [&](int f) {
-                uint32_t* ro = rowoff + (size_t)f * (H + 1);
+                uint32_t* ro = rowoff + (size_t)f * (H + 2);
                 n_runs[(size_t)f] = encode_frame(labels_host + off + (size_t)f * P, H, W, runs + (size_t)f * cap, cap, ro);
                 if (n_runs[(size_t)f] == 0xFFFFFFFFu) ro[0] = 0xFFFFFFFFu;
             };
             hp->pool->run(m, job);
-            LG_CUDA(cudaMemcpyAsync(hp->d_rowoff[slot], rowoff, (size_t)m * (H + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->copy_stream));
-            h2d += (uint64_t)m * (H + 1) * sizeof(uint32_t);
+            // pack the frames' runs back to back: ONE copy per chunk instead of one per frame
+            base[0] = 0;
+            for (int f = 0; f < m; ++f) base[(size_t)f + 1] = base[(size_t)f] + (n_runs[(size_t)f] == 0xFFFFFFFFu ? 0u : n_runs[(size_t)f]);
+            uint32_t* pack = hp->h_pack[slot];
+            const std::function<void(int)> move = [&](int f) {
+                rowoff[(size_t)f * (H + 2) + H + 1] = base[(size_t)f];
+                if (n_runs[(size_t)f] != 0xFFFFFFFFu)
+                    memcpy(pack + base[(size_t)f], runs + (size_t)f * cap, (size_t)n_runs[(size_t)f] * sizeof(uint32_t));
+            };
+            hp->pool->run(m, move);
+            LG_CUDA(cudaMemcpyAsync(hp->d_rowoff[slot], rowoff, (size_t)m * (H + 2) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->copy_stream));
+            h2d += (uint64_t)m * (H + 2) * sizeof(uint32_t);
+            if (base[(size_t)m]) {
+                LG_CUDA(cudaMemcpyAsync(hp->d_runs[slot], pack, (size_t)base[(size_t)m] * sizeof(uint32_t), cudaMemcpyHostToDevice, c->copy_stream));
+                h2d += (uint64_t)base[(size_t)m] * sizeof(uint32_t);
+            }
             for (int f = 0; f < m; ++f) {
                 if (n_runs[(size_t)f] == 0xFFFFFFFFu) {          // too many runs: this frame's labels go as they are
                     LG_CUDA(cudaMemcpyAsync(c->in_labels + off + (size_t)f * P, labels_host + off + (size_t)f * P, P * sizeof(int16_t),
                                             cudaMemcpyHostToDevice, c->copy_stream));
                     h2d += P * sizeof(int16_t);
-                } else {
-                    LG_CUDA(cudaMemcpyAsync(hp->d_runs[slot] + (size_t)f * cap, runs + (size_t)f * cap, (size_t)n_runs[(size_t)f] * sizeof(uint32_t),
-                                            cudaMemcpyHostToDevice, c->copy_stream));
-                    h2d += (uint64_t)n_runs[(size_t)f] * sizeof(uint32_t);
                 }
             }
             LG_CUDA(cudaEventRecord(c->copy_ev[k], c->copy_stream));
             LG_CUDA(cudaEventRecord(hp->copied[slot], c->copy_stream));
             hp->used[slot] = true;
             LG_CUDA(cudaStreamWaitEvent(st, c->copy_ev[k], 0));
-            expand_labels_kernel<<<dim3((H + 7) / 8, m), 256, 0, st>>>(hp->d_runs[slot], hp->run_cap, hp->d_rowoff[slot],
+            expand_labels_kernel<<<dim3((H + 7) / 8, m), 256, 0, st>>>(hp->d_runs[slot], hp->d_rowoff[slot],
                                                                         c->in_labels + off, P, H, W);
             LG_LAUNCH_CHECK();
             LG_CUDA(cudaEventRecord(hp->expanded[slot], st));
