@@ -343,3 +343,67 @@ def test_host_call_run_length_encodes_labels_losslessly(blob):
         else:
             assert np.array_equal(x, y) and np.array_equal(x, z), name
     eng.close()
+
+
+@pytest.mark.parametrize("shape", [(64, 96), (70, 90), (97, 131), (360, 480)])
+def test_edt_argmax_search_on_adversarial_masks(shape):
+    """The branch-and-bound arg-max of the distance transform (cell bounds + Lipschitz quartering) on masks chosen to break
+    its shortcuts: ties along ridges and between mirror-image sources (the FIRST maximum in raster order must win), dense
+    source patterns where nearly every node survives, sources only on the frame's border, a single source in each corner,
+    sparse random points, and a mask without any background."""
+    H, W = shape
+    rng = np.random.default_rng(H * 1000 + W)
+    masks = []
+    def m():
+        return np.ones((H, W), np.uint8)          # 1 = background, 0 = source (lg_edt_squared's convention)
+    for (y, x) in ((0, 0), (0, W - 1), (H - 1, 0), (H - 1, W - 1), (H // 2, W // 2)):
+        a = m(); a[y, x] = 0; masks.append(a)
+    a = m(); a[H // 2, 3] = 0; a[H // 2, W - 4] = 0; masks.append(a)                  # mirror-image sources: a ridge of ties
+    a = m(); a[0, :] = 0; a[-1, :] = 0; masks.append(a)                               # two border rows: the middle row(s) tie
+    a = m(); a[:, 0] = 0; a[:, -1] = 0; a[0, :] = 0; a[-1, :] = 0; masks.append(a)    # the whole border
+    a = m(); a[::2, ::2] = 0; masks.append(a)                                         # dense lattice
+    a = m(); a[(np.indices((H, W)).sum(0) % 2) == 0] = 0; masks.append(a)             # checkerboard: max distance 1
+    a = m(); a[:, ::7] = 0; masks.append(a)                                           # vertical stripes
+    a = m(); a[::5, :] = 0; masks.append(a)                                           # horizontal stripes
+    a = m(); a[rng.random((H, W)) < 0.002] = 0; a[0, 0] = 0; masks.append(a)          # sparse points
+    a = m(); a[rng.random((H, W)) < 0.5] = 0; masks.append(a)                         # salt and pepper
+    a = np.zeros((H, W), np.uint8); masks.append(a)                                   # no background at all
+    a = np.zeros((H, W), np.uint8); a[H - 1, W - 1] = 1; masks.append(a)              # one background pixel, last in raster order
+    masks = np.stack(masks)
+    eng = _engine(len(masks), H, W, 2)
+    _, am = eng.edt_squared(torch.from_numpy(masks), argmax_only=True)
+    am = am.cpu().numpy()
+    for k in range(len(masks)):
+        want = int(O.edt_squared(masks[k]).argmax())
+        assert am[k] == want, f"mask {k}: got {am[k]} ({divmod(int(am[k]), W)}), expected {want} ({divmod(want, W)})"
+    eng.close()
+
+
+@pytest.mark.parametrize("shape", [(203, 317), (360, 480), (97, 1000), (64, 64)])
+def test_band_kernel_statistics_on_boundary_heavy_labels(shape):
+    """leaf_band_kernel on label images where few 8 x 8 blocks are uniform (salt-and-pepper labels, thin stripes, a ragged
+    right / bottom edge): pixel counts, centroids and medians per label are exact against NumPy, the mean depth to float32
+    rounding - the boundary-block path (queued rows, per-label warp reductions, pixel parts of `seg`) carries all of it."""
+    H, W = shape
+    rng = np.random.default_rng(H + 7 * W)
+    frames = []
+    a = rng.integers(0, 6, size=(H, W)).astype(np.int16); frames.append(a)                       # noise: every block is a boundary block
+    a = np.zeros((H, W), np.int16); a[:, ::3] = 1; a[:, 1::3] = 2; frames.append(a)               # one-pixel stripes
+    a = np.zeros((H, W), np.int16); a[H // 4: 3 * H // 4, W // 5: 4 * W // 5] = 3
+    a[H // 3: H // 2, W // 3: W // 2] = 5; a[rng.random((H, W)) < 0.02] = 4; frames.append(a)     # blocks + speckle
+    a = np.full((H, W), 2, np.int16); a[0, 0] = 0; frames.append(a)                               # one leaf covering (almost) everything
+    lab = np.stack(frames)
+    dep = (0.3 + 0.5 * rng.random(lab.shape)).astype(np.float32)
+    eng = _engine(len(lab), H, W, 16)
+    ids, rec = eng.select_leaf(torch.from_numpy(lab), torch.from_numpy(dep), _cam(synth.SMALL))
+    for i in range(len(lab)):
+        present = np.unique(lab[i])
+        for l in present[1:]:                     # the smallest id present is the background
+            r = rec[i][int(l)]
+            mask = lab[i] == l
+            ys, xs = np.nonzero(mask)
+            assert int(r["area"]) == int(mask.sum()), (i, l)
+            assert r["centroid_x"] == xs.sum() / mask.sum() and r["centroid_y"] == ys.sum() / mask.sum(), (i, l)
+            assert np.float32(r["median_depth"]) == np.median(dep[i][mask]), (i, l)
+            np.testing.assert_allclose(r["mean_depth"], dep[i][mask].astype(np.float64).mean(), rtol=3e-7)
+    eng.close()
