@@ -180,6 +180,7 @@ __global__ void __launch_bounds__(TL_NT) cnn_tail_kernel(const float* __restrict
         float acc[TL_PB];
 #pragma unroll
         for (int p = 0; p < TL_PB; ++p) acc[p] = b0[tid];
+#pragma unroll 16      // sixteen weight rows in flight: the loop is a chain of L2 round trips otherwise
         for (int i = 0; i < 256; ++i) {
             const float w = w0[i * 256 + tid];
 #pragma unroll
@@ -193,6 +194,7 @@ __global__ void __launch_bounds__(TL_NT) cnn_tail_kernel(const float* __restrict
         float acc[TL_PB];
 #pragma unroll
         for (int p = 0; p < TL_PB; ++p) acc[p] = b1[tid];
+#pragma unroll 16      // sixteen weight rows in flight: the loop is a chain of L2 round trips otherwise
         for (int i = 0; i < 256; ++i) {
             const float w = w1[i * 128 + tid];
 #pragma unroll
@@ -206,6 +208,7 @@ __global__ void __launch_bounds__(TL_NT) cnn_tail_kernel(const float* __restrict
         float acc[TL_PB];
 #pragma unroll
         for (int p = 0; p < TL_PB; ++p) acc[p] = b2[tid];
+#pragma unroll 16      // sixteen weight rows in flight: the loop is a chain of L2 round trips otherwise
         for (int i = 0; i < 128; ++i) {
             const float w = w2[i * 64 + tid];
 #pragma unroll

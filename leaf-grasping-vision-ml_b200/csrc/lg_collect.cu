@@ -526,15 +526,32 @@ __global__ void __launch_bounds__(CO_NT) collector_points_kernel(lg_context c, L
 
 }  // namespace
 
+int lg_context_dev_alloc(lg_context* c, void** p, size_t bytes);
+// The tip lists (12 bytes per pixel of capacity) belong to the collector alone: its first call allocates them, so that a
+// context that only selects grasps does not carry them.
+static int ensure_collector_scratch(lg_context* c) {
+    if (c->list_key && c->list_idx) return LG_OK;
+    void* p = nullptr;
+    int rc = lg_context_dev_alloc(c, &p, (size_t)c->B * c->P * sizeof(double));
+    if (rc) return rc;
+    c->list_key = static_cast<double*>(p);
+    rc = lg_context_dev_alloc(c, &p, (size_t)c->B * c->P * sizeof(uint32_t));
+    if (rc) return rc;
+    c->list_idx = static_cast<uint32_t*>(p);
+    return LG_OK;
+}
+
 int lg_run_collect(lg_context* c, LgMaskSrc src, const float* depth, int n, unsigned long long seed, unsigned long long first_index,
                    const int32_t* grasp_xy, const double* total, float* patches, lg_sample_meta* meta, int32_t* set_sizes,
                    cudaStream_t st) {
+    { const int rc = ensure_collector_scratch(c); if (rc) return rc; }
     collect_kernel<<<n, CO_NT, 0, st>>>(*c, src, depth, seed, first_index, grasp_xy, total, patches, meta, set_sizes);
     LG_LAUNCH_CHECK();
     return LG_OK;
 }
 
 int lg_run_collector_points(lg_context* c, LgMaskSrc src, int n, int kind, const uint32_t* ranks, int nq, int32_t* xy, cudaStream_t st) {
+    { const int rc = ensure_collector_scratch(c); if (rc) return rc; }
     collector_points_kernel<<<n, CO_NT, 0, st>>>(*c, src, kind, ranks, nq, xy);
     LG_LAUNCH_CHECK();
     return LG_OK;

@@ -135,9 +135,12 @@ struct lg_context {
     double *m_sdf, *m_app, *m_acc, *m_trad;  // [B][P]
     float *m_flat, *m_stem;                  // [B][P]
     uint8_t* m_valid;                        // [B][P]
-    double* list_key;                        // [B][P] compacted positive keys
-    uint32_t* list_idx;                      // [B][P]
+    double* list_key;                        // [B][P] scratch of the sample collector (tip values), allocated by its first call
+    uint32_t* list_idx;                      // [B][P] scratch of the sample collector (tip indices), likewise
     uint32_t* list_n;                        // [B]
+    unsigned long long* tile_key;            // [B][tile_cap] candidate search: best alive key (bits of the double) of every 32 x 8 tile
+    uint32_t* tile_id;                       // [B][tile_cap] and its flat pixel index
+    int tile_cap;                            // ceil(W / 32) * ceil(H / 8)
     float* patches;                          // [B*20][9][32][32]
     float* logits;                           // [B*20], indexed by compact slot
     int32_t* slot_map;                       // [B*20] compact patch index of every (frame, candidate), -1 = no ML score

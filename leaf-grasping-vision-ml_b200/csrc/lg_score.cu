@@ -5,9 +5,9 @@
 //
 //   score_kernel   one pass over the leaf rectangle: masked depth tile -> 5x5 Gaussian -> Sobel ->
 //                  flatness; closed-form approach / accessibility; sdf_score from the chamfer field;
-//                  stem penalty from the leaf bitmask; traditional score; valid mask; compaction of the
-//                  positive keys for the candidate search                     (:256-288, 502-701)
-//   nms_kernel     top-20 greedy pick with the +-10 px mark                      (:447-482)
+//                  stem penalty from the leaf bitmask; traditional score; valid mask     (:256-288, 502-701)
+//   nms_tiles_kernel / nms_kernel   top-20 greedy pick with the +-10 px mark: best alive key per 32 x 8 tile,
+//                  20 rounds of (arg-max over the tiles, refresh of the tiles under the pick)   (:447-482)
 //   gather_kernel  9 x 32 x 32 patch tensor written in the CNN's input layout    (:59-127, 392-445)
 //   fuse_kernel    ML rescale + confidence weighting + 3-D / pre-grasp points    (:133-136, 205-249, 152-180, 754-826)
 #include <math_constants.h>
@@ -97,7 +97,6 @@ __global__ void __launch_bounds__(SC_TW * SC_TH) score_kernel(lg_context c, LgMa
     __syncthreads();
     const int lx = tid % SC_TW, ly = tid / SC_TW;
     const int x = tx0 + lx, y = ty0 + ly;
-    bool want = false;
     double trad = 0.0;
     if (x < r.sx1 && y < r.sy1) {
         const size_t p = (size_t)y * W + x;
@@ -173,20 +172,6 @@ __global__ void __launch_bounds__(SC_TW * SC_TH) score_kernel(lg_context c, LgMa
             if (M) iso = (y == H - 1) ? 0.2 : ((double)y * ((0.2 - 1.0) / (double)(H - 1)) + 1.0);
             iso_out[fo + p] = iso;
         }
-        want = valid && trad > 0.0;
-    }
-    // warp-aggregated append of the positive keys
-    const unsigned ball = __ballot_sync(0xFFFFFFFFu, want);
-    if (ball) {
-        const int lane = tid & 31;
-        unsigned base = 0;
-        if (lane == (__ffs(ball) - 1)) base = atomicAdd(&c.list_n[b], __popc(ball));
-        base = __shfl_sync(0xFFFFFFFFu, base, __ffs(ball) - 1);
-        if (want) {
-            const unsigned pos = base + __popc(ball & ((1u << lane) - 1u));
-            c.list_key[fo + pos] = trad;
-            c.list_idx[fo + pos] = (unsigned)((size_t)y * W + x);
-        }
     }
     }   // tiles
 }
@@ -194,223 +179,215 @@ __global__ void __launch_bounds__(SC_TW * SC_TH) score_kernel(lg_context c, LgMa
 // fill the per-frame maps with their analytic values outside the score rectangle (full mode only needs
 // nothing: the rectangle is the frame).  Not needed in region mode: consumers special-case the outside.
 
-constexpr int NMS_NT = 1024;
-constexpr int NMS_SUB = 6144;      // keys the shared-memory shortlist holds
-constexpr int NMS_TARGET = 5632;   // shortlist = all keys above a histogram threshold, about this many
-constexpr int NMS_BINS = 4096;
-constexpr size_t NMS_SMEM = (size_t)NMS_SUB * (sizeof(double) + sizeof(unsigned)) + NMS_BINS * sizeof(unsigned);
+// ---------------------------------------------------------------------------------------------------
+// candidates
+// ---------------------------------------------------------------------------------------------------
 // _get_candidate_points (grasp_point_selector.py:447-482): 20 rounds of (arg-max of the remaining keys, suppress
-// everything within +-20 px of the pick).  The picks are the first 20 unsuppressed keys in descending order, so they
-// only involve the top few thousand keys: a histogram of the keys (they lie in (0, 1]) gives a threshold, the keys
-// above it go to a shortlist in shared memory and the rounds run there.  If the shortlist runs dry before 20
-// picks the rounds continue on the full list, so the result is that of the full search in every case.
+// everything within +-20 px of the pick).  Whether a pixel is still in the running depends on the picks alone - it is alive
+// iff its key is positive and no earlier pick lies within LG_NMS_REACH of it (Chebyshev) - so no list of keys is edited or
+// rebuilt.  The score rectangle is cut into tiles of 32 x 8 pixels; a table holds every tile's best alive key with its
+// pixel (tile_key / tile_id).  A round is then an arg-max over the table (a few hundred entries in shared memory) and a
+// fresh look at the at most 18 tiles the new pick's 41 x 41 window touches, one warp per tile: 20 rounds cost 40 barriers
+// and 20 trips to the L2, whatever the number of positive keys.  Keys are compared as the bit patterns of positive doubles
+// (same order); among equal keys the larger flat index wins, as in the sequential search over the index-ordered list.
+constexpr int NMS_NT = 640;               // 20 warps: one per tile a pick can touch (3 x 6) and a little spare
+constexpr int NMS_NW = NMS_NT / 32;
+constexpr int NMS_TW = 32, NMS_TH = 8;
+constexpr int NMS_TCACHE = 3072;          // table entries kept in shared memory (a 1440 x 1080 frame has 6075 tiles, a leaf ~300)
+constexpr int NMS_INIT_NT = 256;
+
+struct NmsGeom {
+    int rx0, ry0, rx1, ry1;               // rectangle that carries keys (exclusive upper bounds)
+    int ax0, ay0;                         // origin of the tile grid: the rectangle's corner rounded down to the tile size
+    int tx, ty;                           // tiles per row / column
+};
+__device__ __forceinline__ NmsGeom nms_geom(const LgRegion& r, bool whole_frame, int W, int H) {
+    NmsGeom g;
+    g.rx0 = whole_frame ? 0 : r.sx0; g.ry0 = whole_frame ? 0 : r.sy0;
+    g.rx1 = whole_frame ? W : r.sx1; g.ry1 = whole_frame ? H : r.sy1;
+    g.ax0 = g.rx0 & ~(NMS_TW - 1); g.ay0 = g.ry0 & ~(NMS_TH - 1);
+    g.tx = max(0, (g.rx1 - g.ax0 + NMS_TW - 1) / NMS_TW); g.ty = max(0, (g.ry1 - g.ay0 + NMS_TH - 1) / NMS_TH);
+    return g;
+}
+
+// lexicographic maximum of (key, index) over the warp; every lane gets the result
+__device__ __forceinline__ void nms_warp_max(unsigned long long& k, unsigned& i) {
+    const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+    const unsigned mh = __reduce_max_sync(0xFFFFFFFFu, hi);
+    const unsigned ml = __reduce_max_sync(0xFFFFFFFFu, hi == mh ? lo : 0u);
+    const unsigned mi = __reduce_max_sync(0xFFFFFFFFu, (hi == mh && lo == ml) ? i : 0u);
+    k = ((unsigned long long)mh << 32) | ml;
+    i = mi;
+}
+
+// Best alive key of one tile (all lanes call; lane = column, 8 rows per lane).  The picks live in the lanes: lane q < npick
+// holds pick q in (pqx, pqy).  key == nullptr never happens; valid marks the pixels that may be picked at all.
+__device__ __forceinline__ void nms_tile_best(const double* __restrict__ key, const uint8_t* __restrict__ valid, int W,
+                                              const NmsGeom& g, int tile, int pqx, int pqy, int npick, int lane,
+                                              unsigned long long& bk, unsigned& bi) {
+    const int tcy = tile / g.tx, tcx = tile - tcy * g.tx;
+    const int X0 = g.ax0 + tcx * NMS_TW, Y0 = g.ay0 + tcy * NMS_TH;
+    const int x = X0 + lane;
+    // the picks whose window reaches this tile
+    const bool reach = lane < npick && pqx + LG_NMS_REACH >= X0 && pqx - LG_NMS_REACH <= X0 + NMS_TW - 1 &&
+                       pqy + LG_NMS_REACH >= Y0 && pqy - LG_NMS_REACH <= Y0 + NMS_TH - 1;
+    unsigned rel = __ballot_sync(0xFFFFFFFFu, reach);
+    const bool xin = x >= g.rx0 && x < g.rx1;
+    double kv[NMS_TH];
+    unsigned ok = 0;                      // bit j: row j of this column may be picked
+#pragma unroll
+    for (int j = 0; j < NMS_TH; ++j) {    // all loads of the tile are in flight together
+        const int y = Y0 + j;
+        const bool in = xin && y >= g.ry0 && y < g.ry1;
+        const size_t p = (size_t)y * W + x;
+        kv[j] = in ? key[p] : 0.0;
+        if (in && valid[p]) ok |= 1u << j;
+    }
+    while (rel) {
+        const int q = __ffs(rel) - 1;
+        rel &= rel - 1;
+        const int qx = __shfl_sync(0xFFFFFFFFu, pqx, q), qy = __shfl_sync(0xFFFFFFFFu, pqy, q);
+        const int jlo = max(qy - LG_NMS_REACH - Y0, 0), jhi = min(qy + LG_NMS_REACH - Y0, NMS_TH - 1);
+        if (abs(x - qx) <= LG_NMS_REACH && jlo <= jhi) ok &= ~(((1u << (jhi - jlo + 1)) - 1u) << jlo);
+    }
+    bk = 0ull;
+    int bj = 0;
+#pragma unroll
+    for (int j = 0; j < NMS_TH; ++j) {
+        const bool pos = kv[j] > 0.0;     // false for NaN
+        const unsigned long long kb = (unsigned long long)__double_as_longlong(kv[j]);
+        if (((ok >> j) & 1u) && pos && kb >= bk) { bk = kb; bj = j; }      // a later row is a larger index: it wins a tie
+    }
+    bi = bk ? (unsigned)((size_t)(Y0 + bj) * W + x) : 0u;
+    nms_warp_max(bk, bi);
+}
+
+// the table of every frame before the first pick: a warp per tile.  ext_score / ext_valid: caller-supplied full-frame
+// maps (lg_candidate_points); otherwise the traditional score and the valid mask on the frame's score rectangle.
+__global__ void __launch_bounds__(NMS_INIT_NT) nms_tiles_kernel(lg_context c, const double* ext_score, const uint8_t* ext_valid) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const LgRegion r = c.region[b];
+    if (!ext_score && !r.ok) return;
+    const NmsGeom g = nms_geom(r, ext_score != nullptr, c.W, c.H);
+    const int T = g.tx * g.ty;
+    const size_t fo = (size_t)b * c.P;
+    const double* key = ext_score ? ext_score + fo : c.m_trad + fo;
+    const uint8_t* valid = ext_valid ? ext_valid + fo : c.m_valid + fo;
+    unsigned long long* tk = c.tile_key + (size_t)b * c.tile_cap;
+    uint32_t* ti = c.tile_id + (size_t)b * c.tile_cap;
+    for (int tile = blockIdx.x * (NMS_INIT_NT / 32) + warp; tile < T; tile += gridDim.x * (NMS_INIT_NT / 32)) {
+        unsigned long long bk;
+        unsigned bi;
+        nms_tile_best(key, valid, c.W, g, tile, 0, 0, 0, lane, bk, bi);
+        if (lane == 0) { tk[tile] = bk; ti[tile] = bi; }
+    }
+}
+
 __global__ void __launch_bounds__(NMS_NT) nms_kernel(lg_context c, const double* ext_score, const uint8_t* ext_valid,
                                                       int32_t* ext_xy, int32_t* ext_count) {
-    extern __shared__ __align__(16) unsigned char nms_sm[];
-    double* skey = reinterpret_cast<double*>(nms_sm);
-    unsigned* sidx = reinterpret_cast<unsigned*>(nms_sm + (size_t)NMS_SUB * sizeof(double));
-    unsigned* hist = sidx + NMS_SUB;
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    __shared__ unsigned long long s_tk[NMS_TCACHE];
+    __shared__ unsigned s_ti[NMS_TCACHE];
+    __shared__ unsigned long long wk[2][NMS_NW];
+    __shared__ unsigned wi[2][NMS_NW];
+    __shared__ int px[LG_TOP_K], py[LG_TOP_K];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = c.W;
     const size_t fo = (size_t)b * c.P;
     lg_frame_result* res = &c.results[b];
-    __shared__ int px[LG_TOP_K], py[LG_TOP_K];
-    __shared__ double wk[NMS_NT / 32];
-    __shared__ unsigned wi[NMS_NT / 32];
-    __shared__ int s_found, s_tb;
-    __shared__ unsigned s_m, s_total;
     const LgRegion r = c.region[b];
     if (!ext_score && !r.ok) {
         if (tid == 0) { res->n_candidates = 0; res->n_positive = 0; }
         return;
     }
-    const unsigned n = c.list_n[b];
-    double* key = c.list_key + fo;
-    const unsigned* idx = c.list_idx + fo;
-    int cnt = 0;
-    // rounds [cnt, 20) over the list (k, id)[0, m); suppressed entries are overwritten with -1
-    // ids: flat pixel indices (the global list) or, PACKED, y << 16 | x (the shared-memory shortlist: no division per key
-    // and round); both order like the flat index, which breaks ties between equal keys
-    auto rounds = [&](double* k_, const unsigned* id_, unsigned m, const bool packed) {
-        for (int it = cnt; it < LG_TOP_K; ++it) {
-            double bk = -1.0;
-            unsigned bi = 0;
-            const int qx = it > 0 ? px[it - 1] : 0, qy = it > 0 ? py[it - 1] : 0;
-            for (unsigned i = tid; i < m; i += NMS_NT) {
-                const double k = k_[i];
-                if (!(k > 0.0)) continue;
-                const unsigned id = id_[i];
-                if (it > 0) {
-                    const int x = packed ? (int)(id & 0xFFFFu) : (int)(id % W), y = packed ? (int)(id >> 16) : (int)(id / W);
-                    if (abs(x - qx) <= LG_NMS_REACH && abs(y - qy) <= LG_NMS_REACH) { k_[i] = -1.0; continue; }
-                }
-                if (k > bk || (k == bk && id > bi)) { bk = k; bi = id; }
-            }
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                const double ok = __shfl_xor_sync(0xFFFFFFFFu, bk, d);
-                const unsigned oi = __shfl_xor_sync(0xFFFFFFFFu, bi, d);
-                if (ok > bk || (ok == bk && oi > bi)) { bk = ok; bi = oi; }
-            }
-            if (lane == 0) { wk[tid >> 5] = bk; wi[tid >> 5] = bi; }
-            __syncthreads();
-            if (tid < 32) {      // second level: one warp over the per-warp winners
-                bk = wk[lane]; bi = wi[lane];
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) {
-                    const double ok = __shfl_xor_sync(0xFFFFFFFFu, bk, d);
-                    const unsigned oi = __shfl_xor_sync(0xFFFFFFFFu, bi, d);
-                    if (ok > bk || (ok == bk && oi > bi)) { bk = ok; bi = oi; }
-                }
-                if (tid == 0) {
-                    s_found = bk > 0.0;
-                    if (s_found) {
-                        px[it] = packed ? (int)(bi & 0xFFFFu) : (int)(bi % W); py[it] = packed ? (int)(bi >> 16) : (int)(bi / W);
-                        res->cand_x[it] = px[it]; res->cand_y[it] = py[it]; res->trad[it] = bk;
-                    }
-                }
-            }
-            __syncthreads();
-            if (!s_found) break;
-            ++cnt;
-        }
-    };
-    auto pack_id = [&](unsigned id) { return ((id / (unsigned)W) << 16) | (id % (unsigned)W); };
-    if (n <= (unsigned)NMS_SUB) {
-        for (unsigned i = tid; i < n; i += NMS_NT) { skey[i] = key[i]; sidx[i] = pack_id(idx[i]); }
-        __syncthreads();
-        rounds(skey, sidx, n, true);
-    } else {
-        // shortlist, rounds, and - if the shortlist ran dry before 20 picks - a new shortlist from what is left
-        for (int build = 0; cnt < LG_TOP_K; ++build) {
-            if (build > 0) {   // bring the full list up to date: drop everything the picks so far suppress (themselves included)
-                for (unsigned i = tid; i < n; i += NMS_NT) {
-                    if (!(key[i] > 0.0)) continue;
-                    const unsigned id = idx[i];
-                    const int x = (int)(id % W), y = (int)(id / W);
-                    for (int k = 0; k < cnt; ++k)
-                        if (abs(x - px[k]) <= LG_NMS_REACH && abs(y - py[k]) <= LG_NMS_REACH) { key[i] = -1.0; break; }
-                }
-            }
-            for (int i = tid; i < NMS_BINS; i += NMS_NT) hist[i] = 0;
-            if (tid == 0) { s_m = 0; s_tb = -1; s_total = 0; }
-            __syncthreads();
-            for (unsigned i = tid; i < n; i += NMS_NT) {
-                const double k = key[i];
-                if (k > 0.0) atomicAdd(&hist[min(NMS_BINS - 1, (int)(k * (double)NMS_BINS))], 1u);
-            }
-            __syncthreads();
-            if (tid < 32) {   // threshold bin: the highest bin whose suffix count reaches the target without overflowing
-                constexpr int PER = NMS_BINS / 32;
-                unsigned mine = 0;
-                for (int j = 0; j < PER; ++j) mine += hist[lane * PER + j];
-                unsigned suffix = mine;            // inclusive suffix sum over lanes (higher lanes = higher keys)
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const unsigned t = __shfl_down_sync(0xFFFFFFFFu, suffix, d);
-                    if (lane + d < 32) suffix += t;
-                }
-                if (lane == 0) s_total = suffix;
-                const unsigned above = suffix - mine;                       // keys in higher lanes' bins
-                const bool here = above < (unsigned)NMS_TARGET && suffix >= (unsigned)NMS_TARGET;
-                const unsigned who = __ballot_sync(0xFFFFFFFFu, here);
-                if (who == 0u) {                                             // fewer keys left than the target: take all bins
-                    if (lane == 0) s_tb = 0;
-                } else if (lane == (__ffs(who) - 1)) {
-                    unsigned acc = above;
-                    int tb = (lane + 1) * PER;                               // first bin above this lane's range
-                    for (int j = PER - 1; j >= 0; --j) {
-                        const unsigned h = hist[lane * PER + j];
-                        if (acc + h > (unsigned)NMS_SUB) break;
-                        acc += h; tb = lane * PER + j;
-                        if (acc >= (unsigned)NMS_TARGET) break;
-                    }
-                    s_tb = (acc > 0u) ? tb : -1;                             // -1: a single bin overflows the shortlist
-                }
-            }
-            __syncthreads();
-            const int tb = s_tb;
-            const unsigned total = s_total;
-            if (total == 0u) break;                                          // nothing left to pick from
-            if (tb < 0) { rounds(key, idx, n, false); break; }                      // degenerate key distribution: plain search
-            for (unsigned i0 = 0; i0 < n; i0 += NMS_NT) {
-                const unsigned i = i0 + tid;
-                double k = -1.0;
-                bool take = false;
-                if (i < n) { k = key[i]; take = k > 0.0 && min(NMS_BINS - 1, (int)(k * (double)NMS_BINS)) >= tb; }
-                const unsigned ball = __ballot_sync(0xFFFFFFFFu, take);
-                if (ball) {
-                    unsigned base = 0;
-                    if (lane == 0) base = atomicAdd(&s_m, __popc(ball));
-                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                    const unsigned pos = base + __popc(ball & ((1u << lane) - 1u));
-                    if (take && pos < (unsigned)NMS_SUB) { skey[pos] = k; sidx[pos] = pack_id(idx[i]); }
-                }
-            }
-            __syncthreads();
-            const unsigned m = s_m;
-            // the first round of this call must not apply the "previous pick" test to stale data: the list is up to date
-            rounds(skey, sidx, m, true);
-            if (m == total) break;                                           // the shortlist was everything that is left
-            __syncthreads();
-        }
+    const NmsGeom g = nms_geom(r, ext_score != nullptr, W, c.H);
+    const int T = g.tx * g.ty;
+    const double* key = ext_score ? ext_score + fo : c.m_trad + fo;
+    const uint8_t* valid = ext_valid ? ext_valid + fo : c.m_valid + fo;
+    unsigned long long* tk = c.tile_key + (size_t)b * c.tile_cap;
+    unsigned* ti = c.tile_id + (size_t)b * c.tile_cap;
+    if (T <= NMS_TCACHE) {                 // the usual case: the table lives in shared memory from here on
+        for (int t = tid; t < T; t += NMS_NT) { s_tk[t] = tk[t]; s_ti[t] = ti[t]; }
+        tk = s_tk; ti = s_ti;
     }
-    if (tid == 0) {
+    __syncthreads();
+    int cnt = 0;
+    int pqx = 0, pqy = 0;                  // lane q of every warp holds pick q
+    for (int it = 0; it < LG_TOP_K; ++it) {
+        unsigned long long bk = 0ull;
+        unsigned bi = 0u;
+        for (int t = tid; t < T; t += NMS_NT) {
+            const unsigned long long k = tk[t];
+            const unsigned i = ti[t];
+            if (k > bk || (k == bk && i > bi)) { bk = k; bi = i; }
+        }
+        nms_warp_max(bk, bi);
+        const int par = it & 1;
+        if (lane == 0) { wk[par][warp] = bk; wi[par][warp] = bi; }
+        __syncthreads();
+        bk = lane < NMS_NW ? wk[par][lane] : 0ull;       // every warp reduces the warps' winners: no second broadcast
+        bi = lane < NMS_NW ? wi[par][lane] : 0u;
+        nms_warp_max(bk, bi);
+        if (bk == 0ull) break;                           // no alive key left (uniform)
+        const int qx = (int)(bi % (unsigned)W), qy = (int)(bi / (unsigned)W);
+        if (lane == it) { pqx = qx; pqy = qy; }
+        if (tid == 0) {
+            px[it] = qx; py[it] = qy;
+            res->cand_x[it] = qx; res->cand_y[it] = qy; res->trad[it] = __longlong_as_double((long long)bk);
+        }
+        ++cnt;
+        if (it == LG_TOP_K - 1) break;
+        // the tiles the pick's window touches get their best alive key again
+        const int c0 = (max(qx - LG_NMS_REACH, g.rx0) - g.ax0) / NMS_TW, c1 = (min(qx + LG_NMS_REACH, g.rx1 - 1) - g.ax0) / NMS_TW;
+        const int r0 = (max(qy - LG_NMS_REACH, g.ry0) - g.ay0) / NMS_TH, r1 = (min(qy + LG_NMS_REACH, g.ry1 - 1) - g.ay0) / NMS_TH;
+        const int ncx = c1 - c0 + 1, na = ncx * (r1 - r0 + 1);
+        for (int a = warp; a < na; a += NMS_NW) {
+            const int tile = (r0 + a / ncx) * g.tx + c0 + a % ncx;
+            unsigned long long nk;
+            unsigned ni;
+            nms_tile_best(key, valid, W, g, tile, pqx, pqy, cnt, lane, nk, ni);
+            if (lane == 0) { tk[tile] = nk; ti[tile] = ni; }
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (warp == 0) {
         const int n_pos = cnt;
-        // zero-key fill: every positive key is picked or suppressed by now, so the remaining picks are
-        // the non-suppressed pixels in descending flat index (oracle: candidate_points)
+        // zero-key fill: every positive key is picked or suppressed by now, so the remaining picks are the non-suppressed
+        // pixels in descending flat index (oracle: candidate_points).  Lane q tests pick q; the first pick that hits
+        // decides where the walk continues, as in the sequential loop.
         long long i = (long long)c.P - 1;
         while (cnt < LG_TOP_K && i >= 0) {
             const int x = (int)(i % W), y = (int)(i / W);
-            int hit = -1;
-            for (int k = 0; k < cnt; ++k)
-                if (abs(x - px[k]) <= LG_NMS_REACH && abs(y - py[k]) <= LG_NMS_REACH) { hit = k; break; }
-            if (hit >= 0) {
-                const int nx = px[hit] - LG_NMS_REACH - 1;
+            const unsigned hits = __ballot_sync(0xFFFFFFFFu, lane < cnt && abs(x - pqx) <= LG_NMS_REACH && abs(y - pqy) <= LG_NMS_REACH);
+            if (hits) {
+                const int nx = __shfl_sync(0xFFFFFFFFu, pqx, __ffs(hits) - 1) - LG_NMS_REACH - 1;
                 i = (nx >= 0) ? (long long)y * W + nx : (long long)y * W - 1;
                 continue;
             }
-            px[cnt] = x; py[cnt] = y;
-            res->cand_x[cnt] = x; res->cand_y[cnt] = y;
-            double t;
-            if (ext_score) t = ext_score[fo + i];
-            else if (x >= r.sx0 && x < r.sx1 && y >= r.sy0 && y < r.sy1) t = c.m_trad[fo + i];
-            else t = (double)0.2f;   // outside the leaf rectangle only the (unmasked) flatness term is left, and it is 1
-            res->trad[cnt] = t;
+            if (lane == cnt) { pqx = x; pqy = y; }
+            if (lane == 0) {
+                px[cnt] = x; py[cnt] = y;
+                res->cand_x[cnt] = x; res->cand_y[cnt] = y;
+                double t;
+                if (ext_score) t = ext_score[fo + i];
+                else if (x >= r.sx0 && x < r.sx1 && y >= r.sy0 && y < r.sy1) t = c.m_trad[fo + i];
+                else t = (double)0.2f;   // outside the leaf rectangle only the (unmasked) flatness term is left, and it is 1
+                res->trad[cnt] = t;
+            }
             ++cnt;
             --i;
         }
-        res->n_candidates = cnt;
-        res->n_positive = n_pos;
-        if (cnt == 0) atomicOr(&c.status[b], LG_ST_NO_CANDIDATE);
-        if (ext_xy) {
-            for (int k = 0; k < LG_TOP_K; ++k) {
-                ext_xy[(b * LG_TOP_K + k) * 2] = k < cnt ? px[k] : -1;
-                ext_xy[(b * LG_TOP_K + k) * 2 + 1] = k < cnt ? py[k] : -1;
+        if (lane == 0) {
+            res->n_candidates = cnt;
+            res->n_positive = n_pos;
+            if (cnt == 0) atomicOr(&c.status[b], LG_ST_NO_CANDIDATE);
+            if (ext_xy) {
+                for (int k = 0; k < LG_TOP_K; ++k) {
+                    ext_xy[(b * LG_TOP_K + k) * 2] = k < cnt ? px[k] : -1;
+                    ext_xy[(b * LG_TOP_K + k) * 2 + 1] = k < cnt ? py[k] : -1;
+                }
+                ext_count[b] = cnt;
             }
-            ext_count[b] = cnt;
-        }
-    }
-}
-
-// build the positive-key list from caller-supplied maps (entry for lg_candidate_points)
-__global__ void list_from_maps_kernel(lg_context c, const double* score, const uint8_t* valid) {
-    const int b = blockIdx.y;
-    const size_t fo = (size_t)b * c.P;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool want = false;
-    double k = 0.0;
-    if (i < c.P) { k = score[fo + i] * (double)(valid[fo + i] ? 1 : 0); want = k > 0.0; }
-    const unsigned ball = __ballot_sync(0xFFFFFFFFu, want);
-    if (ball) {
-        const int lane = threadIdx.x & 31;
-        unsigned base = 0;
-        if (lane == (__ffs(ball) - 1)) base = atomicAdd(&c.list_n[b], __popc(ball));
-        base = __shfl_sync(0xFFFFFFFFu, base, __ffs(ball) - 1);
-        if (want) {
-            const unsigned pos = base + __popc(ball & ((1u << lane) - 1u));
-            c.list_key[fo + pos] = k;
-            c.list_idx[fo + pos] = (unsigned)i;
         }
     }
 }
@@ -778,9 +755,18 @@ int lg_run_scores(lg_context* c, LgMaskSrc src, const float* depth, int n, lg_ca
     return LG_OK;
 }
 
+// CTAs per frame of the table kernel: a warp per tile and pass, enough passes in flight to fill the GPU
+static int nms_init_ctas(const lg_context* c, int n) {
+    const int per_cta = NMS_INIT_NT / 32;
+    int g = (LG_NUM_SM_HINT * 8 * 4 + n - 1) / n;
+    const int most = (c->tile_cap + per_cta - 1) / per_cta;
+    return g < 8 ? 8 : (g > most ? most : g);
+}
+
 int lg_run_nms(lg_context* c, int n, cudaStream_t st) {
-    TRY_SMEM(nms_kernel, NMS_SMEM);
-    nms_kernel<<<n, NMS_NT, NMS_SMEM, st>>>(*c, nullptr, nullptr, nullptr, nullptr);
+    nms_tiles_kernel<<<dim3(nms_init_ctas(c, n), n), NMS_INIT_NT, 0, st>>>(*c, nullptr, nullptr);
+    LG_LAUNCH_CHECK();
+    nms_kernel<<<n, NMS_NT, 0, st>>>(*c, nullptr, nullptr, nullptr, nullptr);
     LG_LAUNCH_CHECK();
     return LG_OK;
 }
@@ -830,10 +816,9 @@ int lg_run_candidates_from_maps(lg_context* c, const double* score, const uint8_
                                 cudaStream_t st) {
     clear_list_kernel<<<(n + 63) / 64, 64, 0, st>>>(*c, n);
     LG_LAUNCH_CHECK();
-    list_from_maps_kernel<<<dim3((unsigned)((c->P + 255) / 256), n), 256, 0, st>>>(*c, score, valid);
+    nms_tiles_kernel<<<dim3(nms_init_ctas(c, n), n), NMS_INIT_NT, 0, st>>>(*c, score, valid);
     LG_LAUNCH_CHECK();
-    TRY_SMEM(nms_kernel, NMS_SMEM);
-    nms_kernel<<<n, NMS_NT, NMS_SMEM, st>>>(*c, score, valid, xy, count);
+    nms_kernel<<<n, NMS_NT, 0, st>>>(*c, score, valid, xy, count);
     LG_LAUNCH_CHECK();
     return LG_OK;
 }

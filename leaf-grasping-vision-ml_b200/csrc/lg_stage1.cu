@@ -1271,14 +1271,15 @@ __global__ void __launch_bounds__(AM_NT, 2) edt_argmax_kernel(const uint8_t* __r
             unsigned slot = 0;
             if (lane == 0) slot = atomicAdd(&S.n_items[cur], (unsigned)n);
             slot = __shfl_sync(FULL, slot, 0);
-            if (slot + (unsigned)n <= (unsigned)AM_ITEMS) {
-                if (lane == 0)
-                    for (int q = 0; q < n; ++q) { S.items[cur][slot + q][0] = q4[q][0]; S.items[cur][slot + q][1] = q4[q][1]; }
-            } else {                                            // list full: search these quarters right here
-                for (int q = 0; q < n; ++q) {
-                    const unsigned r0 = __shfl_sync(FULL, q4[q][0], 0), r1 = __shfl_sync(FULL, q4[q][1], 0);
-                    dfs(r0, r1);
-                }
+            // The list takes as many of the quarters as still fit - every slot below n_items is then a node that was really
+            // written (a node with fewer than four quarters at the frame's edge must not leave a hole of stale entries at
+            // the end of the list) - and the rest is searched right here.
+            const int fit = slot >= (unsigned)AM_ITEMS ? 0 : min(n, (int)((unsigned)AM_ITEMS - slot));
+            if (lane == 0)
+                for (int q = 0; q < fit; ++q) { S.items[cur][slot + q][0] = q4[q][0]; S.items[cur][slot + q][1] = q4[q][1]; }
+            for (int q = fit; q < n; ++q) {
+                const unsigned r0 = __shfl_sync(FULL, q4[q][0], 0), r1 = __shfl_sync(FULL, q4[q][1], 0);
+                dfs(r0, r1);
             }
         }
     }
@@ -1323,31 +1324,31 @@ __global__ void __launch_bounds__(AM_NT, 2) edt_argmax_kernel(const uint8_t* __r
                 f = isqrt_floor(d2); cdc = f + (f * f != d2);
                 keep = (double)cdc + rad + 1e-6 >= lower_bound();
             }
-            unsigned todo = __ballot_sync(FULL, keep);
+            int fit = 0;                                        // quarters of this lane's node that went to the list
             if (keep) {
                 unsigned q4[4][2];
                 int n = 0;
                 push_quarters(nx0, ny0, lg, px, py, f, cdc, q4, n, 4);
                 const unsigned slot = atomicAdd(&S.n_items[cur ^ 1], (unsigned)n);
-                if (slot + (unsigned)n <= (unsigned)AM_ITEMS) {
-                    for (int q = 0; q < n; ++q) { S.items[cur ^ 1][slot + q][0] = q4[q][0]; S.items[cur ^ 1][slot + q][1] = q4[q][1]; }
-                    keep = false;                               // placed
-                }
+                // as many as still fit: no slot below n_items stays unwritten (see the first list above)
+                fit = slot >= (unsigned)AM_ITEMS ? 0 : min(n, (int)((unsigned)AM_ITEMS - slot));
+                for (int q = 0; q < fit; ++q) { S.items[cur ^ 1][slot + q][0] = q4[q][0]; S.items[cur ^ 1][slot + q][1] = q4[q][1]; }
+                keep = fit < n;                                 // all placed?
             }
-            // nodes whose quarters did not fit the list are searched depth first, one after the other by the whole warp
+            // quarters that did not fit the list are searched depth first, one after the other by the whole warp
             unsigned left = __ballot_sync(FULL, keep);
-            (void)todo;
             while (left) {
                 const int src = __ffs(left) - 1;
                 left &= left - 1;
                 const int sx0 = __shfl_sync(FULL, nx0, src), sy0 = __shfl_sync(FULL, ny0, src);
                 const int spx = __shfl_sync(FULL, px, src), spy = __shfl_sync(FULL, py, src);
                 const unsigned sf = __shfl_sync(FULL, f, src), sc = __shfl_sync(FULL, cdc, src);
+                const int sfit = __shfl_sync(FULL, fit, src);
                 unsigned q4[4][2];
                 int n = 0;
-                if (lane == 0) push_quarters(sx0, sy0, lg, spx, spy, sf, sc, q4, n, 4);
+                if (lane == 0) push_quarters(sx0, sy0, lg, spx, spy, sf, sc, q4, n, 4);     // same order as on lane `src`
                 n = __shfl_sync(FULL, n, 0);
-                for (int q = 0; q < n; ++q) {
+                for (int q = sfit; q < n; ++q) {
                     const unsigned r0 = __shfl_sync(FULL, q4[q][0], 0), r1 = __shfl_sync(FULL, q4[q][1], 0);
                     dfs(r0, r1);
                 }
