@@ -796,7 +796,7 @@ def run_ours(args):
         print(json.dumps(line))
         return
     if cfg == "cfg3":
-        line = run_frames(args, D, cfg, "CFG3", args.frames or 32, 1, args.unique or 32, D.world == 1 and not args.no_cpu, 1)
+        line = run_frames(args, D, cfg, "CFG3", args.frames or 128, 1, args.unique or 16, D.world == 1 and not args.no_cpu, 1)
     elif cfg == "cfg5":
         B = args.frames or 256
         total = 8192
@@ -811,7 +811,7 @@ def run_ours(args):
         small = argparse.Namespace(**vars(args))
         small.steps, small.warmup, small.lanes = 3, 3, 1
         for name, fn in (("cfg1", lambda: run_cfg1(small, D, iters=20)),
-                         ("cfg3", lambda: run_frames(small, D, "cfg3", "CFG3", 16, 1, 8, False, 1)),
+                         ("cfg3", lambda: run_frames(small, D, "cfg3", "CFG3", 64, 1, 8, False, 1)),
                          ("cfg4", lambda: run_cfg4(small, D, steps=3))):
             try:
                 extra[name] = brief(fn())
@@ -829,7 +829,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--frames", type=int, default=0, help="frames per GPU per call (default 256; cfg3: 32)")
+    ap.add_argument("--frames", type=int, default=0, help="frames per GPU per call (default 256; cfg3: 128 = 69 GB of context)")
     ap.add_argument("--unique", type=int, default=0, help="distinct synthetic frames generated per rank (default: all of them)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cnn", default="bf16", choices=["fp32", "bf16"])

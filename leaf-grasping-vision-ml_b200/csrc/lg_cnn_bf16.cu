@@ -40,6 +40,8 @@ constexpr int TILE_M = 512;     // positions per work item: 4 UMMA tiles of 128 
 constexpr int UMMA_T = 4;
 // weight stages in flight (what shared memory allows; the blocked input stage of the pooled layers is a little larger)
 __host__ __device__ constexpr int nb_stages(int nc, bool pool) { return nc == 64 ? 8 : (pool ? 4 : 5); }
+// layer 0 (KP = 2): one 2 KB stage per tap, so that all nine can stay resident (UmmaConvArgs::wres)
+__host__ __device__ constexpr int nb_stages_kp(int kp, int nc, bool pool) { return kp == 2 ? 9 : nb_stages(nc, pool); }
 constexpr int CONV_THREADS = 416;   // warp 0 producer, warp 1 MMA issuer + TMEM owner, warps 2-9 epilogue, warps 10-12 further MMA issuers
 constexpr int ISSUER2_WARP = 10;
 constexpr int EPI_WARPS = 8;        // two warps per TMEM lane quarter, each taking every other 32-column chunk
@@ -71,6 +73,8 @@ struct UmmaConvArgs {
     int layer;            // 0..5 (timers only)
     long long Rout;       // POOL kernels (2x2 max-pool fused into the epilogue, S = 32 or 16): rows per plane of the pooled output
     int issuers;          // MMA-issuing warps (1, 2 or 4): warp 1 and warps 10.., each owning UMMA_T / issuers accumulator tiles
+    int wres;             // layer 0 only (KP = 2, one channel chunk, one output split): the nine 2 KB weight stages are loaded once
+                          // per CTA and stay in shared memory instead of being streamed again for every item
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -159,7 +163,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int ACC_STAGES = 512 / (UMMA_T * NC);          // 2 (NC = 64) or 1 (NC = 128) accumulator sets in TMEM
     constexpr uint32_t B_STAGE = KP * NC * 16;
-    constexpr int NB_STAGES = nb_stages(NC, POOL);
+    constexpr int NB_STAGES = nb_stages_kp(KP, NC, POOL);
+    const bool wres = KP == 2 && A.wres != 0;
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NC >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t a_stage_bytes = (uint32_t)KP * A.rows * 16;
     unsigned char* sA = smem;
@@ -225,6 +230,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
                 if (a_st == 0) a_ph ^= 1;
             };
             const int first = blockIdx.x;
+            if (wres && first < n_items) {      // all nine taps' weights, once: stage = tap, each barrier completes a single time
+                for (int tap = 0; tap < 9; ++tap) {
+                    const uint32_t bar = smem_u32(&b_full[tap]);
+                    mbar_expect_tx(bar, B_STAGE);
+                    bulk_g2s(smem_u32(sB + (size_t)tap * B_STAGE), A.wt + (size_t)tap * (KP * NC), B_STAGE, bar);
+                }
+            }
             if (first < n_items) issue_a(first, 0);
             for (int item = first; item < n_items; item += gridDim.x) {
                 const int half = item % A.n_split;
@@ -238,6 +250,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
                             if (kc + 1 < A.KC) issue_a(item, kc + 1);
                             else if (item + (int)gridDim.x < n_items) issue_a(item + gridDim.x, 0);
                         }
+                        if (wres) continue;
                         mbar_wait(smem_u32(&b_empty[b_st]), b_ph ^ 1);
                         const uint32_t bar = smem_u32(&b_full[b_st]);
                         mbar_expect_tx(bar, B_STAGE);
@@ -302,11 +315,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
                                 umma_bf16(d_tmem + (uint32_t)(t * NC), ad, bd, IDESC, j == 0 ? first_acc : 1u);
                             }
                         }
-                        tc_commit(smem_u32(&b_empty[b_st]));
+                        if (!wres) tc_commit(smem_u32(&b_empty[b_st]));
                     }
                     __syncwarp();
                     LG_TACC(3, t_issue);
-                    if (++b_st == NB_STAGES) { b_st = 0; b_ph ^= 1; }
+                    // resident weights: stage = tap, and the wait above is always for the stage's one and only phase
+                    if (++b_st == NB_STAGES) { b_st = 0; if (!wres) b_ph ^= 1; }
                 }
                 if (lane == 0) tc_commit(smem_u32(&a_empty[a_st]));
                 __syncwarp();
@@ -347,10 +361,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
             auto store_tile = [&](int t, uint32_t (&v)[CHUNKS][32]) {
                 const long long q = (long long)tile * TILE_M + t * 128 + wq * 32 + lane;
                 bool data = q < Q;
-                if (data) {
-                    const int ql = (int)(q % A.PP);
-                    const int r = ql / A.pitch, cc = ql - r * A.pitch;
-                    data = (r >= 1) && (cc >= 1);
+                if (data) {      // positions stay below 2^31 (65536 patches x 33 x 33): 32-bit division, no 64-bit subroutine per tile
+                    const unsigned ql = (unsigned)q % (unsigned)A.PP;
+                    const unsigned r = ql / (unsigned)A.pitch, cc = ql - r * (unsigned)A.pitch;
+                    data = (r >= 1u) && (cc >= 1u);
                 }
 #pragma unroll
                 for (int j = 0; j < CHUNKS; ++j) {
@@ -593,7 +607,7 @@ inline int a_rows(int S, bool pool) {
 
 template <int KP, int NC, bool POOL>
 size_t conv_smem(int S) {
-    return 2 * (size_t)KP * a_rows(S, POOL) * 16 + (size_t)nb_stages(NC, POOL) * KP * NC * 16 + 256 * sizeof(float) +
+    return 2 * (size_t)KP * a_rows(S, POOL) * 16 + (size_t)nb_stages_kp(KP, NC, POOL) * KP * NC * 16 + 256 * sizeof(float) +
            32 * sizeof(uint64_t) + 16;
 }
 
@@ -686,7 +700,7 @@ extern "C" int lg_cnn_bf16_features(lg_context* c, const float* patches, int n, 
 static int run_cnn_bf16(lg_context* c, const float* patches, int n, const int32_t* n_dev, float* logits, int stop_layer,
                         float* feat_out, cudaStream_t st, int generic_tail) {
     if (!c->cnn.bf16_blob) { lg_set_error("bf16 CNN weights are not prepared"); return LG_E_ARG; }
-    static int sms = 0, issuers = 4, fuse_pool = 1;
+    static int sms = 0, issuers = 4, fuse_pool = 1, wres = 1;
     if (!sms) {
         int dev = 0;
         LG_CUDA(cudaGetDevice(&dev));
@@ -695,6 +709,8 @@ static int run_cnn_bf16(lg_context* c, const float* patches, int n, const int32_
         if (e && (e[0] == '1' || e[0] == '2' || e[0] == '4')) issuers = e[0] - '0';
         const char* fp = getenv("LG_CNN_FUSE_POOL");  // measurement switch: 0 = separate pool kernels after layers 1 and 3
         if (fp && fp[0] == '0') fuse_pool = 0;
+        const char* wr = getenv("LG_CNN_L0_RESIDENT"); // measurement switch: 0 = layer 0 streams its weights per item like the others
+        if (wr && wr[0] == '0') wres = 0;
     }
     // bias pointers inside the fp32 blob; bf16 weights inside bf16_blob
     const float* bias[6];
@@ -728,7 +744,7 @@ static int run_cnn_bf16(lg_context* c, const float* patches, int n, const int32_
             A.R = rows_per_plane(L.S, m);
             A.pitch = L.S + 1; A.PP = A.pitch * A.pitch; A.n_dev = n_dev; A.n_host = m;
             const bool fused_pool = fuse_pool && (l == 1 || l == 3);   // second conv of the 32 px and 16 px blocks
-            A.KC = L.KC; A.n_split = L.cout / L.NC; A.rows = a_rows(L.S, fused_pool); A.cout = L.cout; A.layer = l; A.issuers = issuers;
+            A.KC = L.KC; A.n_split = L.cout / L.NC; A.rows = a_rows(L.S, fused_pool); A.cout = L.cout; A.layer = l; A.issuers = issuers; A.wres = wres;
             A.Rout = rows_per_plane(L.S / 2, m);
             int rc;
             if (L.KP == 2) rc = launch_conv<2, 64, false>(A, L.S, sms, st);

@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(NMS_INIT_NT) nms_tiles_kernel(lg_context c, co
     }
 }
 
-__global__ void __launch_bounds__(NMS_NT) nms_kernel(lg_context c, const double* ext_score, const uint8_t* ext_valid,
+__global__ void __launch_bounds__(NMS_NT, 2) nms_kernel(lg_context c, const double* ext_score, const uint8_t* ext_valid,
                                                       int32_t* ext_xy, int32_t* ext_count) {
     __shared__ unsigned long long s_tk[NMS_TCACHE];
     __shared__ unsigned s_ti[NMS_TCACHE];
@@ -342,6 +342,11 @@ __global__ void __launch_bounds__(NMS_NT) nms_kernel(lg_context c, const double*
         const int ncx = c1 - c0 + 1, na = ncx * (r1 - r0 + 1);
         for (int a = warp; a < na; a += NMS_NW) {
             const int tile = (r0 + a / ncx) * g.tx + c0 + a % ncx;
+            // A tile keeps its entry when it has no alive key anyway or when its best pixel lies outside the new window:
+            // a pick only removes pixels, so a maximum that survives stays the maximum.
+            const unsigned long long ok_ = tk[tile];
+            const unsigned oi = ti[tile];
+            if (ok_ == 0ull || abs((int)(oi % (unsigned)W) - qx) > LG_NMS_REACH || abs((int)(oi / (unsigned)W) - qy) > LG_NMS_REACH) continue;
             unsigned long long nk;
             unsigned ni;
             nms_tile_best(key, valid, W, g, tile, pqx, pqy, cnt, lane, nk, ni);

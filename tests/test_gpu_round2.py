@@ -407,3 +407,31 @@ def test_band_kernel_statistics_on_boundary_heavy_labels(shape):
             assert np.float32(r["median_depth"]) == np.median(dep[i][mask]), (i, l)
             np.testing.assert_allclose(r["mean_depth"], dep[i][mask].astype(np.float64).mean(), rtol=3e-7)
     eng.close()
+
+
+@pytest.mark.parametrize("shape", [(97, 131), (240, 320), (64, 2100), (1080, 1440)])
+def test_candidate_search_ties_sparse_keys_and_large_tables(shape):
+    """nms_tiles_kernel / nms_kernel (best alive key per 32 x 8 tile, 20 rounds) against the sequential greedy pick of the
+    oracle on maps chosen to stress it: scores quantised to eight levels (every pick is a tie: the LARGER flat index must
+    win), keys on a few isolated pixels, a single positive key, NaN / negative / zero scores, sizes that are no multiple
+    of the tile, and a frame with more tiles than the shared-memory table holds (1080 x 1440: 6075 tiles)."""
+    H, W = shape
+    rng = np.random.default_rng(H * 7 + W)
+    maps = []
+    s = np.round(rng.random((H, W)) * 8) / 8; v = (rng.random((H, W)) < 0.7).astype(np.uint8); maps.append((s, v))       # ties everywhere
+    s = rng.random((H, W)); v = (rng.random((H, W)) < 0.002).astype(np.uint8); maps.append((s, v))                       # isolated keys
+    s = np.zeros((H, W)); s[H // 2, W // 3] = 0.5; v = np.ones((H, W), np.uint8); maps.append((s, v))                     # one key
+    s = rng.random((H, W)) - 0.5; s[rng.random((H, W)) < 0.1] = np.nan; v = np.ones((H, W), np.uint8); maps.append((s, v))  # NaN / negative
+    s = np.full((H, W), 0.25); v = np.ones((H, W), np.uint8); maps.append((s, v))                                         # one value everywhere
+    s = rng.random((H, W)); v = np.zeros((H, W), np.uint8); v[:, W - 1] = 1; v[H - 1, :] = 1; maps.append((s, v))          # last row / column only
+    score = np.stack([m[0] for m in maps])
+    valid = np.stack([m[1] for m in maps])
+    eng = _engine(len(maps), H, W, 2)
+    xy, cnt = eng.candidate_points(torch.from_numpy(score), torch.from_numpy(valid))
+    xy, cnt = xy.cpu().numpy(), cnt.cpu().numpy()
+    for k in range(len(maps)):
+        key = np.where(np.isnan(score[k]) | (score[k] <= 0), 0.0, score[k])        # a NaN or negative key is never picked as positive
+        ref = O.candidate_points(key, valid[k].astype(bool))
+        assert cnt[k] == len(ref), k
+        assert [tuple(p) for p in xy[k, :cnt[k]].tolist()] == ref, k
+    eng.close()
