@@ -174,7 +174,8 @@ extern "C" int lg_create(lg_context** out, int max_frames, int height, int width
         int prio_lo = 0, prio_hi = 0;
         if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
         if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, prio_hi);
-        for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->aux2_stream, cudaStreamNonBlocking, prio_hi);
+        for (int i = 0; i < 3 && e == cudaSuccess; ++i) {
             e = cudaEventCreateWithFlags(&c->ev_fork[i], cudaEventDisableTiming);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
         }
@@ -209,11 +210,12 @@ extern "C" void lg_destroy(lg_context* c) {
         if (c->copy_ev[i]) cudaEventDestroy(c->copy_ev[i]);
     if (c->copy_gate) cudaEventDestroy(c->copy_gate);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
         if (c->ev_fork[i]) cudaEventDestroy(c->ev_fork[i]);
         if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
     }
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+    if (c->aux2_stream) cudaStreamDestroy(c->aux2_stream);
     if (c->prof) {
         for (int r = 0; r < LG_PROF_RING; ++r)
             for (int i = 0; i < LG_PROF_MARKS; ++i)
@@ -260,12 +262,14 @@ extern "C" int lg_set_cnn_weights(lg_context* c, const float* blob_host, uint64_
 
 extern "C" uint64_t lg_cnn_model_floats(const lg_cnn_config* cfg) { return lg_cnn_config_ok(cfg) ? lg_cnn_config_floats(cfg) : 0; }
 
+// k = 0, 1: the side stream (stage 1, stage 2); k = 2: the second side stream of stage 2 (no timing marks of its own)
 cudaStream_t lg_fork(lg_context* c, int k, cudaStream_t st) {
     if (!c->overlap) return st;
-    if (cudaEventRecord(c->ev_fork[k], st) != cudaSuccess || cudaStreamWaitEvent(c->aux_stream, c->ev_fork[k], 0) != cudaSuccess)
+    cudaStream_t side = k == 2 ? c->aux2_stream : c->aux_stream;
+    if (cudaEventRecord(c->ev_fork[k], st) != cudaSuccess || cudaStreamWaitEvent(side, c->ev_fork[k], 0) != cudaSuccess)
         return st;
-    lg_mark(c, k == 0 ? LG_M_FORK1 : LG_M_FORK2, c->aux_stream);
-    return c->aux_stream;
+    if (k < 2) lg_mark(c, k == 0 ? LG_M_FORK1 : LG_M_FORK2, side);
+    return side;
 }
 
 int lg_join(lg_context* c, int k, cudaStream_t aux, cudaStream_t st) {
@@ -273,7 +277,7 @@ int lg_join(lg_context* c, int k, cudaStream_t aux, cudaStream_t st) {
         LG_CUDA(cudaEventRecord(c->ev_join[k], aux));
         LG_CUDA(cudaStreamWaitEvent(st, c->ev_join[k], 0));
     }
-    lg_mark(c, k == 0 ? LG_M_JOIN1 : LG_M_JOIN2, st);
+    if (k < 2) lg_mark(c, k == 0 ? LG_M_JOIN1 : LG_M_JOIN2, st);
     return LG_OK;
 }
 
@@ -298,13 +302,15 @@ static int run_stage2(lg_context* c, LgMaskSrc src, const float* depth, int n, l
     // inside transform on the leaf rectangle (+ its distance map), outside transform on the whole frame (max only)
     // Three independent pieces: the inside transform (a chain of row steps), the orientation, and the maximum of the
     // outside transform (sdf normalisation: branch and bound, the sweeps only as a fallback for the frames it flags).
-    // The two short ones run on the side stream beside the inside transform.
+    // They share no scratch, so each of the two short ones gets a side stream of its own beside the inside transform.
     cudaStream_t aux = lg_fork(c, 1, st);
+    cudaStream_t aux2 = lg_fork(c, 2, st);
     int rc = lg_run_orientation(c, src, n, aux);
-    if (!rc) rc = lg_run_outside_max(c, src, n, aux);
-    lg_mark(c, LG_M_ORIENT, aux);
+    if (!rc) rc = lg_run_outside_max(c, src, n, aux2);
+    lg_mark(c, LG_M_ORIENT, aux);                   // serialised (overlap off): after both; overlapped: the orientation's end
     if (!rc) rc = lg_run_chamfer(c, src, n, full ? 0 : 1, 0, 2, 0, 1, c->di, nullptr, c->dt_max, c->need_full, st);
-    const int rcj = lg_join(c, 1, aux, st);        // also on an error path: the side stream must not stay unordered
+    int rcj = lg_join(c, 1, aux, st);               // also on an error path: the side streams must not stay unordered
+    { const int rcj2 = lg_join(c, 2, aux2, st); if (!rcj) rcj = rcj2; }
     if (!rc && !rcj) rc = lg_run_chamfer(c, src, n, full ? 0 : 1, 0, 2, 1, 1, c->di, nullptr, c->dt_max, c->need_full, st);
     lg_mark(c, LG_M_CHAMFER, st);
     if (rc) return rc;

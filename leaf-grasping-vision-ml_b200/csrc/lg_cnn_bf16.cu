@@ -100,6 +100,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "}\n" ::"r"(bar), "r"(parity)
         : "memory");
 }
+// one non-blocking look at a barrier phase: 1 = complete.  The answer takes ~100 cycles to arrive; whoever asks early and
+// reads it late does not pay for them.
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
@@ -181,7 +196,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
                                                      // on tile t start as soon as the epilogue has read tile t
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2 * UMMA_T);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // The warp index through a shuffle: the compiler then knows it is the same in all lanes, keeps everything derived from it
+    // (accumulator tile, descriptors) in uniform registers and feeds tcgen05.mma from them directly - with threadIdx.x >> 5
+    // every MMA is preceded by an elect / register-to-uniform "waterfall" of ~20 dependent instructions.
+    const int warp = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int n_patches = A.n_dev ? min(*A.n_dev, A.n_host) : A.n_host;
     const long long Q = (long long)n_patches * A.PP;                       // positions that carry data
     const int n_tiles = (int)((Q + A.pitch + 1 + TILE_M - 1) / TILE_M);      // + the zero row behind the last patch
@@ -210,7 +228,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xFFFFFFFFu, *tmem_slot, 0);      // uniform for the compiler, like the warp index
 
     if (warp == 0) {
         // ===== producer: bulk copies of the input tile (once per channel chunk) and of the per-tap weights =====
@@ -270,6 +288,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
         if (issuer >= A.issuers) goto done;
         const int t_count = UMMA_T / A.issuers, t_base = issuer * t_count;
         int a_st = 0, a_ph = 0, b_st = 0, b_ph = 0, acc_st = 0, acc_ph = 0;
+        bool w_ready = false;                              // resident weights (layer 0): their nine stages have arrived
+        uint32_t b_ok = 0;                                 // weight stage b_st is already known to be complete (probed one tap ahead)
         const uint32_t rows2 = 2u * (uint32_t)A.rows;      // two planes (one K = 16 step) in 16-byte units
 #ifdef LG_CNN_TIMING
         long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -282,13 +302,58 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
                 LG_TACC(0, t0);
             }
             tc_fence_after();
+            if (KP == 2 && wres) {
+                // Layer 0 with resident weights: nothing to wait for between the taps, so the item's nine MMAs per tile go out
+                // back to back (a wait on an mbarrier costs ~100 cycles even when it is already complete, and this layer has
+                // one MMA per tap and tile).
+                if (!w_ready) {
+                    LG_T0(t0);
+                    for (int tap = 0; tap < 9; ++tap) mbar_wait(smem_u32(&b_full[tap]), 0);
+                    LG_TACC(2, t0);
+                    w_ready = true;
+                }
+                { LG_T0(t0); mbar_wait(smem_u32(&a_full[a_st]), a_ph); LG_TACC(1, t0); }
+                tc_fence_after();
+                LG_T0(t_issue);
+                if (lane == 0) {
+                    const uint32_t a_base = smem_u32(sA + (size_t)a_st * a_stage_bytes);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc_st * UMMA_T * NC);
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int ky = tap / 3, kx = tap - ky * 3;
+                        const uint32_t a_lo = desc_lo(a_base + (uint32_t)(ky * A.pitch + kx) * 16, A.rows * 16);
+                        const uint32_t b_lo = desc_lo(smem_u32(sB + (size_t)tap * B_STAGE), NC * 16);
+#pragma unroll
+                        for (int tt = 0; tt < UMMA_T; ++tt) {
+                            if (tt >= t_count) break;
+                            const int t = t_base + tt;
+                            const uint64_t ad = ((uint64_t)DESC_HI << 32) | (uint64_t)(a_lo + (uint32_t)(t * 128));
+                            const uint64_t bd = ((uint64_t)DESC_HI << 32) | (uint64_t)b_lo;
+                            umma_bf16(d_tmem + (uint32_t)(t * NC), ad, bd, IDESC, tap != 0 ? 1u : 0u);
+                        }
+                    }
+                    tc_commit(smem_u32(&a_empty[a_st]));
+                    tc_commit(smem_u32(&acc_full[acc_st]));
+                }
+                __syncwarp();
+                LG_TACC(3, t_issue);
+                a_st ^= 1;
+                if (a_st == 0) a_ph ^= 1;
+                if (++acc_st == ACC_STAGES) { acc_st = 0; acc_ph ^= 1; }
+                continue;
+            }
             for (int kc = 0; kc < A.KC; ++kc) {
                 { LG_T0(t0); mbar_wait(smem_u32(&a_full[a_st]), a_ph); LG_TACC(1, t0); }
                 const uint32_t a_base = smem_u32(sA + (size_t)a_st * a_stage_bytes);
 #pragma unroll 1
                 for (int tap = 0; tap < 9; ++tap) {
-                    { LG_T0(t0); mbar_wait(smem_u32(&b_full[b_st]), b_ph); LG_TACC(2, t0); }
+                    { LG_T0(t0); if (!b_ok) mbar_wait(smem_u32(&b_full[b_st]), b_ph); LG_TACC(2, t0); }
                     tc_fence_after();
+                    // Ask for the NEXT weight stage now: the barrier's answer travels while this tap's MMAs are issued, so
+                    // the next turn of the loop starts without the round trip when the stage has already landed.
+                    int nb_st = b_st + 1, nb_ph = b_ph;
+                    if (nb_st == NB_STAGES) { nb_st = 0; nb_ph ^= 1; }
+                    b_ok = mbar_test(smem_u32(&b_full[nb_st]), nb_ph);
                     LG_T0(t_issue);
                     if (lane == 0) {
                         // One thread must issue an MMA every 32 (N = 64) / 64 (N = 128) cycles to keep the tensor pipe
@@ -315,12 +380,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
                                 umma_bf16(d_tmem + (uint32_t)(t * NC), ad, bd, IDESC, j == 0 ? first_acc : 1u);
                             }
                         }
-                        if (!wres) tc_commit(smem_u32(&b_empty[b_st]));
+                        tc_commit(smem_u32(&b_empty[b_st]));
                     }
                     __syncwarp();
                     LG_TACC(3, t_issue);
-                    // resident weights: stage = tap, and the wait above is always for the stage's one and only phase
-                    if (++b_st == NB_STAGES) { b_st = 0; if (!wres) b_ph ^= 1; }
+                    b_st = nb_st; b_ph = nb_ph;
                 }
                 if (lane == 0) tc_commit(smem_u32(&a_empty[a_st]));
                 __syncwarp();
@@ -375,9 +439,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
                     for (int g = 0; g < 4; ++g) {
                         uint4 w = make_uint4(0, 0, 0, 0);
                         if (data) {
+                            // the eight biases as two 128-bit shared-memory loads (32-byte aligned: multiples of 8 floats)
+                            const float4 b0 = *reinterpret_cast<const float4*>(bs + g * 8), b1 = *reinterpret_cast<const float4*>(bs + g * 8 + 4);
+                            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                             float f[8];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) f[e] = fmaxf(__uint_as_float(v[j][g * 8 + e]) + bs[g * 8 + e], 0.f);
+                            for (int e = 0; e < 8; ++e) f[e] = fmaxf(__uint_as_float(v[j][g * 8 + e]) + bb[e], 0.f);
                             w.x = pack_bf16x2(f[0], f[1]); w.y = pack_bf16x2(f[2], f[3]);
                             w.z = pack_bf16x2(f[4], f[5]); w.w = pack_bf16x2(f[6], f[7]);
                         }
@@ -401,10 +468,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_umma_kernel(UmmaConvA
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         uint32_t w[4];
+                        const float4 b0 = *reinterpret_cast<const float4*>(bs + g * 8), b1 = *reinterpret_cast<const float4*>(bs + g * 8 + 4);
+                        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const float f0 = fmaxf(__uint_as_float(v[j][g * 8 + 2 * e]) + bs[g * 8 + 2 * e], 0.f);
-                            const float f1 = fmaxf(__uint_as_float(v[j][g * 8 + 2 * e + 1]) + bs[g * 8 + 2 * e + 1], 0.f);
+                            const float f0 = fmaxf(__uint_as_float(v[j][g * 8 + 2 * e]) + bb[2 * e], 0.f);
+                            const float f1 = fmaxf(__uint_as_float(v[j][g * 8 + 2 * e + 1]) + bb[2 * e + 1], 0.f);
                             uint32_t m = pack_bf16x2(f0, f1);
                             uint32_t o1 = __shfl_xor_sync(0xFFFFFFFFu, m, 1);
                             __nv_bfloat162 a = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&m), *reinterpret_cast<__nv_bfloat162*>(&o1));

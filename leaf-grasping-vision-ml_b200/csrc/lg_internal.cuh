@@ -168,8 +168,8 @@ struct lg_context {
     cudaEvent_t copy_gate;                   // the caller's stream reached the start of this host call
     // Independent branches run side by side: the distance transform of the leaf union next to the per-leaf
     // statistics, the orientation next to the chamfer transforms.  aux_stream forks from and joins the caller's stream.
-    cudaStream_t aux_stream;
-    cudaEvent_t ev_fork[2], ev_join[2];
+    cudaStream_t aux_stream, aux2_stream;
+    cudaEvent_t ev_fork[3], ev_join[3];
     int overlap;
     // optional per-stage timing (lg_set_profiling): events recorded on the stream the stage runs on
     LgProf* prof;                            // host-side state, kept out of this struct: kernels take the struct by value

@@ -62,7 +62,9 @@ __global__ void __launch_bounds__(SC_TW * SC_TH) score_kernel(lg_context c, LgMa
     for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
     const int tx0 = r.sx0 + (tile % tiles_x) * SC_TW, ty0 = r.sy0 + (tile / tiles_x) * SC_TH;
     __syncthreads();     // the previous tile's readers of zt / st are done
-    // masked depth tile with reflect-101 borders (image_processor.py:60-61)
+    // masked depth tile with reflect-101 borders (image_processor.py:60-61); at most three turns per thread, unrolled so
+    // that their label and depth loads are all in flight together
+#pragma unroll
     for (int i = tid; i < (SC_TH + 6) * (SC_TW + 6); i += SC_TW * SC_TH) {
         const int ly = i / (SC_TW + 6), lx = i - ly * (SC_TW + 6);
         const int y = reflect101(ty0 - 3 + ly, H), x = reflect101(tx0 - 3 + lx, W);

@@ -11,7 +11,7 @@ import sys
 
 STAGE_OF = [("leaf_band", "leaf_stats"), ("leaf_median", "median"), ("edt_argmax", "edt_rows"), ("select_leaf", "select"),
             ("chamfer", "chamfer"), ("outside_max", "orientation"), ("leaf_boundary", "orientation"), ("orient", "orientation"),
-            ("score_kernel", "score_maps"), ("nms_kernel", "candidates"), ("gather_kernel", "patches"), ("compact_slots", "patches"),
+            ("score_kernel", "score_maps"), ("nms_tiles", "candidates"), ("nms_kernel", "candidates"), ("gather_kernel", "patches"), ("compact_slots", "patches"),
             ("conv3x3_umma", "cnn"), ("pool2x2", "cnn"), ("pack_input", "cnn"), ("cnn_tail", "cnn"), ("fuse_kernel", "fuse")]
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
