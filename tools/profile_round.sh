@@ -3,6 +3,7 @@
 export R=${R:-r5}
 set -x
 mkdir -p gpurun_out/$R
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/$R/smoke.log 2>&1; tail -2 gpurun_out/$R/smoke.log
 python bench.py --steps 20 --warmup 3 > gpurun_out/$R/bench_n1.json 2> gpurun_out/$R/bench_n1.err
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/$R/bench_reference_n1.json 2> gpurun_out/$R/bench_reference_n1.err
 for c in cfg1 cfg3 cfg4 cfg5; do python bench.py --config $c --steps 3 --warmup 3 --no-cpu > gpurun_out/$R/bench_$c.json 2> gpurun_out/$R/bench_$c.err; done
