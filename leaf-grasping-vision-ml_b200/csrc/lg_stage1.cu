@@ -184,6 +184,9 @@ __device__ __forceinline__ void band_add_runs(const BandShared& S, int il, int x
     }
 }
 
+// a hint, no register held: the line starts its way from DRAM to L2 while the CTA does something else
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // the 8 labels of pixels [p0, p0 + np) of a frame (np < 8: the rest reads as -1)
 template <bool VEC>
 __device__ __forceinline__ void load_labels8(const int16_t* __restrict__ lp, size_t p0, int np, int (&lab)[TS_PX]) {
@@ -259,6 +262,10 @@ __global__ void __launch_bounds__(MAX_NT, MIN_CTAS) leaf_band_kernel(lg_context 
         }
         if (uni) {
             code = (int)(pat & 0xFFFFu);
+            if (code >= 1) {             // a leaf block: its depth rows are wanted after the offsets scan - start them towards L2 now
+#pragma unroll
+                for (int r = 0; r < LG_BAND; ++r) prefetch_l2(dp + (size_t)(row0 + r) * W + x0);
+            }
             const uint8_t v = code >= 1 ? 0xFFu : 0u;
 #pragma unroll
             for (int r = 0; r < LG_BAND; ++r) ub[(size_t)(row0 + r) * pitch + tid] = v;
@@ -335,6 +342,7 @@ __global__ void __launch_bounds__(MAX_NT, MIN_CTAS) leaf_band_kernel(lg_context 
         }
         if (have) S.prel[it] = make_uint4(rel[0] | (rel[1] << 16), rel[2] | (rel[3] << 16), rel[4] | (rel[5] << 16), rel[6] | (rel[7] << 16));
         if (np > 0) {
+            if (bits) prefetch_l2(dp + (size_t)y * W + xs);      // this row's depth is read in the second boundary phase
             ub[(size_t)y * pitch + blk] = (uint8_t)bits;
             if (bits) atomicMin(&s_first, (unsigned)((size_t)y * W) + (unsigned)xs + (unsigned)(__ffs(bits) - 1));
             if (bad) s_bad = 1;
