@@ -153,7 +153,7 @@ extern "C" int lg_create(lg_context** out, int max_frames, int height, int width
     A(&c->hull, B * (size_t)(12 * (height + 2))); A(&c->orient, B);
     A(&c->m_sdf, B * P); A(&c->m_app, B * P); A(&c->m_acc, B * P); A(&c->m_trad, B * P);
     A(&c->m_flat, B * P); A(&c->m_stem, B * P); A(&c->m_valid, B * P);
-    A(&c->list_n, B);        // (list_key / list_idx, the sample collector's scratch, are allocated by its first call)
+    // (the sample collector's tip lists, 12 bytes per pixel of capacity, are allocated by its first call: lg_collect.cu)
     c->tile_cap = ((width + 31) / 32) * ((height + 7) / 8);
     A(&c->tile_key, B * (size_t)c->tile_cap); A(&c->tile_id, B * (size_t)c->tile_cap);
     A(&c->patches, B * LG_TOP_K * (size_t)(LG_CHANNELS * LG_PATCH * LG_PATCH)); A(&c->logits, B * LG_TOP_K);

@@ -10,7 +10,7 @@
 // (seed, frame index, purpose, counter) - oracle.CollectorRng restates it and the golden vectors were made by
 // injecting that generator into the unmodified reference.
 //
-// Scratch (all free once the batch has been processed): NMS key lists -> ordered tip list; chamfer forward-pass
+// Scratch (all free once the batch has been processed): the collector's own tip lists (allocated by its first call); chamfer forward-pass
 // buffer -> the two erosion maps; hull work array -> header, stem row offsets, border turn-back points.
 #include <math_constants.h>
 
@@ -338,8 +338,8 @@ struct Sets {
 
 __device__ Sets frame_sets(const lg_context& c, int b) {
     Sets S;
-    S.tip_idx = c.list_idx + (size_t)b * c.P;
-    S.tip_val = reinterpret_cast<float*>(c.list_key + (size_t)b * c.P);
+    S.tip_idx = c.tip_idx_buf + (size_t)b * c.P;
+    S.tip_val = reinterpret_cast<float*>(c.tip_val_buf + (size_t)b * c.P);
     uint8_t* e = reinterpret_cast<uint8_t*>(c.dt_fwd);
     S.e1 = e + (size_t)b * c.P;
     S.e2 = e + ((size_t)c.B + b) * c.P;
@@ -530,14 +530,14 @@ int lg_context_dev_alloc(lg_context* c, void** p, size_t bytes);
 // The tip lists (12 bytes per pixel of capacity) belong to the collector alone: its first call allocates them, so that a
 // context that only selects grasps does not carry them.
 static int ensure_collector_scratch(lg_context* c) {
-    if (c->list_key && c->list_idx) return LG_OK;
+    if (c->tip_val_buf && c->tip_idx_buf) return LG_OK;
     void* p = nullptr;
     int rc = lg_context_dev_alloc(c, &p, (size_t)c->B * c->P * sizeof(double));
     if (rc) return rc;
-    c->list_key = static_cast<double*>(p);
+    c->tip_val_buf = static_cast<double*>(p);
     rc = lg_context_dev_alloc(c, &p, (size_t)c->B * c->P * sizeof(uint32_t));
     if (rc) return rc;
-    c->list_idx = static_cast<uint32_t*>(p);
+    c->tip_idx_buf = static_cast<uint32_t*>(p);
     return LG_OK;
 }
 

@@ -135,9 +135,8 @@ struct lg_context {
     double *m_sdf, *m_app, *m_acc, *m_trad;  // [B][P]
     float *m_flat, *m_stem;                  // [B][P]
     uint8_t* m_valid;                        // [B][P]
-    double* list_key;                        // [B][P] scratch of the sample collector (tip values), allocated by its first call
-    uint32_t* list_idx;                      // [B][P] scratch of the sample collector (tip indices), likewise
-    uint32_t* list_n;                        // [B]
+    double* tip_val_buf;                     // [B][P] scratch of the sample collector (tip values, used as float), allocated by its first call
+    uint32_t* tip_idx_buf;                   // [B][P] scratch of the sample collector (tip indices), likewise
     unsigned long long* tile_key;            // [B][tile_cap] candidate search: best alive key (bits of the double) of every 32 x 8 tile
     uint32_t* tile_id;                       // [B][tile_cap] and its flat pixel index
     int tile_cap;                            // ceil(W / 32) * ceil(H / 8)

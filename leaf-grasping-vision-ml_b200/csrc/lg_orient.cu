@@ -520,7 +520,7 @@ __global__ void mask_clear_kernel(lg_context c, int n) {
     if (b >= n) return;
     size_t o = (size_t)b * c.L + 1;
     c.bx0[o] = 0xFFFFFFFFu; c.by0[o] = 0xFFFFFFFFu; c.bx1[o] = 0; c.by1[o] = 0;
-    c.status[b] = 0; c.list_n[b] = 0;
+    c.status[b] = 0;
 }
 
 }  // namespace

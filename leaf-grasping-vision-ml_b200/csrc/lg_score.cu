@@ -399,9 +399,9 @@ __global__ void __launch_bounds__(NMS_NT, 2) nms_kernel(lg_context c, const doub
     }
 }
 
-__global__ void clear_list_kernel(lg_context c, int n) {
+__global__ void clear_status_kernel(lg_context c, int n) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < n) { c.list_n[b] = 0; c.status[b] = 0; }
+    if (b < n) c.status[b] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -821,7 +821,7 @@ int lg_run_export_maps(lg_context* c, int n, double* sdf, double* app, float* fl
 
 int lg_run_candidates_from_maps(lg_context* c, const double* score, const uint8_t* valid, int n, int32_t* xy, int32_t* count,
                                 cudaStream_t st) {
-    clear_list_kernel<<<(n + 63) / 64, 64, 0, st>>>(*c, n);
+    clear_status_kernel<<<(n + 63) / 64, 64, 0, st>>>(*c, n);
     LG_LAUNCH_CHECK();
     nms_tiles_kernel<<<dim3(nms_init_ctas(c, n), n), NMS_INIT_NT, 0, st>>>(*c, score, valid);
     LG_LAUNCH_CHECK();
