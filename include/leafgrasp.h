@@ -143,6 +143,17 @@ int lg_set_score_weights(lg_context* ctx, double approach, double sdf, double fl
 int lg_set_host_label_rle(lg_context* ctx, int on);
 int lg_host_call_bytes(const lg_context* ctx, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
 
+/* The encoder those host threads run (pure host code, needs no device): the runs of one label image, one 32-bit word
+ * `first column | label << 16` per run - a run starts at column 0 of every row and wherever a label differs from its left
+ * neighbour - with rowoff[y] = index of row y's first run and rowoff[height] = the number of runs (rowoff holds height + 1
+ * words).  Returns the number of runs, or 0xFFFFFFFF when they do not fit run_cap (or an argument is bad; width <= 65535).
+ * isa: -1 = the fastest version the CPU supports (lg_rle_host_isa: 2 AVX-512BW, 32 labels per step; 1 AVX2, 16; 0 portable),
+ * 0..2 = that version if the CPU has it; every version produces the same words.  Replaces nothing in the reference: it is
+ * the price of not sending leaf_grasp_node_v3.py:110's mask tensor over the link as it is. */
+uint32_t lg_rle_encode_labels(const int16_t* labels, int height, int width, uint32_t* runs, uint32_t run_cap,
+                              uint32_t* rowoff, int isa);
+int lg_rle_host_isa(void);
+
 /* 1: page-locked host memory known to CUDA, 0: pageable (or not host memory), < 0: error. */
 int lg_host_memory_is_pinned(const void* host_ptr);
 

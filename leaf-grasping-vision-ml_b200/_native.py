@@ -94,6 +94,8 @@ SYMBOLS = {
     "lg_host_memory_is_pinned": (C.c_int, [_P]),
     "lg_set_host_label_rle": (C.c_int, [_P, C.c_int]),
     "lg_host_call_bytes": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "lg_rle_encode_labels": (C.c_uint32, [_P, C.c_int, C.c_int, _P, C.c_uint32, _P, C.c_int]),
+    "lg_rle_host_isa": (C.c_int, []),
     "lg_set_score_weights": (C.c_int, [_P, C.c_double, C.c_double, C.c_double, C.c_double]),
     "lg_launch_count": (C.c_uint64, []),
     "lg_sizeof_frame_result": (C.c_uint64, []),

@@ -29,6 +29,10 @@
 int lg_process_batch_device_impl(lg_context* c, const int16_t* labels, const float* depth, int frames, const lg_camera* cam,
                                  lg_frame_result* results, float* rec_out, int use_bf16_cnn, void* stream);
 int lg_context_dev_alloc(lg_context* c, void** p, size_t bytes);
+// lg_rle_host.cpp (host compiler, AVX-512BW / AVX2 / portable by what the CPU has): the runs of one frame; returns their
+// number, or 0xFFFFFFFF when they do not fit `run_cap`
+extern "C" uint32_t lg_rle_encode_labels(const int16_t* labels, int height, int width, uint32_t* runs, uint32_t run_cap,
+                                         uint32_t* rowoff, int isa);
 
 namespace {
 
@@ -106,32 +110,6 @@ struct HostPipe {
     cudaEvent_t expanded[RLE_SLOTS] = {};   // the slot's device buffers have been read
     bool used[RLE_SLOTS] = {};
 };
-
-// runs of one frame; returns the number of runs, or 0xFFFFFFFF when they do not fit `cap`
-uint32_t encode_frame(const int16_t* lab, int H, int W, uint32_t* runs, uint32_t cap, uint32_t* rowoff) {
-    uint32_t n = 0;
-    for (int y = 0; y < H; ++y) {
-        rowoff[y] = n;
-        const uint16_t* row = reinterpret_cast<const uint16_t*>(lab) + (size_t)y * W;
-        int x = 0;
-        while (x < W) {
-            const uint16_t cur = row[x];
-            if (n >= cap) return 0xFFFFFFFFu;
-            runs[n++] = (uint32_t)x | ((uint32_t)cur << 16);
-            ++x;
-            const unsigned long long pat = (unsigned long long)cur * 0x0001000100010001ull;
-            while (x + 4 <= W) {                 // four labels at a time while they repeat
-                unsigned long long w;
-                memcpy(&w, row + x, 8);
-                if (w != pat) break;
-                x += 4;
-            }
-            while (x < W && row[x] == cur) ++x;
-        }
-    }
-    rowoff[H] = n;
-    return n;
-}
 
 // one warp per image row: the row's runs (first column | label << 16) back into int16 labels
 __global__ void __launch_bounds__(256) expand_labels_kernel(const uint32_t* __restrict__ runs_all,
@@ -302,7 +280,7 @@ extern "C" int lg_process_batch_host(lg_context* c, const int16_t* labels_host, 
             std::vector<uint32_t> n_runs((size_t)m), base((size_t)m + 1);
             const std::function<void(int)> job = [&](int f) {
                 uint32_t* ro = rowoff + (size_t)f * (H + 2);
-                n_runs[(size_t)f] = encode_frame(labels_host + off + (size_t)f * P, H, W, runs + (size_t)f * cap, cap, ro);
+                n_runs[(size_t)f] = lg_rle_encode_labels(labels_host + off + (size_t)f * P, H, W, runs + (size_t)f * cap, cap, ro, -1);
                 if (n_runs[(size_t)f] == 0xFFFFFFFFu) ro[0] = 0xFFFFFFFFu;
             };
             hp->pool->run(m, job);

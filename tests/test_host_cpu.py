@@ -310,3 +310,69 @@ def test_collector_host_bookkeeping_and_file_format(tmp_path):
     assert col3.samples == [] and not os.path.exists(tmp_path / "d" / "training_data.pt")
     with pytest.raises(Exception):
         col3.collect_sample(torch.zeros(4, 4, dtype=torch.bool), torch.zeros(4, 4), None, {}, (1, 1), 0.5)   # no engine
+
+
+def _rle_reference(lab):
+    """NumPy statement of the run format (include/leafgrasp.h: lg_rle_encode_labels)."""
+    H, W = lab.shape
+    u = lab.view(np.uint16).astype(np.uint32)
+    start = np.ones((H, W), dtype=bool)
+    start[:, 1:] = u[:, 1:] != u[:, :-1]
+    ys, xs = np.nonzero(start)
+    runs = xs.astype(np.uint32) | (u[ys, xs] << 16)
+    rowoff = np.concatenate([[0], np.cumsum(start.sum(axis=1))]).astype(np.uint32)
+    return runs, rowoff
+
+
+def _rle_expand(runs, rowoff, H, W):
+    out = np.empty((H, W), dtype=np.uint16)
+    for y in range(H):
+        r = runs[rowoff[y]:rowoff[y + 1]]
+        x0 = (r & 0xFFFF).astype(np.int64)
+        x1 = np.append(x0[1:], W)
+        out[y] = np.repeat((r >> 16).astype(np.uint16), x1 - x0)
+    return out.view(np.int16)
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (3, 15), (5, 16), (7, 17), (9, 33), (16, 47), (8, 64), (37, 1440), (360, 480), (20, 4099)])
+def test_host_label_encoder_versions_agree_and_invert(shape):
+    """The label encoder of lg_process_batch_host (csrc/lg_rle_host.cpp) is host code, so it is checked here: every
+    instruction-set version the CPU offers writes exactly the words of the NumPy statement of the format, expanding the runs
+    gives the image back (negative ids and noise included), and a run table that is too small is reported, not overrun."""
+    import ctypes as C
+    from leafgrasp_b200 import _native as N, synth
+    h = N.lib()
+    H, W = shape
+    rng = np.random.default_rng(H * 10007 + W)
+    if (H, W) == (360, 480):
+        images = [synth.make_frame(synth.SMALL, 7, k)[0] for k in range(3)]
+    else:
+        blocky = np.repeat(np.repeat(rng.integers(0, 40, size=(-(-H // 4), -(-W // 37))), 4, axis=0), 37, axis=1)[:H, :W]
+        images = [blocky.astype(np.int16),
+                  rng.integers(-3, 3, size=(H, W)).astype(np.int16),                    # noise, negative ids
+                  np.full((H, W), 32767, dtype=np.int16),
+                  (np.arange(W)[None, :] % 2 * -32768 + np.zeros((H, 1))).astype(np.int16)]   # a run per pixel
+    best = h.lg_rle_host_isa()
+    assert 0 <= best <= 2
+    for lab in images:
+        lab = np.ascontiguousarray(lab)
+        want_runs, want_off = _rle_reference(lab)
+        n = len(want_runs)
+        assert np.array_equal(_rle_expand(want_runs, want_off, H, W), lab)
+        for isa in [-1] + list(range(best + 1)):
+            runs = np.full(n + 8, 0xDEADBEEF, dtype=np.uint32)
+            off = np.full(H + 2, 0xDEADBEEF, dtype=np.uint32)
+            got = h.lg_rle_encode_labels(lab.ctypes.data_as(C.c_void_p), H, W, runs.ctypes.data_as(C.c_void_p), n,
+                                         off.ctypes.data_as(C.c_void_p), isa)
+            assert got == n, (isa, got, n)
+            assert np.array_equal(runs[:n], want_runs) and np.all(runs[n:] == 0xDEADBEEF), isa
+            assert np.array_equal(off[:H + 1], want_off) and off[H + 1] == 0xDEADBEEF, isa
+            if n > 1:                                   # one word too few: overflow, and nothing written past the table
+                runs[:] = 0xDEADBEEF
+                got = h.lg_rle_encode_labels(lab.ctypes.data_as(C.c_void_p), H, W, runs.ctypes.data_as(C.c_void_p), n - 1,
+                                             off.ctypes.data_as(C.c_void_p), isa)
+                assert got == 0xFFFFFFFF and np.all(runs[n - 1:] == 0xDEADBEEF), isa
+    bad = np.zeros((2, 2), dtype=np.int16)
+    assert h.lg_rle_encode_labels(None, 2, 2, None, 4, None, -1) == 0xFFFFFFFF
+    assert h.lg_rle_encode_labels(bad.ctypes.data_as(C.c_void_p), 2, 70000, bad.ctypes.data_as(C.c_void_p), 4,
+                                  bad.ctypes.data_as(C.c_void_p), -1) == 0xFFFFFFFF
