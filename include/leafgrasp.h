@@ -121,7 +121,7 @@ uint64_t lg_cnn_model_floats(const lg_cnn_config* cfg);   /* 0 for an unsupporte
 int lg_process_batch(lg_context* ctx, const int16_t* labels, const float* depth, int frames,
                      const lg_camera* cam_host, lg_frame_result* results, int use_bf16_cnn, void* stream);
 
-/* Same, but labels/depth/results are HOST buffers: copies in (32-frame chunks on a copy stream, each chunk processed
+/* Same, but labels/depth/results are HOST buffers: copies in (16-frame chunks on a copy stream, each chunk processed
  * as soon as it has landed), runs, copies the results back and synchronises the stream.  This is the call the
  * end-to-end benchmark makes.  The inputs should be PINNED (cudaHostAlloc / cudaHostRegister / torch pin_memory):
  * pageable memory is accepted, but CUDA then stages every copy through its own pinned buffer and the copies no longer

@@ -4,7 +4,7 @@
 // End to end the path is bound by the host-to-device link: 9.33 MB per 1440 x 1080 frame (int16 labels 3.11 MB + float32
 // depth 6.22 MB) against ~4 ms of kernels per 256 frames.  Two things keep the link busy and its load small:
 //
-//   * chunks of 32 frames are copied on a private stream and processed on the caller's stream as soon as their event
+//   * chunks of 16 frames are copied on a private stream and processed on the caller's stream as soon as their event
 //     fires, so the kernels hide under the copies;
 //   * the LABEL image does not cross the link as it is.  An instance-label image is piecewise constant (a few dozen runs
 //     per row), so host threads run-length encode it inside the call - one 32-bit word (first column | label << 16) per

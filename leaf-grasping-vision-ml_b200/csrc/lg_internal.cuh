@@ -27,7 +27,7 @@
 #define LG_PROF_RING 32
 #define LG_BND_CAP 16384
 #define LG_MAX_HOST_CHUNKS 64
-#define LG_HOST_CHUNK_FRAMES 32
+#define LG_HOST_CHUNK_FRAMES 16
 enum LgMark { LG_M_START = 0, LG_M_STATS, LG_M_SCATTER, LG_M_MEDIAN, LG_M_EDT_COL, LG_M_EDT_ROW, LG_M_SELECT, LG_M_CHAMFER,
               LG_M_ORIENT, LG_M_SCORE, LG_M_NMS, LG_M_GATHER, LG_M_CNN, LG_M_FUSE, LG_M_COUNT,
               // fork / join points of the auxiliary stream (not stages): see lg_stage_times

@@ -94,7 +94,7 @@ def test_smooth_depth_against_reference_golden():
 def test_candidate_records_written_by_fusion_kernel(blob):
     """lg_set_record_output: the [frames, 20, 4] float32 block the all-gather sends is written by fuse_kernel and equals
     the records derived from the result structs - for the device entry point, the chunked host entry point (40 frames =
-    two chunks) and with two lanes."""
+    three chunks) and with two lanes."""
     from leafgrasp_b200 import dist as lgd
     spec = synth.SMALL
     n = 40
@@ -319,7 +319,7 @@ def test_host_call_run_length_encodes_labels_losslessly(blob):
     device).  Lossless: every field of the results equals the device-resident call's and the raw-copy call's, the link
     carries depth + ~3 % of the label bytes, and a frame of label noise (more runs than the staging holds) goes raw."""
     spec = synth.CFG2
-    n = 40                                                     # two chunks of 32
+    n = 40                                                     # three chunks (16 + 16 + 8)
     lab, dep = synth.make_batch(spec, SEED, 500, n)
     rng = np.random.default_rng(5)
     lab[7] = rng.integers(0, 3, size=lab[7].shape).astype(np.int16)      # noise: ~1 M runs
