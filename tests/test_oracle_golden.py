@@ -21,10 +21,11 @@ RTOL, ATOL = 1e-6, 1e-7
 
 
 META2 = json.load(open(os.path.join(GOLD, "golden_meta_r2.json")))     # second set (make_golden_r2.py)
+META3 = json.load(open(os.path.join(GOLD, "golden_meta_r3.json")))     # third set (make_golden_r3.py): CPU-side pinning only
 
 
 def _frames():
-    return [(f["spec"], f["index"], f["file"]) for f in META["frames"] + META2["frames"]]
+    return [(f["spec"], f["index"], f["file"]) for f in META["frames"] + META2["frames"] + META3["frames"]]
 
 
 @pytest.fixture(scope="module")
